@@ -1,0 +1,137 @@
+/* mdm.h -- C ABI of libmdm_sm100.so: the B200 (sm_100a) kernels behind the masked-diffusion
+ * hot path of hytae1993/masked-diffusion-model.
+ *
+ * The reference has no native/FFI boundary: its hot path sits behind
+ * Python call signatures.  This header is the *new* native boundary the Python drop-in modules
+ * (`masked-diffusion-model_b200/{scheduler,sampler,trainer_masked*}.py`) bind through ctypes.
+ * Each group cites the reference code it replaces (paths relative to /root/reference/code).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MDM_E_* code on failure; the message of
+ *     the last failure on the calling thread is available from mdm_last_error();
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller (PyTorch)
+ *     owns every buffer, including workspaces -- the library never allocates device memory;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises, so every entry point can be captured into a CUDA graph;
+ *   - images are NCHW contiguous (the reference's layout); activations inside the denoiser
+ *     are NHWC bf16 with an explicit channel stride `ld` (elements) so that channel slices of
+ *     a concat buffer can be passed without copies;
+ *   - there is NO CPU fallback: calling a compute entry point without a CUDA device fails.
+ */
+#ifndef MDM_H_
+#define MDM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDM_OK 0
+#define MDM_E_ARG (-1)      /* invalid argument */
+#define MDM_E_CUDA (-2)     /* CUDA runtime / driver error */
+#define MDM_E_UNSUPPORTED (-3)
+
+/* element types of image/activation buffers */
+#define MDM_F32 0
+#define MDM_BF16 1
+
+/* fill value for degraded pixels: scheduler.py:298-317 (`mean_option`) */
+#define MDM_FILL_CONST 0            /* float(mean_option)                         */
+#define MDM_FILL_DEGRADED_AREA 1    /* mean of img over masked-out pixels         */
+#define MDM_FILL_NON_DEGRADED 2     /* -sum(img*m)/sum(1-m) per channel, NaN -> 0 */
+/* `mean_area`: scheduler.py:303-309 */
+#define MDM_AREA_IMAGE 0
+#define MDM_AREA_CHANNEL 1
+
+const char* mdm_last_error(void);
+int mdm_version(void);
+/* 1 when a CUDA device is usable by this process, 0 otherwise (never raises) */
+int mdm_device_available(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Random stream: a device-resident copy of torch's CPU mt19937 engine.
+ * Replaces the CPU draws at scheduler.py:282,288,294,434,440,446,496,507,620,658,675,703-707
+ * (all `torch.FloatTensor(...).uniform_/normal_` and `torch.randperm` run on the CPU generator
+ * in the reference, whatever the model device -- SURVEY.md section 3.2.1 / quirk q15).
+ *
+ * `rng` points to MDM_RNG_WORDS uint32 on the device: words[0..623] = engine state,
+ * words[624] = position inside the current block (624 = regenerate before the next draw).
+ * Kernels consume the stream in order and write the advanced state back, so consecutive
+ * calls on one stream continue the sequence with no host round trip.
+ * ------------------------------------------------------------------------------------------- */
+#define MDM_RNG_WORDS 625
+
+/* host helper: init_genrand(seed) == torch.manual_seed(seed) (left_=1 -> position 624) */
+int mdm_rng_seed_host(uint32_t* state_host /*[625]*/, uint32_t seed);
+
+/* n raw 32-bit outputs (untransformed) */
+int mdm_rng_raw(uint32_t* rng, uint32_t* out, int64_t n, void* stream);
+/* advance the stream by n words, nothing written (scheduler.py:703-705: a uniform draw whose
+ * value is discarded but whose words are consumed -- quirk q8) */
+int mdm_rng_skip(uint32_t* rng, int64_t n, void* stream);
+/* FloatTensor(n).uniform_(a,b): float32((w & 0xFFFFFF) * 2^-24) * (b-a) + a */
+int mdm_rng_uniform(uint32_t* rng, float* out, int64_t n, float a, float b, void* stream);
+/* FloatTensor(n).normal_(mean,std), n % 16 == 0: 16-wide Box-Muller blocks, optionally scaled
+ * per sample in float64 (`random * ratio`, scheduler.py:680-684,713-717): out[b, :] =
+ * float32(double(normal) * ratio[b]).  ratio may be NULL (no scaling). */
+int mdm_rng_normal(uint32_t* rng, float* out, int batch, int64_t per_sample, float mean,
+                   float std, const double* ratio, void* stream);
+/* thresholding masks, scheduler.py:288-296 / 440-448 / 496-513:
+ *   mask[b, j] = (uniform_(0,1)[b, j] > ratio[b])  <=>  (w & 0xFFFFFF) > floor(ratio[b] * 2^24)
+ * one byte per element (1 = keep, 0 = degrade).  When ratio2/mask2 are non-NULL the same
+ * uniform field is thresholded a second time (degrade_dependent_base_sampling). */
+int mdm_rng_threshold_mask(uint32_t* rng, const double* ratio, uint8_t* mask,
+                           const double* ratio2, uint8_t* mask2, int batch, int64_t per_sample,
+                           void* stream);
+/* indexing masks, scheduler.py:279-284 / 431-436: per sample, torch.randperm(HW)[:count[b]]
+ * positions are zeroed.  words_ws: workspace of batch*(HW-1) uint32. */
+int mdm_rng_randperm_mask(uint32_t* rng, const int64_t* count, uint8_t* mask,
+                          uint32_t* words_ws, int batch, int hw, void* stream);
+/* torch.randint(lo, hi, (n,)) on the CPU generator: w % (hi-lo) + lo (trainer_masked.py:114
+ * when the batch lives on the CPU generator; int64 output) */
+int mdm_rng_randint(uint32_t* rng, int64_t* out, int64_t n, int64_t lo, int64_t hi, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1: fill + composite given a mask.  Replaces scheduler.py:298-321 (degrade_training),
+ * :450-475 (degrade_independent_base_sampling), :572-598 (degrade_with_mask).
+ *   x_t          = (1-m)*fill + m*img            [batch, C, HW] float32
+ *   mask_f32     = m as float32                  [batch, mask_ch, HW]     (optional)
+ *   degrade_mask = (1-m)*fill + m                [batch, C, HW] float32   (optional)
+ *   fill_out     = fill value                    [batch, C] float32       (optional)
+ * img: [batch, C, HW] float32 or bf16.  mask: [batch, mask_ch, HW] bytes, mask_ch in {1, C}.
+ * ws: workspace of mdm_degrade_ws_floats(batch, C, HW) floats.
+ * ------------------------------------------------------------------------------------------- */
+int64_t mdm_degrade_ws_floats(int batch, int channels, int hw);
+int mdm_degrade(const void* img, int img_dtype, const uint8_t* mask, int mask_ch, int fill_mode,
+                float fill_const, int mean_area, float* x_t, float* mask_f32,
+                float* degrade_mask, float* fill_out, float* ws, int batch, int channels, int hw,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5: one restoration-loop update.  Replaces sampler.py:143-152 and :167-216:
+ *   s0      = (((x_t + shift) + net) - shift)              (x_t + shift is what the denoiser saw)
+ *   D_t     = degrade(s0, mask_t),  D_next = degrade(s0, mask_next)
+ *   x_next  = momentum ? x_t + (D_next - D_t) : D_next      (base_momentum / base_sampling)
+ *   x_in_next = x_next + shift_next                         (input of the next denoiser call)
+ * net: [batch,C,HW] float32 NCHW (denoiser output).  shift / shift_next: float32 with element
+ * strides (sb, sc, sp) so (B,1,1,1), (B,3,1,1), (B,1,H,W) and (B,3,H,W) shifts are all
+ * addressable; NULL means zero.  `update` = 0 leaves x_t untouched (last iteration, i == 0).
+ * s0_out optional.  ws as for mdm_degrade, twice the size.
+ * ------------------------------------------------------------------------------------------- */
+int mdm_sampler_step(const float* x_t, const float* net,
+                     const float* shift, int64_t sb, int64_t sc, int64_t sp,
+                     const uint8_t* mask_t, const uint8_t* mask_next, int mask_ch,
+                     int fill_mode, float fill_const, int mean_area, int momentum, int update,
+                     const float* shift_next, int64_t nb, int64_t nc, int64_t np_,
+                     float* x_next, float* x_in_next, float* s0_out, float* ws,
+                     int batch, int channels, int hw, void* stream);
+
+/* x_in = x + shift (scheduler.py:757-766 perturb_shift), strides as above */
+int mdm_add_shift(const float* x, const float* shift, int64_t sb, int64_t sc, int64_t sp,
+                  float* out, int batch, int channels, int hw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDM_H_ */

@@ -1,0 +1,62 @@
+// Shared helpers for libmdm_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../../include/mdm.h"
+
+namespace mdm {
+
+void set_error(const char* fmt, ...);
+
+#define MDM_CHECK_ARG(cond, ...)             \
+  do {                                       \
+    if (!(cond)) {                           \
+      ::mdm::set_error(__VA_ARGS__);         \
+      return MDM_E_ARG;                      \
+    }                                        \
+  } while (0)
+
+#define MDM_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::mdm::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return MDM_E_CUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+#define MDM_LAUNCH_CHECK() MDM_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; result valid in every thread. `red` must hold >= 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (lane < nw) ? red[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+__device__ __forceinline__ float ld_as_float(const float* p, int64_t i) { return p[i]; }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p, int64_t i) {
+  return __bfloat162float(p[i]);
+}
+
+}  // namespace mdm

@@ -1,0 +1,293 @@
+// K1 (fill + composite) and K5 (restoration-loop update) -- HBM-bound elementwise kernels.
+//
+// Reference: scheduler.py:298-321 (degrade_training), :450-475 (degrade_independent_base_
+// sampling), :572-598 (degrade_with_mask); sampler.py:143-152,167-216 (loop body).
+//
+// Layout: images NCHW, one (batch, channel) plane = HW contiguous elements; masks are one byte
+// per pixel ([batch, mask_ch, HW], mask_ch = 1 or C), written by rng.cu.  Each plane is cut into
+// chunks of CHUNK elements; one CTA owns one chunk, every thread moves 16-byte vectors.
+//
+// The fill value is a per-sample (or per-channel) masked mean, i.e. a reduction over the
+// sample that must finish before the composite can start: pass 1 writes per-chunk partial sums
+// (no atomics -> deterministic), pass 2 re-reduces the <= C*nchunk partials of its sample in a
+// fixed order (identical in every CTA of that sample) and does the composite.  The second read
+// of the image hits L2 for the shapes on this path (<= 50 MB per tensor, 126 MB L2).
+//
+// Arithmetic is the reference's, op for op and unfused (__fmul_rn/__fadd_rn), so that given the
+// same fill the composite is bit-identical, including the 0*NaN = NaN behaviour when a sample
+// has no degraded pixel.
+#include "common.cuh"
+
+namespace mdm {
+
+constexpr int DG_THREADS = 256;
+constexpr int DG_VEC_PER_THREAD = 4;                              // 4 x float4 per thread
+constexpr int DG_CHUNK = DG_THREADS * DG_VEC_PER_THREAD * 4;      // 4096 elements
+
+struct Shift {
+  const float* p;
+  int64_t sb, sc, sp;
+  __device__ __forceinline__ float at(int b, int c, int i) const {
+    return p ? p[b * sb + c * sc + (int64_t)i * sp] : 0.0f;
+  }
+};
+
+// partials layout per sample: [C][nchunk][3] = {sum img*(1-m), sum img*m, sum (1-m)}
+__device__ __forceinline__ float fill_value(const float* part, int c, int C, int nchunk, int fill_mode,
+                                            float fill_const, int mean_area) {
+  if (fill_mode == MDM_FILL_CONST) return fill_const;
+  if (fill_mode == MDM_FILL_DEGRADED_AREA) {
+    float s = 0.f, n = 0.f;
+    const int c0 = (mean_area == MDM_AREA_IMAGE) ? 0 : c;
+    const int c1 = (mean_area == MDM_AREA_IMAGE) ? C : c + 1;
+    for (int cc = c0; cc < c1; ++cc)
+      for (int k = 0; k < nchunk; ++k) {
+        s += part[(cc * nchunk + k) * 3 + 0];
+        n += part[(cc * nchunk + k) * 3 + 2];
+      }
+    return __fdiv_rn(s, n);  // 0/0 -> NaN when nothing is degraded, as in the reference
+  }
+  float s = 0.f, n = 0.f;  // MDM_FILL_NON_DEGRADED: always per channel (dims (2,3))
+  for (int k = 0; k < nchunk; ++k) {
+    s += part[(c * nchunk + k) * 3 + 1];
+    n += part[(c * nchunk + k) * 3 + 2];
+  }
+  float v = __fmul_rn(__fdiv_rn(s, n), -1.0f);
+  return isnan(v) ? 0.0f : v;
+}
+
+__device__ __forceinline__ float composite(float m, float fill, float x) {
+  // ((1-masks) * mean_pixel) + masks * img
+  return __fadd_rn(__fmul_rn(__fsub_rn(1.0f, m), fill), __fmul_rn(m, x));
+}
+
+// ---- K1 pass 1 -----------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(DG_THREADS) degrade_stats_kernel(const T* __restrict__ img,
+                                                                   const uint8_t* __restrict__ mask,
+                                                                   int mask_ch, float* __restrict__ ws,
+                                                                   int C, int hw, int nchunk) {
+  __shared__ float red[32];
+  const int chunk = blockIdx.x, plane = blockIdx.y;  // plane = b*C + c
+  const int b = plane / C, c = plane % C;
+  const T* x = img + (int64_t)plane * hw;
+  const uint8_t* m = mask + ((int64_t)b * mask_ch + (mask_ch == 1 ? 0 : c)) * hw;
+  float s0 = 0.f, s1 = 0.f, n0 = 0.f;
+  const int base = chunk * DG_CHUNK;
+  const int end = min(base + DG_CHUNK, hw);
+  for (int i = base + threadIdx.x; i < end; i += DG_THREADS) {
+    const float v = ld_as_float(x, i);
+    const float mk = (float)m[i];
+    s0 += __fmul_rn(v, __fsub_rn(1.0f, mk));
+    s1 += __fmul_rn(v, mk);
+    n0 += __fsub_rn(1.0f, mk);
+  }
+  s0 = block_sum(s0, red);
+  s1 = block_sum(s1, red);
+  n0 = block_sum(n0, red);
+  if (threadIdx.x == 0) {
+    float* o = ws + ((int64_t)plane * nchunk + chunk) * 3;
+    o[0] = s0; o[1] = s1; o[2] = n0;
+  }
+}
+
+// ---- K1 pass 2 -----------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(DG_THREADS) degrade_apply_kernel(
+    const T* __restrict__ img, const uint8_t* __restrict__ mask, int mask_ch, int fill_mode,
+    float fill_const, int mean_area, const float* __restrict__ ws, float* __restrict__ x_t,
+    float* __restrict__ mask_f32, float* __restrict__ degrade_mask, float* __restrict__ fill_out,
+    int C, int hw, int nchunk) {
+  const int chunk = blockIdx.x, plane = blockIdx.y;
+  const int b = plane / C, c = plane % C;
+  const float fill = fill_value(ws + (int64_t)b * C * nchunk * 3, c, C, nchunk, fill_mode, fill_const, mean_area);
+  if (fill_out && chunk == 0 && threadIdx.x == 0) fill_out[plane] = fill;
+  const T* x = img + (int64_t)plane * hw;
+  const uint8_t* m = mask + ((int64_t)b * mask_ch + (mask_ch == 1 ? 0 : c)) * hw;
+  float* o = x_t + (int64_t)plane * hw;
+  float* dm = degrade_mask ? degrade_mask + (int64_t)plane * hw : nullptr;
+  float* mf = (mask_f32 && (mask_ch != 1 || c == 0)) ? mask_f32 + ((int64_t)b * mask_ch + (mask_ch == 1 ? 0 : c)) * hw : nullptr;
+  const int base = chunk * DG_CHUNK;
+  const int end = min(base + DG_CHUNK, hw);
+  if ((hw & 3) == 0 && sizeof(T) == 4) {
+    for (int i = base + threadIdx.x * 4; i < end; i += DG_THREADS * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i);
+      const uchar4 mk = *reinterpret_cast<const uchar4*>(m + i);
+      const float m0 = mk.x, m1 = mk.y, m2 = mk.z, m3 = mk.w;
+      float4 r;
+      r.x = composite(m0, fill, v.x); r.y = composite(m1, fill, v.y);
+      r.z = composite(m2, fill, v.z); r.w = composite(m3, fill, v.w);
+      *reinterpret_cast<float4*>(o + i) = r;
+      if (dm) {
+        float4 d;
+        d.x = composite(m0, fill, 1.0f); d.y = composite(m1, fill, 1.0f);
+        d.z = composite(m2, fill, 1.0f); d.w = composite(m3, fill, 1.0f);
+        *reinterpret_cast<float4*>(dm + i) = d;
+      }
+      if (mf) *reinterpret_cast<float4*>(mf + i) = make_float4(m0, m1, m2, m3);
+    }
+  } else {
+    for (int i = base + threadIdx.x; i < end; i += DG_THREADS) {
+      const float v = ld_as_float(x, i);
+      const float mk = (float)m[i];
+      o[i] = composite(mk, fill, v);
+      if (dm) dm[i] = composite(mk, fill, 1.0f);
+      if (mf) mf[i] = mk;
+    }
+  }
+}
+
+// ---- K5 pass 1: x0_hat and its masked sums under both masks -----------------------------------
+__device__ __forceinline__ float x0_hat(float xt, float net, float sh) {
+  // shifted = x_t + shift; shifted_0 = shifted + net; sample_0 = shifted_0 - shift  (sampler.py:143-152)
+  return __fsub_rn(__fadd_rn(__fadd_rn(xt, sh), net), sh);
+}
+
+__global__ void __launch_bounds__(DG_THREADS) sampler_stats_kernel(
+    const float* __restrict__ x_t, const float* __restrict__ net, Shift shift,
+    const uint8_t* __restrict__ mask_t, const uint8_t* __restrict__ mask_n, int mask_ch,
+    float* __restrict__ ws_t, float* __restrict__ ws_n, int C, int hw, int nchunk) {
+  __shared__ float red[32];
+  const int chunk = blockIdx.x, plane = blockIdx.y;
+  const int b = plane / C, c = plane % C;
+  const int64_t po = (int64_t)plane * hw;
+  const int64_t mo = ((int64_t)b * mask_ch + (mask_ch == 1 ? 0 : c)) * hw;
+  float a0 = 0.f, a1 = 0.f, an = 0.f, b0 = 0.f, b1 = 0.f, bn = 0.f;
+  const int base = chunk * DG_CHUNK;
+  const int end = min(base + DG_CHUNK, hw);
+  for (int i = base + threadIdx.x; i < end; i += DG_THREADS) {
+    const float v = x0_hat(x_t[po + i], net[po + i], shift.at(b, c, i));
+    const float mt = (float)mask_t[mo + i], mn = (float)mask_n[mo + i];
+    a0 += __fmul_rn(v, __fsub_rn(1.0f, mt)); a1 += __fmul_rn(v, mt); an += __fsub_rn(1.0f, mt);
+    b0 += __fmul_rn(v, __fsub_rn(1.0f, mn)); b1 += __fmul_rn(v, mn); bn += __fsub_rn(1.0f, mn);
+  }
+  a0 = block_sum(a0, red); a1 = block_sum(a1, red); an = block_sum(an, red);
+  b0 = block_sum(b0, red); b1 = block_sum(b1, red); bn = block_sum(bn, red);
+  if (threadIdx.x == 0) {
+    float* o = ws_t + ((int64_t)plane * nchunk + chunk) * 3;
+    o[0] = a0; o[1] = a1; o[2] = an;
+    o = ws_n + ((int64_t)plane * nchunk + chunk) * 3;
+    o[0] = b0; o[1] = b1; o[2] = bn;
+  }
+}
+
+// ---- K5 pass 2 -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DG_THREADS) sampler_update_kernel(
+    const float* __restrict__ x_t, const float* __restrict__ net, Shift shift,
+    const uint8_t* __restrict__ mask_t, const uint8_t* __restrict__ mask_n, int mask_ch, int fill_mode,
+    float fill_const, int mean_area, int momentum, int update, Shift shift_next,
+    const float* __restrict__ ws_t, const float* __restrict__ ws_n, float* __restrict__ x_next,
+    float* __restrict__ x_in_next, float* __restrict__ s0_out, int C, int hw, int nchunk) {
+  const int chunk = blockIdx.x, plane = blockIdx.y;
+  const int b = plane / C, c = plane % C;
+  const int64_t po = (int64_t)plane * hw;
+  const int64_t mo = ((int64_t)b * mask_ch + (mask_ch == 1 ? 0 : c)) * hw;
+  const int64_t wo = (int64_t)b * C * nchunk * 3;
+  const float f_t = update ? fill_value(ws_t + wo, c, C, nchunk, fill_mode, fill_const, mean_area) : 0.f;
+  const float f_n = update ? fill_value(ws_n + wo, c, C, nchunk, fill_mode, fill_const, mean_area) : 0.f;
+  const int base = chunk * DG_CHUNK;
+  const int end = min(base + DG_CHUNK, hw);
+  for (int i = base + threadIdx.x; i < end; i += DG_THREADS) {
+    const float xt = x_t[po + i];
+    const float v = x0_hat(xt, net[po + i], shift.at(b, c, i));
+    if (s0_out) s0_out[po + i] = v;
+    float xn = xt;
+    if (update) {
+      const float d_t = composite((float)mask_t[mo + i], f_t, v);
+      const float d_n = composite((float)mask_n[mo + i], f_n, v);
+      xn = momentum ? __fadd_rn(xt, __fsub_rn(d_n, d_t)) : d_n;  // sampler.py:206-216
+    }
+    if (x_next) x_next[po + i] = xn;
+    if (x_in_next) x_in_next[po + i] = __fadd_rn(xn, shift_next.at(b, c, i));
+  }
+}
+
+__global__ void __launch_bounds__(DG_THREADS) add_shift_kernel(const float* __restrict__ x, Shift shift,
+                                                               float* __restrict__ out, int C, int hw) {
+  const int plane = blockIdx.y, b = plane / C, c = plane % C;
+  const int64_t po = (int64_t)plane * hw;
+  const int base = blockIdx.x * DG_CHUNK;
+  const int end = min(base + DG_CHUNK, hw);
+  for (int i = base + threadIdx.x; i < end; i += DG_THREADS) out[po + i] = __fadd_rn(x[po + i], shift.at(b, c, i));
+}
+
+static inline int nchunks(int hw) { return (hw + DG_CHUNK - 1) / DG_CHUNK; }
+
+}  // namespace mdm
+
+using namespace mdm;
+
+extern "C" {
+
+int64_t mdm_degrade_ws_floats(int batch, int channels, int hw) {
+  if (batch <= 0 || channels <= 0 || hw <= 0) return 0;
+  return (int64_t)batch * channels * nchunks(hw) * 3;
+}
+
+int mdm_degrade(const void* img, int img_dtype, const uint8_t* mask, int mask_ch, int fill_mode,
+                float fill_const, int mean_area, float* x_t, float* mask_f32, float* degrade_mask,
+                float* fill_out, float* ws, int batch, int channels, int hw, void* stream) {
+  MDM_CHECK_ARG(img && mask && x_t, "img/mask/x_t is NULL");
+  MDM_CHECK_ARG(batch > 0 && channels > 0 && hw > 0, "empty image batch");
+  MDM_CHECK_ARG(mask_ch == 1 || mask_ch == channels, "mask_ch must be 1 or C");
+  MDM_CHECK_ARG(img_dtype == MDM_F32 || img_dtype == MDM_BF16, "img dtype");
+  MDM_CHECK_ARG(fill_mode >= 0 && fill_mode <= 2, "fill_mode");
+  MDM_CHECK_ARG(fill_mode == MDM_FILL_CONST || ws, "workspace is NULL");
+  MDM_CHECK_ARG((int64_t)batch * channels <= 65535, "batch*channels exceeds grid.y");
+  const int nc = nchunks(hw);
+  dim3 grid(nc, batch * channels);
+  cudaStream_t st = as_stream(stream);
+  if (fill_mode != MDM_FILL_CONST) {
+    if (img_dtype == MDM_F32)
+      degrade_stats_kernel<float><<<grid, DG_THREADS, 0, st>>>((const float*)img, mask, mask_ch, ws, channels, hw, nc);
+    else
+      degrade_stats_kernel<__nv_bfloat16><<<grid, DG_THREADS, 0, st>>>((const __nv_bfloat16*)img, mask, mask_ch, ws, channels, hw, nc);
+    MDM_LAUNCH_CHECK();
+  }
+  if (img_dtype == MDM_F32)
+    degrade_apply_kernel<float><<<grid, DG_THREADS, 0, st>>>((const float*)img, mask, mask_ch, fill_mode, fill_const, mean_area, ws, x_t, mask_f32, degrade_mask, fill_out, channels, hw, nc);
+  else
+    degrade_apply_kernel<__nv_bfloat16><<<grid, DG_THREADS, 0, st>>>((const __nv_bfloat16*)img, mask, mask_ch, fill_mode, fill_const, mean_area, ws, x_t, mask_f32, degrade_mask, fill_out, channels, hw, nc);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_sampler_step(const float* x_t, const float* net, const float* shift, int64_t sb, int64_t sc,
+                     int64_t sp, const uint8_t* mask_t, const uint8_t* mask_next, int mask_ch,
+                     int fill_mode, float fill_const, int mean_area, int momentum, int update,
+                     const float* shift_next, int64_t nb, int64_t nc_, int64_t np_, float* x_next,
+                     float* x_in_next, float* s0_out, float* ws, int batch, int channels, int hw,
+                     void* stream) {
+  MDM_CHECK_ARG(x_t && net, "x_t/net is NULL");
+  MDM_CHECK_ARG(batch > 0 && channels > 0 && hw > 0, "empty image batch");
+  MDM_CHECK_ARG(!update || (mask_t && mask_next), "masks are NULL");
+  MDM_CHECK_ARG(mask_ch == 1 || mask_ch == channels, "mask_ch must be 1 or C");
+  MDM_CHECK_ARG(fill_mode >= 0 && fill_mode <= 2, "fill_mode");
+  MDM_CHECK_ARG((int64_t)batch * channels <= 65535, "batch*channels exceeds grid.y");
+  const int nc = nchunks(hw);
+  dim3 grid(nc, batch * channels);
+  cudaStream_t st = as_stream(stream);
+  Shift s{shift, sb, sc, sp}, sn{shift_next, nb, nc_, np_};
+  float* ws_t = ws;
+  float* ws_n = ws ? ws + mdm_degrade_ws_floats(batch, channels, hw) : nullptr;
+  if (update && fill_mode != MDM_FILL_CONST) {
+    MDM_CHECK_ARG(ws, "workspace is NULL");
+    sampler_stats_kernel<<<grid, DG_THREADS, 0, st>>>(x_t, net, s, mask_t, mask_next, mask_ch, ws_t, ws_n, channels, hw, nc);
+    MDM_LAUNCH_CHECK();
+  }
+  sampler_update_kernel<<<grid, DG_THREADS, 0, st>>>(x_t, net, s, mask_t, mask_next, mask_ch, fill_mode, fill_const, mean_area, momentum, update, sn, ws_t, ws_n, x_next, x_in_next, s0_out, channels, hw, nc);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_add_shift(const float* x, const float* shift, int64_t sb, int64_t sc, int64_t sp, float* out,
+                  int batch, int channels, int hw, void* stream) {
+  MDM_CHECK_ARG(x && out, "x/out is NULL");
+  MDM_CHECK_ARG(batch > 0 && channels > 0 && hw > 0, "empty image batch");
+  dim3 grid(nchunks(hw), batch * channels);
+  add_shift_kernel<<<grid, DG_THREADS, 0, as_stream(stream)>>>(x, Shift{shift, sb, sc, sp}, out, channels, hw);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+}  // extern "C"
