@@ -31,7 +31,7 @@ def pack_torch_state(seed: int, key: np.ndarray, pos: int, template: torch.Tenso
     buf = bytearray(template.numpy().tobytes()) if template is not None else bytearray(5056)
     struct.pack_into("<QiiQ", buf, 0, seed, 625 - pos, 1, pos)
     buf[24:24 + MT_N * 8] = key.astype("<u8").tobytes()
-    return torch.frombuffer(bytes(buf), dtype=torch.uint8).clone()
+    return torch.frombuffer(buf, dtype=torch.uint8).clone()
 
 
 class DeviceMT19937:
@@ -39,6 +39,8 @@ class DeviceMT19937:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("DeviceMT19937 needs a CUDA device (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.state = torch.empty(_lib.RNG_WORDS, dtype=torch.int32, device=self.device)
         self.seed = 0
         self._template = None

@@ -211,8 +211,6 @@ class Sampler:
                 x_t, x_next = x_next, x_t
                 x_in, x_in_next = x_in_next, x_in
                 shift_e, sb, sc, sp = shift_ne, nb, nc, np_
-                # keep buffers of this iteration alive until the side stream is done with them
-                net.record_stream(main)
         S.release_rng_to_torch()
         visual = hist if history else [None] * len(HISTORY_NAMES)
         return sample_0, visual

@@ -122,9 +122,17 @@ class Scheduler:
             self._tables[key] = (ratio, counts)
         return self._tables[key]
 
+    @staticmethod
+    def _norm_device(device):
+        d = torch.device(device)
+        if d.type == "cuda" and d.index is None:
+            d = torch.device("cuda", torch.cuda.current_device())
+        return d
+
     def adopt_torch_rng(self, device, generator=None):
         """Copy torch's CPU generator state to the device; masks continue from there."""
-        if self.rng is None or self.rng.device != torch.device(device):
+        device = self._norm_device(device)
+        if self.rng is None or self.rng.device != device:
             self.rng = DeviceMT19937(device)
         self.rng.adopt_torch(generator)
         return self.rng
@@ -135,7 +143,7 @@ class Scheduler:
             self.rng.release_to_torch(generator)
 
     def _rng_for(self, device):
-        if self.rng is None or self.rng.device != torch.device(device):
+        if self.rng is None or self.rng.device != self._norm_device(device):
             self.adopt_torch_rng(device)
         return self.rng
 

@@ -47,7 +47,8 @@ def test_degrade_against_reference_golden(golden, name):
     np.testing.assert_allclose(d_img.cpu().numpy(), g[f"{name}/degrade_img"], atol=FILL_TOL, rtol=0)
     np.testing.assert_allclose(d_mask.cpu().numpy(), g[f"{name}/degrade_mask"], atol=FILL_TOL, rtol=0)
     kept = gm.bool()
-    assert torch.equal(d_img.cpu()[kept], torch.from_numpy(g[f"{name}/degrade_img"])[kept])   # kept pixels exact
+    assert torch.allclose(d_img.cpu()[kept], torch.from_numpy(g[f"{name}/degrade_img"])[kept], atol=0, rtol=0,
+                          equal_nan=True)                                      # kept pixels exact (NaN rows: quirk q6)
     s_img, s_masks, s_mean = S.degrade_independent_base_sampling(n, x0.float(), a.mean_option, a.mean_area)
     np.testing.assert_allclose(s_img.cpu().numpy(), g[f"{name}/s_img"], atol=FILL_TOL, rtol=0)
     w = S.degrade_with_mask(x0.float(), s_masks, a.mean_option, a.mean_area)
@@ -115,7 +116,8 @@ def test_degrade_against_oracle(cfg, shape):
     out = S.degrade_training(S.get_black_area_num_pixels_time(ts.cuda()), x0.cuda(), a.mean_option, a.mean_area)
     assert torch.equal(out[1].cpu(), ref[1].contiguous())
     for o, r in zip((out[0], out[2], out[3]), (ref[0], ref[2], ref[3])):
-        assert torch.allclose(o.cpu(), r, atol=FILL_TOL, rtol=0, equal_nan=True)       # NaN pattern kept (quirk q6)
+        assert torch.allclose(o.cpu(), r, atol=FILL_TOL, rtol=1e-5, equal_nan=True)    # NaN pattern kept (quirk q6);
+        # rtol: non_degraded_area divides a ~HW-term sum by a handful of pixels, |fill| can reach ~50
     k, p = S.rng.export()
     ok, op = O.rng.state_words()
     assert p == op and np.array_equal(k, ok)
