@@ -131,6 +131,45 @@ int mdm_sampler_step(const float* x_t, const float* net,
 int mdm_add_shift(const float* x, const float* shift, int64_t sb, int64_t sc, int64_t sp,
                   float* out, int batch, int channels, int hw, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Denoiser (K2/K3/K4): replaces the cuDNN/cuBLAS/ATen calls behind `diffusers.UNet2DModel`
+ * (reference utils/model.py:24-32; call sites trainer_masked.py:125, sampler.py:145).
+ * Activations: NHWC bf16, channel stride `ld` in elements (multiple of 8) so channel slices of a
+ * concat buffer are addressable.  Weights: bf16 packed [cout][k*k][cin] (K-major for fprop).
+ * Spatial sizes must be powers of two (32/64/128/256 on this path).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mdm_conv_args {
+  const void* x;        /* fprop/wgrad: layer input [N][H*s][W*s][cin]; dgrad: dy [N][H][W][cout] */
+  long long ld_x;
+  int cin;
+  const void* w;        /* packed bf16 weights [cout][k*k][cin] */
+  void* y;              /* fprop: output [N][H][W][cout]; dgrad: dx [N][H][W][cin]; wgrad: dy (read) */
+  long long ld_y;
+  int cout;
+  int N, H, W;          /* batch and OUTPUT spatial size */
+  int ksize, stride;    /* 1|3, 1|2 */
+  const float* bias;    /* [cout] or NULL */
+  const float* rowvec;  /* per-sample vector added to every pixel of sample n: [N][ld_rowvec] */
+  long long ld_rowvec;
+  const void* resid;    /* bf16 residual added in the epilogue, or NULL */
+  long long ld_resid;
+  int accumulate;       /* add to the existing contents of y */
+  float* y_f32;         /* optional fp32 copy of the result, row-major [N*H*W][cout or cin] */
+  const void* x2;       /* fprop only: fused 1x1 shortcut segment (second K range) */
+  long long ld_x2;
+  int cin2;
+  const void* w2;       /* bf16 [cout][1][cin2] */
+  float* dw;            /* wgrad output fp32 [cout][k*k][cin], accumulated atomically */
+  long long w_col0;     /* dgrad/wgrad on a channel slice of a wider packed weight */
+  int w_cols;
+} mdm_conv_args;
+
+/* tcgen05/TMEM implicit GEMM fed by TMA (csrc/igemm.cu) */
+int mdm_conv_fprop(const mdm_conv_args* a, void* stream);
+int mdm_conv_dgrad(const mdm_conv_args* a, void* stream);   /* stride-1 layers */
+int mdm_conv_wgrad(const mdm_conv_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

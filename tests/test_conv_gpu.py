@@ -1,0 +1,104 @@
+"""GPU: tcgen05 implicit-GEMM conv (fprop / dgrad / wgrad) against torch's fp32 conv2d on the
+same bf16-rounded operands.  Tolerance: the kernel accumulates bf16 products in fp32 (exact
+products, fp32 sums); the output is rounded to bf16 -> relative error <= 2^-8 per element plus
+summation-order noise; stated as |err| <= 1e-2 * max|ref| (fprop/dgrad, bf16 output) and
+<= 2e-3 * max|ref| for wgrad (fp32 output, split-K atomics)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def nhwc(t):   # NCHW fp32 -> NHWC bf16 contiguous
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(t):
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+CASES = [
+    # N, H(out), cin, cout, k, stride
+    (2, 32, 128, 128, 3, 1),
+    (3, 16, 128, 256, 3, 1),
+    (2, 8, 256, 256, 3, 1),
+    (5, 4, 512, 512, 3, 1),
+    (16, 2, 512, 512, 3, 1),
+    (7, 1, 1024, 512, 3, 1),
+    (2, 16, 384, 256, 1, 1),
+    (2, 16, 128, 128, 3, 2),
+    (4, 4, 256, 256, 3, 2),
+    (1, 128, 128, 128, 3, 1),
+    (200, 1, 512, 512, 1, 1),        # a Linear: 200 rows
+]
+
+
+@pytest.mark.parametrize("N,H,cin,cout,k,stride", CASES)
+def test_fprop(N, H, cin, cout, k, stride):
+    from mdm_b200 import denoiser_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(N, cin, H * stride, H * stride, device="cuda", generator=g)
+    w = torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g)
+    rv = torch.randn(N, cout, device="cuda", generator=g)
+    res = torch.randn(N, cout, H, H, device="cuda", generator=g)
+    xb, wb, resb = nhwc(x), ops.pack_conv_weight(w).to(torch.bfloat16), nhwc(res)
+    y = torch.empty(N, H, H, cout, device="cuda", dtype=torch.bfloat16)
+    ops.conv_fprop(xb, wb, y, N, H, H, k, stride, bias=b, rowvec=rv, resid=resb)
+    ref = F.conv2d(nchw(xb), ops.unpack_conv_weight(wb.float(), k), b, stride=stride, padding=k // 2)
+    ref = ref + rv[:, :, None, None] + nchw(resb)
+    err = (nchw(y) - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item(), err
+
+
+def test_fprop_fused_shortcut_and_slices():
+    """conv3x3(a) + conv1x1(x) in one accumulator; inputs/outputs are channel slices of wider buffers."""
+    from mdm_b200 import denoiser_ops as ops
+    N, H, cin, cout, cx = 2, 16, 256, 256, 384
+    g = torch.Generator(device="cuda").manual_seed(1)
+    abuf = torch.randn(N, H, H, cin + 64, device="cuda", generator=g).to(torch.bfloat16)
+    xbuf = torch.randn(N, H, H, cx + 128, device="cuda", generator=g).to(torch.bfloat16)
+    a, x = abuf[..., 64:], xbuf[..., :cx]
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (9 * cin) ** 0.5)
+    ws = (torch.randn(cout, cx, 1, 1, device="cuda", generator=g) / cx ** 0.5)
+    wb, wsb = ops.pack_conv_weight(w).to(torch.bfloat16), ops.pack_conv_weight(ws).to(torch.bfloat16)
+    ybuf = torch.zeros(N, H, H, cout + 256, device="cuda", dtype=torch.bfloat16)
+    y = ybuf[..., 256:]
+    yf = torch.empty(N * H * H, cout, device="cuda")
+    ops.conv_fprop(a, wb, y, N, H, H, 3, 1, x2=x, w2=wsb, y_f32=yf)
+    ref = F.conv2d(nchw(a), ops.unpack_conv_weight(wb.float(), 3), padding=1) + F.conv2d(nchw(x), ops.unpack_conv_weight(wsb.float(), 1))
+    assert (nchw(y) - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert (yf.view(N, H, H, cout).permute(0, 3, 1, 2) - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    assert ybuf[..., :256].abs().max().item() == 0          # nothing written outside the slice
+
+
+@pytest.mark.parametrize("N,H,cin,cout,k,stride", [c for c in CASES if c[5] == 1])
+def test_dgrad(N, H, cin, cout, k, stride):
+    from mdm_b200 import denoiser_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    dy = torch.randn(N, cout, H, H, device="cuda", generator=g)
+    w = torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cout * k * k) ** 0.5
+    dyb, wb = nhwc(dy), ops.pack_conv_weight(w).to(torch.bfloat16)
+    dx = torch.empty(N, H, H, cin, device="cuda", dtype=torch.bfloat16)
+    ops.conv_dgrad(dyb, wb, dx, N, H, H, k)
+    ref = torch.nn.grad.conv2d_input((N, cin, H, H), ops.unpack_conv_weight(wb.float(), k), nchw(dyb), padding=k // 2)
+    err = (nchw(dx) - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item(), err
+    # accumulate into existing contents
+    ops.conv_dgrad(dyb, wb, dx, N, H, H, k, accumulate=True)
+    assert (nchw(dx) - 2 * ref).abs().max().item() <= 2.5e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("N,H,cin,cout,k,stride", CASES)
+def test_wgrad(N, H, cin, cout, k, stride):
+    from mdm_b200 import denoiser_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(N, cin, H * stride, H * stride, device="cuda", generator=g)
+    dy = torch.randn(N, cout, H, H, device="cuda", generator=g)
+    xb, dyb = nhwc(x), nhwc(dy)
+    dw = torch.zeros(cout, k * k, cin, device="cuda")
+    ops.conv_wgrad(xb, dyb, dw, N, H, H, k, stride)
+    ref = torch.nn.grad.conv2d_weight(nchw(xb), (cout, cin, k, k), nchw(dyb), stride=stride, padding=k // 2)
+    err = (ops.unpack_conv_weight(dw, k) - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-4, err
