@@ -150,6 +150,7 @@ typedef struct mdm_conv_args {
   int N, H, W;          /* batch and OUTPUT spatial size */
   int ksize, stride;    /* 1|3, 1|2 */
   const float* bias;    /* [cout] or NULL */
+  const float* bias2;   /* second bias (fused shortcut), or NULL */
   const float* rowvec;  /* per-sample vector added to every pixel of sample n: [N][ld_rowvec] */
   long long ld_rowvec;
   const void* resid;    /* bf16 residual added in the epilogue, or NULL */
@@ -169,6 +170,65 @@ typedef struct mdm_conv_args {
 int mdm_conv_fprop(const mdm_conv_args* a, void* stream);
 int mdm_conv_dgrad(const mdm_conv_args* a, void* stream);   /* stride-1 layers */
 int mdm_conv_wgrad(const mdm_conv_args* a, void* stream);
+
+/* K2: GroupNorm (+SiLU) forward / backward (csrc/nn_kernels.cu).  x, y, dy, dx: NHWC bf16 with
+ * channel strides; stats: [N][G][2] = (mean, rstd) fp32 written by fwd, read by bwd;
+ * ws: mdm_gn_ws_floats() floats.  bwd: dx = d/dx [silu](gn(x)) . dy (+ add), dgamma/dbeta
+ * accumulated (fp32 atomics). */
+int64_t mdm_gn_ws_floats(int N, int HW, int C, int G);
+int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma,
+                    const float* beta, float* stats, float* ws, int N, int HW, int C, int G,
+                    float eps, int silu, void* stream);
+int mdm_gn_silu_bwd(const void* x, long long ld_x, const void* dy, long long ld_dy, const void* add,
+                    long long ld_add, const void* add2, long long ld_add2, void* dx, long long ld_dx, const float* gamma,
+                    const float* beta, const float* stats, float* dgamma, float* dbeta, float* ws,
+                    int N, int HW, int C, int G, int silu, void* stream);
+
+/* first / last convolution (image channels C <= 4): planar fp32 NCHW image <-> NHWC bf16.
+ * w in the checkpoint layout: conv_in [cout][C][3][3], conv_out [C][cin][3][3] (fp32). */
+int mdm_conv_in_fwd(const float* img, const float* w, const float* bias, void* y, long long ld_y,
+                    int N, int C, int H, int W, int cout, void* stream);
+int mdm_conv_in_wgrad(const float* img, const void* dy, long long ld_dy, float* dw, float* dbias,
+                      int N, int C, int H, int W, int cout, void* stream);
+int mdm_conv_out_fwd(const void* x, long long ld_x, const float* w, const float* bias, float* y,
+                     int N, int C, int H, int W, int cin, void* stream);
+int mdm_conv_out_bwd(const void* x, long long ld_x, const float* w, const float* dy, void* dx,
+                     long long ld_dx, float* dw, float* dbias, int N, int C, int H, int W, int cin,
+                     void* stream);
+
+/* nearest 2x upsample, its adjoint, and zero insertion (turns a stride-2 dgrad into a stride-1 one) */
+int mdm_upsample2x_fwd(const void* x, long long ld_x, void* y, long long ld_y, int N, int H, int W, int C, void* stream);
+int mdm_upsample2x_bwd(const void* dy, long long ld_dy, void* dx, long long ld_dx, int N, int H, int W, int C, void* stream);
+int mdm_zero_insert2x(const void* x, long long ld_x, void* y, long long ld_y, int N, int H, int W, int C, void* stream);
+
+/* K4 attention core, head_dim 8, L tokens: qkv [N*L][3C] bf16 -> out [N*L][C] bf16 */
+int mdm_attention_fwd(const void* qkv, void* out, int N, int L, int C, void* stream);
+int mdm_attention_bwd(const void* qkv, const void* dout, void* dqkv, int N, int L, int C, void* stream);
+
+/* small pieces of the time-embedding path and of the loss */
+int mdm_timestep_embedding(const float* t, void* out_bf16, int N, int dim, void* stream);
+int mdm_silu_fwd(const float* x, void* y_bf16, int64_t n, void* stream);
+int mdm_silu_bwd(const float* x, const float* dy, void* dx_bf16, int64_t n, void* stream);
+int mdm_colsum(const void* dy, long long ld, float* out, float* out2, int64_t rows, int C, void* stream);
+int mdm_sample_colsum(const void* dy, long long ld, float* out, long long ld_out, float* dbias, int N, int HW, int C, void* stream);
+/* recon = (x_in + net) - shift; loss = mean(w_b (recon - x0)^2); dnet = dloss/dnet
+ * (trainer_masked.py:126-140, trainer_masked_mean_shift.py:142-159).  ws: 1024 floats. */
+int mdm_mse_residual(const float* x_in, const float* net, const float* shift, const float* x0,
+                     const float* weight, float* dnet, float* recon, float* loss, float* ws,
+                     int64_t per_sample, int64_t total, void* stream);
+int mdm_cast_f32_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+
+/* Fused optimiser tail: global-norm clip + Adam/AdamW/SGD + EMA + bf16 weight mirror over the flat
+ * parameter buffer (replaces trainer_masked.py:144-153).
+ * mdm_grad_sumsq: out[0] = sum g^2 (ws: 1024 floats).  mdm_adam_ema_step: mode 0 Adam, 1 AdamW,
+ * 2 SGD; gnorm_sq (device scalar, may be NULL) feeds torch's clip rule
+ * coef = min(1, max_norm / (norm + 1e-6)); grad_scale multiplies g first (1/world for a summed
+ * all-reduce); ema / p_bf16 may be NULL. */
+int mdm_grad_sumsq(const float* g, int64_t n, float* ws, float* out, void* stream);
+int mdm_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, int64_t n,
+                      const float* gnorm_sq, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, float bias_c1, float bias_c2, float max_norm, float ema_decay,
+                      float grad_scale, int mode, void* stream);
 
 #ifdef __cplusplus
 }

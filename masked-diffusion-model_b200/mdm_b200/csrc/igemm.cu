@@ -132,6 +132,7 @@ struct IgemmArgs {
   __nv_bfloat16* out;
   long long ld_out;
   const float* bias;
+  const float* bias2;
   const float* rowvec;
   long long ld_rowvec;
   int rows_per_vec;
@@ -290,6 +291,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         if (args.bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + col + j);
+        }
+        if (args.bias2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias2 + col + j);
         }
         if (rv) {
 #pragma unroll
@@ -455,7 +460,7 @@ using namespace mdm;
 extern "C" {
 
 int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
-  MDM_CHECK_ARG(c && c->x && c->w && c->y, "conv_fprop: NULL pointer");
+  MDM_CHECK_ARG(c && c->x && c->w && (c->y || c->y_f32), "conv_fprop: NULL pointer");
   MDM_CHECK_ARG(c->ksize == 1 || c->ksize == 3, "conv_fprop: ksize must be 1 or 3");
   MDM_CHECK_ARG(c->stride == 1 || c->stride == 2, "conv_fprop: stride must be 1 or 2");
   MDM_CHECK_ARG(c->cin % 64 == 0 && c->cout % 128 == 0, "conv_fprop: cin %% 64 / cout %% 128 (got %d, %d)", c->cin, c->cout);
@@ -474,7 +479,7 @@ int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
   a.M_total = c->N * c->H * c->W;
   a.N_total = c->cout;
   a.out = (__nv_bfloat16*)c->y; a.ld_out = c->ld_y;
-  a.bias = c->bias; a.rowvec = c->rowvec; a.ld_rowvec = c->ld_rowvec; a.rows_per_vec = c->H * c->W;
+  a.bias = c->bias; a.bias2 = c->bias2; a.rowvec = c->rowvec; a.ld_rowvec = c->ld_rowvec; a.rows_per_vec = c->H * c->W;
   a.resid = (const __nv_bfloat16*)c->resid; a.ld_resid = c->ld_resid;
   a.accumulate = c->accumulate;
   a.out_f32 = c->y_f32;
@@ -505,7 +510,7 @@ int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
 
 // dgrad of a stride-1 conv: dx[pix][ci] (+)= sum_tap sum_co dy[pix - tap][co] * w[co][tap][ci]
 int mdm_conv_dgrad(const mdm_conv_args* c, void* stream) {
-  MDM_CHECK_ARG(c && c->x && c->w && c->y, "conv_dgrad: NULL pointer");
+  MDM_CHECK_ARG(c && c->x && c->w && (c->y || c->y_f32), "conv_dgrad: NULL pointer");
   MDM_CHECK_ARG(c->ksize == 1 || c->ksize == 3, "conv_dgrad: ksize must be 1 or 3");
   MDM_CHECK_ARG(c->stride == 1, "conv_dgrad: stride-2 layers go through zero insertion first");
   MDM_CHECK_ARG(c->cout % 64 == 0 && c->cin % 128 == 0, "conv_dgrad: cout %% 64 / cin %% 128 (got %d, %d)", c->cout, c->cin);

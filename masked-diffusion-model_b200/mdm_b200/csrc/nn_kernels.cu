@@ -1,0 +1,859 @@
+// Denoiser kernels that are not GEMMs: GroupNorm+SiLU (K2) forward/backward, the 3-channel
+// first/last convolutions, nearest upsample, low-resolution attention core (K4), timestep
+// embedding, bias / time-embedding gradient reductions, fused residual + MSE loss.
+//
+// All activations NHWC bf16 with channel stride `ld`; statistics and reductions in fp32/fp64.
+// These kernels are HBM-bound: 8-byte (4 x bf16) vector accesses, a fixed channel-vector per
+// thread (no per-element division), warp-shuffle + shared-memory reductions, per-chunk partial
+// sums instead of atomics where the result feeds a normalisation.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mdm {
+
+typedef __nv_bfloat16 bf16;
+
+struct bf16x4 {
+  __nv_bfloat162 a, b;
+};
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  const bf16x4 v = *reinterpret_cast<const bf16x4*>(p);
+  const float2 x = __bfloat1622float2(v.a), y = __bfloat1622float2(v.b);
+  return make_float4(x.x, x.y, y.x, y.y);
+}
+__device__ __forceinline__ void st4(bf16* p, float4 f) {
+  bf16x4 v;
+  v.a = __floats2bfloat162_rn(f.x, f.y);
+  v.b = __floats2bfloat162_rn(f.z, f.w);
+  *reinterpret_cast<bf16x4*>(p) = v;
+}
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + __expf(-z)); }
+__device__ __forceinline__ float siluf_(float z) { return z * sigmoidf_(z); }
+__device__ __forceinline__ float dsiluf_(float z) {
+  const float s = sigmoidf_(z);
+  return s * (1.0f + z * (1.0f - s));
+}
+
+// =============================================================================================
+// K2: GroupNorm (+SiLU).  grid = (chunks, N); thread <-> fixed 4-channel vector(s); rows strided.
+// =============================================================================================
+constexpr int GN_MAX_GROUPS = 32;
+
+struct GnGeom {
+  int HW, C, G, cpg, V, lanes, R, chunk_pix, nchunk;
+};
+
+__device__ __forceinline__ void gn_thread_map(const GnGeom& g, int& r, int& lane_c) {
+  r = threadIdx.x / g.lanes;
+  lane_c = threadIdx.x % g.lanes;
+}
+
+__global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ ws, GnGeom g) {
+  __shared__ float acc[GN_MAX_GROUPS * 2];
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  if (threadIdx.x < GN_MAX_GROUPS * 2) acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  int r, lane_c;
+  gn_thread_map(g, r, lane_c);
+  const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
+  const bf16* base = x + (long long)n * g.HW * ld;
+  if (r < g.R) {
+    for (int cv = lane_c; cv < g.V; cv += g.lanes) {
+      float s = 0.f, ss = 0.f;
+      for (int p = p0 + r; p < p1; p += g.R) {
+        const float4 v = ld4(base + (long long)p * ld + cv * 4);
+        s += (v.x + v.y) + (v.z + v.w);
+        ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+      const int grp = (cv * 4) / g.cpg;
+      atomicAdd(&acc[grp * 2], s);
+      atomicAdd(&acc[grp * 2 + 1], ss);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < g.G * 2) ws[((long long)(n * g.nchunk + chunk)) * GN_MAX_GROUPS * 2 + threadIdx.x] = acc[threadIdx.x];
+}
+
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ld, bf16* __restrict__ y, long long ldy,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ ws, float* __restrict__ stats, float eps, int silu, GnGeom g) {
+  __shared__ float mr[GN_MAX_GROUPS * 2];
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  if (threadIdx.x < g.G) {
+    double s = 0.0, ss = 0.0;
+    for (int k = 0; k < g.nchunk; ++k) {
+      const float* w = ws + ((long long)(n * g.nchunk + k)) * GN_MAX_GROUPS * 2 + threadIdx.x * 2;
+      s += w[0];
+      ss += w[1];
+    }
+    const double cnt = (double)g.HW * g.cpg;
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    mr[threadIdx.x * 2] = (float)mean;
+    mr[threadIdx.x * 2 + 1] = rstd;
+    if (chunk == 0 && stats) {
+      stats[((long long)n * g.G + threadIdx.x) * 2] = (float)mean;
+      stats[((long long)n * g.G + threadIdx.x) * 2 + 1] = rstd;
+    }
+  }
+  __syncthreads();
+  int r, lane_c;
+  gn_thread_map(g, r, lane_c);
+  if (r >= g.R) return;
+  const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
+  const bf16* xb = x + (long long)n * g.HW * ld;
+  bf16* yb = y + (long long)n * g.HW * ldy;
+  for (int cv = lane_c; cv < g.V; cv += g.lanes) {
+    const int grp = (cv * 4) / g.cpg;
+    const float mean = mr[grp * 2], rstd = mr[grp * 2 + 1];
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + cv * 4);
+    const float4 be = *reinterpret_cast<const float4*>(beta + cv * 4);
+    for (int p = p0 + r; p < p1; p += g.R) {
+      const float4 v = ld4(xb + (long long)p * ld + cv * 4);
+      float4 z;
+      z.x = (v.x - mean) * rstd * ga.x + be.x;
+      z.y = (v.y - mean) * rstd * ga.y + be.y;
+      z.z = (v.z - mean) * rstd * ga.z + be.z;
+      z.w = (v.w - mean) * rstd * ga.w + be.w;
+      if (silu) { z.x = siluf_(z.x); z.y = siluf_(z.y); z.z = siluf_(z.z); z.w = siluf_(z.w); }
+      st4(yb + (long long)p * ldy + cv * 4, z);
+    }
+  }
+}
+
+// backward pass 1: per (n, chunk, group) sums of dxhat and dxhat*xhat; per-channel dgamma/dbeta
+__global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, long long ld, const bf16* __restrict__ dy, long long lddy,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ stats, float* __restrict__ ws,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int silu, GnGeom g) {
+  __shared__ float acc[GN_MAX_GROUPS * 2];
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  if (threadIdx.x < GN_MAX_GROUPS * 2) acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  int r, lane_c;
+  gn_thread_map(g, r, lane_c);
+  const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
+  const bf16* xb = x + (long long)n * g.HW * ld;
+  const bf16* db = dy + (long long)n * g.HW * lddy;
+  if (r < g.R) {
+    for (int cv = lane_c; cv < g.V; cv += g.lanes) {
+      const int grp = (cv * 4) / g.cpg;
+      const float mean = stats[((long long)n * g.G + grp) * 2], rstd = stats[((long long)n * g.G + grp) * 2 + 1];
+      const float4 ga = *reinterpret_cast<const float4*>(gamma + cv * 4);
+      const float4 be = *reinterpret_cast<const float4*>(beta + cv * 4);
+      float s1 = 0.f, s2 = 0.f;
+      float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), dbt = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p = p0 + r; p < p1; p += g.R) {
+        const float4 v = ld4(xb + (long long)p * ld + cv * 4);
+        float4 d = ld4(db + (long long)p * lddy + cv * 4);
+        float4 xh;
+        xh.x = (v.x - mean) * rstd; xh.y = (v.y - mean) * rstd; xh.z = (v.z - mean) * rstd; xh.w = (v.w - mean) * rstd;
+        if (silu) {
+          d.x *= dsiluf_(xh.x * ga.x + be.x); d.y *= dsiluf_(xh.y * ga.y + be.y);
+          d.z *= dsiluf_(xh.z * ga.z + be.z); d.w *= dsiluf_(xh.w * ga.w + be.w);
+        }
+        dg.x += d.x * xh.x; dg.y += d.y * xh.y; dg.z += d.z * xh.z; dg.w += d.w * xh.w;
+        dbt.x += d.x; dbt.y += d.y; dbt.z += d.z; dbt.w += d.w;
+        const float e0 = d.x * ga.x, e1 = d.y * ga.y, e2 = d.z * ga.z, e3 = d.w * ga.w;
+        s1 += (e0 + e1) + (e2 + e3);
+        s2 += (e0 * xh.x + e1 * xh.y) + (e2 * xh.z + e3 * xh.w);
+      }
+      atomicAdd(&acc[grp * 2], s1);
+      atomicAdd(&acc[grp * 2 + 1], s2);
+      if (dgamma) {
+        atomicAdd(dgamma + cv * 4 + 0, dg.x); atomicAdd(dgamma + cv * 4 + 1, dg.y);
+        atomicAdd(dgamma + cv * 4 + 2, dg.z); atomicAdd(dgamma + cv * 4 + 3, dg.w);
+        atomicAdd(dbeta + cv * 4 + 0, dbt.x); atomicAdd(dbeta + cv * 4 + 1, dbt.y);
+        atomicAdd(dbeta + cv * 4 + 2, dbt.z); atomicAdd(dbeta + cv * 4 + 3, dbt.w);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < g.G * 2) ws[((long long)(n * g.nchunk + chunk)) * GN_MAX_GROUPS * 2 + threadIdx.x] = acc[threadIdx.x];
+}
+
+// backward pass 2: dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat)) (+ add)
+__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, long long ld, const bf16* __restrict__ dy, long long lddy,
+                                    const bf16* __restrict__ add, long long ldadd, const bf16* __restrict__ add2,
+                                    long long ldadd2, bf16* __restrict__ dx, long long lddx,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ stats, const float* __restrict__ ws, int silu, GnGeom g) {
+  __shared__ float m12[GN_MAX_GROUPS * 2];
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  if (threadIdx.x < g.G) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < g.nchunk; ++k) {
+      const float* w = ws + ((long long)(n * g.nchunk + k)) * GN_MAX_GROUPS * 2 + threadIdx.x * 2;
+      s1 += w[0];
+      s2 += w[1];
+    }
+    const double cnt = (double)g.HW * g.cpg;
+    m12[threadIdx.x * 2] = (float)(s1 / cnt);
+    m12[threadIdx.x * 2 + 1] = (float)(s2 / cnt);
+  }
+  __syncthreads();
+  int r, lane_c;
+  gn_thread_map(g, r, lane_c);
+  if (r >= g.R) return;
+  const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
+  const bf16* xb = x + (long long)n * g.HW * ld;
+  const bf16* db = dy + (long long)n * g.HW * lddy;
+  const bf16* ab = add ? add + (long long)n * g.HW * ldadd : nullptr;
+  const bf16* ab2 = add2 ? add2 + (long long)n * g.HW * ldadd2 : nullptr;
+  bf16* ob = dx + (long long)n * g.HW * lddx;
+  for (int cv = lane_c; cv < g.V; cv += g.lanes) {
+    const int grp = (cv * 4) / g.cpg;
+    const float mean = stats[((long long)n * g.G + grp) * 2], rstd = stats[((long long)n * g.G + grp) * 2 + 1];
+    const float m1 = m12[grp * 2], m2 = m12[grp * 2 + 1];
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + cv * 4);
+    const float4 be = *reinterpret_cast<const float4*>(beta + cv * 4);
+    for (int p = p0 + r; p < p1; p += g.R) {
+      const float4 v = ld4(xb + (long long)p * ld + cv * 4);
+      float4 d = ld4(db + (long long)p * lddy + cv * 4);
+      float4 xh;
+      xh.x = (v.x - mean) * rstd; xh.y = (v.y - mean) * rstd; xh.z = (v.z - mean) * rstd; xh.w = (v.w - mean) * rstd;
+      if (silu) {
+        d.x *= dsiluf_(xh.x * ga.x + be.x); d.y *= dsiluf_(xh.y * ga.y + be.y);
+        d.z *= dsiluf_(xh.z * ga.z + be.z); d.w *= dsiluf_(xh.w * ga.w + be.w);
+      }
+      float4 o;
+      o.x = rstd * (d.x * ga.x - m1 - xh.x * m2);
+      o.y = rstd * (d.y * ga.y - m1 - xh.y * m2);
+      o.z = rstd * (d.z * ga.z - m1 - xh.z * m2);
+      o.w = rstd * (d.w * ga.w - m1 - xh.w * m2);
+      if (ab) {
+        const float4 a = ld4(ab + (long long)p * ldadd + cv * 4);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      if (ab2) {
+        const float4 a = ld4(ab2 + (long long)p * ldadd2 + cv * 4);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      st4(ob + (long long)p * lddx + cv * 4, o);
+    }
+  }
+}
+
+static int gn_geom(GnGeom& g, int HW, int C, int G, int* threads, int* nchunk) {
+  if (C % (4 * G) != 0 || G > GN_MAX_GROUPS) { set_error("GroupNorm: C=%d must be a multiple of 4*G (G=%d <= 32)", C, G); return MDM_E_ARG; }
+  g.HW = HW; g.C = C; g.G = G; g.cpg = C / G; g.V = C / 4;
+  g.lanes = g.V < 256 ? g.V : 256;
+  g.R = 256 / g.lanes; if (g.R < 1) g.R = 1;
+  *threads = g.lanes * g.R; if (*threads < 64) *threads = 64;
+  // ~32K elements per CTA
+  int chunk = (32768 + C - 1) / C;
+  chunk = ((chunk + g.R - 1) / g.R) * g.R;
+  if (chunk > HW) chunk = HW;
+  if (chunk < 1) chunk = 1;
+  g.chunk_pix = chunk;
+  g.nchunk = (HW + chunk - 1) / chunk;
+  *nchunk = g.nchunk;
+  return MDM_OK;
+}
+
+// =============================================================================================
+// First conv (C_img -> cout, 3x3): planar fp32 image in, NHWC bf16 out.  thread <-> output
+// channel, weights in registers, input rows staged in shared memory (broadcast reads).  The same
+// kernel is the dgrad of the LAST conv (flip = 1: dy image in, dx NHWC out).
+// =============================================================================================
+constexpr int PL_MAXC = 4;       // image channels supported (1..4)
+constexpr int PL_TW = 32;        // pixels per tile (along W)
+
+template <int FLIP_T>
+__global__ void planar_to_nhwc_conv_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                           const float* __restrict__ bias, bf16* __restrict__ y, long long ldy,
+                                           int C, int H, int W, int cout, int w_is_out_layout) {
+  // tile: one image row h, PL_TW pixels
+  __shared__ float tile[PL_MAXC][3][PL_TW + 2];
+  const int tiles_w = (W + PL_TW - 1) / PL_TW;
+  const int tw = blockIdx.x % tiles_w, h = blockIdx.x / tiles_w, n = blockIdx.y;
+  const int w0 = tw * PL_TW;
+  for (int i = threadIdx.x; i < C * 3 * (PL_TW + 2); i += blockDim.x) {
+    const int c = i / (3 * (PL_TW + 2)), rem = i % (3 * (PL_TW + 2)), rr = rem / (PL_TW + 2), xx = rem % (PL_TW + 2);
+    const int hh = h + rr - 1, ww = w0 + xx - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = img[(((long long)n * C + c) * H + hh) * W + ww];
+    tile[c][rr][xx] = v;
+  }
+  __syncthreads();
+  for (int co = threadIdx.x; co < cout; co += blockDim.x) {
+    float wr[PL_MAXC][9];
+#pragma unroll
+    for (int c = 0; c < PL_MAXC; ++c)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int tt = FLIP_T ? 8 - t : t;
+        // conv_in weight [cout][C][3][3]; conv_out weight [C][cin=cout here][3][3]
+        wr[c][t] = c < C ? (w_is_out_layout ? w[((long long)c * cout + co) * 9 + tt] : w[((long long)co * C + c) * 9 + tt]) : 0.f;
+      }
+    const float b = bias ? bias[co] : 0.f;
+    for (int px = 0; px < PL_TW && w0 + px < W; ++px) {
+      float acc = b;
+#pragma unroll
+      for (int c = 0; c < PL_MAXC; ++c)
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          if (c < C) acc += tile[c][t / 3][px + (t % 3)] * wr[c][t];
+      y[(((long long)n * H + h) * W + w0 + px) * ldy + co] = __float2bfloat16(acc);
+    }
+  }
+}
+
+// wgrad twin: dw[..] += sum_p nhwc[p][co] * img[c][p + tap]; dbias[co] += sum_p nhwc[p][co]
+template <int FLIP_T>
+__global__ void planar_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ t, long long ldt,
+                                    float* __restrict__ dw, float* __restrict__ dbias, int C, int H, int W, int cout,
+                                    int w_is_out_layout, int rows_per_cta) {
+  __shared__ float tile[PL_MAXC][3][PL_TW + 2];
+  const int tiles_w = (W + PL_TW - 1) / PL_TW;
+  const int n = blockIdx.y;
+  const int co = threadIdx.x;
+  float acc[PL_MAXC][9];
+  float accb = 0.f;
+#pragma unroll
+  for (int c = 0; c < PL_MAXC; ++c)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[c][k] = 0.f;
+  for (int job = blockIdx.x * rows_per_cta; job < min((blockIdx.x + 1) * rows_per_cta, H * tiles_w); ++job) {
+    const int tw = job % tiles_w, h = job / tiles_w, w0 = tw * PL_TW;
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * 3 * (PL_TW + 2); i += blockDim.x) {
+      const int c = i / (3 * (PL_TW + 2)), rem = i % (3 * (PL_TW + 2)), rr = rem / (PL_TW + 2), xx = rem % (PL_TW + 2);
+      const int hh = h + rr - 1, ww = w0 + xx - 1;
+      float v = 0.f;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = img[(((long long)n * C + c) * H + hh) * W + ww];
+      tile[c][rr][xx] = v;
+    }
+    __syncthreads();
+    if (co < cout) {
+      for (int px = 0; px < PL_TW && w0 + px < W; ++px) {
+        const float d = __bfloat162float(t[(((long long)n * H + h) * W + w0 + px) * ldt + co]);
+        accb += d;
+#pragma unroll
+        for (int c = 0; c < PL_MAXC; ++c)
+#pragma unroll
+          for (int k = 0; k < 9; ++k)
+            if (c < C) acc[c][k] += d * tile[c][k / 3][px + (k % 3)];
+      }
+    }
+  }
+  if (co < cout) {
+#pragma unroll
+    for (int c = 0; c < PL_MAXC; ++c)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        if (c >= C) continue;
+        const int kk = FLIP_T ? 8 - k : k;
+        float* dst = w_is_out_layout ? dw + ((long long)c * cout + co) * 9 + kk : dw + ((long long)co * C + c) * 9 + kk;
+        atomicAdd(dst, acc[c][k]);
+      }
+    if (dbias) atomicAdd(dbias + co, accb);
+  }
+}
+
+// last conv forward: NHWC bf16 [.,cin] -> planar fp32 [N][C][H][W]; thread <-> pixel
+__global__ void nhwc_to_planar_conv_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ w,
+                                           const float* __restrict__ bias, float* __restrict__ y, int C, int H, int W, int cin) {
+  extern __shared__ float wsm[];  // [9][cin][4]
+  for (int i = threadIdx.x; i < 9 * cin * 4; i += blockDim.x) {
+    const int c = i & 3, ci = (i >> 2) % cin, t = (i >> 2) / cin;
+    wsm[i] = c < C ? w[((long long)c * cin + ci) * 9 + t] : 0.f;
+  }
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (p >= (long long)H * W) return;
+  const int h = (int)(p / W), ww = (int)(p % W);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int t = 0; t < 9; ++t) {
+    const int hh = h + t / 3 - 1, wx = ww + t % 3 - 1;
+    if (hh < 0 || hh >= H || wx < 0 || wx >= W) continue;
+    const bf16* xp = x + (((long long)n * H + hh) * W + wx) * ldx;
+    const float4* wp = reinterpret_cast<const float4*>(wsm + (long long)t * cin * 4);
+    for (int ci = 0; ci < cin; ci += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xp + ci);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h2[e]);
+        const float4 w0 = wp[ci + e * 2], w1 = wp[ci + e * 2 + 1];
+        a0 += f.x * w0.x + f.y * w1.x; a1 += f.x * w0.y + f.y * w1.y;
+        a2 += f.x * w0.z + f.y * w1.z; a3 += f.x * w0.w + f.y * w1.w;
+      }
+    }
+  }
+  const float accs[4] = {a0, a1, a2, a3};
+  for (int c = 0; c < C; ++c) y[(((long long)n * C + c) * H + h) * W + ww] = accs[c] + (bias ? bias[c] : 0.f);
+}
+
+__global__ void planar_sum_kernel(const float* __restrict__ img, float* __restrict__ out, int C, long long hw) {
+  // out[c] += sum over n, hw of img[n][c][:]
+  __shared__ float red[32];
+  const int c = blockIdx.y % C, n = blockIdx.y / C;
+  const float* p = img + ((long long)n * C + c) * hw;
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) s += p[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out + c, s);
+}
+
+// =============================================================================================
+// nearest 2x upsample (fwd), its adjoint (sum of the 2x2 block), zero insertion (stride-2 dgrad)
+// =============================================================================================
+__global__ void upsample2x_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                  int H, int W, int C, long long total_vec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int V = C / 8;
+  const int cv = (int)(i % V);
+  long long p = i / V;  // output pixel (n, ho, wo)
+  const int wo = (int)(p % (2 * W)); p /= (2 * W);
+  const int ho = (int)(p % (2 * H)); const long long n = p / (2 * H);
+  const uint4 v = *reinterpret_cast<const uint4*>(x + ((n * H + ho / 2) * W + wo / 2) * ldx + cv * 8);
+  *reinterpret_cast<uint4*>(y + ((n * 2 * H + ho) * 2 * W + wo) * ldy + cv * 8) = v;
+}
+
+__global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, long long ldy, bf16* __restrict__ dx, long long ldx,
+                                      int H, int W, int C, long long total_vec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int V = C / 4;
+  const int cv = (int)(i % V);
+  long long p = i / V;  // input pixel (n, h, w)
+  const int w = (int)(p % W); p /= W;
+  const int h = (int)(p % H); const long long n = p / H;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const float4 v = ld4(dy + ((n * 2 * H + 2 * h + a) * 2 * W + 2 * w + b) * ldy + cv * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  st4(dx + ((n * H + h) * W + w) * ldx + cv * 4, s);
+}
+
+__global__ void zero_insert2x_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                     int H, int W, int C, long long total_vec) {
+  // y[n][2h][2w] = x[n][h][w], zero elsewhere; y is [N][2H][2W][C]
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int V = C / 8;
+  const int cv = (int)(i % V);
+  long long p = i / V;
+  const int wo = (int)(p % (2 * W)); p /= (2 * W);
+  const int ho = (int)(p % (2 * H)); const long long n = p / (2 * H);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (((ho | wo) & 1) == 0) v = *reinterpret_cast<const uint4*>(x + ((n * H + ho / 2) * W + wo / 2) * ldx + cv * 8);
+  *reinterpret_cast<uint4*>(y + ((n * 2 * H + ho) * 2 * W + wo) * ldy + cv * 8) = v;
+}
+
+// =============================================================================================
+// K4: attention core for L <= 256 tokens, head_dim 8 (heads = C/8).  qkv: [N*L][3C] bf16.
+// One CTA per (head, n); K and V of the head live in shared memory; one thread per query.
+// (The q/k/v/out projections, >99% of the attention FLOPs, are tcgen05 GEMMs in igemm.cu; the
+// L x L x 8 core is far too small for a tensor-core tile.)
+// =============================================================================================
+constexpr int ATT_D = 8;
+__global__ void attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int C, float scale) {
+  extern __shared__ float att_sm[];  // K[L][8], V[L][8]
+  float* Ks = att_sm;
+  float* Vs = att_sm + L * ATT_D;
+  const int head = blockIdx.x, n = blockIdx.y;
+  const bf16* base = qkv + (long long)n * L * 3 * C + head * ATT_D;
+  for (int i = threadIdx.x; i < L * ATT_D; i += blockDim.x) {
+    const int j = i / ATT_D, d = i % ATT_D;
+    Ks[i] = __bfloat162float(base[(long long)j * 3 * C + C + d]);
+    Vs[i] = __bfloat162float(base[(long long)j * 3 * C + 2 * C + d]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    float q[ATT_D];
+    for (int d = 0; d < ATT_D; ++d) q[d] = __bfloat162float(base[(long long)i * 3 * C + d]) * scale;
+    float m = -INFINITY, l = 0.f, acc[ATT_D];
+    for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
+    for (int j = 0; j < L; ++j) {
+      float s = 0.f;
+      for (int d = 0; d < ATT_D; ++d) s += q[d] * Ks[j * ATT_D + d];
+      const float mn = fmaxf(m, s);
+      const float corr = __expf(m - mn), p = __expf(s - mn);
+      l = l * corr + p;
+      for (int d = 0; d < ATT_D; ++d) acc[d] = acc[d] * corr + p * Vs[j * ATT_D + d];
+      m = mn;
+    }
+    const float inv = 1.0f / l;
+    bf16* o = out + ((long long)n * L + i) * C + head * ATT_D;
+    for (int d = 0; d < ATT_D; ++d) o[d] = __float2bfloat16(acc[d] * inv);
+  }
+}
+
+__global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
+                                     int L, int C, float scale) {
+  extern __shared__ float att_sm[];  // K, V, dK, dV : 4 * L * 8
+  float* Ks = att_sm;
+  float* Vs = Ks + L * ATT_D;
+  float* dKs = Vs + L * ATT_D;
+  float* dVs = dKs + L * ATT_D;
+  const int head = blockIdx.x, n = blockIdx.y;
+  const bf16* base = qkv + (long long)n * L * 3 * C + head * ATT_D;
+  for (int i = threadIdx.x; i < L * ATT_D; i += blockDim.x) {
+    const int j = i / ATT_D, d = i % ATT_D;
+    Ks[i] = __bfloat162float(base[(long long)j * 3 * C + C + d]);
+    Vs[i] = __bfloat162float(base[(long long)j * 3 * C + 2 * C + d]);
+    dKs[i] = 0.f;
+    dVs[i] = 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    float q[ATT_D], dO[ATT_D], dq[ATT_D];
+    for (int d = 0; d < ATT_D; ++d) {
+      q[d] = __bfloat162float(base[(long long)i * 3 * C + d]);
+      dO[d] = __bfloat162float(dout[((long long)n * L + i) * C + head * ATT_D + d]);
+      dq[d] = 0.f;
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < L; ++j) {
+      float s = 0.f;
+      for (int d = 0; d < ATT_D; ++d) s += q[d] * Ks[j * ATT_D + d];
+      s *= scale;
+      const float mn = fmaxf(m, s);
+      l = l * __expf(m - mn) + __expf(s - mn);
+      m = mn;
+    }
+    const float inv = 1.0f / l;
+    float Di = 0.f;  // sum_j P_ij * (dO_i . v_j)
+    for (int j = 0; j < L; ++j) {
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < ATT_D; ++d) { s += q[d] * Ks[j * ATT_D + d]; dp += dO[d] * Vs[j * ATT_D + d]; }
+      Di += __expf(s * scale - m) * inv * dp;
+    }
+    for (int jj = 0; jj < L; ++jj) {
+      const int j = (jj + i) % L;  // stagger to spread the shared-memory atomics
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < ATT_D; ++d) { s += q[d] * Ks[j * ATT_D + d]; dp += dO[d] * Vs[j * ATT_D + d]; }
+      const float p = __expf(s * scale - m) * inv;
+      const float ds = p * (dp - Di) * scale;
+      for (int d = 0; d < ATT_D; ++d) {
+        dq[d] += ds * Ks[j * ATT_D + d];
+        atomicAdd(&dKs[j * ATT_D + d], ds * q[d]);
+        atomicAdd(&dVs[j * ATT_D + d], p * dO[d]);
+      }
+    }
+    bf16* o = dqkv + ((long long)n * L + i) * 3 * C + head * ATT_D;
+    for (int d = 0; d < ATT_D; ++d) o[d] = __float2bfloat16(dq[d]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L * ATT_D; i += blockDim.x) {
+    const int j = i / ATT_D, d = i % ATT_D;
+    bf16* o = dqkv + ((long long)n * L + j) * 3 * C + head * ATT_D;
+    o[C + d] = __float2bfloat16(dKs[i]);
+    o[2 * C + d] = __float2bfloat16(dVs[i]);
+  }
+}
+
+// =============================================================================================
+// small elementwise / reductions
+// =============================================================================================
+// diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): [cos(t f_k), sin(t f_k)], f_k = exp(-ln(1e4) k / half)
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, bf16* __restrict__ out, int N, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * dim) return;
+  const int n = i / dim, k = i % dim, half = dim / 2;
+  const int kk = k < half ? k : k - half;
+  const float f = expf(-9.210340371976184f * (float)kk / (float)half);
+  const float a = t[n] * f;
+  out[i] = __float2bfloat16(k < half ? cosf(a) : sinf(a));
+}
+
+// y = silu(x) elementwise; x fp32 [rows][C] -> y bf16  (time-embedding MLP; tiny)
+__global__ void silu_f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2bfloat16(siluf_(x[i]));
+}
+// dx = dy * silu'(x): dy fp32, x fp32 -> dx bf16
+__global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, bf16* __restrict__ dx, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dx[i] = __float2bfloat16(dy[i] * dsiluf_(x[i]));
+}
+
+// out[c] += sum over rows of dy[row][c]   (bias gradients); grid = (C/64.., row chunks)
+__global__ void colsum_kernel(const bf16* __restrict__ dy, long long ld, float* __restrict__ out, float* __restrict__ out2, long long rows, int C, int rows_per_cta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += __bfloat162float(dy[r * ld + c]);
+  atomicAdd(out + c, s);
+  if (out2) atomicAdd(out2 + c, s);
+}
+
+// out[n][c] (fp32, ld_out) = sum over the HW pixels of sample n of dy[(n*HW+p)][c]; optional dbias[c] += same
+__global__ void sample_colsum_kernel(const bf16* __restrict__ dy, long long ld, float* __restrict__ out, long long ld_out,
+                                     float* __restrict__ dbias, int HW, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (c >= C) return;
+  float s = 0.f;
+  const bf16* p = dy + (long long)n * HW * ld + c;
+  for (int i = 0; i < HW; ++i) s += __bfloat162float(p[(long long)i * ld]);
+  out[(long long)n * ld_out + c] = s;
+  if (dbias) atomicAdd(dbias + c, s);
+}
+
+// fused residual + MSE (trainer_masked.py:126-140 / trainer_masked_mean_shift.py:142-159):
+//   recon = (x_in + net) - shift ; loss = mean(w_b * (recon - x0)^2) ; dnet = 2 w_b (recon - x0) / numel
+__global__ void mse_residual_kernel(const float* __restrict__ x_in, const float* __restrict__ net,
+                                    const float* __restrict__ shift, const float* __restrict__ x0,
+                                    const float* __restrict__ weight, float* __restrict__ dnet,
+                                    float* __restrict__ recon_out, float* __restrict__ partial, long long per_sample,
+                                    long long total, float inv_total) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float r = __fadd_rn(x_in[i], net[i]);
+    if (shift) r = __fsub_rn(r, shift[i]);
+    const float d = r - x0[i];
+    const float w = weight ? weight[i / per_sample] : 1.0f;
+    s += w * d * d;
+    if (dnet) dnet[i] = 2.0f * w * d * inv_total;
+    if (recon_out) recon_out[i] = r;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+__global__ void mse_finalize_kernel(const float* __restrict__ partial, int n, float inv_total, float* __restrict__ loss) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *loss = s * inv_total;
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    st4(y + i, v);
+  } else {
+    for (long long j = i; j < n; ++j) y[j] = __float2bfloat16(x[j]);
+  }
+}
+
+}  // namespace mdm
+
+using namespace mdm;
+
+#define GRID1D(n, t) (unsigned)(((n) + (t) - 1) / (t))
+
+extern "C" {
+
+int64_t mdm_gn_ws_floats(int N, int HW, int C, int G) {
+  GnGeom g; int th, nc;
+  if (gn_geom(g, HW, C, G, &th, &nc)) return 0;
+  return (int64_t)N * nc * GN_MAX_GROUPS * 2;
+}
+
+int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma, const float* beta,
+                    float* stats, float* ws, int N, int HW, int C, int G, float eps, int silu, void* stream) {
+  MDM_CHECK_ARG(x && y && gamma && beta && ws, "gn_silu_fwd: NULL pointer");
+  MDM_CHECK_ARG(ld_x % 4 == 0 && ld_y % 4 == 0, "gn_silu_fwd: channel strides must be multiples of 4");
+  GnGeom g; int th, nc;
+  int rc = gn_geom(g, HW, C, G, &th, &nc);
+  if (rc) return rc;
+  dim3 grid(nc, N);
+  gn_stats_kernel<<<grid, th, 0, as_stream(stream)>>>((const bf16*)x, ld_x, ws, g);
+  MDM_LAUNCH_CHECK();
+  gn_apply_kernel<<<grid, th, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta, ws, stats, eps, silu, g);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_gn_silu_bwd(const void* x, long long ld_x, const void* dy, long long ld_dy, const void* add, long long ld_add,
+                    const void* add2, long long ld_add2, void* dx, long long ld_dx, const float* gamma, const float* beta, const float* stats, float* dgamma,
+                    float* dbeta, float* ws, int N, int HW, int C, int G, int silu, void* stream) {
+  MDM_CHECK_ARG(x && dy && dx && gamma && beta && stats && ws, "gn_silu_bwd: NULL pointer");
+  GnGeom g; int th, nc;
+  int rc = gn_geom(g, HW, C, G, &th, &nc);
+  if (rc) return rc;
+  dim3 grid(nc, N);
+  gn_bwd_stats_kernel<<<grid, th, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, gamma, beta, stats, ws, dgamma, dbeta, silu, g);
+  MDM_LAUNCH_CHECK();
+  gn_bwd_apply_kernel<<<grid, th, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (const bf16*)add, ld_add, (const bf16*)add2, ld_add2, (bf16*)dx, ld_dx, gamma, beta, stats, ws, silu, g);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_conv_in_fwd(const float* img, const float* w, const float* bias, void* y, long long ld_y, int N, int C, int H,
+                    int W, int cout, void* stream) {
+  MDM_CHECK_ARG(img && w && y, "conv_in_fwd: NULL pointer");
+  MDM_CHECK_ARG(C >= 1 && C <= PL_MAXC, "conv_in_fwd: image channels must be 1..4 (got %d)", C);
+  dim3 grid(H * ((W + PL_TW - 1) / PL_TW), N);
+  planar_to_nhwc_conv_kernel<0><<<grid, 128, 0, as_stream(stream)>>>(img, w, bias, (bf16*)y, ld_y, C, H, W, cout, 0);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_conv_in_wgrad(const float* img, const void* dy, long long ld_dy, float* dw, float* dbias, int N, int C, int H,
+                      int W, int cout, void* stream) {
+  MDM_CHECK_ARG(img && dy && dw, "conv_in_wgrad: NULL pointer");
+  MDM_CHECK_ARG(C >= 1 && C <= PL_MAXC && cout <= 1024, "conv_in_wgrad: C in 1..4, cout <= 1024");
+  const int jobs = H * ((W + PL_TW - 1) / PL_TW);
+  const int rows_per_cta = 8;
+  dim3 grid((jobs + rows_per_cta - 1) / rows_per_cta, N);
+  const int th = ((cout + 31) / 32) * 32;
+  planar_wgrad_kernel<0><<<grid, th, 0, as_stream(stream)>>>(img, (const bf16*)dy, ld_dy, dw, dbias, C, H, W, cout, 0, rows_per_cta);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_conv_out_fwd(const void* x, long long ld_x, const float* w, const float* bias, float* y, int N, int C, int H,
+                     int W, int cin, void* stream) {
+  MDM_CHECK_ARG(x && w && y, "conv_out_fwd: NULL pointer");
+  MDM_CHECK_ARG(C >= 1 && C <= PL_MAXC && cin % 8 == 0, "conv_out_fwd: C in 1..4, cin %% 8");
+  const size_t smem = (size_t)9 * cin * 4 * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    MDM_CUDA(cudaFuncSetAttribute(nhwc_to_planar_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  dim3 grid(GRID1D((long long)H * W, 128), N);
+  nhwc_to_planar_conv_kernel<<<grid, 128, smem, as_stream(stream)>>>((const bf16*)x, ld_x, w, bias, y, C, H, W, cin);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+/* backward of the last conv: dx (NHWC bf16) = dgrad(dy planar fp32); dw[C][cin][3][3], dbias[C] accumulated */
+int mdm_conv_out_bwd(const void* x, long long ld_x, const float* w, const float* dy, void* dx, long long ld_dx, float* dw,
+                     float* dbias, int N, int C, int H, int W, int cin, void* stream) {
+  MDM_CHECK_ARG(x && w && dy, "conv_out_bwd: NULL pointer");
+  MDM_CHECK_ARG(C >= 1 && C <= PL_MAXC && cin <= 1024, "conv_out_bwd: C in 1..4, cin <= 1024");
+  cudaStream_t st = as_stream(stream);
+  if (dx) {
+    dim3 grid(H * ((W + PL_TW - 1) / PL_TW), N);
+    planar_to_nhwc_conv_kernel<1><<<grid, 128, 0, st>>>(dy, w, nullptr, (bf16*)dx, ld_dx, C, H, W, cin, 1);
+    MDM_LAUNCH_CHECK();
+  }
+  if (dw) {
+    const int jobs = H * ((W + PL_TW - 1) / PL_TW);
+    const int rows_per_cta = 8;
+    dim3 grid((jobs + rows_per_cta - 1) / rows_per_cta, N);
+    const int th = ((cin + 31) / 32) * 32;
+    planar_wgrad_kernel<1><<<grid, th, 0, st>>>(dy, (const bf16*)x, ld_x, dw, nullptr, C, H, W, cin, 1, rows_per_cta);
+    MDM_LAUNCH_CHECK();
+  }
+  if (dbias) {
+    dim3 grid(8, N * C);
+    planar_sum_kernel<<<grid, 256, 0, st>>>(dy, dbias, C, (long long)H * W);
+    MDM_LAUNCH_CHECK();
+  }
+  return MDM_OK;
+}
+
+int mdm_upsample2x_fwd(const void* x, long long ld_x, void* y, long long ld_y, int N, int H, int W, int C, void* stream) {
+  MDM_CHECK_ARG(x && y && C % 8 == 0, "upsample2x_fwd: bad arguments");
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<GRID1D(total, 256), 256, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (bf16*)y, ld_y, H, W, C, total);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_upsample2x_bwd(const void* dy, long long ld_dy, void* dx, long long ld_dx, int N, int H, int W, int C, void* stream) {
+  MDM_CHECK_ARG(dy && dx && C % 4 == 0, "upsample2x_bwd: bad arguments");
+  const long long total = (long long)N * H * W * (C / 4);
+  upsample2x_bwd_kernel<<<GRID1D(total, 256), 256, 0, as_stream(stream)>>>((const bf16*)dy, ld_dy, (bf16*)dx, ld_dx, H, W, C, total);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_zero_insert2x(const void* x, long long ld_x, void* y, long long ld_y, int N, int H, int W, int C, void* stream) {
+  MDM_CHECK_ARG(x && y && C % 8 == 0, "zero_insert2x: bad arguments");
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  zero_insert2x_kernel<<<GRID1D(total, 256), 256, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (bf16*)y, ld_y, H, W, C, total);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_attention_fwd(const void* qkv, void* out, int N, int L, int C, void* stream) {
+  MDM_CHECK_ARG(qkv && out && C % ATT_D == 0 && L >= 1 && L <= 1024, "attention_fwd: bad arguments (L=%d C=%d)", L, C);
+  const int th = L < 32 ? 32 : (L > 256 ? 256 : ((L + 31) / 32) * 32);
+  const size_t smem = (size_t)2 * L * ATT_D * sizeof(float);
+  dim3 grid(C / ATT_D, N);
+  attention_fwd_kernel<<<grid, th, smem, as_stream(stream)>>>((const bf16*)qkv, (bf16*)out, L, C, 1.0f / sqrtf((float)ATT_D));
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_attention_bwd(const void* qkv, const void* dout, void* dqkv, int N, int L, int C, void* stream) {
+  MDM_CHECK_ARG(qkv && dout && dqkv && C % ATT_D == 0 && L >= 1 && L <= 1024, "attention_bwd: bad arguments");
+  const int th = L < 32 ? 32 : (L > 256 ? 256 : ((L + 31) / 32) * 32);
+  const size_t smem = (size_t)4 * L * ATT_D * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    MDM_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  dim3 grid(C / ATT_D, N);
+  attention_bwd_kernel<<<grid, th, smem, as_stream(stream)>>>((const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, L, C, 1.0f / sqrtf((float)ATT_D));
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_timestep_embedding(const float* t, void* out, int N, int dim, void* stream) {
+  MDM_CHECK_ARG(t && out && dim % 2 == 0, "timestep_embedding: bad arguments");
+  timestep_embedding_kernel<<<GRID1D(N * dim, 256), 256, 0, as_stream(stream)>>>(t, (bf16*)out, N, dim);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_silu_fwd(const float* x, void* y, int64_t n, void* stream) {
+  MDM_CHECK_ARG(x && y, "silu_fwd: NULL pointer");
+  silu_f32_to_bf16_kernel<<<GRID1D(n, 256), 256, 0, as_stream(stream)>>>(x, (bf16*)y, n);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_silu_bwd(const float* x, const float* dy, void* dx, int64_t n, void* stream) {
+  MDM_CHECK_ARG(x && dy && dx, "silu_bwd: NULL pointer");
+  silu_bwd_kernel<<<GRID1D(n, 256), 256, 0, as_stream(stream)>>>(x, dy, (bf16*)dx, n);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_colsum(const void* dy, long long ld, float* out, float* out2, int64_t rows, int C, void* stream) {
+  MDM_CHECK_ARG(dy && out, "colsum: NULL pointer");
+  int rows_per_cta = 256;
+  dim3 grid(GRID1D(C, 128), (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
+  colsum_kernel<<<grid, 128, 0, as_stream(stream)>>>((const bf16*)dy, ld, out, out2, rows, C, rows_per_cta);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_sample_colsum(const void* dy, long long ld, float* out, long long ld_out, float* dbias, int N, int HW, int C, void* stream) {
+  MDM_CHECK_ARG(dy && out, "sample_colsum: NULL pointer");
+  dim3 grid(GRID1D(C, 128), N);
+  sample_colsum_kernel<<<grid, 128, 0, as_stream(stream)>>>((const bf16*)dy, ld, out, ld_out, dbias, HW, C);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_mse_residual(const float* x_in, const float* net, const float* shift, const float* x0, const float* weight,
+                     float* dnet, float* recon, float* loss, float* ws, int64_t per_sample, int64_t total, void* stream) {
+  MDM_CHECK_ARG(x_in && net && x0 && loss && ws, "mse_residual: NULL pointer");
+  const int blocks = (int)((total + 256 * 8 - 1) / (256 * 8) < 1024 ? (total + 256 * 8 - 1) / (256 * 8) : 1024);
+  const float inv = 1.0f / (float)total;
+  mse_residual_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x_in, net, shift, x0, weight, dnet, recon, ws, per_sample, total, inv);
+  MDM_LAUNCH_CHECK();
+  mse_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(ws, blocks, inv, loss);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
+  MDM_CHECK_ARG(x && y, "cast: NULL pointer");
+  f32_to_bf16_kernel<<<GRID1D((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(x, (bf16*)y, n);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,814 @@
+"""B200-native denoiser: the U-Net the reference builds at utils/model.py:3-33
+(`diffusers.UNet2DModel`), executed entirely by the sm_100a kernels behind
+include/mdm.h -- tcgen05 implicit-GEMM convolutions/linears, fused GroupNorm+SiLU, attention core.
+
+Surface kept from diffusers (what the reference calls): `model(x, t).sample`, `.device`,
+`.config`, `.parameters()`, `.train()/.eval()`, `.state_dict()/.load_state_dict()` with the
+diffusers key names and NCHW fp32 tensors, `.save_pretrained()/.from_pretrained()`.
+
+Data layout in HBM
+  * parameters: ONE flat fp32 master buffer (and one flat fp32 gradient buffer of the same
+    layout) + a flat bf16 mirror read by the GEMMs.  3x3/1x1 conv weights are stored packed
+    [cout][kh*kw][cin] (K-major for fprop, directly the layout wgrad produces); q/k/v weights
+    are adjacent so one [3C][C] GEMM does the three projections; every resnet's
+    `time_emb_proj` is adjacent so ONE GEMM projects the time embedding for all 32 resnets.
+    `state_dict()` converts to/from the checkpoint layout.
+  * activations: NHWC bf16.  Skip connections are never copied: the producer of a skip tensor
+    writes straight into its slice of the up-path concat buffer (channel stride = C_h + C_skip)
+    and every consumer addresses the slice through the stride.
+  * gradients of activations mirror that aliasing, so the concat backward is free as well.
+
+The forward/backward "programs" are built once per (batch, size) and replayed; every launch is
+stream-ordered with no host sync, so a whole step can be captured in a CUDA graph.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from types import SimpleNamespace
+
+import torch
+
+from . import denoiser_ops as ops
+
+G = 32  # norm_num_groups
+
+
+def default_config(dim_channel=3, dim_height=32, num_attention=1, base=128, layers_per_block=2):
+    """utils/model.py:3-33 (`MyModel`) as a config dict with the diffusers field names."""
+    attn_down = {1: (4,), 2: (3, 4), 3: (2, 3, 4), 4: (1, 2, 3, 4), 5: (1, 2, 3, 4, 5)}
+    attn_up = {1: (1,), 2: (1, 2), 3: (1, 2, 3), 4: (1, 2, 3, 4), 5: (0, 1, 2, 3, 4)}
+    if num_attention not in attn_down:
+        raise NotImplementedError("not implemented")
+    b = base
+    return dict(
+        _class_name="UNet2DModel", sample_size=dim_height, in_channels=dim_channel, out_channels=dim_channel,
+        layers_per_block=layers_per_block, block_out_channels=[b, b, 2 * b, 2 * b, 4 * b, 4 * b],
+        down_block_types=["AttnDownBlock2D" if i in attn_down[num_attention] else "DownBlock2D" for i in range(6)],
+        up_block_types=["AttnUpBlock2D" if i in attn_up[num_attention] else "UpBlock2D" for i in range(6)],
+        act_fn="silu", attention_head_dim=8, norm_num_groups=32, norm_eps=1e-5,
+        time_embedding_type="positional", flip_sin_to_cos=True, freq_shift=0,
+        downsample_padding=1, add_attention=True, center_input_sample=False, dropout=0.0,
+        mid_block_scale_factor=1, downsample_type="conv", upsample_type="conv",
+        resnet_time_scale_shift="default", attn_norm_num_groups=None,
+        class_embed_type=None, num_class_embeds=None, num_train_timesteps=None,
+    )
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter book-keeping
+# ---------------------------------------------------------------------------------------------
+class ParamSpec:
+    __slots__ = ("name", "shape", "kind", "offset", "numel")
+
+    def __init__(self, name, shape, kind):
+        self.name, self.shape, self.kind = name, tuple(shape), kind   # kind: conv | plain
+        self.numel = math.prod(shape)
+        self.offset = None
+
+
+class Act:
+    """symbolic NHWC activation; storage assigned after the graph is known"""
+    __slots__ = ("N", "H", "W", "C", "alias", "val", "grad", "has_upstream_grad", "name")
+
+    def __init__(self, N, H, W, C, name=""):
+        self.N, self.H, self.W, self.C = N, H, W, C
+        self.alias = None          # (parent Act, channel offset)
+        self.val = None
+        self.grad = None
+        self.has_upstream_grad = False   # a later consumer (the up path) already wrote into .grad
+        self.name = name
+
+
+class UNet2DModelB200:
+    def __init__(self, device="cuda", **config):
+        cfg = default_config()
+        cfg.update(config)
+        self.config = SimpleNamespace(**cfg)
+        self._cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("UNet2DModelB200 runs on a CUDA device only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.training = True
+        self.dtype = torch.float32
+        self._specs = []           # ordered ParamSpec list (flat layout order)
+        self._by_name = {}
+        self._build_layers()
+        self._alloc_params()
+        self._plans = {}
+        self._anchor = torch.zeros(1, device=self.device, requires_grad=True)   # hooks the kernels into autograd
+        self.reset_parameters()
+
+    # -- structure ------------------------------------------------------------------------------
+    def _p(self, name, shape, kind="plain"):
+        s = ParamSpec(name, shape, kind)
+        self._specs.append(s)
+        self._by_name[name] = s
+        return name
+
+    def _build_layers(self):
+        cfg = self._cfg
+        boc = cfg["block_out_channels"]
+        n = cfg["layers_per_block"]
+        temb = boc[0] * 4
+        self.temb_dim = temb
+        L = SimpleNamespace()
+        L.resnets = []             # in execution order, for the batched time-embedding projection
+        self._p("conv_in.weight", (boc[0], cfg["in_channels"], 3, 3))
+        self._p("conv_in.bias", (boc[0],))
+        self._p("time_embedding.linear_1.weight", (temb, boc[0]))
+        self._p("time_embedding.linear_1.bias", (temb,))
+        self._p("time_embedding.linear_2.weight", (temb, temb))
+        self._p("time_embedding.linear_2.bias", (temb,))
+
+        def resnet(prefix, cin, cout):
+            r = SimpleNamespace(prefix=prefix, cin=cin, cout=cout, shortcut=cin != cout)
+            self._p(f"{prefix}.norm1.weight", (cin,)); self._p(f"{prefix}.norm1.bias", (cin,))
+            self._p(f"{prefix}.conv1.weight", (cout, 9, cin), "conv"); self._p(f"{prefix}.conv1.bias", (cout,))
+            self._p(f"{prefix}.norm2.weight", (cout,)); self._p(f"{prefix}.norm2.bias", (cout,))
+            self._p(f"{prefix}.conv2.weight", (cout, 9, cout), "conv"); self._p(f"{prefix}.conv2.bias", (cout,))
+            if r.shortcut:
+                self._p(f"{prefix}.conv_shortcut.weight", (cout, 1, cin), "conv"); self._p(f"{prefix}.conv_shortcut.bias", (cout,))
+            L.resnets.append(r)
+            return r
+
+        def attention(prefix, c):
+            a = SimpleNamespace(prefix=prefix, c=c)
+            self._p(f"{prefix}.group_norm.weight", (c,)); self._p(f"{prefix}.group_norm.bias", (c,))
+            for nm in ("to_q", "to_k", "to_v"):          # adjacent -> one [3C][C] matrix
+                self._p(f"{prefix}.{nm}.weight", (c, c))
+            for nm in ("to_q", "to_k", "to_v"):
+                self._p(f"{prefix}.{nm}.bias", (c,))
+            self._p(f"{prefix}.to_out.0.weight", (c, c)); self._p(f"{prefix}.to_out.0.bias", (c,))
+            return a
+
+        L.down = []
+        c = boc[0]
+        for i, ty in enumerate(cfg["down_block_types"]):
+            cin, c = c, boc[i]
+            blk = SimpleNamespace(resnets=[], attns=[], down=None)
+            for j in range(n):
+                blk.resnets.append(resnet(f"down_blocks.{i}.resnets.{j}", cin if j == 0 else c, c))
+            if ty.startswith("Attn"):
+                blk.attns = [attention(f"down_blocks.{i}.attentions.{j}", c) for j in range(n)]
+            if i != len(boc) - 1:
+                blk.down = f"down_blocks.{i}.downsamplers.0.conv"
+                self._p(blk.down + ".weight", (c, 9, c), "conv"); self._p(blk.down + ".bias", (c,))
+            L.down.append(blk)
+        L.mid = SimpleNamespace()
+        L.mid.res0 = resnet("mid_block.resnets.0", boc[-1], boc[-1])
+        L.mid.attn = attention("mid_block.attentions.0", boc[-1])
+        L.mid.res1 = resnet("mid_block.resnets.1", boc[-1], boc[-1])
+        L.up = []
+        rev = list(reversed(boc))
+        c = rev[0]
+        for i, ty in enumerate(cfg["up_block_types"]):
+            cprev, c = c, rev[i]
+            cin = rev[min(i + 1, len(boc) - 1)]
+            blk = SimpleNamespace(resnets=[], attns=[], up=None, skip_c=[])
+            for j in range(n + 1):
+                skip = cin if j == n else c
+                rin = cprev if j == 0 else c
+                blk.resnets.append(resnet(f"up_blocks.{i}.resnets.{j}", rin + skip, c))
+                blk.skip_c.append(skip)
+            if ty.startswith("Attn"):
+                blk.attns = [attention(f"up_blocks.{i}.attentions.{j}", c) for j in range(n + 1)]
+            if i != len(boc) - 1:
+                blk.up = f"up_blocks.{i}.upsamplers.0.conv"
+                self._p(blk.up + ".weight", (c, 9, c), "conv"); self._p(blk.up + ".bias", (c,))
+            L.up.append(blk)
+        self._p("conv_norm_out.weight", (boc[0],)); self._p("conv_norm_out.bias", (boc[0],))
+        self._p("conv_out.weight", (cfg["out_channels"], boc[0], 3, 3)); self._p("conv_out.bias", (cfg["out_channels"],))
+        # time_emb_proj of every resnet, adjacent (ONE GEMM for all of them)
+        off = 0
+        for r in L.resnets:
+            self._p(f"{r.prefix}.time_emb_proj.weight", (r.cout, temb))
+            r.tproj_off = off
+            off += r.cout
+        for r in L.resnets:
+            self._p(f"{r.prefix}.time_emb_proj.bias", (r.cout,))
+        L.tproj_total = off
+        self.layers = L
+
+    def _alloc_params(self):
+        off = 0
+        for s in self._specs:
+            off = (off + 63) // 64 * 64          # 256-byte alignment of every tensor (TMA needs 16)
+            s.offset = off
+            off += s.numel
+        self.numel_flat = (off + 63) // 64 * 64
+        dev = self.device
+        self.flat_param = torch.zeros(self.numel_flat, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(self.numel_flat, dtype=torch.float32, device=dev)
+        self.flat_bf16 = torch.zeros(self.numel_flat, dtype=torch.bfloat16, device=dev)
+        self._params = {}
+        for s in self._specs:
+            p = torch.nn.Parameter(self.flat_param[s.offset:s.offset + s.numel].view(s.shape), requires_grad=True)
+            p.grad = self.flat_grad[s.offset:s.offset + s.numel].view(s.shape)
+            p._mdm_model = self
+            self._params[s.name] = p
+        self._bf16_stale = True
+
+    def num_parameters(self):
+        return sum(s.numel for s in self._specs)
+
+    # views ------------------------------------------------------------------------------------
+    def w32(self, name):
+        s = self._by_name[name]
+        return self.flat_param[s.offset:s.offset + s.numel].view(s.shape)
+
+    def g32(self, name):
+        s = self._by_name[name]
+        return self.flat_grad[s.offset:s.offset + s.numel].view(s.shape)
+
+    def w16(self, name):
+        s = self._by_name[name]
+        return self.flat_bf16[s.offset:s.offset + s.numel].view(s.shape)
+
+    def _span(self, first, last, shape, which):
+        a, b = self._by_name[first], self._by_name[last]
+        buf = {"w16": self.flat_bf16, "w32": self.flat_param, "g32": self.flat_grad}[which]
+        n = math.prod(shape)
+        assert b.offset + b.numel - a.offset == n, "adjacent parameters are not contiguous"
+        return buf[a.offset:a.offset + n].view(shape)
+
+    # -- nn.Module-like surface ----------------------------------------------------------------------
+    def parameters(self):
+        return list(self._params.values())
+
+    def named_parameters(self):
+        return list(self._params.items())
+
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def to(self, *a, **k):
+        return self
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()
+
+    def mark_params_updated(self):
+        """call after the fp32 master was changed by a kernel torch cannot see (fused optimizer);
+        in-place torch ops on the parameters are detected through the tensor version counter."""
+        self._bf16_stale = True
+
+    def _refresh_bf16(self):
+        v = self.flat_param._version
+        if self._bf16_stale or v != getattr(self, "_bf16_version", None):
+            ops.cast_f32_bf16(self.flat_param, self.flat_bf16)
+            self._bf16_stale = False
+            self._bf16_version = v
+
+    def reset_parameters(self, seed=None):
+        """PyTorch default init of the corresponding nn.Conv2d / nn.Linear / nn.GroupNorm."""
+        g = torch.Generator(device="cpu")
+        if seed is not None:
+            g.manual_seed(seed)
+        else:
+            g.manual_seed(torch.initial_seed() & 0x7FFFFFFF)
+        with torch.no_grad():
+            for s in self._specs:
+                w = self.w32(s.name)
+                if s.name.endswith("norm1.weight") or s.name.endswith("norm2.weight") or s.name.endswith("group_norm.weight") or s.name == "conv_norm_out.weight":
+                    w.fill_(1.0)
+                elif "norm" in s.name and s.name.endswith(".bias"):
+                    w.zero_()
+                elif s.name.endswith(".weight"):
+                    fan_in = math.prod(s.shape[1:])
+                    bound = 1.0 / math.sqrt(fan_in)
+                    w.copy_(((torch.rand(s.shape, generator=g) * 2 - 1) * bound).to(w.device))
+                else:  # bias of conv / linear: U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+                    wname = s.name[:-4] + "weight"
+                    fan_in = math.prod(self._by_name[wname].shape[1:])
+                    bound = 1.0 / math.sqrt(fan_in)
+                    w.copy_(((torch.rand(s.shape, generator=g) * 2 - 1) * bound).to(w.device))
+        self.mark_params_updated()
+
+    # checkpoint layout: diffusers key names, NCHW fp32
+    def state_dict(self):
+        out = {}
+        order = self._checkpoint_order()
+        for name in order:
+            s = self._by_name[name]
+            w = self.w32(name).detach()
+            if s.kind == "conv":
+                k = int(round(math.sqrt(s.shape[1])))
+                w = ops.unpack_conv_weight(w, k)
+            out[name] = w.clone()
+        return out
+
+    def state_dict_grads(self):
+        """gradients in the checkpoint layout (tests / DDP debugging)"""
+        out = {}
+        for s in self._specs:
+            g = self.g32(s.name).detach()
+            if s.kind == "conv":
+                g = ops.unpack_conv_weight(g, int(round(math.sqrt(s.shape[1]))))
+            out[s.name] = g.clone()
+        return out
+
+    def _checkpoint_order(self):
+        return [s.name for s in self._specs]
+
+    def load_state_dict(self, sd, strict=True):
+        missing = [n for n in self._by_name if n not in sd]
+        unexpected = [n for n in sd if n not in self._by_name]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing {missing[:5]}..., unexpected {unexpected[:5]}...")
+        with torch.no_grad():
+            for name, t in sd.items():
+                if name not in self._by_name:
+                    continue
+                s = self._by_name[name]
+                t = t.to(device=self.device, dtype=torch.float32)
+                if s.kind == "conv":
+                    t = ops.pack_conv_weight(t)
+                if tuple(t.shape) != s.shape:
+                    raise RuntimeError(f"size mismatch for {name}: {tuple(t.shape)} vs {s.shape}")
+                self.w32(name).copy_(t)
+        self.mark_params_updated()
+        return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
+
+    def register_to_config(self, **kw):
+        for k, v in kw.items():
+            setattr(self.config, k, v)
+            self._cfg[k] = v
+
+    def save_pretrained(self, save_directory, **_):
+        from safetensors.torch import save_file
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = dict(self._cfg)
+        cfg["_diffusers_version"] = "0.26.0"
+        with open(os.path.join(save_directory, "config.json"), "w") as f:
+            json.dump(cfg, f, indent=2)
+        save_file({k: v.cpu().contiguous() for k, v in self.state_dict().items()},
+                  os.path.join(save_directory, "diffusion_pytorch_model.safetensors"))
+
+    @classmethod
+    def load_config(cls, path, subfolder=None, **_):
+        d = os.path.join(path, subfolder) if subfolder else path
+        if os.path.isdir(d):
+            d = os.path.join(d, "config.json")
+        with open(d) as f:
+            return json.load(f)
+
+    @classmethod
+    def from_config(cls, config, device="cuda", **_):
+        cfg = {k: v for k, v in dict(config).items() if not k.startswith("_") or k == "_class_name"}
+        return cls(device=device, **cfg)
+
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, device="cuda", **_):
+        from safetensors.torch import load_file
+        d = os.path.join(path, subfolder) if subfolder else path
+        model = cls.from_config(cls.load_config(d), device=device)
+        model.load_state_dict(load_file(os.path.join(d, "diffusion_pytorch_model.safetensors")))
+        return model
+
+    # ------------------------------------------------------------------------------------------
+    # plan: symbolic graph -> buffers -> forward / backward programs
+    # ------------------------------------------------------------------------------------------
+    def _plan(self, B, S, need_grad):
+        key = (B, S, need_grad)
+        if key in self._plans:
+            return self._plans[key]
+        P = _Plan(self, B, S, need_grad)
+        self._plans[key] = P
+        return P
+
+    def __call__(self, sample, timestep, return_dict=True):
+        return self.forward(sample, timestep)
+
+    def forward(self, sample: torch.Tensor, timestep):
+        if not sample.is_cuda:
+            raise RuntimeError("denoiser input must be a CUDA tensor (no CPU fallback)")
+        B, C, H, W = sample.shape
+        if H != W or (H & (H - 1)) != 0:
+            raise RuntimeError(f"denoiser: square power-of-two images only (got {H}x{W})")
+        t = timestep
+        if not torch.is_tensor(t):
+            t = torch.tensor([float(t)], device=sample.device)
+        t = t.to(device=sample.device, dtype=torch.float32)
+        if t.dim() == 0:
+            t = t[None]
+        t = t.expand(B).contiguous()
+        need_grad = self.training and torch.is_grad_enabled()
+        plan = self._plan(B, H, need_grad)
+        self._refresh_bf16()
+        x = sample.float().contiguous()
+        self._last_plan = plan
+        if need_grad:
+            out = _DenoiserFn.apply(self._anchor, plan, x, t)
+        else:
+            out = plan.run_forward(x, t)
+        return SimpleNamespace(sample=out)
+
+    def backward(self, d_out: torch.Tensor):
+        """Backpropagate d(loss)/d(sample output) (NCHW fp32) through the last training forward;
+        accumulates into `flat_grad` / every `p.grad`."""
+        plan = self._last_plan
+        if not plan.need_grad:
+            raise RuntimeError("backward() needs a forward in train mode with grad enabled")
+        plan.run_backward(d_out.float().contiguous())
+
+
+class _DenoiserFn(torch.autograd.Function):
+    """Makes `loss.backward()` (what the reference trainers call through accelerate) run the
+    hand-written backward program; parameter gradients are accumulated into `flat_grad`."""
+
+    @staticmethod
+    def forward(ctx, anchor, plan, x, t):
+        ctx.plan = plan
+        return plan.run_forward(x, t)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        ctx.plan.run_backward(d_out.float().contiguous())
+        return torch.zeros_like(ctx.plan.m._anchor), None, None, None
+
+
+class _Plan:
+    """Buffers and the two launch sequences for one (batch, size)."""
+
+    def __init__(self, m: UNet2DModelB200, B, S, need_grad):
+        self.m, self.B, self.S, self.need_grad = m, B, S, need_grad
+        self.dev = m.device
+        self.fwd, self.bwd = [], []
+        self.acts = []
+        self._scratch = {}
+        self._build()
+
+    # -- storage helpers ---------------------------------------------------------------------------
+    def act(self, H, C, name=""):
+        a = Act(self.B, H, H, C, name)
+        self.acts.append(a)
+        return a
+
+    def new(self, shape, dtype=torch.bfloat16, zero=False):
+        return (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.dev)
+
+    def scratch(self, tag, shape, dtype=torch.bfloat16):
+        """backward temporaries, shared by all layers (sized for the largest user)"""
+        n = math.prod(shape)
+        key = (tag, dtype)
+        cur = self._scratch.get(key)
+        if cur is None or cur.numel() < n:
+            self._scratch[key] = cur = torch.empty(n, dtype=dtype, device=self.dev)
+        return (tag, dtype, tuple(shape))
+
+    def sget(self, ref):
+        tag, dtype, shape = ref
+        return self._scratch[(tag, dtype)][:math.prod(shape)].view(shape)
+
+    def _materialise(self):
+        for a in self.acts:
+            if a.alias is None and a.val is None:
+                a.val = self.new((a.N, a.H, a.W, a.C))
+                if self.need_grad:
+                    a.grad = self.new((a.N, a.H, a.W, a.C))
+        for a in self.acts:
+            if a.alias is not None:
+                parent, c0 = a.alias
+                a.val = parent.val[..., c0:c0 + a.C]
+                if self.need_grad:
+                    a.grad = parent.grad[..., c0:c0 + a.C]
+
+    # -- graph -------------------------------------------------------------------------------------
+    def _build(self):
+        m, B, S = self.m, self.B, self.S
+        L = m.layers
+        cfg = m._cfg
+        boc = cfg["block_out_channels"]
+        eps = cfg["norm_eps"]
+        self.eps = eps
+        ng = self.need_grad
+        dev = self.dev
+        temb = m.temb_dim
+        # ---- time embedding ------------------------------------------------------------------------
+        self.t_in = self.new((B,), torch.float32)
+        self.x_in = self.new((B, cfg["in_channels"], S, S), torch.float32)
+        self.out = self.new((B, cfg["out_channels"], S, S), torch.float32)
+        te0 = self.new((B, boc[0]))
+        e1_f32 = self.new((B, temb), torch.float32)
+        e1_act = self.new((B, temb))
+        e2_f32 = self.new((B, temb), torch.float32)
+        e2_act = self.new((B, temb))
+        tproj = self.new((B, L.tproj_total), torch.float32)
+        self.tproj = tproj
+        first, last = L.resnets[0].prefix, L.resnets[-1].prefix
+        w_tp = m._span(f"{first}.time_emb_proj.weight", f"{last}.time_emb_proj.weight", (L.tproj_total, temb), "w16")
+        b_tp = m._span(f"{first}.time_emb_proj.bias", f"{last}.time_emb_proj.bias", (L.tproj_total,), "w32")
+        f = self.fwd
+        f.append(lambda: ops.timestep_embedding(self.t_in, te0, B, boc[0]))
+        f.append(lambda: ops.conv_fprop(te0, m.w16("time_embedding.linear_1.weight"), None, B, 1, 1, 1, 1,
+                                        bias=m.w32("time_embedding.linear_1.bias"), y_f32=e1_f32, cout=temb))
+        f.append(lambda: ops.silu_fwd(e1_f32, e1_act))
+        f.append(lambda: ops.conv_fprop(e1_act, m.w16("time_embedding.linear_2.weight"), None, B, 1, 1, 1, 1,
+                                        bias=m.w32("time_embedding.linear_2.bias"), y_f32=e2_f32, cout=temb))
+        f.append(lambda: ops.silu_fwd(e2_f32, e2_act))
+        f.append(lambda: ops.conv_fprop(e2_act, w_tp, None, B, 1, 1, 1, 1, bias=b_tp, y_f32=tproj, cout=L.tproj_total))
+        if ng:
+            self.d_tproj = self.new((B, L.tproj_total), torch.float32)
+            d_tproj16 = self.new((B, L.tproj_total))
+            d_e2act = self.new((B, temb), torch.float32)
+            d_e2 = self.new((B, temb))
+            d_e1act = self.new((B, temb), torch.float32)
+            d_e1 = self.new((B, temb))
+            g_tp = m._span(f"{first}.time_emb_proj.weight", f"{last}.time_emb_proj.weight", (L.tproj_total, 1, temb), "g32")
+            gb_tp = m._span(f"{first}.time_emb_proj.bias", f"{last}.time_emb_proj.bias", (L.tproj_total,), "g32")
+
+            def temb_bwd():
+                ops.cast_f32_bf16(self.d_tproj, d_tproj16)
+                ops.conv_dgrad(d_tproj16, w_tp, None, B, 1, 1, 1, dx_f32=d_e2act, cin=temb)
+                ops.conv_wgrad(e2_act, d_tproj16, g_tp, B, 1, 1, 1, 1)
+                ops.colsum(d_tproj16, gb_tp, B, L.tproj_total)
+                ops.silu_bwd(e2_f32, d_e2act, d_e2)
+                ops.conv_dgrad(d_e2, m.w16("time_embedding.linear_2.weight"), None, B, 1, 1, 1, dx_f32=d_e1act, cin=temb)
+                ops.conv_wgrad(e1_act, d_e2, m.g32("time_embedding.linear_2.weight").view(temb, 1, temb), B, 1, 1, 1, 1)
+                ops.colsum(d_e2, m.g32("time_embedding.linear_2.bias"), B, temb)
+                ops.silu_bwd(e1_f32, d_e1act, d_e1)
+                ops.conv_wgrad(te0, d_e1, m.g32("time_embedding.linear_1.weight").view(temb, 1, boc[0]), B, 1, 1, 1, 1)
+                ops.colsum(d_e1, m.g32("time_embedding.linear_1.bias"), B, temb)
+            self._temb_bwd = temb_bwd
+
+        # ---- symbolic pass -------------------------------------------------------------------------
+        self._ops = []        # (kind, dict) in forward order
+        h = self.act(S, boc[0], "conv_in")
+        self._ops.append(("conv_in", dict(out=h)))
+        skips = [h]
+        res = S
+        for i, blk in enumerate(L.down):
+            for j, r in enumerate(blk.resnets):
+                h = self._sym_resnet(r, h, res)
+                if blk.attns:
+                    h = self._sym_attn(blk.attns[j], h, res)
+                skips.append(h)
+            if blk.down:
+                o = self.act(res // 2, h.C, blk.down)
+                self._ops.append(("down", dict(name=blk.down, x=h, out=o, H=res // 2)))
+                res //= 2
+                h = o
+                skips.append(h)
+        h = self._sym_resnet(L.mid.res0, h, res)
+        h = self._sym_attn(L.mid.attn, h, res)
+        h = self._sym_resnet(L.mid.res1, h, res)
+        for i, blk in enumerate(L.up):
+            for j, r in enumerate(blk.resnets):
+                s = skips.pop()
+                assert s.C == blk.skip_c[j] and s.H == res, (s.C, blk.skip_c[j], s.H, res)
+                cat = self.act(res, h.C + s.C, f"cat.{r.prefix}")
+                assert h.alias is None and s.alias is None
+                h.alias = (cat, 0)
+                s.alias = (cat, h.C)
+                s.has_upstream_grad = True
+                h = self._sym_resnet(r, cat, res)
+                if blk.attns:
+                    h = self._sym_attn(blk.attns[j], h, res)
+            if blk.up:
+                o = self.act(res * 2, h.C, blk.up)
+                self._ops.append(("up", dict(name=blk.up, x=h, out=o, H=res)))
+                res *= 2
+                h = o
+        self._ops.append(("head", dict(x=h)))
+        self._materialise()
+        # ---- emit programs ---------------------------------------------------------------------------
+        emit = dict(conv_in=self._emit_conv_in, resnet=self._emit_resnet, attn=self._emit_attn, down=self._emit_down,
+                    up=self._emit_up, head=self._emit_head)
+        bw_chunks = []
+        for kind, d in self._ops:
+            fw, bw = emit[kind](**d)
+            self.fwd += fw
+            bw_chunks.append(bw)
+        if ng:
+            for bw in reversed(bw_chunks):
+                self.bwd += bw
+            self.bwd.append(self._temb_bwd)
+
+    def _sym_resnet(self, r, x, res):
+        out = self.act(res, r.cout, r.prefix)
+        self._ops.append(("resnet", dict(r=r, x=x, out=out, H=res)))
+        return out
+
+    def _sym_attn(self, a, x, res):
+        out = self.act(res, a.c, a.prefix)
+        self._ops.append(("attn", dict(a=a, x=x, out=out, H=res)))
+        return out
+
+    # -- emitters: return (forward launches, backward launches) ---------------------------------------
+    def _gn_ws(self, HW, C):
+        n = max(1, ops.gn_ws_floats(self.B, HW, C))
+        cur = getattr(self, "_gnws", None)
+        if cur is None or cur.numel() < n:
+            self._gnws = torch.empty(n, dtype=torch.float32, device=self.dev)
+        return lambda: self._gnws
+
+    def _emit_conv_in(self, out):
+        m, B, S = self.m, self.B, self.S
+        C = m._cfg["in_channels"]
+        fw = [lambda: ops.conv_in_fwd(self.x_in, m.w32("conv_in.weight"), m.w32("conv_in.bias"), out.val, B, C, S, S, out.C)]
+        bw = [lambda: ops.conv_in_wgrad(self.x_in, out.grad, m.g32("conv_in.weight"), m.g32("conv_in.bias"), B, C, S, S, out.C)]
+        return fw, bw
+
+    def _emit_resnet(self, r, x, out, H):
+        m, B = self.m, self.B
+        HW = H * H
+        p = r.prefix
+        ng = self.need_grad
+        a1 = self.new((B, H, H, r.cin)) if ng else None
+        h1 = self.new((B, H, H, r.cout)) if ng else None
+        a2 = self.new((B, H, H, r.cout)) if ng else None
+        st1 = self.new((B, G, 2), torch.float32)
+        st2 = self.new((B, G, 2), torch.float32)
+        if not ng:   # inference: temporaries shared by all layers
+            ra1 = self.scratch("a1", (B, H, H, r.cin))
+            rh1 = self.scratch("h1", (B, H, H, r.cout))
+            ra2 = self.scratch("a2", (B, H, H, r.cout))
+        ws1, ws2 = self._gn_ws(HW, r.cin), self._gn_ws(HW, r.cout)
+        tp = self.tproj[:, r.tproj_off:r.tproj_off + r.cout]
+        ld_tp = self.tproj.shape[1]
+        eps = self.eps
+
+        def A1():
+            return a1 if ng else self.sget(ra1)
+
+        def H1():
+            return h1 if ng else self.sget(rh1)
+
+        def A2():
+            return a2 if ng else self.sget(ra2)
+
+        fw = [
+            lambda: ops.gn_silu_fwd(x.val, A1(), m.w32(f"{p}.norm1.weight"), m.w32(f"{p}.norm1.bias"), st1, ws1(), B, HW, r.cin, G, eps, True),
+            lambda: ops.conv_fprop(A1(), m.w16(f"{p}.conv1.weight"), H1(), B, H, H, 3, 1, bias=m.w32(f"{p}.conv1.bias"), rowvec=tp, ld_rowvec=ld_tp),
+            lambda: ops.gn_silu_fwd(H1(), A2(), m.w32(f"{p}.norm2.weight"), m.w32(f"{p}.norm2.bias"), st2, ws2(), B, HW, r.cout, G, eps, True),
+        ]
+        if r.shortcut:
+            fw.append(lambda: ops.conv_fprop(A2(), m.w16(f"{p}.conv2.weight"), out.val, B, H, H, 3, 1, bias=m.w32(f"{p}.conv2.bias"),
+                                             bias2=m.w32(f"{p}.conv_shortcut.bias"), x2=x.val, w2=m.w16(f"{p}.conv_shortcut.weight")))
+        else:
+            fw.append(lambda: ops.conv_fprop(A2(), m.w16(f"{p}.conv2.weight"), out.val, B, H, H, 3, 1, bias=m.w32(f"{p}.conv2.bias"), resid=x.val))
+        bw = []
+        if ng:
+            rd_a2 = self.scratch("d_a2", (B, H, H, r.cout))
+            rd_h1 = self.scratch("d_h1", (B, H, H, r.cout))
+            rd_a1 = self.scratch("d_a1", (B, H, H, r.cin))
+            has_up = x.has_upstream_grad
+
+            def backward():
+                d_out = out.grad
+                d_a2, d_h1, d_a1 = self.sget(rd_a2), self.sget(rd_h1), self.sget(rd_a1)
+                ops.conv_dgrad(d_out, m.w16(f"{p}.conv2.weight"), d_a2, B, H, H, 3)
+                ops.conv_wgrad(a2, d_out, m.g32(f"{p}.conv2.weight"), B, H, H, 3, 1)
+                if r.shortcut:
+                    ops.conv_wgrad(x.val, d_out, m.g32(f"{p}.conv_shortcut.weight"), B, H, H, 1, 1)
+                    ops.colsum(d_out, m.g32(f"{p}.conv2.bias"), B * HW, r.cout, out2=m.g32(f"{p}.conv_shortcut.bias"))
+                else:
+                    ops.colsum(d_out, m.g32(f"{p}.conv2.bias"), B * HW, r.cout)
+                ops.gn_silu_bwd(h1, d_a2, d_h1, m.w32(f"{p}.norm2.weight"), m.w32(f"{p}.norm2.bias"), st2,
+                                m.g32(f"{p}.norm2.weight"), m.g32(f"{p}.norm2.bias"), ws2(), B, HW, r.cout, G, True)
+                ops.sample_colsum(d_h1, self.d_tproj[:, r.tproj_off:], self.d_tproj.shape[1], m.g32(f"{p}.conv1.bias"), B, HW, r.cout)
+                ops.conv_dgrad(d_h1, m.w16(f"{p}.conv1.weight"), d_a1, B, H, H, 3)
+                ops.conv_wgrad(a1, d_h1, m.g32(f"{p}.conv1.weight"), B, H, H, 3, 1)
+                add = None
+                if r.shortcut:
+                    ops.conv_dgrad(d_out, m.w16(f"{p}.conv_shortcut.weight"), x.grad, B, H, H, 1, accumulate=has_up)
+                    add = x.grad
+                elif has_up:
+                    add = x.grad
+                ops.gn_silu_bwd(x.val, d_a1, x.grad, m.w32(f"{p}.norm1.weight"), m.w32(f"{p}.norm1.bias"), st1,
+                                m.g32(f"{p}.norm1.weight"), m.g32(f"{p}.norm1.bias"), ws1(), B, HW, r.cin, G, True,
+                                add=add, add2=None if r.shortcut else d_out)
+            bw = [backward]
+        return fw, bw
+
+    def _emit_attn(self, a, x, out, H):
+        m, B = self.m, self.B
+        L_, C = H * H, a.c
+        p = a.prefix
+        ng = self.need_grad
+        y = self.new((B * L_, C))
+        qkv = self.new((B * L_, 3 * C))
+        att = self.new((B * L_, C))
+        st = self.new((B, G, 2), torch.float32)
+        ws = self._gn_ws(L_, C)
+        w_qkv = m._span(f"{p}.to_q.weight", f"{p}.to_v.weight", (3 * C, C), "w16")
+        b_qkv = m._span(f"{p}.to_q.bias", f"{p}.to_v.bias", (3 * C,), "w32")
+        eps = self.eps
+        fw = [
+            lambda: ops.gn_silu_fwd(x.val, y, m.w32(f"{p}.group_norm.weight"), m.w32(f"{p}.group_norm.bias"), st, ws(), B, L_, C, G, eps, False),
+            lambda: ops.conv_fprop(y, w_qkv, qkv, B * L_, 1, 1, 1, 1, bias=b_qkv),
+            lambda: ops.attention_fwd(qkv, att, B, L_, C),
+            lambda: ops.conv_fprop(att, m.w16(f"{p}.to_out.0.weight"), out.val, B * L_, 1, 1, 1, 1,
+                                   bias=m.w32(f"{p}.to_out.0.bias"), resid=x.val),
+        ]
+        bw = []
+        if ng:
+            rd_att = self.scratch("d_att", (B * L_, C))
+            rd_qkv = self.scratch("d_qkv", (B * L_, 3 * C))
+            rd_y = self.scratch("d_y", (B * L_, C))
+            g_qkv = m._span(f"{p}.to_q.weight", f"{p}.to_v.weight", (3 * C, 1, C), "g32")
+            gb_qkv = m._span(f"{p}.to_q.bias", f"{p}.to_v.bias", (3 * C,), "g32")
+            has_up = x.has_upstream_grad
+
+            def backward():
+                d_out = out.grad
+                d_att, d_qkv, d_y = self.sget(rd_att), self.sget(rd_qkv), self.sget(rd_y)
+                ops.conv_dgrad(d_out, m.w16(f"{p}.to_out.0.weight"), d_att, B * L_, 1, 1, 1)
+                ops.conv_wgrad(att, d_out, m.g32(f"{p}.to_out.0.weight").view(C, 1, C), B * L_, 1, 1, 1, 1)
+                ops.colsum(d_out, m.g32(f"{p}.to_out.0.bias"), B * L_, C)
+                ops.attention_bwd(qkv, d_att, d_qkv, B, L_, C)
+                ops.conv_dgrad(d_qkv, w_qkv, d_y, B * L_, 1, 1, 1)
+                ops.conv_wgrad(y, d_qkv, g_qkv, B * L_, 1, 1, 1, 1)
+                ops.colsum(d_qkv, gb_qkv, B * L_, 3 * C)
+                ops.gn_silu_bwd(x.val, d_y, x.grad, m.w32(f"{p}.group_norm.weight"), m.w32(f"{p}.group_norm.bias"), st,
+                                m.g32(f"{p}.group_norm.weight"), m.g32(f"{p}.group_norm.bias"), ws(), B, L_, C, G, False,
+                                add=x.grad if has_up else None, add2=d_out)
+            bw = [backward]
+        return fw, bw
+
+    def _emit_down(self, name, x, out, H):
+        m, B = self.m, self.B
+        C = x.C
+        fw = [lambda: ops.conv_fprop(x.val, m.w16(name + ".weight"), out.val, B, H, H, 3, 2, bias=m.w32(name + ".bias"))]
+        bw = []
+        if self.need_grad:
+            rz = self.scratch("zins", (B, 2 * H, 2 * H, C))
+            has_up = x.has_upstream_grad
+
+            def backward():
+                z = self.sget(rz)
+                ops.zero_insert2x(out.grad, z, B, H, H, C)
+                ops.conv_dgrad(z, m.w16(name + ".weight"), x.grad, B, 2 * H, 2 * H, 3, accumulate=has_up)
+                ops.conv_wgrad(x.val, out.grad, m.g32(name + ".weight"), B, H, H, 3, 2)
+                ops.colsum(out.grad, m.g32(name + ".bias"), B * H * H, C)
+            bw = [backward]
+        return fw, bw
+
+    def _emit_up(self, name, x, out, H):
+        m, B = self.m, self.B
+        C = x.C
+        ng = self.need_grad
+        u = self.new((B, 2 * H, 2 * H, C)) if ng else None
+        ru = None if ng else self.scratch("ups", (B, 2 * H, 2 * H, C))
+
+        def U():
+            return u if ng else self.sget(ru)
+        fw = [lambda: ops.upsample2x_fwd(x.val, U(), B, H, H, C),
+              lambda: ops.conv_fprop(U(), m.w16(name + ".weight"), out.val, B, 2 * H, 2 * H, 3, 1, bias=m.w32(name + ".bias"))]
+        bw = []
+        if ng:
+            rdu = self.scratch("d_ups", (B, 2 * H, 2 * H, C))
+
+            def backward():
+                du = self.sget(rdu)
+                ops.conv_dgrad(out.grad, m.w16(name + ".weight"), du, B, 2 * H, 2 * H, 3)
+                ops.conv_wgrad(u, out.grad, m.g32(name + ".weight"), B, 2 * H, 2 * H, 3, 1)
+                ops.colsum(out.grad, m.g32(name + ".bias"), B * 4 * H * H, C)
+                ops.upsample2x_bwd(du, x.grad, B, H, H, C)
+            bw = [backward]
+        return fw, bw
+
+    def _emit_head(self, x):
+        m, B, S = self.m, self.B, self.S
+        C, Co = x.C, m._cfg["out_channels"]
+        a = self.new((B, S, S, C))
+        st = self.new((B, G, 2), torch.float32)
+        ws = self._gn_ws(S * S, C)
+        eps = self.eps
+        fw = [lambda: ops.gn_silu_fwd(x.val, a, m.w32("conv_norm_out.weight"), m.w32("conv_norm_out.bias"), st, ws(), B, S * S, C, G, eps, True),
+              lambda: ops.conv_out_fwd(a, m.w32("conv_out.weight"), m.w32("conv_out.bias"), self.out, B, Co, S, S, C)]
+        bw = []
+        if self.need_grad:
+            rda = self.scratch("d_head", (B, S, S, C))
+            self.d_out = self.new((B, Co, S, S), torch.float32)
+
+            def backward():
+                da = self.sget(rda)
+                ops.conv_out_bwd(a, m.w32("conv_out.weight"), self.d_out, da, m.g32("conv_out.weight"), m.g32("conv_out.bias"), B, Co, S, S, C)
+                ops.gn_silu_bwd(x.val, da, x.grad, m.w32("conv_norm_out.weight"), m.w32("conv_norm_out.bias"), st,
+                                m.g32("conv_norm_out.weight"), m.g32("conv_norm_out.bias"), ws(), B, S * S, C, G, True)
+            bw = [backward]
+        return fw, bw
+
+    # -- execution ---------------------------------------------------------------------------------
+    def run_forward(self, x, t):
+        self.x_in.copy_(x)
+        self.t_in.copy_(t)
+        if not getattr(self, "static_output", False):
+            self.out = torch.empty_like(self.out)      # callers may keep the previous result
+        for op in self.fwd:
+            op()
+        return self.out
+
+    def run_backward(self, d_out):
+        self.d_out.copy_(d_out)
+        for op in self.bwd:
+            op()

@@ -20,7 +20,7 @@ class ConvArgs(Structure):
         ("y", c_void_p), ("ld_y", c_longlong), ("cout", c_int),
         ("N", c_int), ("H", c_int), ("W", c_int),
         ("ksize", c_int), ("stride", c_int),
-        ("bias", c_void_p), ("rowvec", c_void_p), ("ld_rowvec", c_longlong),
+        ("bias", c_void_p), ("bias2", c_void_p), ("rowvec", c_void_p), ("ld_rowvec", c_longlong),
         ("resid", c_void_p), ("ld_resid", c_longlong), ("accumulate", c_int),
         ("y_f32", c_void_p),
         ("x2", c_void_p), ("ld_x2", c_longlong), ("cin2", c_int), ("w2", c_void_p),
@@ -29,10 +29,32 @@ class ConvArgs(Structure):
 
 
 _P = c_void_p
+_LL = c_longlong
+_I64 = ctypes.c_int64
 _lib.register({
     "mdm_conv_fprop": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_conv_dgrad": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_conv_wgrad": (c_int, [POINTER(ConvArgs), _P]),
+    "mdm_gn_ws_floats": (_I64, [c_int, c_int, c_int, c_int]),
+    "mdm_gn_silu_fwd": (c_int, [_P, _LL, _P, _LL, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
+    "mdm_gn_silu_bwd": (c_int, [_P, _LL, _P, _LL, _P, _LL, _P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P,
+                                c_int, c_int, c_int, c_int, c_int, _P]),
+    "mdm_conv_in_fwd": (c_int, [_P, _P, _P, _P, _LL, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mdm_conv_in_wgrad": (c_int, [_P, _P, _LL, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mdm_conv_out_fwd": (c_int, [_P, _LL, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mdm_conv_out_bwd": (c_int, [_P, _LL, _P, _P, _P, _LL, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mdm_upsample2x_fwd": (c_int, [_P, _LL, _P, _LL, c_int, c_int, c_int, c_int, _P]),
+    "mdm_upsample2x_bwd": (c_int, [_P, _LL, _P, _LL, c_int, c_int, c_int, c_int, _P]),
+    "mdm_zero_insert2x": (c_int, [_P, _LL, _P, _LL, c_int, c_int, c_int, c_int, _P]),
+    "mdm_attention_fwd": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+    "mdm_attention_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "mdm_timestep_embedding": (c_int, [_P, _P, c_int, c_int, _P]),
+    "mdm_silu_fwd": (c_int, [_P, _P, _I64, _P]),
+    "mdm_silu_bwd": (c_int, [_P, _P, _P, _I64, _P]),
+    "mdm_colsum": (c_int, [_P, _LL, _P, _P, _I64, c_int, _P]),
+    "mdm_sample_colsum": (c_int, [_P, _LL, _P, _LL, _P, c_int, c_int, c_int, _P]),
+    "mdm_mse_residual": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
+    "mdm_cast_f32_bf16": (c_int, [_P, _P, _I64, _P]),
 })
 
 
@@ -50,39 +72,46 @@ def pix_ld(t: torch.Tensor) -> int:
 
 
 def conv_fprop(x, w, y, N, H, W, ksize=3, stride=1, bias=None, rowvec=None, resid=None, accumulate=False,
-               y_f32=None, x2=None, w2=None):
+               y_f32=None, x2=None, w2=None, bias2=None, cout=None, ld_rowvec=None):
     """y[N,H,W,cout] = conv(x, w) (+bias +rowvec[n] +resid) ; x: [N,H*s,W*s,cin] view, w packed
     bf16 [cout, k*k, cin]; optional fused 1x1 shortcut (x2, w2)."""
     a = ConvArgs()
     a.x, a.ld_x, a.cin = _dp(x), pix_ld(x), x.shape[-1]
     a.w = _dp(w)
-    a.y, a.ld_y, a.cout = _dp(y), pix_ld(y), y.shape[-1]
+    if y is not None:
+        a.y, a.ld_y, a.cout = _dp(y), pix_ld(y), y.shape[-1]
+    else:
+        a.y, a.ld_y, a.cout = None, 8, cout
     a.N, a.H, a.W, a.ksize, a.stride = N, H, W, ksize, stride
     a.bias = _dp(bias)
+    a.bias2 = _dp(bias2)
     if rowvec is not None:
-        a.rowvec, a.ld_rowvec = _dp(rowvec), rowvec.stride(0)
+        a.rowvec, a.ld_rowvec = _dp(rowvec), (ld_rowvec if ld_rowvec is not None else rowvec.stride(0))
     if resid is not None:
         a.resid, a.ld_resid = _dp(resid), pix_ld(resid)
     a.accumulate = int(accumulate)
     a.y_f32 = _dp(y_f32)
     if x2 is not None:
         a.x2, a.ld_x2, a.cin2, a.w2 = _dp(x2), pix_ld(x2), x2.shape[-1], _dp(w2)
-    check(lib().mdm_conv_fprop(ctypes.byref(a), stream_ptr(y.device)))
+    check(lib().mdm_conv_fprop(ctypes.byref(a), stream_ptr(x.device)))
 
 
-def conv_dgrad(dy, w, dx, N, H, W, ksize=3, resid=None, accumulate=False, dx_f32=None):
+def conv_dgrad(dy, w, dx, N, H, W, ksize=3, resid=None, accumulate=False, dx_f32=None, cin=None):
     """dx[N,H,W,cin] (+)= dgrad(dy[N,H,W,cout], w[cout,k*k,cin]) for a stride-1 layer."""
     a = ConvArgs()
     a.x, a.ld_x, a.cout = _dp(dy), pix_ld(dy), dy.shape[-1]
     a.w = _dp(w)
-    a.y, a.ld_y, a.cin = _dp(dx), pix_ld(dx), dx.shape[-1]
+    if dx is not None:
+        a.y, a.ld_y, a.cin = _dp(dx), pix_ld(dx), dx.shape[-1]
+    else:
+        a.y, a.ld_y, a.cin = None, 8, cin
     a.N, a.H, a.W, a.ksize, a.stride = N, H, W, ksize, 1
     if resid is not None:
         a.resid, a.ld_resid = _dp(resid), pix_ld(resid)
     a.accumulate = int(accumulate)
     a.y_f32 = _dp(dx_f32)
     a.w_cols = w.shape[-1]
-    check(lib().mdm_conv_dgrad(ctypes.byref(a), stream_ptr(dx.device)))
+    check(lib().mdm_conv_dgrad(ctypes.byref(a), stream_ptr(dy.device)))
 
 
 def conv_wgrad(x, dy, dw, N, H, W, ksize=3, stride=1):
@@ -105,3 +134,91 @@ def pack_conv_weight(w_nchw: torch.Tensor) -> torch.Tensor:
 def unpack_conv_weight(w_packed: torch.Tensor, k: int) -> torch.Tensor:
     co, taps, ci = w_packed.shape
     return w_packed.reshape(co, k, k, ci).permute(0, 3, 1, 2).contiguous()
+
+
+# ---- non-GEMM kernels -------------------------------------------------------------------------------
+def _s(t):
+    return stream_ptr(t.device)
+
+
+def gn_ws_floats(N, HW, C, G=32):
+    return int(lib().mdm_gn_ws_floats(N, HW, C, G))
+
+
+def gn_silu_fwd(x, y, gamma, beta, stats, ws, N, HW, C, G=32, eps=1e-5, silu=True):
+    check(lib().mdm_gn_silu_fwd(_dp(x), pix_ld(x), _dp(y), pix_ld(y), _dp(gamma), _dp(beta), _dp(stats), _dp(ws),
+                                N, HW, C, G, eps, int(silu), _s(x)))
+
+
+def gn_silu_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, ws, N, HW, C, G=32, silu=True, add=None, add2=None):
+    check(lib().mdm_gn_silu_bwd(_dp(x), pix_ld(x), _dp(dy), pix_ld(dy),
+                                _dp(add), pix_ld(add) if add is not None else 0,
+                                _dp(add2), pix_ld(add2) if add2 is not None else 0,
+                                _dp(dx), pix_ld(dx), _dp(gamma), _dp(beta), _dp(stats), _dp(dgamma), _dp(dbeta),
+                                _dp(ws), N, HW, C, G, int(silu), _s(x)))
+
+
+def conv_in_fwd(img, w, bias, y, N, C, H, W, cout):
+    check(lib().mdm_conv_in_fwd(_dp(img), _dp(w), _dp(bias), _dp(y), pix_ld(y), N, C, H, W, cout, _s(img)))
+
+
+def conv_in_wgrad(img, dy, dw, dbias, N, C, H, W, cout):
+    check(lib().mdm_conv_in_wgrad(_dp(img), _dp(dy), pix_ld(dy), _dp(dw), _dp(dbias), N, C, H, W, cout, _s(img)))
+
+
+def conv_out_fwd(x, w, bias, y, N, C, H, W, cin):
+    check(lib().mdm_conv_out_fwd(_dp(x), pix_ld(x), _dp(w), _dp(bias), _dp(y), N, C, H, W, cin, _s(x)))
+
+
+def conv_out_bwd(x, w, dy, dx, dw, dbias, N, C, H, W, cin):
+    check(lib().mdm_conv_out_bwd(_dp(x), pix_ld(x), _dp(w), _dp(dy), _dp(dx), pix_ld(dx) if dx is not None else 0,
+                                 _dp(dw), _dp(dbias), N, C, H, W, cin, _s(x)))
+
+
+def upsample2x_fwd(x, y, N, H, W, C):
+    check(lib().mdm_upsample2x_fwd(_dp(x), pix_ld(x), _dp(y), pix_ld(y), N, H, W, C, _s(x)))
+
+
+def upsample2x_bwd(dy, dx, N, H, W, C):
+    check(lib().mdm_upsample2x_bwd(_dp(dy), pix_ld(dy), _dp(dx), pix_ld(dx), N, H, W, C, _s(dy)))
+
+
+def zero_insert2x(x, y, N, H, W, C):
+    check(lib().mdm_zero_insert2x(_dp(x), pix_ld(x), _dp(y), pix_ld(y), N, H, W, C, _s(x)))
+
+
+def attention_fwd(qkv, out, N, L, C):
+    check(lib().mdm_attention_fwd(_dp(qkv), _dp(out), N, L, C, _s(qkv)))
+
+
+def attention_bwd(qkv, dout, dqkv, N, L, C):
+    check(lib().mdm_attention_bwd(_dp(qkv), _dp(dout), _dp(dqkv), N, L, C, _s(qkv)))
+
+
+def timestep_embedding(t, out, N, dim):
+    check(lib().mdm_timestep_embedding(_dp(t), _dp(out), N, dim, _s(t)))
+
+
+def silu_fwd(x_f32, y_bf16):
+    check(lib().mdm_silu_fwd(_dp(x_f32), _dp(y_bf16), x_f32.numel(), _s(x_f32)))
+
+
+def silu_bwd(x_f32, dy_f32, dx_bf16):
+    check(lib().mdm_silu_bwd(_dp(x_f32), _dp(dy_f32), _dp(dx_bf16), x_f32.numel(), _s(x_f32)))
+
+
+def colsum(dy, out, rows, C, out2=None):
+    check(lib().mdm_colsum(_dp(dy), pix_ld(dy), _dp(out), _dp(out2), rows, C, _s(dy)))
+
+
+def sample_colsum(dy, out, ld_out, dbias, N, HW, C):
+    check(lib().mdm_sample_colsum(_dp(dy), pix_ld(dy), _dp(out), ld_out, _dp(dbias), N, HW, C, _s(dy)))
+
+
+def mse_residual(x_in, net, shift, x0, weight, dnet, recon, loss, ws, per_sample):
+    check(lib().mdm_mse_residual(_dp(x_in), _dp(net), _dp(shift), _dp(x0), _dp(weight), _dp(dnet), _dp(recon), _dp(loss),
+                                 _dp(ws), per_sample, x_in.numel(), _s(x_in)))
+
+
+def cast_f32_bf16(x, y):
+    check(lib().mdm_cast_f32_bf16(_dp(x), _dp(y), x.numel(), _s(x)))

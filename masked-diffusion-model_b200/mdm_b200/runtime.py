@@ -1,0 +1,485 @@
+"""Host-side runtime the reference gets from `accelerate` / `diffusers` (both absent from the image
+and third-party): a data-parallel `Accelerator`, `EMAModel`, the warm-up
+LR schedules and a fused optimiser.  Same call surface the reference uses
+(main_train_masked.py:116-227,299-307; trainer_masked.py:124-166,268).
+
+One process per GPU (torchrun / RANK, LOCAL_RANK, WORLD_SIZE); gradients are averaged with NCCL
+all-reduce on the flat fp32 gradient buffer (gloo on CPU for the logic tests)."""
+from __future__ import annotations
+
+import contextlib
+import json
+import math
+import os
+import pickle
+import random
+from datetime import timedelta
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# ---------------------------------------------------------------------------------------------
+# LR schedules (diffusers.optimization get_*_schedule_with_warmup semantics)
+# ---------------------------------------------------------------------------------------------
+def _cosine(step, w, total, cycles):
+    if step < w:
+        return step / max(1, w)
+    p = (step - w) / max(1, total - w)
+    return max(0.0, 0.5 * (1.0 + math.cos(math.pi * cycles * 2.0 * p)))
+
+
+def _hard_cosine(step, w, total, cycles):
+    if step < w:
+        return step / max(1, w)
+    p = (step - w) / max(1, total - w)
+    if p >= 1.0:
+        return 0.0
+    return max(0.0, 0.5 * (1.0 + math.cos(math.pi * ((cycles * p) % 1.0))))
+
+
+def _constant(step, w, total, cycles):
+    return step / max(1.0, w) if step < w else 1.0
+
+
+def _linear(step, w, total, cycles):
+    if step < w:
+        return step / max(1, w)
+    return max(0.0, (total - step) / max(1, total - w))
+
+
+SCHEDULES = {"cosine": _cosine, "hard_cosine": _hard_cosine, "constant": _constant, "linear": _linear}
+
+
+class LambdaSchedule:
+    """torch LambdaLR-shaped schedule for any optimiser exposing `param_groups`."""
+
+    def __init__(self, optimizer, name, num_warmup_steps, num_training_steps=0, num_cycles=0.5):
+        self.optimizer = optimizer
+        self.fn = SCHEDULES[name]
+        self.w, self.total, self.cycles = num_warmup_steps, num_training_steps, num_cycles
+        self.base_lrs = [g.setdefault("initial_lr", g["lr"]) for g in optimizer.param_groups]
+        self.last_epoch = 0
+        self.steps_per_call = 1           # accelerate: num_processes scheduler steps per optimiser step
+        self._apply()
+
+    def _apply(self):
+        lam = self.fn(self.last_epoch, self.w, self.total, self.cycles)
+        self._last = [b * lam for b in self.base_lrs]
+        for g, lr in zip(self.optimizer.param_groups, self._last):
+            g["lr"] = lr
+
+    def step(self):
+        self.last_epoch += self.steps_per_call
+        self._apply()
+
+    def get_last_lr(self):
+        return list(self._last)
+
+    def state_dict(self):
+        return {"last_epoch": self.last_epoch, "base_lrs": self.base_lrs}
+
+    def load_state_dict(self, sd):
+        self.last_epoch = sd["last_epoch"]
+        self.base_lrs = sd["base_lrs"]
+        self._apply()
+
+
+def get_scheduler(name, optimizer, num_warmup_steps, num_training_steps=0, num_cycles=0.5):
+    return LambdaSchedule(optimizer, name, num_warmup_steps, num_training_steps, num_cycles)
+
+
+# ---------------------------------------------------------------------------------------------
+# EMA (diffusers.training_utils.EMAModel semantics)
+# ---------------------------------------------------------------------------------------------
+class EMAModel:
+    def __init__(self, parameters, decay=0.9999, min_decay=0.0, update_after_step=0, use_ema_warmup=False,
+                 inv_gamma=1.0, power=2.0 / 3.0, model_cls=None, model_config=None, **_):
+        parameters = list(parameters)
+        self._model = getattr(parameters[0], "_mdm_model", None) if parameters else None
+        if self._model is not None:
+            self.flat = self._model.flat_param.detach().clone()
+            self.shadow_params = [self.flat[s.offset:s.offset + s.numel].view(s.shape) for s in self._model._specs]
+        else:
+            self.flat = None
+            self.shadow_params = [p.clone().detach() for p in parameters]
+        self.temp_stored_params = None
+        self.decay, self.min_decay, self.update_after_step = decay, min_decay, update_after_step
+        self.use_ema_warmup, self.inv_gamma, self.power = use_ema_warmup, inv_gamma, power
+        self.optimization_step = 0
+        self.cur_decay_value = None
+        self.model_cls, self.model_config = model_cls, model_config
+        self._fused_done = False
+
+    def get_decay(self, optimization_step: int) -> float:
+        step = max(0, optimization_step - self.update_after_step - 1)
+        if step <= 0:
+            return 0.0
+        cur = 1 - (1 + step / self.inv_gamma) ** -self.power if self.use_ema_warmup else (1 + step) / (10 + step)
+        return max(min(cur, self.decay), self.min_decay)
+
+    @torch.no_grad()
+    def step(self, parameters):
+        self.optimization_step += 1
+        decay = self.get_decay(self.optimization_step)
+        self.cur_decay_value = decay
+        if self._fused_done:              # the fused optimiser kernel already applied this update
+            self._fused_done = False
+            return
+        one_minus = 1 - decay
+        if self.flat is not None:
+            self.flat.sub_(one_minus * (self.flat - self._model.flat_param))
+            return
+        for s, p in zip(self.shadow_params, list(parameters)):
+            if p.requires_grad:
+                s.sub_(one_minus * (s - p.to(s.dtype)))
+            else:
+                s.copy_(p)
+
+    def copy_to(self, parameters):
+        if self.flat is not None:
+            self._model.flat_param.data.copy_(self.flat)
+            self._model.mark_params_updated()
+            return
+        for s, p in zip(self.shadow_params, list(parameters)):
+            p.data.copy_(s.to(p.device).data)
+
+    def store(self, parameters):
+        if self.flat is not None:
+            self.temp_stored_params = self._model.flat_param.detach().clone()
+        else:
+            self.temp_stored_params = [p.detach().cpu().clone() for p in parameters]
+
+    def restore(self, parameters):
+        if self.temp_stored_params is None:
+            raise RuntimeError("This ExponentialMovingAverage has no `store()`ed weights to `restore()`")
+        if self.flat is not None:
+            self._model.flat_param.data.copy_(self.temp_stored_params)
+            self._model.mark_params_updated()
+        else:
+            for c, p in zip(self.temp_stored_params, parameters):
+                p.data.copy_(c.data)
+        self.temp_stored_params = None
+
+    def to(self, device=None, dtype=None):
+        if self.flat is None:
+            self.shadow_params = [p.to(device=device, dtype=dtype) if p.is_floating_point() else p.to(device=device)
+                                  for p in self.shadow_params]
+        return self
+
+    def state_dict(self):
+        return {"decay": self.decay, "min_decay": self.min_decay, "optimization_step": self.optimization_step,
+                "update_after_step": self.update_after_step, "use_ema_warmup": self.use_ema_warmup,
+                "inv_gamma": self.inv_gamma, "power": self.power, "shadow_params": [p.clone() for p in self.shadow_params]}
+
+    def load_state_dict(self, sd):
+        for k in ("decay", "min_decay", "optimization_step", "update_after_step", "use_ema_warmup", "inv_gamma", "power"):
+            if k in sd:
+                setattr(self, k, sd[k])
+        sp = sd.get("shadow_params")
+        if sp is not None:
+            for s, n in zip(self.shadow_params, sp):
+                s.copy_(n.to(s.device))
+
+    def save_pretrained(self, path):
+        if self.model_cls is None:
+            raise ValueError("`save_pretrained` can only be used if `model_cls` was defined at __init__.")
+        model = self.model_cls.from_config(self.model_config if isinstance(self.model_config, dict) else vars(self.model_config))
+        sd = self.state_dict()
+        sd.pop("shadow_params")
+        model.register_to_config(**sd)
+        self.copy_to(model.parameters()) if self.flat is None else model.flat_param.data.copy_(self.flat)
+        model.mark_params_updated() if hasattr(model, "mark_params_updated") else None
+        model.save_pretrained(path)
+
+    @classmethod
+    def from_pretrained(cls, path, model_cls):
+        cfg = model_cls.load_config(path)
+        model = model_cls.from_pretrained(path)
+        ema = cls(model.parameters(), model_cls=model_cls, model_config=model.config)
+        ema.load_state_dict({k: cfg[k] for k in ("decay", "min_decay", "optimization_step", "update_after_step",
+                                                 "use_ema_warmup", "inv_gamma", "power") if k in cfg})
+        return ema
+
+
+# ---------------------------------------------------------------------------------------------
+# fused optimiser
+# ---------------------------------------------------------------------------------------------
+class FusedOptimizer:
+    """torch.optim-shaped optimiser over the denoiser's flat parameter buffer: one kernel does
+    clip + Adam/AdamW/SGD (+ EMA, + bf16 weight mirror).  csrc/optim.cu."""
+
+    def __init__(self, model, name="adamw", lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=None):
+        from . import optim_ops
+        self._ops = optim_ops
+        self.model = model
+        self.name = name.lower()
+        if weight_decay is None:
+            weight_decay = 0.01 if self.name == "adamw" else 0.0
+        self.param_groups = [dict(params=model.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)]
+        self.m = torch.zeros_like(model.flat_param) if self.name != "sgd" else None
+        self.v = torch.zeros_like(model.flat_param) if self.name != "sgd" else None
+        self.step_count = 0
+        self._ws = torch.empty(1024, dtype=torch.float32, device=model.device)
+        self._gnorm_sq = torch.zeros(1, dtype=torch.float32, device=model.device)
+        self._clip = 0.0
+        self.ema = None
+        self.grad_scale = 1.0
+
+    def attach_ema(self, ema: EMAModel):
+        if ema is not None and ema.flat is not None:
+            self.ema = ema
+
+    def set_clip(self, max_norm: float):
+        """global-norm clipping fused into the next step(); returns the (lazy, device) total norm"""
+        self._ops.grad_sumsq(self.model.flat_grad, self._ws, self._gnorm_sq)
+        self._clip = float(max_norm)
+        return self._gnorm_sq.sqrt() * self.grad_scale
+
+    def step(self):
+        g = self.param_groups[0]
+        self.step_count += 1
+        b1, b2 = g["betas"]
+        bc1 = 1.0 - b1 ** self.step_count
+        bc2 = 1.0 - b2 ** self.step_count
+        ema_flat, ema_decay = None, 0.0
+        if self.ema is not None:
+            ema_decay = self.ema.get_decay(self.ema.optimization_step + 1)
+            ema_flat = self.ema.flat
+            self.ema._fused_done = True
+        self._ops.adam_ema_step(self.model.flat_param, self.model.flat_grad, self.m, self.v, ema_flat, self.model.flat_bf16,
+                                self._gnorm_sq if self._clip > 0 else None, g["lr"], b1, b2, g["eps"], g["weight_decay"],
+                                bc1, bc2, self._clip, ema_decay, self.grad_scale, self._ops.MODE[self.name])
+        self._clip = 0.0
+        # the kernel refreshed the bf16 mirror itself
+        self.model._bf16_stale = False
+        self.model._bf16_version = self.model.flat_param._version
+
+    def zero_grad(self, set_to_none=False):
+        self.model.flat_grad.zero_()
+
+    def state_dict(self):
+        return {"step": self.step_count, "m": self.m, "v": self.v,
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        self.step_count = sd["step"]
+        if self.m is not None:
+            self.m.copy_(sd["m"]); self.v.copy_(sd["v"])
+        for g, n in zip(self.param_groups, sd["param_groups"]):
+            g.update(n)
+
+
+# ---------------------------------------------------------------------------------------------
+# Accelerator
+# ---------------------------------------------------------------------------------------------
+class InitProcessGroupKwargs:
+    def __init__(self, timeout=timedelta(seconds=1800), **_):
+        self.timeout = timeout
+
+
+class _ShardedLoader:
+    """every `world`-th batch of the wrapped loader, starting at `rank` (accelerate's BatchSamplerShard)"""
+
+    def __init__(self, loader, rank, world, device):
+        self.loader, self.rank, self.world, self.device = loader, rank, world, device
+
+    def __len__(self):
+        return len(self.loader) // self.world
+
+    def __iter__(self):
+        n = len(self) * self.world
+        for i, batch in enumerate(self.loader):
+            if i >= n:
+                break
+            if i % self.world == self.rank:
+                yield _to_device(batch, self.device)
+
+
+def _to_device(batch, device):
+    if torch.is_tensor(batch):
+        return batch.to(device, non_blocking=True)
+    if isinstance(batch, (list, tuple)):
+        return type(batch)(_to_device(b, device) for b in batch)
+    if isinstance(batch, dict):
+        return {k: _to_device(v, device) for k, v in batch.items()}
+    return batch
+
+
+class Accelerator:
+    def __init__(self, gradient_accumulation_steps=1, mixed_precision="no", kwargs_handlers=None, device=None, **_):
+        self.gradient_accumulation_steps = int(gradient_accumulation_steps)
+        self.mixed_precision = mixed_precision or "no"
+        self.rank = int(os.environ.get("RANK", 0))
+        self.num_processes = int(os.environ.get("WORLD_SIZE", 1))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", 0))
+        use_cuda = torch.cuda.is_available() and device != "cpu"
+        if use_cuda:
+            torch.cuda.set_device(self.local_rank)
+            self.device = torch.device("cuda", self.local_rank)
+        else:
+            self.device = torch.device("cpu")
+        timeout = timedelta(seconds=1800)
+        for h in kwargs_handlers or []:
+            timeout = getattr(h, "timeout", timeout)
+        if self.num_processes > 1 and not dist.is_initialized():
+            dist.init_process_group(backend="nccl" if use_cuda else "gloo", timeout=timeout)
+        self.sync_gradients = True
+        self._accum = 0
+        self._models, self._optimizers, self._schedulers = [], [], []
+        self._save_hooks, self._load_hooks = [], []
+
+    # -- properties ----------------------------------------------------------------------------
+    @property
+    def is_main_process(self):
+        return self.rank == 0
+
+    @property
+    def is_local_main_process(self):
+        return self.local_rank == 0
+
+    def print(self, *a, **k):
+        if self.is_local_main_process:
+            print(*a, **k)
+
+    def init_trackers(self, *a, **k):
+        pass
+
+    def wait_for_everyone(self):
+        # The reference barriers every batch (trainer_masked.py:166); the gradient all-reduce already
+        # orders the ranks, so this is a no-op kept for API parity.
+        pass
+
+    def barrier(self):
+        if self.num_processes > 1:
+            dist.barrier()
+
+    # -- prepare ---------------------------------------------------------------------------------
+    def prepare(self, *objs):
+        out = []
+        for o in objs:
+            if hasattr(o, "flat_param") or isinstance(o, torch.nn.Module):
+                self._models.append(o)
+                if isinstance(o, torch.nn.Module):
+                    o.to(self.device)
+                self._broadcast_params(o)
+                out.append(o)
+            elif isinstance(o, (FusedOptimizer, torch.optim.Optimizer)):
+                self._optimizers.append(o)
+                if isinstance(o, FusedOptimizer):
+                    o.grad_scale = 1.0 / self.num_processes if self.num_processes > 1 else 1.0
+                out.append(o)
+            elif hasattr(o, "get_last_lr"):
+                if hasattr(o, "steps_per_call"):
+                    o.steps_per_call = self.num_processes
+                self._schedulers.append(o)
+                out.append(o)
+            elif hasattr(o, "__iter__") and hasattr(o, "__len__"):
+                out.append(_ShardedLoader(o, self.rank, self.num_processes, self.device) if self.num_processes > 1 or self.device.type == "cuda" else o)
+            else:
+                out.append(o)
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def _broadcast_params(self, model):
+        if self.num_processes <= 1:
+            return
+        if hasattr(model, "flat_param"):
+            dist.broadcast(model.flat_param.data, src=0)
+            model.mark_params_updated()
+        else:
+            for p in model.parameters():
+                dist.broadcast(p.data, src=0)
+
+    # -- training step ---------------------------------------------------------------------------
+    @contextlib.contextmanager
+    def accumulate(self, model=None):
+        self._accum += 1
+        self.sync_gradients = self._accum % self.gradient_accumulation_steps == 0
+        yield
+
+    def backward(self, loss):
+        if self.gradient_accumulation_steps > 1:
+            loss = loss / self.gradient_accumulation_steps
+        loss.backward()
+        if self.sync_gradients:
+            self.all_reduce_gradients()
+
+    def all_reduce_gradients(self):
+        if self.num_processes <= 1:
+            return
+        fused = any(isinstance(o, FusedOptimizer) for o in self._optimizers)
+        for m in self._models:
+            if hasattr(m, "flat_grad"):
+                dist.all_reduce(m.flat_grad, op=dist.ReduceOp.SUM)
+                if not fused:                       # the fused optimiser folds 1/world into its kernel
+                    m.flat_grad.mul_(1.0 / self.num_processes)
+            else:
+                for p in m.parameters():
+                    if p.grad is not None:
+                        dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+                        p.grad.mul_(1.0 / self.num_processes)
+
+    def clip_grad_norm_(self, parameters, max_norm, norm_type=2):
+        for o in self._optimizers:
+            if isinstance(o, FusedOptimizer):
+                return o.set_clip(max_norm)
+        return torch.nn.utils.clip_grad_norm_(list(parameters), max_norm, norm_type=norm_type)
+
+    # -- checkpoints (accelerate layout) ---------------------------------------
+    def register_save_state_pre_hook(self, hook):
+        self._save_hooks.append(hook)
+
+    def register_load_state_pre_hook(self, hook):
+        self._load_hooks.append(hook)
+
+    def save_state(self, output_dir):
+        os.makedirs(output_dir, exist_ok=True)
+        models = list(self._models)
+        weights = [m.state_dict() for m in models]
+        for h in self._save_hooks:
+            h(models, weights, output_dir)
+        if self.is_main_process:
+            for i, w in enumerate(weights):      # whatever the hooks did not pop
+                torch.save(w, os.path.join(output_dir, "pytorch_model.bin" if i == 0 else f"pytorch_model_{i}.bin"))
+            for i, o in enumerate(self._optimizers):
+                torch.save(o.state_dict(), os.path.join(output_dir, "optimizer.bin" if i == 0 else f"optimizer_{i}.bin"))
+            for i, s in enumerate(self._schedulers):
+                torch.save(s.state_dict(), os.path.join(output_dir, "scheduler.bin" if i == 0 else f"scheduler_{i}.bin"))
+        states = {"random_state": random.getstate(), "numpy_random_seed": np.random.get_state(),
+                  "torch_manual_seed": torch.get_rng_state()}
+        if torch.cuda.is_available():
+            states["torch_cuda_manual_seed"] = torch.cuda.get_rng_state_all()
+        with open(os.path.join(output_dir, f"random_states_{self.rank}.pkl"), "wb") as f:
+            pickle.dump(states, f)
+        return output_dir
+
+    def load_state(self, input_dir):
+        models = list(self._models)
+        for h in self._load_hooks:
+            h(models, input_dir)
+        for i, m in enumerate(models):           # models the hooks did not pop
+            p = os.path.join(input_dir, "pytorch_model.bin" if i == 0 else f"pytorch_model_{i}.bin")
+            if os.path.exists(p):
+                m.load_state_dict(torch.load(p, map_location="cpu"))
+        for i, o in enumerate(self._optimizers):
+            p = os.path.join(input_dir, "optimizer.bin" if i == 0 else f"optimizer_{i}.bin")
+            if os.path.exists(p):
+                o.load_state_dict(torch.load(p, map_location=self.device, weights_only=False))
+        for i, s in enumerate(self._schedulers):
+            p = os.path.join(input_dir, "scheduler.bin" if i == 0 else f"scheduler_{i}.bin")
+            if os.path.exists(p):
+                s.load_state_dict(torch.load(p, weights_only=False))
+        p = os.path.join(input_dir, f"random_states_{self.rank}.pkl")
+        if os.path.exists(p):
+            with open(p, "rb") as f:
+                st = pickle.load(f)
+            random.setstate(st["random_state"])
+            np.random.set_state(st["numpy_random_seed"])
+            torch.set_rng_state(st["torch_manual_seed"])
+            if "torch_cuda_manual_seed" in st and torch.cuda.is_available():
+                torch.cuda.set_rng_state_all(st["torch_cuda_manual_seed"])
+
+    def save_model(self, model, save_directory, **_):
+        os.makedirs(save_directory, exist_ok=True)
+        torch.save(model.state_dict(), os.path.join(save_directory, "pytorch_model.bin"))
