@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""bench.py -- masked-diffusion hot path on B200: training samples/s (BASELINE.json configs[1]:
+masked U-Net, 3x32x32, bf16 activations, batch 128 per GPU, data parallel) with a secondary
+masked-sampling line (configs[3] shape, 3x128x128), the roofline of the dominant kernel and the
+reference's CPU path timed on the same box.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (N>1: under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+
+One JSON line on stdout (rank 0).  A "step" = one `Trainer._run_batch` (trainer_masked.py:95-183):
+timestep draw, K1 degradation, U-Net forward/backward, fused loss, clip + AdamW + EMA.
+  value : samples/s with the batches already resident in HBM (device timed, max over ranks)
+  e2e   : samples/s through the same public call with HOST (pinned) batches copied in every step and
+          the step's loss read back -- the number to compare with the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "masked-diffusion-model_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+import torch
+
+METRIC = "train_samples_per_sec"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (reference default, main_train_masked.py:370)")
+    ap.add_argument("--size", type=int, default=32)
+    ap.add_argument("--channels", type=int, default=3)
+    ap.add_argument("--method", default="base", choices=["base", "mean_shift"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-sampling", action="store_true", help="skip the secondary masked-sampling measurement")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--sample-size", type=int, default=128)
+    ap.add_argument("--sample-batch", type=int, default=256)
+    ap.add_argument("--sample-steps", type=int, default=6)
+    ap.add_argument("--ref-batch", type=int, default=8, help="samples per reference-arm step (bounded sample of the workload)")
+    return ap.parse_args()
+
+
+def workload_args(a, mixed="bf16"):
+    """the reference's flag set for this workload (main_train_masked.py:347-417)"""
+    from mdm_b200.config import default_args
+    ns = default_args(data_size=a.size, in_channel=a.channels, out_channel=a.channels, batch_size=a.batch,
+                      ddpm_num_steps=1000, ddpm_schedule="log", select_degrade_pixel="indexing",
+                      mean_option="degraded_area", mean_area="image-wise", method=a.method,
+                      shift_type="noise_with_perturbation", sample_latent_shape="zero",
+                      momentum_adaptive="base_momentum", sampling_mask_dependency="independent",
+                      mixed_precision=mixed, use_ema=True, optim="adamw", lr=1e-4)
+    return ns
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed region
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index=0, period=0.05):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        self.index, self.period = index, period
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80,
+                 "sw_thermal_slowdown": 0x20, "sync_boost": 0x10, "applications_clocks": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def build_trainer(a, wa):
+    import main_train_masked as M
+    torch.manual_seed(0)
+    torch.cuda.manual_seed_all(0)
+    np.random.seed(0)
+    wa.model = "default"
+    wa.num_attention = 1
+    wa.gradient_accumulation_steps = 1
+    wa.ema_max_decay, wa.ema_inv_gamma, wa.ema_power = 0.9999, 1.0, 0.75
+    wa.cuda_graph = not a.no_graph
+    model = M.get_model(wa)
+    ema = M.get_ema(wa, model)
+    acc = M.get_accelerator(wa, ema)
+    M.get_weight_type(wa, acc)
+    opt = M.get_optimizer(model, wa.optim, wa.lr)
+    sched = M.get_scheduler("cosine", opt, num_warmup_steps=500, num_training_steps=100000, num_cycles=0.5)
+    model, opt, sched = acc.prepare(model, opt, sched)
+    if a.method == "base":
+        tr = M.BaseTrainer(wa, None, None, model, ema, opt, sched, acc)
+    else:
+        tr = M.MeanShiftTrainer(wa, None, None, [None, None, None], model, ema, opt, sched, acc)
+    tr.prepare_schedule()
+    tr.timesteps_used_epoch = tr.Scheduler.get_timesteps_epoch(0, 1)
+    model.train()
+    return tr, model, acc
+
+
+def conv_flops_per_step(model, B, S):
+    """algorithmic FLOPs (2*MAC) of one training step = 3 x forward (fprop + dgrad + wgrad), SURVEY.md 8d"""
+    from mdm_b200.config import unet_forward_flops
+    return 3.0 * B * unet_forward_flops(model._cfg, S)
+
+
+def timed_steps(run_step, steps, dev, world):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        run_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    return ms
+
+
+def roofline_pass(tr, model, batch_dev, peaks):
+    """time every tcgen05 implicit-GEMM launch of ONE eager step with CUDA events on the launching
+    stream; achieved = algorithmic conv/linear FLOPs of those launches / their summed duration"""
+    from mdm_b200 import denoiser_ops as ops
+    rec = []
+    orig = {}
+
+    def wrap(name, flops_fn):
+        f = getattr(ops, name)
+        orig[name] = f
+
+        def g(*args, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = f(*args, **kw)
+            e1.record()
+            rec.append((name, flops_fn(*args, **kw), e0, e1))
+            return r
+        setattr(ops, name, g)
+
+    def fl_fprop(x, w, y, N, H, W, ksize=3, stride=1, **kw):
+        cout = y.shape[-1] if y is not None else kw.get("cout")
+        f = 2.0 * N * H * W * cout * ksize * ksize * x.shape[-1]
+        if kw.get("x2") is not None:
+            f += 2.0 * N * H * W * cout * kw["x2"].shape[-1]
+        return f
+
+    def fl_dgrad(dy, w, dx, N, H, W, ksize=3, **kw):
+        cin = dx.shape[-1] if dx is not None else kw.get("cin")
+        return 2.0 * N * H * W * cin * ksize * ksize * dy.shape[-1]
+
+    def fl_wgrad(x, dy, dw, N, H, W, ksize=3, stride=1):
+        return 2.0 * N * H * W * dy.shape[-1] * ksize * ksize * x.shape[-1]
+
+    wrap("conv_fprop", fl_fprop)
+    wrap("conv_dgrad", fl_dgrad)
+    wrap("conv_wgrad", fl_wgrad)
+    saved = tr.args.cuda_graph
+    tr.args.cuda_graph = False
+    tr._graphs.clear()
+    try:
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        tr._run_batch(0, (batch_dev,), 0, 1, 0, None, None)
+        s1.record()
+        torch.cuda.synchronize()
+    finally:
+        for k, f in orig.items():
+            setattr(ops, k, f)
+        tr.args.cuda_graph = saved
+        tr._graphs.clear()
+    total_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in rec)
+    total_fl = sum(f for _, f, _, _ in rec)
+    by = {}
+    for name, f, e0, e1 in rec:
+        d = by.setdefault(name, [0, 0.0, 0.0])
+        d[0] += 1
+        d[1] += f
+        d[2] += e0.elapsed_time(e1)
+    achieved = total_fl / (total_ms * 1e-3) / 1e12 if total_ms > 0 else 0.0
+    peak = peaks.get("bf16_tflops_sustained", 1373.8)
+    return {
+        "bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv/linear: fprop+dgrad+wgrad)",
+        "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+        "traffic": None,
+        "launches_per_step": len(rec), "avg_launch_us": round(1e3 * total_ms / max(1, len(rec)), 2),
+        "kernel_ms_per_step": round(total_ms, 3),
+        "by_kind": {k: {"launches": v[0], "tflops": round(v[1] / (v[2] * 1e-3) / 1e12, 2) if v[2] > 0 else None,
+                        "ms": round(v[2], 3)} for k, v in by.items()},
+        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback (B200_PROFILING.md)",
+    }
+
+
+def sampling_line(a, model, dev, world):
+    """secondary metric: masked-sampling throughput at the configs[3] shape through `Sampler.sample`"""
+    import sampler as sampler_mod
+    import scheduler as scheduler_mod
+    from mdm_b200.config import default_args
+    from mdm_b200.denoiser import UNet2DModelB200, default_config
+    S, N, n = a.sample_size, a.sample_batch, a.sample_steps
+    sa = default_args(data_size=S, in_channel=3, out_channel=3, ddpm_num_steps=1000, ddpm_schedule="linear",
+                      select_degrade_pixel="thresholding", degrade_channel="1-channel", mean_option="0",
+                      mean_area="image-wise", method="base", shift_type="noise_with_perturbation",
+                      sample_latent_shape="zero", momentum_adaptive="base_momentum",
+                      sampling_mask_dependency="independent", sample_num=N)
+    sa.weight_dtype = torch.float32
+    m = UNet2DModelB200(device=dev, **default_config(3, S))
+    m.reset_parameters(seed=0)
+    m.eval()
+    Sch = scheduler_mod.Scheduler(sa)
+    Tp = Sch.update_ddpm_num_steps(1000)
+    ts = Sch.get_timesteps_epoch(0, 1)
+    smp = sampler_mod.Sampler(None, sa, Sch, [None, None, None])
+    torch.manual_seed(0)
+    smp.sample(m, ts[-2:])                        # warm-up (plans, workspaces)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out, _ = smp.sample(m, ts[-n:])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    from mdm_b200.config import unet_forward_flops
+    fl = N * unet_forward_flops(m._cfg, S)
+    del m
+    torch.cuda.empty_cache()
+    return {"metric": "masked_sampling_images_per_sec", "unit": "images/s (1000 denoising steps per image)",
+            "value": round(world * N / (ms * 1e-3 * 1000), 4), "denoise_steps_per_s": round(1e3 / ms, 3),
+            "ms_per_denoise_step": round(ms, 3), "timed_steps": n, "extrapolated_to_steps": 1000,
+            "denoiser_tflops": round(fl / (ms * 1e-3) / 1e12, 2),
+            "config": {"workload": f"sampler.py restoration loop, {N}x3x{S}x{S} per GPU, thresholding/linear, T=1000",
+                       "finite": bool(torch.isfinite(out).all().item())}}
+
+
+def cpu_reference_step(a, ref_batch, threads):
+    """The reference algorithm on the host: scheduler/trainer algebra of the oracle (restating
+    scheduler.py + trainer_masked.py:95-183) + the fp32 PyTorch restatement of diffusers.UNet2DModel,
+    torch CPU, all host threads.  Returns a closure running ONE optimisation step on `ref_batch` samples."""
+    from oracle.mdm_oracle import OracleRNG, OracleScheduler, default_args, oracle_train_step
+    from oracle.unet_ref import UNet2DModelRef, unet_config
+    torch.set_num_threads(threads)
+    ra = default_args(data_size=a.size, in_channel=a.channels, out_channel=a.channels, ddpm_num_steps=1000,
+                      ddpm_schedule="log", select_degrade_pixel="indexing", mean_option="degraded_area",
+                      mean_area="image-wise", method=a.method, shift_type="noise_with_perturbation")
+    ra.weight_dtype = torch.float32
+    torch.manual_seed(0)
+    net = UNet2DModelRef(**unet_config(a.channels, a.size))
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4)
+    S = OracleScheduler(ra, OracleRNG(0))
+    S.update_ddpm_num_steps()
+    ts = S.get_timesteps_epoch(0, 1)
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.rand(ref_batch, a.channels, a.size, a.size, generator=g) * 2 - 1
+
+    def step():
+        loss, _ = oracle_train_step(ra, S, net, x0, ts, a.method)
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+        return float(loss)
+    return step
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    step = cpu_reference_step(a, a.ref_batch, threads)
+    for _ in range(max(1, min(a.warmup, 2))):
+        step()
+    steps = max(1, a.steps)
+    t0 = time.perf_counter()
+    budget = 240.0
+    done = 0
+    for _ in range(steps):
+        step()
+        done += 1
+        if time.perf_counter() - t0 > budget:
+            break
+    dt = time.perf_counter() - t0
+    v = done * a.ref_batch / dt
+    sample = f"{done} steps x {a.ref_batch} samples of the {a.channels}x{a.size}x{a.size} training step, fp32, torch CPU"
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": a.gpus, "steps": done,
+            "warmup": min(a.warmup, 2), "ms_per_step": round(1e3 * dt / done, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"masked U-Net {a.channels}x{a.size}x{a.size} training step ({a.method} trainer), "
+                                   f"batch {a.batch}/GPU", "reference_sample": sample},
+            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(a):
+    import torch.distributed as dist
+    from mdm_b200 import _lib
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this is the B200 path, there is no CPU fallback "
+                         "(use --impl reference for the host baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    wa = workload_args(a)
+    tr, model, acc = build_trainer(a, wa)
+    B, C, S = a.batch, a.channels, a.size
+    # synthetic data: 8 distinct uniform [-1, 1] batches per rank (different shards per rank), pinned host copies
+    g = torch.Generator().manual_seed(1000 + rank)
+    host = [(torch.rand(B, C, S, S, generator=g) * 2 - 1).pin_memory() for _ in range(8)]
+    devb = [h.to(dev) for h in host]
+    torch.manual_seed(0)                       # every rank seeds 0 (main_train_masked.py:441-445): identical masks
+    tr.Scheduler.adopt_torch_rng(dev)
+
+    def step_resident(i):
+        return tr._run_batch(i, (devb[i % 8],), 0, 1, 0, None, None)
+
+    def step_host(i):
+        x = host[i % 8].to(dev, non_blocking=True)          # H2D from pinned memory inside the timed region
+        return tr._run_batch(i, (x,), 0, 1, 0, None, None)  # reads the loss back (D2H) every step
+
+    for i in range(max(a.warmup, 3)):
+        step_resident(i)
+    torch.cuda.synchronize()
+    l0 = _lib.lib().mdm_launch_count()
+    if not a.no_graph:
+        # launches of one step = what the captured graph holds; re-count them with one eager step
+        tr.args.cuda_graph = False
+        saved = tr._graphs
+        tr._graphs = {}
+        step_resident(0)
+        torch.cuda.synchronize()
+        per_step = _lib.lib().mdm_launch_count() - l0
+        tr.args.cuda_graph = True
+        tr._graphs = saved
+    with ClockSampler(local) as clk:
+        ms = timed_steps(step_resident, a.steps, dev, world)
+    if a.no_graph:
+        per_step = (_lib.lib().mdm_launch_count() - l0) // max(1, a.steps)
+    for i in range(2):
+        step_host(i)
+    ms_e2e = timed_steps(step_host, a.steps, dev, world)
+    loss_last = step_resident(0)
+    loss_last = loss_last[0] if isinstance(loss_last, tuple) else loss_last
+    value = world * B * a.steps / (ms * 1e-3)
+    e2e = world * B * a.steps / (ms_e2e * 1e-3)
+    fl_step = conv_flops_per_step(model, B, S)
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"masked U-Net {C}x{S}x{S} training step ({a.method} trainer, trainer_masked.py:95-183), "
+                               f"113.67M-param UNet2DModel config, bf16 activations / fp32 master weights + AdamW + EMA",
+                   "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                   "cuda_graph": not a.no_graph,
+                   "l2": "per-step working set (weights 0.68 GB + activations > 2 GB) exceeds the 126 MB L2; "
+                         "8 distinct input batches rotate"},
+        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": B * C * S * S * 4, "d2h_bytes_per_step": 12,
+                "ms_per_step": round(ms_e2e / a.steps, 3)},
+        "gpu_launches": int(per_step * a.steps),
+        "gpu_launches_per_step": int(per_step),
+        "model_tflops": round(fl_step * world / (ms / a.steps * 1e-3) / 1e12, 2),
+        "loss": round(float(loss_last), 5),
+        "clocks": clk.summary(),
+    }
+    if rank == 0 and not a.no_roofline:
+        line["roofline"] = roofline_pass(tr, model, devb[0], peaks)
+    if world > 1:
+        dist.barrier()
+    if not a.no_sampling:
+        del tr
+        torch.cuda.empty_cache()
+        try:
+            line["sampling"] = sampling_line(a, model, dev, world)
+        except Exception as e:  # secondary metric must not take the headline down
+            line["sampling"] = {"error": repr(e)[:300]}
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        step = cpu_reference_step(a, a.ref_batch, threads)
+        step()
+        t0 = time.perf_counter()
+        n = 0
+        while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 20):
+            step()
+            n += 1
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": round(n * a.ref_batch / dt, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{n} steps x {a.ref_batch} samples of the same training step, fp32 torch CPU "
+                                          f"(oracle restatement of trainer_masked.py + UNet2DModel)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,8 @@ const char* mdm_last_error(void);
 int mdm_version(void);
 /* 1 when a CUDA device is usable by this process, 0 otherwise (never raises) */
 int mdm_device_available(void);
+/* number of kernels this library has launched (or captured into a CUDA graph) in this process */
+long long mdm_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Random stream: a device-resident copy of torch's CPU mt19937 engine.
@@ -229,6 +231,11 @@ int mdm_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, 
                       const float* gnorm_sq, float lr, float beta1, float beta2, float eps,
                       float weight_decay, float bias_c1, float bias_c2, float max_norm, float ema_decay,
                       float grad_scale, int mode, void* stream);
+/* same, with the per-step scalars read from DEVICE memory: hyper[4] = {lr, bias_c1, bias_c2,
+ * ema_decay}, so the launch can sit inside a replayed CUDA graph while the LR schedule advances. */
+int mdm_adam_ema_step_dev(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, int64_t n,
+                          const float* gnorm_sq, const float* hyper, float beta1, float beta2, float eps,
+                          float weight_decay, float max_norm, float grad_scale, int mode, void* stream);
 
 #ifdef __cplusplus
 }

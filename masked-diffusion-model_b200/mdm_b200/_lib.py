@@ -24,6 +24,7 @@ _SIGS = {
     "mdm_last_error": (c_char_p, []),
     "mdm_version": (c_int, []),
     "mdm_device_available": (c_int, []),
+    "mdm_launch_count": (ctypes.c_longlong, []),
     "mdm_rng_seed_host": (c_int, [_P, c_uint32]),
     "mdm_rng_raw": (c_int, [_P, _P, c_int64, _P]),
     "mdm_rng_skip": (c_int, [_P, c_int64, _P]),

@@ -5,6 +5,7 @@
 
 namespace mdm {
 static thread_local char g_err[1024] = "";
+long long g_launch_count = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -16,6 +17,7 @@ void set_error(const char* fmt, ...) {
 extern "C" {
 const char* mdm_last_error(void) { return mdm::g_err; }
 int mdm_version(void) { return 100; }
+long long mdm_launch_count(void) { return mdm::g_launch_count; }
 int mdm_device_available(void) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);

@@ -29,7 +29,13 @@ void set_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
-#define MDM_LAUNCH_CHECK() MDM_CUDA(cudaGetLastError())
+// every kernel launch of the library passes through here: count it (mdm_launch_count()) and check it
+extern long long g_launch_count;
+#define MDM_LAUNCH_CHECK()              \
+  do {                                  \
+    ++::mdm::g_launch_count;            \
+    MDM_CUDA(cudaGetLastError());       \
+  } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

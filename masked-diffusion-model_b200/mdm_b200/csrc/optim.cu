@@ -44,7 +44,10 @@ struct AdamArgs {
 
 __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, float* __restrict__ ema, __nv_bfloat16* __restrict__ p16,
-                                long long n, const float* __restrict__ gnorm_sq, AdamArgs a) {
+                                long long n, const float* __restrict__ gnorm_sq, const float* __restrict__ hyper, AdamArgs a) {
+  if (hyper) {  // per-step scalars read from device memory so that a captured CUDA graph can be replayed
+    a.lr = hyper[0]; a.bias_c1 = hyper[1]; a.bias_c2 = hyper[2]; a.ema_decay = hyper[3];
+  }
   float coef = a.grad_scale;
   if (gnorm_sq && a.max_norm > 0.f) {
     // torch.nn.utils.clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6), clamped to 1
@@ -89,7 +92,9 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
 }
 
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ ema,
-                           __nv_bfloat16* __restrict__ p16, long long n, const float* __restrict__ gnorm_sq, AdamArgs a) {
+                           __nv_bfloat16* __restrict__ p16, long long n, const float* __restrict__ gnorm_sq,
+                           const float* __restrict__ hyper, AdamArgs a) {
+  if (hyper) { a.lr = hyper[0]; a.ema_decay = hyper[3]; }
   float coef = a.grad_scale;
   if (gnorm_sq && a.max_norm > 0.f) coef *= fminf(1.0f, a.max_norm / (sqrtf(*gnorm_sq) * a.grad_scale + 1e-6f));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -116,22 +121,38 @@ int mdm_grad_sumsq(const float* g, int64_t n, float* ws, float* out, void* strea
   return MDM_OK;
 }
 
-int mdm_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, int64_t n,
-                      const float* gnorm_sq, float lr, float beta1, float beta2, float eps, float weight_decay,
-                      float bias_c1, float bias_c2, float max_norm, float ema_decay, float grad_scale, int mode,
-                      void* stream) {
+static int adam_launch(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, int64_t n,
+                       const float* gnorm_sq, const float* hyper, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, float bias_c1, float bias_c2, float max_norm, float ema_decay,
+                       float grad_scale, int mode, void* stream) {
   MDM_CHECK_ARG(p && g && n > 0 && n % 4 == 0, "adam_ema_step: n must be a positive multiple of 4");
   MDM_CHECK_ARG(mode >= 0 && mode <= 2, "adam_ema_step: mode 0 = Adam, 1 = AdamW, 2 = SGD");
   AdamArgs a{lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2, max_norm, ema_decay, grad_scale, mode == 1};
   const int blocks = kNumSMs * 8;
   if (mode == 2) {
-    sgd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, ema, (__nv_bfloat16*)p_bf16, n, gnorm_sq, a);
+    sgd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, ema, (__nv_bfloat16*)p_bf16, n, gnorm_sq, hyper, a);
   } else {
     MDM_CHECK_ARG(m && v, "adam_ema_step: moment buffers are NULL");
-    adam_ema_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, ema, (__nv_bfloat16*)p_bf16, n, gnorm_sq, a);
+    adam_ema_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, ema, (__nv_bfloat16*)p_bf16, n, gnorm_sq, hyper, a);
   }
   MDM_LAUNCH_CHECK();
   return MDM_OK;
+}
+
+int mdm_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, int64_t n,
+                      const float* gnorm_sq, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      float bias_c1, float bias_c2, float max_norm, float ema_decay, float grad_scale, int mode,
+                      void* stream) {
+  return adam_launch(p, g, m, v, ema, p_bf16, n, gnorm_sq, nullptr, lr, beta1, beta2, eps, weight_decay, bias_c1,
+                     bias_c2, max_norm, ema_decay, grad_scale, mode, stream);
+}
+
+int mdm_adam_ema_step_dev(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, int64_t n,
+                          const float* gnorm_sq, const float* hyper, float beta1, float beta2, float eps,
+                          float weight_decay, float max_norm, float grad_scale, int mode, void* stream) {
+  MDM_CHECK_ARG(hyper, "adam_ema_step_dev: hyper is NULL");
+  return adam_launch(p, g, m, v, ema, p_bf16, n, gnorm_sq, hyper, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f,
+                     max_norm, 0.f, grad_scale, mode, stream);
 }
 
 }  // extern "C"

@@ -99,7 +99,6 @@ class UNet2DModelB200:
         self._build_layers()
         self._alloc_params()
         self._plans = {}
-        self._anchor = torch.zeros(1, device=self.device, requires_grad=True)   # hooks the kernels into autograd
         self.reset_parameters()
 
     # -- structure ------------------------------------------------------------------------------
@@ -406,7 +405,10 @@ class UNet2DModelB200:
         x = sample.float().contiguous()
         self._last_plan = plan
         if need_grad:
-            out = _DenoiserFn.apply(self._anchor, plan, x, t)
+            # a fresh leaf created on the CURRENT stream hooks the kernels into autograd (a long-lived leaf
+            # would pin its AccumulateGrad node to the construction-time stream and break graph capture)
+            anchor = torch.zeros(1, device=self.device, requires_grad=True)
+            out = _DenoiserFn.apply(anchor, plan, x, t)
         else:
             out = plan.run_forward(x, t)
         return SimpleNamespace(sample=out)
@@ -432,7 +434,7 @@ class _DenoiserFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         ctx.plan.run_backward(d_out.float().contiguous())
-        return torch.zeros_like(ctx.plan.m._anchor), None, None, None
+        return None, None, None, None
 
 
 class _Plan:

@@ -223,6 +223,7 @@ class FusedOptimizer:
         self.step_count = 0
         self._ws = torch.empty(1024, dtype=torch.float32, device=model.device)
         self._gnorm_sq = torch.zeros(1, dtype=torch.float32, device=model.device)
+        self._hyper = torch.zeros(4, dtype=torch.float32, device=model.device)
         self._clip = 0.0
         self.ema = None
         self.grad_scale = 1.0
@@ -237,24 +238,36 @@ class FusedOptimizer:
         self._clip = float(max_norm)
         return self._gnorm_sq.sqrt() * self.grad_scale
 
-    def step(self):
+    def upload_hyper(self):
+        """host part of a step: advance the step count and send (lr, bias corrections, EMA decay) to the
+        device.  Kept apart from `launch()` so that `launch()` can live inside a replayed CUDA graph."""
         g = self.param_groups[0]
         self.step_count += 1
         b1, b2 = g["betas"]
-        bc1 = 1.0 - b1 ** self.step_count
-        bc2 = 1.0 - b2 ** self.step_count
-        ema_flat, ema_decay = None, 0.0
+        ema_decay = 0.0
         if self.ema is not None:
             ema_decay = self.ema.get_decay(self.ema.optimization_step + 1)
-            ema_flat = self.ema.flat
             self.ema._fused_done = True
-        self._ops.adam_ema_step(self.model.flat_param, self.model.flat_grad, self.m, self.v, ema_flat, self.model.flat_bf16,
-                                self._gnorm_sq if self._clip > 0 else None, g["lr"], b1, b2, g["eps"], g["weight_decay"],
-                                bc1, bc2, self._clip, ema_decay, self.grad_scale, self._ops.MODE[self.name])
-        self._clip = 0.0
+        self._hyper.copy_(torch.tensor([g["lr"], 1.0 - b1 ** self.step_count, 1.0 - b2 ** self.step_count, ema_decay],
+                                       dtype=torch.float32), non_blocking=True)
+
+    def launch(self, clip=None):
+        """device part of a step (one kernel): clip + Adam/AdamW/SGD + EMA + bf16 mirror"""
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        clip = self._clip if clip is None else clip
+        self._ops.adam_ema_step_dev(self.model.flat_param, self.model.flat_grad, self.m, self.v,
+                                    self.ema.flat if self.ema is not None else None, self.model.flat_bf16,
+                                    self._gnorm_sq if clip > 0 else None, self._hyper, b1, b2, g["eps"],
+                                    g["weight_decay"], clip, self.grad_scale, self._ops.MODE[self.name])
         # the kernel refreshed the bf16 mirror itself
         self.model._bf16_stale = False
         self.model._bf16_version = self.model.flat_param._version
+
+    def step(self):
+        self.upload_hyper()
+        self.launch()
+        self._clip = 0.0
 
     def zero_grad(self, set_to_none=False):
         self.model.flat_grad.zero_()
@@ -402,7 +415,7 @@ class Accelerator:
         if self.gradient_accumulation_steps > 1:
             loss = loss / self.gradient_accumulation_steps
         loss.backward()
-        if self.sync_gradients:
+        if self.sync_gradients and not getattr(self, "_defer_all_reduce", False):
             self.all_reduce_gradients()
 
     def all_reduce_gradients(self):

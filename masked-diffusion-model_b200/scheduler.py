@@ -240,11 +240,13 @@ class Scheduler:
     # ------------------------------------------------------------------------------------------
     # scheduler.py:266-323
     # ------------------------------------------------------------------------------------------
-    def degrade_training(self, black_area_num, img, mean_option=None, mean_area=None):
+    def degrade_training(self, black_area_num, img, mean_option=None, mean_area=None, want_degrade_mask=True):
+        """`want_degrade_mask=False` (not a reference argument) skips materialising `degrade_mask`, which
+        only the reference's image grids read; the slot is then None."""
         mask_ch = self._mask_channels()
         mb = self.make_mask_bytes(black_area_num, img.device)
         x_t, mask_f, dmask, fill = self._composite(img, mb, mask_ch, mean_option, mean_area,
-                                                   want_mask=True, want_degrade_mask=True)
+                                                   want_mask=True, want_degrade_mask=want_degrade_mask)
         masks = mask_f.expand_as(img) if mask_ch == 1 else mask_f
         mean_mask = fill.expand(img.shape[0], img.shape[1], self.height, self.width)
         return x_t, masks, dmask, mean_mask
@@ -340,6 +342,9 @@ class Scheduler:
 
     # scheduler.py:780-794
     def get_weight_timesteps(self, timesteps: torch.Tensor, power_base=2.0):
-        alpha = torch.linspace(start=1, end=0, steps=self.updated_ddpm_num_steps)
-        power = torch.pow(power_base, alpha).to(timesteps.device)
+        key = ("weight_t", float(power_base), self.updated_ddpm_num_steps, str(timesteps.device))
+        power = self._ws.get(key)
+        if power is None:       # cached on the device (the reference rebuilds + uploads it every call)
+            alpha = torch.linspace(start=1, end=0, steps=self.updated_ddpm_num_steps)
+            power = self._ws[key] = torch.pow(power_base, alpha).to(timesteps.device)
         return power[timesteps]
