@@ -166,6 +166,8 @@ typedef struct mdm_conv_args {
   float* dw;            /* wgrad output fp32 [cout][k*k][cin], accumulated atomically */
   long long w_col0;     /* dgrad/wgrad on a channel slice of a wider packed weight */
   int w_cols;
+  float* splitk_ws;     /* optional ZEROED fp32 workspace: lets small-M fprop/dgrad layers split K over the SMs */
+  long long splitk_ws_floats; /* (needs N*H*W*cout floats; left zeroed again on return) */
 } mdm_conv_args;
 
 /* tcgen05/TMEM implicit GEMM fed by TMA (csrc/igemm.cu) */
@@ -175,8 +177,10 @@ int mdm_conv_wgrad(const mdm_conv_args* a, void* stream);
 
 /* K2: GroupNorm (+SiLU) forward / backward (csrc/nn_kernels.cu).  x, y, dy, dx: NHWC bf16 with
  * channel strides; stats: [N][G][2] = (mean, rstd) fp32 written by fwd, read by bwd;
- * ws: mdm_gn_ws_floats() floats.  bwd: dx = d/dx [silu](gn(x)) . dy (+ add), dgamma/dbeta
- * accumulated (fp32 atomics). */
+ * ws: mdm_gn_ws_floats() floats.  bwd: dx = d/dx [silu](gn(x)) . dy (+ add + add2), dgamma/dbeta
+ * accumulated (fp32 atomics); optional colsum[n][c] += sum over the pixels of sample n of the GroupNorm
+ * part of dx (row stride ld_colsum) and dbias[c] += the same over all samples -- the gradients of the
+ * time-embedding projection and of the bias of the convolution that produced x. */
 int64_t mdm_gn_ws_floats(int N, int HW, int C, int G);
 int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma,
                     const float* beta, float* stats, float* ws, int N, int HW, int C, int G,
@@ -184,6 +188,7 @@ int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, cons
 int mdm_gn_silu_bwd(const void* x, long long ld_x, const void* dy, long long ld_dy, const void* add,
                     long long ld_add, const void* add2, long long ld_add2, void* dx, long long ld_dx, const float* gamma,
                     const float* beta, const float* stats, float* dgamma, float* dbeta, float* ws,
+                    float* colsum, long long ld_colsum, float* dbias,
                     int N, int HW, int C, int G, int silu, void* stream);
 
 /* first / last convolution (image channels C <= 4): planar fp32 NCHW image <-> NHWC bf16.

@@ -16,10 +16,15 @@
 //   dgrad : D[pix][ci] = sum_tap sum_co dY[pix-tap][co] * W[co][tap][ci]     A K-major, B MN-major
 //   wgrad : D[co][ci]  = sum_pix dY[pix][co] * X[pix+tap][ci]   (per tap)   A,B MN-major, split-K
 //
-// One CTA = one 128x128 output tile; 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer
-// (+TMEM allocator), warps 2-5 = epilogue (TMEM -> registers -> bias / time-embedding /
-// residual -> bf16 NHWC store, or fp32 atomic accumulation for wgrad).  A 4-stage mbarrier ring
-// connects producer and issuer; tcgen05.commit releases stages and publishes the accumulator.
+// PERSISTENT, warp-specialised kernel: one CTA per SM walks a static list of work items (output
+// tile x K split); 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM allocator),
+// warps 2-5 = epilogue.  Three pipelines: a 4-stage smem ring (TMA -> MMA), TWO TMEM accumulators
+// (MMA -> epilogue: the epilogue of tile i overlaps the main loop of tile i+1) and two 32 KB smem
+// staging tiles (epilogue -> TMA store / TMA reduce-add; the residual / accumulate operand is TMA-
+// loaded into the same staging tile while the main loop runs).  Epilogues:
+//   store : + bias (+ second bias) + per-sample time-embedding vector + residual -> bf16 NHWC TMA store
+//   reduce: fp32 TMA reduce-add into global memory -- wgrad (split over pixels) and split-K partials of
+//           small-M fprop/dgrad layers (finished by splitk_finalize_kernel).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -31,9 +36,13 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = TILE_M * TILE_K * 2;   // 16 KB
 constexpr int B_BYTES = TILE_N * TILE_K * 2;   // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_BYTES = 32768;               // one staging tile: 128 x 128 bf16, or 2 boxes of 128 x 32 fp32
 constexpr int IGEMM_THREADS = 192;
-constexpr int IGEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 128;
+constexpr int SMEM_EPI_OFF = STAGES * STAGE_BYTES;
+constexpr int SMEM_BIAS_OFF = SMEM_EPI_OFF + 2 * EPI_BYTES;   // 128 floats
+constexpr int SMEM_BAR_OFF = SMEM_BIAS_OFF + 512;
+constexpr int IGEMM_SMEM = SMEM_BAR_OFF + 256 + 1024 /*alignment slack*/;
+constexpr int TMEM_COLS = 256;                 // two 128-column fp32 accumulators
 
 // ---- raw PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -43,6 +52,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -75,6 +87,29 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* dst, u
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -119,47 +154,74 @@ __host__ __device__ constexpr uint32_t make_idesc(int a_mn, int b_mn) {
 }
 
 struct IgemmArgs {
-  int mode;  // 0: activation GEMM (fprop / dgrad), 1: wgrad
+  int mode;   // 0: activation GEMM (fprop / dgrad), 1: wgrad
+  int epi;    // 0: bf16 TMA store (+bias/rowvec/C tile), 1: fp32 TMA reduce-add
   int nseg;
   int seg_taps[2];
   int seg_kc[2];
   signed char tap_dh[2][9], tap_dw[2][9], tap_b[2][9];
   int a_stride[2];
   int b_mn_major;
-  int H, W;            // spatial extent the M tiles walk over
+  int H, W;             // spatial extent the M tiles walk over
   int M_total, N_total;
-  // epilogue (mode 0)
-  __nv_bfloat16* out;
-  long long ld_out;
+  // persistent schedule: work item w -> (tile, K split)
+  int num_work, num_n, splits;
+  int iters_total, iters_per_split;   // mode 0: (tap, k-chunk) iterations; mode 1: 64-pixel chunks
+  // epilogue 0
   const float* bias;
   const float* bias2;
   const float* rowvec;
   long long ld_rowvec;
   int rows_per_vec;
-  const __nv_bfloat16* resid;
-  long long ld_resid;
-  int accumulate;
+  int has_c;            // a [128 x 128] bf16 tile of mapC (residual, or the output itself) is added
+  int store_bf16;       // 0: no bf16 output (fp32 copy only)
   float* out_f32;       // optional fp32 copy [M][N_total] (row-major, ld = N_total)
-  // wgrad (mode 1)
-  float* dw;
-  long long ld_dw;      // taps * ci_total
+  // wgrad
+  int taps;             // valid taps
   int ci_total;
-  int taps;
-  int kchunks_total;    // 64-pixel chunks
-  int kchunks_per_split;
-  int pw, ph;           // 64-pixel box geometry: pw*ph*pn = 64
+  int w_col0;
+  int num_co;
 };
+
+struct Work {
+  int m_tile, n_tile;   // mode 0: pixel tile, cout tile;  mode 1: cout tile, cin tile
+  int tap;              // mode 1
+  int it0, nit;         // iteration range
+};
+
+__device__ __forceinline__ Work decode_work(const IgemmArgs& a, int w) {
+  Work k;
+  const int z = w % a.splits;
+  const int t = w / a.splits;
+  if (a.mode == 0) {
+    k.n_tile = t % a.num_n;
+    k.m_tile = t / a.num_n;
+    k.tap = 0;
+  } else {
+    k.m_tile = t % a.num_co;
+    const int y = t / a.num_co;
+    k.tap = y % a.taps;
+    k.n_tile = y / a.taps;
+  }
+  k.it0 = z * a.iters_per_split;
+  k.nit = min(a.iters_per_split, a.iters_total - k.it0);
+  return k;
+}
 
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
              const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
+             const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapD,
              const __grid_constant__ IgemmArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS_OFF);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint64_t* c_full_bar = tmem_empty_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_full_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -168,10 +230,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);   // one arrival per epilogue warp
+      mbar_init(&c_full_bar[s], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapB0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapD) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
@@ -181,68 +248,60 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  // ---- iteration space -------------------------------------------------------------------------
-  int total_it;
-  int kc_begin = 0;
-  if (args.mode == 0) {
-    total_it = args.seg_taps[0] * args.seg_kc[0] + (args.nseg > 1 ? args.seg_taps[1] * args.seg_kc[1] : 0);
-  } else {
-    kc_begin = blockIdx.z * args.kchunks_per_split;
-    int kc_end = min(kc_begin + args.kchunks_per_split, args.kchunks_total);
-    total_it = max(kc_end - kc_begin, 0);
-  }
+  const int w_first = blockIdx.x, w_step = gridDim.x;
 
   if (warp == 0 && lane == 0) {
     // ============================== TMA producer ==============================================
-    if (args.mode == 0) {
-      const int p0 = blockIdx.x * TILE_M;
-      const int w0 = p0 % args.W, h0 = (p0 / args.W) % args.H, n0 = p0 / (args.W * args.H);
-      const int ncol0 = blockIdx.y * TILE_N;
-      int it = 0;
-      for (int seg = 0; seg < args.nseg; ++seg) {
-        const CUtensorMap* mA = seg == 0 ? &mapA0 : &mapA1;
-        const CUtensorMap* mB = seg == 0 ? &mapB0 : &mapB1;
-        const int st = args.a_stride[seg];
-        for (int tap = 0; tap < args.seg_taps[seg]; ++tap) {
+    int g = 0;   // stage counter across work items
+    for (int w = w_first; w < args.num_work; w += w_step) {
+      const Work k = decode_work(args, w);
+      if (args.mode == 0) {
+        const int p0 = k.m_tile * TILE_M;
+        const int w0 = p0 % args.W, h0 = (p0 / args.W) % args.H, n0 = p0 / (args.W * args.H);
+        const int ncol0 = k.n_tile * TILE_N;
+        const int seg0_total = args.seg_taps[0] * args.seg_kc[0];
+        for (int i = 0; i < k.nit; ++i, ++g) {
+          int it = k.it0 + i;
+          const int seg = it >= seg0_total ? 1 : 0;
+          if (seg) it -= seg0_total;
+          const int tap = it / args.seg_kc[seg], kc = it % args.seg_kc[seg];
+          const CUtensorMap* mA = seg == 0 ? &mapA0 : &mapA1;
+          const CUtensorMap* mB = seg == 0 ? &mapB0 : &mapB1;
+          const int st = args.a_stride[seg];
           const int dh = args.tap_dh[seg][tap], dw = args.tap_dw[seg][tap], tb = args.tap_b[seg][tap];
-          for (int kc = 0; kc < args.seg_kc[seg]; ++kc, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* a_dst = smem + s * STAGE_BYTES;
-            uint8_t* b_dst = a_dst + A_BYTES;
-            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-            tma_load_4d(mA, a_dst, &full_bar[s], kc * TILE_K, w0 * st + dw, h0 * st + dh, n0);
-            if (!args.b_mn_major) {
-              tma_load_3d(mB, b_dst, &full_bar[s], kc * TILE_K, tb, ncol0);
-            } else {
-              tma_load_3d(mB, b_dst, &full_bar[s], ncol0, tb, kc * TILE_K);
-              tma_load_3d(mB, b_dst + 8192, &full_bar[s], ncol0 + 64, tb, kc * TILE_K);
-            }
+          const int s = g % STAGES;
+          const uint32_t ph = (g / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* a_dst = smem + s * STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_4d(mA, a_dst, &full_bar[s], kc * TILE_K, w0 * st + dw, h0 * st + dh, n0);
+          if (!args.b_mn_major) {
+            tma_load_3d(mB, b_dst, &full_bar[s], kc * TILE_K, tb, ncol0);
+          } else {
+            tma_load_3d(mB, b_dst, &full_bar[s], ncol0, tb, kc * TILE_K);
+            tma_load_3d(mB, b_dst + 8192, &full_bar[s], ncol0 + 64, tb, kc * TILE_K);
           }
         }
-      }
-    } else {
-      // wgrad: A = dY (MN-major, M = co), B = X shifted by the tap (MN-major, N = ci)
-      const int co0 = blockIdx.x * TILE_M;
-      const int ci_tile = blockIdx.y / args.taps, tap = blockIdx.y % args.taps;
-      const int ci0 = ci_tile * TILE_N;
-      const int dh = args.tap_dh[0][tap], dw = args.tap_dw[0][tap];
-      const int st = args.a_stride[0];
-      for (int it = 0; it < total_it; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        const int p0 = (kc_begin + it) * TILE_K;  // 64 pixels of dY
-        const int w0 = p0 % args.W, h0 = (p0 / args.W) % args.H, n0 = p0 / (args.W * args.H);
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* a_dst = smem + s * STAGE_BYTES;
-        uint8_t* b_dst = a_dst + A_BYTES;
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_4d(&mapA0, a_dst, &full_bar[s], co0, w0, h0, n0);
-        tma_load_4d(&mapA0, a_dst + 8192, &full_bar[s], co0 + 64, w0, h0, n0);
-        tma_load_4d(&mapB0, b_dst, &full_bar[s], ci0, w0 * st + dw, h0 * st + dh, n0);
-        tma_load_4d(&mapB0, b_dst + 8192, &full_bar[s], ci0 + 64, w0 * st + dw, h0 * st + dh, n0);
+      } else {
+        // wgrad: A = dY (MN-major, M = co), B = X shifted by the tap (MN-major, N = ci)
+        const int co0 = k.m_tile * TILE_M, ci0 = k.n_tile * TILE_N;
+        const int dh = args.tap_dh[0][k.tap], dw = args.tap_dw[0][k.tap];
+        const int st = args.a_stride[0];
+        for (int i = 0; i < k.nit; ++i, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (g / STAGES) & 1;
+          const int p0 = (k.it0 + i) * TILE_K;  // 64 pixels of dY
+          const int w0 = p0 % args.W, h0 = (p0 / args.W) % args.H, n0 = p0 / (args.W * args.H);
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* a_dst = smem + s * STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_4d(&mapA0, a_dst, &full_bar[s], co0, w0, h0, n0);
+          tma_load_4d(&mapA0, a_dst + 8192, &full_bar[s], co0 + 64, w0, h0, n0);
+          tma_load_4d(&mapB0, b_dst, &full_bar[s], ci0, w0 * st + dw, h0 * st + dh, n0);
+          tma_load_4d(&mapB0, b_dst + 8192, &full_bar[s], ci0 + 64, w0 * st + dw, h0 * st + dh, n0);
+        }
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -250,117 +309,170 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     const int a_mn = args.mode == 1 ? 1 : 0;
     const int b_mn = args.mode == 1 ? 1 : args.b_mn_major;
     const uint32_t idesc = make_idesc(a_mn, b_mn);
-    for (int it = 0; it < total_it; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      mbar_wait(&full_bar[s], ph);
+    int g = 0, local = 0;
+    for (int w = w_first; w < args.num_work; w += w_step, ++local) {
+      const Work k = decode_work(args, w);
+      const int acc = local & 1;
+      mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
       tcgen05_fence_after();
-      const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
-      const uint32_t b_base = a_base + A_BYTES;
+      const uint32_t tmem_d = tmem_base + acc * TILE_N;
+      for (int i = 0; i < k.nit; ++i, ++g) {
+        const int s = g % STAGES;
+        const uint32_t ph = (g / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_base = a_base + A_BYTES;
 #pragma unroll
-      for (int k = 0; k < TILE_K / 16; ++k) {
-        const uint64_t da = a_mn ? desc_mnmajor(a_base, k) : desc_kmajor(a_base, k);
-        const uint64_t db = b_mn ? desc_mnmajor(b_base, k) : desc_kmajor(b_base, k);
-        umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+        for (int kk = 0; kk < TILE_K / 16; ++kk) {
+          const uint64_t da = a_mn ? desc_mnmajor(a_base, kk) : desc_kmajor(a_base, kk);
+          const uint64_t db = b_mn ? desc_mnmajor(b_base, kk) : desc_kmajor(b_base, kk);
+          umma_bf16(tmem_d, da, db, idesc, (i | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
       }
-      umma_commit(&empty_bar[s]);
+      umma_commit(&tmem_full_bar[acc]);
     }
-    umma_commit(tmem_full_bar);
   } else if (warp >= 2) {
     // ============================== epilogue ==================================================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    if (total_it > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      tcgen05_fence_after();
-    }
+    const int row = q * 32 + lane;          // row of the 128 x 128 tile held by this thread
+    const int et = threadIdx.x - 64;        // 0..127
+    const uint32_t sw = (uint32_t)(row & 7);
+    uint8_t* stg_base = smem + SMEM_EPI_OFF;
     uint32_t v[32];
-    if (args.mode == 0) {
-      const long long p = (long long)blockIdx.x * TILE_M + row;
-      const bool valid = p < args.M_total;
-      const int ncol0 = blockIdx.y * TILE_N;
-      const float* rv = (args.rowvec && valid) ? args.rowvec + (p / args.rows_per_vec) * args.ld_rowvec : nullptr;
+    int local = 0;
+    if (args.has_c && et == 0 && w_first < args.num_work) {   // C tile of the first work item
+      const Work k = decode_work(args, w_first);
+      mbar_expect_tx(&c_full_bar[0], EPI_BYTES);
+      tma_load_2d(&mapC, stg_base, &c_full_bar[0], k.n_tile * TILE_N, k.m_tile * TILE_M);
+      tma_load_2d(&mapC, stg_base + 16384, &c_full_bar[0], k.n_tile * TILE_N + 64, k.m_tile * TILE_M);
+    }
+    for (int w = w_first; w < args.num_work; w += w_step, ++local) {
+      const Work k = decode_work(args, w);
+      const int acc = local & 1;
+      const uint32_t tmem_acc = tmem_base + acc * TILE_N + ((uint32_t)(q * 32) << 16);
+      if (args.epi == 0) {
+        const int buf = local & 1;
+        uint8_t* stg = stg_base + buf * EPI_BYTES;
+        const int ncol0 = k.n_tile * TILE_N;
+        const long long p = (long long)k.m_tile * TILE_M + row;
+        const bool valid = p < args.M_total;
+        bias_s[et] = (args.bias ? __ldg(args.bias + ncol0 + et) : 0.f) + (args.bias2 ? __ldg(args.bias2 + ncol0 + et) : 0.f);
+        const float* rv = (args.rowvec && valid) ? args.rowvec + (p / args.rows_per_vec) * args.ld_rowvec + ncol0 : nullptr;
+        if (args.has_c) mbar_wait(&c_full_bar[buf], (local >> 1) & 1);
+        epi_bar_sync();   // bias_s visible; staging[buf] is free (thread 0 waited for its last TMA store below)
+        mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1);
+        tcgen05_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < TILE_N / 32; ++cc) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
-        if (!valid) continue;
-        const int col = ncol0 + cc * 32;
-        float f[32];
+        for (int cc = 0; cc < TILE_N / 32; ++cc) {
+          tmem_ld32(tmem_acc + cc * 32, v);
+          if (cc == TILE_N / 32 - 1) {      // accumulator fully read: hand it back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (args.bias) {
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + j4 * 4);
+            f[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b4.x;
+            f[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b4.y;
+            f[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
+            f[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
+          }
+          if (rv) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + col + j);
-        }
-        if (args.bias2) {
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(rv + cc * 32) + j4);
+              f[j4 * 4 + 0] += r4.x; f[j4 * 4 + 1] += r4.y; f[j4 * 4 + 2] += r4.z; f[j4 * 4 + 3] += r4.w;
+            }
+          }
+          // staging address of this thread's four 16-byte pieces: box = 64 columns, rows of 128 B, 128B swizzle
+          uint8_t* rowp = stg + (cc >> 1) * 16384 + row * 128;
+          const uint32_t jb = (uint32_t)(cc & 1) * 4;
+          if (args.has_c) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias2 + col + j);
-        }
-        if (rv) {
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rowp + (((jb + j4) ^ sw) << 4));
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __ldg(rv + col + j);
-        }
-        if (args.resid) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(args.resid + p * args.ld_resid + col);
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __bfloat1622float2(h2[e]);
+                f[j4 * 8 + e * 2] += t.x;
+                f[j4 * 8 + e * 2 + 1] += t.y;
+              }
+            }
+          }
+          if (args.out_f32 && valid) {
+            float4* o = reinterpret_cast<float4*>(args.out_f32 + p * (long long)args.N_total + ncol0 + cc * 32);
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const uint4 u = r4[j4];
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+            for (int j4 = 0; j4 < 8; ++j4) o[j4] = make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
+          }
+          if (args.store_bf16) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 t = __bfloat1622float2(h2[e]);
-              f[j4 * 8 + e * 2] += t.x;
-              f[j4 * 8 + e * 2 + 1] += t.y;
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint4 u;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[j4 * 8 + e * 2], f[j4 * 8 + e * 2 + 1]);
+              *reinterpret_cast<uint4*>(rowp + (((jb + j4) ^ sw) << 4)) = u;
             }
           }
         }
-        __nv_bfloat16* optr = args.out ? args.out + p * args.ld_out + col : nullptr;
-        if (args.accumulate && optr) {
-          const uint4* o4 = reinterpret_cast<const uint4*>(optr);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const uint4 u = o4[j4];
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 t = __bfloat1622float2(h2[e]);
-              f[j4 * 8 + e * 2] += t.x;
-              f[j4 * 8 + e * 2 + 1] += t.y;
-            }
+        fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+        epi_bar_sync();
+        if (et == 0 && args.store_bf16) {
+          tma_store_2d(&mapD, stg, ncol0, k.m_tile * TILE_M);
+          tma_store_2d(&mapD, stg + 16384, ncol0 + 64, k.m_tile * TILE_M);
+          bulk_commit();
+          bulk_wait_read<1>();   // every store but the one just issued has read its smem: the OTHER tile is free
+          const int wn = w + w_step;
+          if (args.has_c && wn < args.num_work) {
+            const Work kn = decode_work(args, wn);
+            uint8_t* so = stg_base + (buf ^ 1) * EPI_BYTES;
+            mbar_expect_tx(&c_full_bar[buf ^ 1], EPI_BYTES);
+            tma_load_2d(&mapC, so, &c_full_bar[buf ^ 1], kn.n_tile * TILE_N, kn.m_tile * TILE_M);
+            tma_load_2d(&mapC, so + 16384, &c_full_bar[buf ^ 1], kn.n_tile * TILE_N + 64, kn.m_tile * TILE_M);
           }
         }
-        if (optr) {
-          uint4* o4 = reinterpret_cast<uint4*>(optr);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            uint4 u;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[j4 * 8 + e * 2], f[j4 * 8 + e * 2 + 1]);
-            o4[j4] = u;
-          }
+      } else {
+        // fp32 reduce-add: 4 chunks of 32 columns -> 4 boxes {32 fp32, 128 rows} (2 per staging tile)
+        int x0, y0;
+        if (args.mode == 1) {
+          x0 = args.tap_b[0][k.tap] * args.ci_total + args.w_col0 + k.n_tile * TILE_N;
+          y0 = k.m_tile * TILE_M;
+        } else {
+          x0 = k.n_tile * TILE_N;
+          y0 = k.m_tile * TILE_M;
         }
-        if (args.out_f32) {
-          float4* o = reinterpret_cast<float4*>(args.out_f32 + p * (long long)args.N_total + col);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) o[j4] = make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
-        }
-      }
-    } else if (total_it > 0) {
-      const int ci_tile = blockIdx.y / args.taps, tap = blockIdx.y % args.taps;
-      const long long co = (long long)blockIdx.x * TILE_M + row;
-      const bool valid = co < args.M_total;
-      float* dst = args.dw + co * args.ld_dw + (long long)tap * args.ci_total + ci_tile * TILE_N;
+        if (et == 0) bulk_wait_read<0>();   // the previous item's reductions have read the staging tiles
+        epi_bar_sync();
+        mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1);
+        tcgen05_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < TILE_N / 32; ++cc) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
-        if (!valid) continue;
+        for (int cc = 0; cc < TILE_N / 32; ++cc) {
+          tmem_ld32(tmem_acc + cc * 32, v);
+          if (cc == TILE_N / 32 - 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          uint8_t* rowp = stg_base + cc * 16384 + row * 128;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (ci_tile * TILE_N + cc * 32 + j < args.N_total) atomicAdd(dst + cc * 32 + j, __uint_as_float(v[j]));
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<uint4*>(rowp + (((uint32_t)j4 ^ sw) << 4)) = make_uint4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        }
+        fence_proxy_async();
+        epi_bar_sync();
+        if (et == 0) {
+#pragma unroll
+          for (int cc = 0; cc < TILE_N / 32; ++cc) tma_reduce_add_2d(&mapD, stg_base + cc * 16384, x0 + cc * 32, y0);
+          bulk_commit();
         }
       }
     }
+    if (et == 0) bulk_wait_all();   // global writes of this CTA complete before it exits
     tcgen05_fence_before();
   }
 
@@ -368,6 +480,43 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// split-K epilogue of small-M fprop / dgrad layers: ws[M][N] fp32 partial sums -> + bias (+bias2) + rowvec
+// + residual (or the old output when accumulating) -> bf16 (and/or fp32) ; ws is re-zeroed for its next user.
+__global__ void splitk_finalize_kernel(float* __restrict__ ws, int M, int N, const float* __restrict__ bias,
+                                       const float* __restrict__ bias2, const float* __restrict__ rowvec, long long ld_rowvec,
+                                       int rows_per_vec, const __nv_bfloat16* resid, long long ld_resid,
+                                       __nv_bfloat16* out, long long ld_out, float* __restrict__ out_f32) {
+  const int n4 = N / 4;
+  const long long total = (long long)M * n4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / n4;
+    const int c = (int)(i % n4) * 4;
+    float4* wp = reinterpret_cast<float4*>(ws + r * N + c);
+    float4 a = *wp;
+    *wp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) { const float4 b = *reinterpret_cast<const float4*>(bias + c); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+    if (bias2) { const float4 b = *reinterpret_cast<const float4*>(bias2 + c); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+    if (rowvec) {
+      const float4 b = *reinterpret_cast<const float4*>(rowvec + (r / rows_per_vec) * ld_rowvec + c);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (resid) {
+      const uint2 u = *reinterpret_cast<const uint2*>(resid + r * ld_resid + c);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+      const float2 t0 = __bfloat1622float2(h2[0]), t1 = __bfloat1622float2(h2[1]);
+      a.x += t0.x; a.y += t0.y; a.z += t1.x; a.w += t1.y;
+    }
+    if (out) {
+      uint2 u;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+      h2[0] = __floats2bfloat162_rn(a.x, a.y);
+      h2[1] = __floats2bfloat162_rn(a.z, a.w);
+      *reinterpret_cast<uint2*>(out + r * ld_out + c) = u;
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * N + c) = a;
   }
 }
 
@@ -422,6 +571,26 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int cols, int taps, int r
   return MDM_OK;
 }
 
+// epilogue map: row-major 2-D [rows][cols] with row stride ld (elements); bf16 box {64, 128} or fp32 box {32, 128},
+// both 128 bytes wide with the 128B swizzle (the staging tiles are written in that layout)
+static int make_tile_map(CUtensorMap* m, const void* ptr, bool f32, long long cols, long long rows, long long ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return MDM_E_CUDA; }
+  const int es_bytes = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : 64), 128};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                   strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(tile) failed: %d (ptr=%p f32=%d cols=%lld rows=%lld ld=%lld)", (int)r, ptr, (int)f32, cols, rows, ld);
+    return MDM_E_CUDA;
+  }
+  return MDM_OK;
+}
+
 // split `count` pixels (a power of two <= 128) of an [N][H][W] raster into a TMA box (bw, bh, bn)
 static void pixel_box(int count, int H, int W, int* bw, int* bh, int* bn) {
   *bw = W < count ? W : count;
@@ -441,16 +610,87 @@ static int ensure_smem_attr() {
   return MDM_OK;
 }
 
-static void fill_taps(IgemmArgs& a, int seg, int ksize, bool flip) {
-  a.seg_taps[seg] = ksize * ksize;
+// taps of a k x k filter that can touch a valid input pixel (a 3x3 filter on a 1x1 map only has its centre):
+// out extent H x W, input extent (H*stride) x (W*stride), input coordinate = out*stride + d
+static void fill_taps(IgemmArgs& a, int seg, int ksize, bool flip, int H, int W, int stride) {
   const int half = ksize / 2;
+  int n = 0;
   for (int r = 0; r < ksize; ++r)
     for (int s = 0; s < ksize; ++s) {
-      const int t = r * ksize + s;
-      a.tap_dh[seg][t] = (signed char)(flip ? half - r : r - half);
-      a.tap_dw[seg][t] = (signed char)(flip ? half - s : s - half);
-      a.tap_b[seg][t] = (signed char)t;
+      const int dh = flip ? half - r : r - half, dw = flip ? half - s : s - half;
+      bool okh = false, okw = false;
+      for (int h = 0; h < H && !okh; ++h) okh = h * stride + dh >= 0 && h * stride + dh < H * stride;
+      for (int w = 0; w < W && !okw; ++w) okw = w * stride + dw >= 0 && w * stride + dw < W * stride;
+      if (!okh || !okw) continue;
+      a.tap_dh[seg][n] = (signed char)dh;
+      a.tap_dw[seg][n] = (signed char)dw;
+      a.tap_b[seg][n] = (signed char)(r * ksize + s);
+      ++n;
     }
+  a.seg_taps[seg] = n;
+}
+
+static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CUtensorMap& mA1, const CUtensorMap& mB1,
+                        const CUtensorMap& mC, const CUtensorMap& mD, const IgemmArgs& a, void* stream) {
+  const int grid = a.num_work < kNumSMs ? a.num_work : kNumSMs;
+  igemm_kernel<<<grid, IGEMM_THREADS, IGEMM_SMEM, as_stream(stream)>>>(mA0, mB0, mA1, mB1, mC, mD, a);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+// fprop / dgrad share this: choose a K split for small grids, launch, finish split-K partials
+static int run_activation_gemm(IgemmArgs& a, const CUtensorMap& mA0, const CUtensorMap& mB0, const CUtensorMap& mA1,
+                               const CUtensorMap& mB1, const mdm_conv_args* c, void* out, long long ld_out, void* stream) {
+  const int num_m = (a.M_total + TILE_M - 1) / TILE_M;
+  a.num_n = a.N_total / TILE_N;
+  const int tiles = num_m * a.num_n;
+  a.iters_total = a.seg_taps[0] * a.seg_kc[0] + (a.nseg > 1 ? a.seg_taps[1] * a.seg_kc[1] : 0);
+  int splits = 1;
+  const long long ws_need = (long long)a.M_total * a.N_total;
+  if (c->splitk_ws && c->splitk_ws_floats >= ws_need && tiles * 2 <= kNumSMs && a.iters_total >= 8) {
+    splits = kNumSMs / tiles;
+    if (splits > a.iters_total / 4) splits = a.iters_total / 4;
+    if (splits < 1) splits = 1;
+  }
+  a.iters_per_split = (a.iters_total + splits - 1) / splits;
+  a.splits = (a.iters_total + a.iters_per_split - 1) / a.iters_per_split;
+  a.num_work = tiles * a.splits;
+  const void* c_ptr = c->accumulate ? out : c->resid;
+  const long long c_ld = c->accumulate ? ld_out : c->ld_resid;
+  CUtensorMap mC, mD;
+  int rc;
+  if (a.splits == 1) {
+    a.epi = 0;
+    a.store_bf16 = out != nullptr ? 1 : 0;
+    a.has_c = (c_ptr != nullptr && out != nullptr) ? 1 : 0;
+    mD = mA0;   // placeholder when nothing is TMA-stored (fp32-only output of the tiny Linear layers)
+    if (out) {
+      rc = make_tile_map(&mD, out, false, a.N_total, a.M_total, ld_out);
+      if (rc) return rc;
+    }
+    mC = mD;
+    if (a.has_c) {
+      rc = make_tile_map(&mC, c_ptr, false, a.N_total, a.M_total, c_ld);
+      if (rc) return rc;
+    }
+    return launch_igemm(mA0, mB0, mA1, mB1, mC, mD, a, stream);
+  }
+  // split-K: fp32 partials reduce-added into the (zero) workspace, then one elementwise pass
+  a.epi = 1;
+  a.has_c = 0;
+  rc = make_tile_map(&mD, c->splitk_ws, true, a.N_total, a.M_total, a.N_total);
+  if (rc) return rc;
+  mC = mD;
+  const float* bias = a.bias; const float* bias2 = a.bias2; const float* rowvec = a.rowvec;
+  rc = launch_igemm(mA0, mB0, mA1, mB1, mC, mD, a, stream);
+  if (rc) return rc;
+  const long long total4 = ws_need / 4;
+  const int blocks = (int)((total4 + 255) / 256 < 4 * kNumSMs ? (total4 + 255) / 256 : 4 * kNumSMs);
+  splitk_finalize_kernel<<<blocks, 256, 0, as_stream(stream)>>>(c->splitk_ws, a.M_total, a.N_total, bias, bias2, rowvec,
+                                                                a.ld_rowvec, a.rows_per_vec, (const __nv_bfloat16*)c_ptr, c_ld,
+                                                                (__nv_bfloat16*)out, ld_out, c->y_f32);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
 }
 
 }  // namespace mdm
@@ -472,16 +712,13 @@ int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
   memset(&a, 0, sizeof(a));
   a.mode = 0;
   a.nseg = 1;
-  fill_taps(a, 0, c->ksize, false);
+  fill_taps(a, 0, c->ksize, false, c->H, c->W, c->stride);
   a.seg_kc[0] = c->cin / 64;
   a.a_stride[0] = c->stride;
   a.H = c->H; a.W = c->W;
   a.M_total = c->N * c->H * c->W;
   a.N_total = c->cout;
-  a.out = (__nv_bfloat16*)c->y; a.ld_out = c->ld_y;
   a.bias = c->bias; a.bias2 = c->bias2; a.rowvec = c->rowvec; a.ld_rowvec = c->ld_rowvec; a.rows_per_vec = c->H * c->W;
-  a.resid = (const __nv_bfloat16*)c->resid; a.ld_resid = c->ld_resid;
-  a.accumulate = c->accumulate;
   a.out_f32 = c->y_f32;
   int bw, bh, bn;
   pixel_box(128, c->H, c->W, &bw, &bh, &bn);
@@ -494,7 +731,7 @@ int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
   if (c->x2) {  // fused 1x1 shortcut: extra K segment on a second activation / weight pair
     MDM_CHECK_ARG(c->w2 && c->cin2 % 64 == 0 && c->ld_x2 % 8 == 0, "conv_fprop: bad shortcut segment");
     a.nseg = 2;
-    fill_taps(a, 1, 1, false);
+    fill_taps(a, 1, 1, false, c->H, c->W, 1);
     a.seg_kc[1] = c->cin2 / 64;
     a.a_stride[1] = 1;
     rc = make_act_map(&mA1, c->x2, c->ld_x2, c->cin2, c->W, c->H, c->N, bw, bh, bn, 1);
@@ -502,10 +739,7 @@ int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
     rc = make_w_map(&mB1, c->w2, c->cin2, 1, c->cout, 128);
     if (rc) return rc;
   }
-  dim3 grid((a.M_total + TILE_M - 1) / TILE_M, c->cout / TILE_N, 1);
-  igemm_kernel<<<grid, IGEMM_THREADS, IGEMM_SMEM, as_stream(stream)>>>(mA0, mB0, mA1, mB1, a);
-  MDM_LAUNCH_CHECK();
-  return MDM_OK;
+  return run_activation_gemm(a, mA0, mB0, mA1, mB1, c, c->y, c->ld_y, stream);
 }
 
 // dgrad of a stride-1 conv: dx[pix][ci] (+)= sum_tap sum_co dy[pix - tap][co] * w[co][tap][ci]
@@ -523,17 +757,15 @@ int mdm_conv_dgrad(const mdm_conv_args* c, void* stream) {
   memset(&a, 0, sizeof(a));
   a.mode = 0;
   a.nseg = 1;
-  fill_taps(a, 0, c->ksize, true);
+  fill_taps(a, 0, c->ksize, true, c->H, c->W, 1);
   a.seg_kc[0] = c->cout / 64;
   a.a_stride[0] = 1;
   a.b_mn_major = 1;
   a.H = c->H; a.W = c->W;
   a.M_total = c->N * c->H * c->W;
   a.N_total = c->cin;
-  a.out = (__nv_bfloat16*)c->y; a.ld_out = c->ld_y;
-  a.resid = (const __nv_bfloat16*)c->resid; a.ld_resid = c->ld_resid;
-  a.accumulate = c->accumulate;
   a.out_f32 = c->y_f32;
+  a.rows_per_vec = 1;
   int bw, bh, bn;
   pixel_box(128, c->H, c->W, &bw, &bh, &bn);
   CUtensorMap mA0, mB0;
@@ -543,57 +775,57 @@ int mdm_conv_dgrad(const mdm_conv_args* c, void* stream) {
   // w_cols: full row length of the packed weight (>= cin when cin is a slice); w_col0 offsets the slice
   rc = make_w_map(&mB0, (const __nv_bfloat16*)c->w + c->w_col0, c->w_cols ? c->w_cols : c->cin, c->ksize * c->ksize, c->cout, 64);
   if (rc) return rc;
-  dim3 grid((a.M_total + TILE_M - 1) / TILE_M, c->cin / TILE_N, 1);
-  igemm_kernel<<<grid, IGEMM_THREADS, IGEMM_SMEM, as_stream(stream)>>>(mA0, mB0, mA0, mB0, a);
-  MDM_LAUNCH_CHECK();
-  return MDM_OK;
+  return run_activation_gemm(a, mA0, mB0, mA0, mB0, c, c->y, c->ld_y, stream);
 }
 
-// wgrad: dw[co][tap][ci] += sum_pix dy[pix][co] * x[pix*stride + tap][ci]   (fp32, atomic split-K)
+// wgrad: dw[co][tap][ci] += sum_pix dy[pix][co] * x[pix*stride + tap][ci]   (fp32, TMA reduce-add, split over pixels)
 int mdm_conv_wgrad(const mdm_conv_args* c, void* stream) {
   MDM_CHECK_ARG(c && c->x && c->y && c->dw, "conv_wgrad: NULL pointer");
   MDM_CHECK_ARG(c->ksize == 1 || c->ksize == 3, "conv_wgrad: ksize must be 1 or 3");
   MDM_CHECK_ARG(c->stride == 1 || c->stride == 2, "conv_wgrad: stride must be 1 or 2");
   MDM_CHECK_ARG(c->cin % 128 == 0 && c->cout % 128 == 0, "conv_wgrad: cin, cout %% 128 (got %d, %d)", c->cin, c->cout);
   MDM_CHECK_ARG(is_pow2(c->H) && is_pow2(c->W), "conv_wgrad: H, W must be powers of two");
+  MDM_CHECK_ARG(c->w_col0 % 4 == 0, "conv_wgrad: w_col0 must be a multiple of 4");
   int rc = ensure_smem_attr();
   if (rc) return rc;
   // x = layer input [N][H*s][W*s][cin], y = dy [N][H][W][cout]
   IgemmArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = 1;
-  fill_taps(a, 0, c->ksize, false);
-  a.taps = c->ksize * c->ksize;
+  a.epi = 1;
+  fill_taps(a, 0, c->ksize, false, c->H, c->W, c->stride);
+  a.taps = a.seg_taps[0];
   a.a_stride[0] = c->stride;
   a.H = c->H; a.W = c->W;
   a.M_total = c->cout;
   a.N_total = c->cin;
-  a.dw = c->dw;
   a.ci_total = c->w_cols ? c->w_cols : c->cin;
-  a.ld_dw = (long long)a.taps * a.ci_total;
-  a.dw += c->w_col0;
+  a.w_col0 = (int)c->w_col0;
+  a.num_co = c->cout / TILE_M;
+  a.num_n = c->cin / TILE_N;
   const long long pixels = (long long)c->N * c->H * c->W;
-  a.kchunks_total = (int)((pixels + 63) / 64);
-  // split K so that the grid fills the machine (~2 waves), at least 4 chunks per CTA
-  const int tiles = (c->cout / TILE_M) * (c->cin / TILE_N) * a.taps;
+  a.iters_total = (int)((pixels + 63) / 64);
+  // split the pixel (K) range so that ~2 work items per SM exist, at least 4 chunks each
+  const int tiles = a.num_co * a.num_n * a.taps;
   int split = (2 * kNumSMs + tiles - 1) / tiles;
   if (split < 1) split = 1;
-  int per = (a.kchunks_total + split - 1) / split;
+  int per = (a.iters_total + split - 1) / split;
   if (per < 4) per = 4;
-  if (per > a.kchunks_total) per = a.kchunks_total;
-  split = (a.kchunks_total + per - 1) / per;
-  a.kchunks_per_split = per;
+  if (per > a.iters_total) per = a.iters_total;
+  a.iters_per_split = per;
+  a.splits = (a.iters_total + per - 1) / per;
+  a.num_work = tiles * a.splits;
   int pw, ph, pn;
   pixel_box(64, c->H, c->W, &pw, &ph, &pn);
-  CUtensorMap mA0, mB0;
+  CUtensorMap mA0, mB0, mD;
   rc = make_act_map(&mA0, c->y, c->ld_y, c->cout, c->W, c->H, c->N, pw, ph, pn, 1);
   if (rc) return rc;
   rc = make_act_map(&mB0, c->x, c->ld_x, c->cin, c->W * c->stride, c->H * c->stride, c->N, pw, ph, pn, c->stride);
   if (rc) return rc;
-  dim3 grid(c->cout / TILE_M, (c->cin / TILE_N) * a.taps, split);
-  igemm_kernel<<<grid, IGEMM_THREADS, IGEMM_SMEM, as_stream(stream)>>>(mA0, mB0, mA0, mB0, a);
-  MDM_LAUNCH_CHECK();
-  return MDM_OK;
+  const long long row = (long long)c->ksize * c->ksize * a.ci_total;
+  rc = make_tile_map(&mD, c->dw, true, row, c->cout, row);
+  if (rc) return rc;
+  return launch_igemm(mA0, mB0, mA0, mB0, mD, mD, a, stream);
 }
 
 }  // extern "C"

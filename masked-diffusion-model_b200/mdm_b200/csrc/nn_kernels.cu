@@ -36,48 +36,102 @@ __device__ __forceinline__ float dsiluf_(float z) {
 }
 
 // =============================================================================================
-// K2: GroupNorm (+SiLU).  grid = (chunks, N); thread <-> fixed 4-channel vector(s); rows strided.
+// K2: GroupNorm (+SiLU) forward / backward.  HBM-bound: every access is a 16-byte (8 x bf16) vector,
+// a thread keeps a FIXED 8-channel slice (its per-channel constants live in registers) and walks
+// pixels with GN_UNROLL independent loads in flight; grid = (pixel chunks, N).
+//   fwd : stats pass (per-chunk partial sums -> ws) + apply pass (the re-read hits the 126 MB L2)
+//   bwd : stats pass (per-channel dgamma/dbeta partials reduced in shared memory, ONE global atomic
+//         per channel per CTA; the two group sums follow from them: sum(d*gamma) = sum_c gamma_c dbeta_c,
+//         sum(d*gamma*xhat) = sum_c gamma_c dgamma_c) + apply pass, which can also emit the per-sample
+//         column sums of dx (the time-embedding / conv-bias gradients) so no separate reduction runs.
 // =============================================================================================
 constexpr int GN_MAX_GROUPS = 32;
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_C = 2048;
 
 struct GnGeom {
-  int HW, C, G, cpg, V, lanes, R, chunk_pix, nchunk;
+  int HW, C, G, cpg, L, R, chunk_pix, nchunk;
 };
 
-__device__ __forceinline__ void gn_thread_map(const GnGeom& g, int& r, int& lane_c) {
-  r = threadIdx.x / g.lanes;
-  lane_c = threadIdx.x % g.lanes;
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __bfloat1622float2(h[e]);
+    f[2 * e] = t.x;
+    f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+  return u;
+}
+__device__ __forceinline__ uint4 ldg16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// add the 8 per-channel values of a thread into per-group shared accumulators (slot = 2*group + which)
+__device__ __forceinline__ void group_scatter(float* acc, int which, int c0, int cpg, const float (&v)[8]) {
+  int gcur = c0 / cpg;
+  float run = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int gj = (c0 + j) / cpg;
+    if (gj != gcur) {
+      atomicAdd(&acc[gcur * 2 + which], run);
+      run = 0.f;
+      gcur = gj;
+    }
+    run += v[j];
+  }
+  atomicAdd(&acc[gcur * 2 + which], run);
 }
 
-__global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ ws, GnGeom g) {
+template <int UNROLL>
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __restrict__ x, long long ld,
+                                                              float* __restrict__ ws, GnGeom g) {
   __shared__ float acc[GN_MAX_GROUPS * 2];
   const int n = blockIdx.y, chunk = blockIdx.x;
   if (threadIdx.x < GN_MAX_GROUPS * 2) acc[threadIdx.x] = 0.f;
   __syncthreads();
-  int r, lane_c;
-  gn_thread_map(g, r, lane_c);
-  const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
-  const bf16* base = x + (long long)n * g.HW * ld;
+  const int lane = threadIdx.x % g.L, r = threadIdx.x / g.L;
   if (r < g.R) {
-    for (int cv = lane_c; cv < g.V; cv += g.lanes) {
-      float s = 0.f, ss = 0.f;
-      for (int p = p0 + r; p < p1; p += g.R) {
-        const float4 v = ld4(base + (long long)p * ld + cv * 4);
-        s += (v.x + v.y) + (v.z + v.w);
-        ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
+    const bf16* base = x + (long long)n * g.HW * ld + lane * 8;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    for (int p = p0 + r; p < p1; p += g.R * UNROLL) {
+      uint4 v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int pp = p + u * g.R;
+        v[u] = pp < p1 ? ldg16(base + (long long)pp * ld) : make_uint4(0, 0, 0, 0);
       }
-      const int grp = (cv * 4) / g.cpg;
-      atomicAdd(&acc[grp * 2], s);
-      atomicAdd(&acc[grp * 2 + 1], ss);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += f[j];
+          q[j] = fmaf(f[j], f[j], q[j]);
+        }
+      }
     }
+    group_scatter(acc, 0, lane * 8, g.cpg, s);
+    group_scatter(acc, 1, lane * 8, g.cpg, q);
   }
   __syncthreads();
   if (threadIdx.x < g.G * 2) ws[((long long)(n * g.nchunk + chunk)) * GN_MAX_GROUPS * 2 + threadIdx.x] = acc[threadIdx.x];
 }
 
-__global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ld, bf16* __restrict__ y, long long ldy,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ ws, float* __restrict__ stats, float eps, int silu, GnGeom g) {
+template <int UNROLL>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __restrict__ x, long long ld, bf16* __restrict__ y,
+                                                              long long ldy, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const float* __restrict__ ws,
+                                                              float* __restrict__ stats, float eps, int silu, GnGeom g) {
   __shared__ float mr[GN_MAX_GROUPS * 2];
   const int n = blockIdx.y, chunk = blockIdx.x;
   if (threadIdx.x < g.G) {
@@ -100,89 +154,141 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ld, bf16* 
     }
   }
   __syncthreads();
-  int r, lane_c;
-  gn_thread_map(g, r, lane_c);
+  const int lane = threadIdx.x % g.L, r = threadIdx.x / g.L;
   if (r >= g.R) return;
-  const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
-  const bf16* xb = x + (long long)n * g.HW * ld;
-  bf16* yb = y + (long long)n * g.HW * ldy;
-  for (int cv = lane_c; cv < g.V; cv += g.lanes) {
-    const int grp = (cv * 4) / g.cpg;
+  const int c0 = lane * 8;
+  float sc[8], sh[8];   // y = x * sc + sh
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int grp = (c0 + j) / g.cpg;
     const float mean = mr[grp * 2], rstd = mr[grp * 2 + 1];
-    const float4 ga = *reinterpret_cast<const float4*>(gamma + cv * 4);
-    const float4 be = *reinterpret_cast<const float4*>(beta + cv * 4);
-    for (int p = p0 + r; p < p1; p += g.R) {
-      const float4 v = ld4(xb + (long long)p * ld + cv * 4);
-      float4 z;
-      z.x = (v.x - mean) * rstd * ga.x + be.x;
-      z.y = (v.y - mean) * rstd * ga.y + be.y;
-      z.z = (v.z - mean) * rstd * ga.z + be.z;
-      z.w = (v.w - mean) * rstd * ga.w + be.w;
-      if (silu) { z.x = siluf_(z.x); z.y = siluf_(z.y); z.z = siluf_(z.z); z.w = siluf_(z.w); }
-      st4(yb + (long long)p * ldy + cv * 4, z);
-    }
+    const float ga = gamma[c0 + j], be = beta[c0 + j];
+    sc[j] = rstd * ga;
+    sh[j] = be - mean * rstd * ga;
   }
-}
-
-// backward pass 1: per (n, chunk, group) sums of dxhat and dxhat*xhat; per-channel dgamma/dbeta
-__global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, long long ld, const bf16* __restrict__ dy, long long lddy,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                    const float* __restrict__ stats, float* __restrict__ ws,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int silu, GnGeom g) {
-  __shared__ float acc[GN_MAX_GROUPS * 2];
-  const int n = blockIdx.y, chunk = blockIdx.x;
-  if (threadIdx.x < GN_MAX_GROUPS * 2) acc[threadIdx.x] = 0.f;
-  __syncthreads();
-  int r, lane_c;
-  gn_thread_map(g, r, lane_c);
   const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
-  const bf16* xb = x + (long long)n * g.HW * ld;
-  const bf16* db = dy + (long long)n * g.HW * lddy;
+  const bf16* xb = x + (long long)n * g.HW * ld + c0;
+  bf16* yb = y + (long long)n * g.HW * ldy + c0;
+  for (int p = p0 + r; p < p1; p += g.R * UNROLL) {
+    uint4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int pp = p + u * g.R;
+      if (pp < p1) v[u] = ldg16(xb + (long long)pp * ld);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int pp = p + u * g.R;
+      if (pp >= p1) break;
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float z = fmaf(f[j], sc[j], sh[j]);
+        if (silu) z = siluf_(z);
+        f[j] = z;
+      }
+      *reinterpret_cast<uint4*>(yb + (long long)pp * ldy) = pack8(f);
+    }
+  }
+}
+
+// backward pass 1: per-channel dgamma / dbeta partials; per (n, chunk, group) sums of d*gamma and d*gamma*xhat
+template <int UNROLL>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __restrict__ x, long long ld,
+                                                                  const bf16* __restrict__ dy, long long lddy,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ stats, float* __restrict__ ws,
+                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                  int silu, GnGeom g) {
+  extern __shared__ float gn_sm[];   // sdg[C], sdb[C]
+  float* sdg = gn_sm;
+  float* sdb = gn_sm + g.C;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) gn_sm[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x % g.L, r = threadIdx.x / g.L;
   if (r < g.R) {
-    for (int cv = lane_c; cv < g.V; cv += g.lanes) {
-      const int grp = (cv * 4) / g.cpg;
+    const int c0 = lane * 8;
+    float rs[8], mb[8], ga[8], be[8], dg[8], db[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int grp = (c0 + j) / g.cpg;
       const float mean = stats[((long long)n * g.G + grp) * 2], rstd = stats[((long long)n * g.G + grp) * 2 + 1];
-      const float4 ga = *reinterpret_cast<const float4*>(gamma + cv * 4);
-      const float4 be = *reinterpret_cast<const float4*>(beta + cv * 4);
-      float s1 = 0.f, s2 = 0.f;
-      float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), dbt = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int p = p0 + r; p < p1; p += g.R) {
-        const float4 v = ld4(xb + (long long)p * ld + cv * 4);
-        float4 d = ld4(db + (long long)p * lddy + cv * 4);
-        float4 xh;
-        xh.x = (v.x - mean) * rstd; xh.y = (v.y - mean) * rstd; xh.z = (v.z - mean) * rstd; xh.w = (v.w - mean) * rstd;
-        if (silu) {
-          d.x *= dsiluf_(xh.x * ga.x + be.x); d.y *= dsiluf_(xh.y * ga.y + be.y);
-          d.z *= dsiluf_(xh.z * ga.z + be.z); d.w *= dsiluf_(xh.w * ga.w + be.w);
+      rs[j] = rstd;
+      mb[j] = -mean * rstd;
+      ga[j] = gamma[c0 + j];
+      be[j] = beta[c0 + j];
+      dg[j] = db[j] = 0.f;
+    }
+    const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
+    const bf16* xb = x + (long long)n * g.HW * ld + c0;
+    const bf16* dbp = dy + (long long)n * g.HW * lddy + c0;
+    for (int p = p0 + r; p < p1; p += g.R * UNROLL) {
+      uint4 vx[UNROLL], vd[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int pp = p + u * g.R;
+        const bool ok = pp < p1;
+        vx[u] = ok ? ldg16(xb + (long long)pp * ld) : make_uint4(0, 0, 0, 0);
+        vd[u] = ok ? ldg16(dbp + (long long)pp * lddy) : make_uint4(0, 0, 0, 0);   // d = 0 -> no contribution
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        float fx[8], fd[8];
+        unpack8(vx[u], fx);
+        unpack8(vd[u], fd);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(fx[j], rs[j], mb[j]);
+          float d = fd[j];
+          if (silu) d *= dsiluf_(fmaf(xh, ga[j], be[j]));
+          dg[j] = fmaf(d, xh, dg[j]);
+          db[j] += d;
         }
-        dg.x += d.x * xh.x; dg.y += d.y * xh.y; dg.z += d.z * xh.z; dg.w += d.w * xh.w;
-        dbt.x += d.x; dbt.y += d.y; dbt.z += d.z; dbt.w += d.w;
-        const float e0 = d.x * ga.x, e1 = d.y * ga.y, e2 = d.z * ga.z, e3 = d.w * ga.w;
-        s1 += (e0 + e1) + (e2 + e3);
-        s2 += (e0 * xh.x + e1 * xh.y) + (e2 * xh.z + e3 * xh.w);
       }
-      atomicAdd(&acc[grp * 2], s1);
-      atomicAdd(&acc[grp * 2 + 1], s2);
-      if (dgamma) {
-        atomicAdd(dgamma + cv * 4 + 0, dg.x); atomicAdd(dgamma + cv * 4 + 1, dg.y);
-        atomicAdd(dgamma + cv * 4 + 2, dg.z); atomicAdd(dgamma + cv * 4 + 3, dg.w);
-        atomicAdd(dbeta + cv * 4 + 0, dbt.x); atomicAdd(dbeta + cv * 4 + 1, dbt.y);
-        atomicAdd(dbeta + cv * 4 + 2, dbt.z); atomicAdd(dbeta + cv * 4 + 3, dbt.w);
-      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sdg[c0 + j], dg[j]);
+      atomicAdd(&sdb[c0 + j], db[j]);
     }
   }
   __syncthreads();
-  if (threadIdx.x < g.G * 2) ws[((long long)(n * g.nchunk + chunk)) * GN_MAX_GROUPS * 2 + threadIdx.x] = acc[threadIdx.x];
+  if (dgamma) {
+    for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+      atomicAdd(dgamma + c, sdg[c]);
+      atomicAdd(dbeta + c, sdb[c]);
+    }
+  }
+  if (threadIdx.x < g.G) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = threadIdx.x * g.cpg; c < (threadIdx.x + 1) * g.cpg; ++c) {
+      const float gm = gamma[c];
+      s1 = fmaf(gm, sdb[c], s1);
+      s2 = fmaf(gm, sdg[c], s2);
+    }
+    float* w = ws + ((long long)(n * g.nchunk + chunk)) * GN_MAX_GROUPS * 2 + threadIdx.x * 2;
+    w[0] = s1;
+    w[1] = s2;
+  }
 }
 
-// backward pass 2: dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat)) (+ add)
-__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, long long ld, const bf16* __restrict__ dy, long long lddy,
-                                    const bf16* __restrict__ add, long long ldadd, const bf16* __restrict__ add2,
-                                    long long ldadd2, bf16* __restrict__ dx, long long lddx,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                    const float* __restrict__ stats, const float* __restrict__ ws, int silu, GnGeom g) {
+// backward pass 2: dx = rstd * (d*gamma - mean(d*gamma) - xhat * mean(d*gamma*xhat)) (+ add + add2);
+// optionally colsum[n][c] += sum_pixels dx and dbias[c] += the same (conv bias / time-embedding gradients)
+template <int UNROLL>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(
+    const bf16* __restrict__ x, long long ld, const bf16* __restrict__ dy, long long lddy, const bf16* add /* may alias dx */,
+    long long ldadd, const bf16* __restrict__ add2, long long ldadd2, bf16* dx, long long lddx,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
+    const float* __restrict__ ws, int silu, float* __restrict__ colsum, long long ld_colsum, float* __restrict__ dbias,
+    GnGeom g) {
+  extern __shared__ float gn_sm[];   // scs[C] when colsum
   __shared__ float m12[GN_MAX_GROUPS * 2];
   const int n = blockIdx.y, chunk = blockIdx.x;
+  const bool want_cs = colsum != nullptr || dbias != nullptr;
+  if (want_cs)
+    for (int c = threadIdx.x; c < g.C; c += blockDim.x) gn_sm[c] = 0.f;
   if (threadIdx.x < g.G) {
     double s1 = 0.0, s2 = 0.0;
     for (int k = 0; k < g.nchunk; ++k) {
@@ -195,56 +301,100 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, long long ld, co
     m12[threadIdx.x * 2 + 1] = (float)(s2 / cnt);
   }
   __syncthreads();
-  int r, lane_c;
-  gn_thread_map(g, r, lane_c);
-  if (r >= g.R) return;
-  const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
-  const bf16* xb = x + (long long)n * g.HW * ld;
-  const bf16* db = dy + (long long)n * g.HW * lddy;
-  const bf16* ab = add ? add + (long long)n * g.HW * ldadd : nullptr;
-  const bf16* ab2 = add2 ? add2 + (long long)n * g.HW * ldadd2 : nullptr;
-  bf16* ob = dx + (long long)n * g.HW * lddx;
-  for (int cv = lane_c; cv < g.V; cv += g.lanes) {
-    const int grp = (cv * 4) / g.cpg;
-    const float mean = stats[((long long)n * g.G + grp) * 2], rstd = stats[((long long)n * g.G + grp) * 2 + 1];
-    const float m1 = m12[grp * 2], m2 = m12[grp * 2 + 1];
-    const float4 ga = *reinterpret_cast<const float4*>(gamma + cv * 4);
-    const float4 be = *reinterpret_cast<const float4*>(beta + cv * 4);
-    for (int p = p0 + r; p < p1; p += g.R) {
-      const float4 v = ld4(xb + (long long)p * ld + cv * 4);
-      float4 d = ld4(db + (long long)p * lddy + cv * 4);
-      float4 xh;
-      xh.x = (v.x - mean) * rstd; xh.y = (v.y - mean) * rstd; xh.z = (v.z - mean) * rstd; xh.w = (v.w - mean) * rstd;
-      if (silu) {
-        d.x *= dsiluf_(xh.x * ga.x + be.x); d.y *= dsiluf_(xh.y * ga.y + be.y);
-        d.z *= dsiluf_(xh.z * ga.z + be.z); d.w *= dsiluf_(xh.w * ga.w + be.w);
+  const int lane = threadIdx.x % g.L, r = threadIdx.x / g.L;
+  if (r < g.R) {
+    const int c0 = lane * 8;
+    float rs[8], mb[8], ga[8], be[8], m1[8], m2[8], cs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int grp = (c0 + j) / g.cpg;
+      const float mean = stats[((long long)n * g.G + grp) * 2], rstd = stats[((long long)n * g.G + grp) * 2 + 1];
+      rs[j] = rstd;
+      mb[j] = -mean * rstd;
+      ga[j] = gamma[c0 + j];
+      be[j] = beta[c0 + j];
+      m1[j] = m12[grp * 2];
+      m2[j] = m12[grp * 2 + 1];
+      cs[j] = 0.f;
+    }
+    const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
+    const long long sample = (long long)n * g.HW;
+    const bf16* xb = x + sample * ld + c0;
+    const bf16* dbp = dy + sample * lddy + c0;
+    const bf16* ab = add ? add + sample * ldadd + c0 : nullptr;
+    const bf16* ab2 = add2 ? add2 + sample * ldadd2 + c0 : nullptr;
+    bf16* ob = dx + sample * lddx + c0;
+    for (int p = p0 + r; p < p1; p += g.R * UNROLL) {
+      uint4 vx[UNROLL], vd[UNROLL], va[UNROLL], vb[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int pp = p + u * g.R;
+        if (pp < p1) {
+          vx[u] = ldg16(xb + (long long)pp * ld);
+          vd[u] = ldg16(dbp + (long long)pp * lddy);
+          if (ab) va[u] = *reinterpret_cast<const uint4*>(ab + (long long)pp * ldadd);   // may alias dx: plain load
+          if (ab2) vb[u] = ldg16(ab2 + (long long)pp * ldadd2);
+        }
       }
-      float4 o;
-      o.x = rstd * (d.x * ga.x - m1 - xh.x * m2);
-      o.y = rstd * (d.y * ga.y - m1 - xh.y * m2);
-      o.z = rstd * (d.z * ga.z - m1 - xh.z * m2);
-      o.w = rstd * (d.w * ga.w - m1 - xh.w * m2);
-      if (ab) {
-        const float4 a = ld4(ab + (long long)p * ldadd + cv * 4);
-        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int pp = p + u * g.R;
+        if (pp >= p1) break;
+        float fx[8], fd[8], o[8];
+        unpack8(vx[u], fx);
+        unpack8(vd[u], fd);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(fx[j], rs[j], mb[j]);
+          float d = fd[j];
+          if (silu) d *= dsiluf_(fmaf(xh, ga[j], be[j]));
+          o[j] = rs[j] * (d * ga[j] - m1[j] - xh * m2[j]);
+        }
+        if (want_cs) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cs[j] += o[j];
+        }
+        if (ab) {
+          float fa[8];
+          unpack8(va[u], fa);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += fa[j];
+        }
+        if (ab2) {
+          float fb[8];
+          unpack8(vb[u], fb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += fb[j];
+        }
+        *reinterpret_cast<uint4*>(ob + (long long)pp * lddx) = pack8(o);
       }
-      if (ab2) {
-        const float4 a = ld4(ab2 + (long long)p * ldadd2 + cv * 4);
-        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-      }
-      st4(ob + (long long)p * lddx + cv * 4, o);
+    }
+    if (want_cs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&gn_sm[c0 + j], cs[j]);
+    }
+  }
+  if (want_cs) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+      const float v = gn_sm[c];
+      if (colsum) atomicAdd(colsum + (long long)n * ld_colsum + c, v);
+      if (dbias) atomicAdd(dbias + c, v);
     }
   }
 }
 
-static int gn_geom(GnGeom& g, int HW, int C, int G, int* threads, int* nchunk) {
-  if (C % (4 * G) != 0 || G > GN_MAX_GROUPS) { set_error("GroupNorm: C=%d must be a multiple of 4*G (G=%d <= 32)", C, G); return MDM_E_ARG; }
-  g.HW = HW; g.C = C; g.G = G; g.cpg = C / G; g.V = C / 4;
-  g.lanes = g.V < 256 ? g.V : 256;
-  g.R = 256 / g.lanes; if (g.R < 1) g.R = 1;
-  *threads = g.lanes * g.R; if (*threads < 64) *threads = 64;
-  // ~32K elements per CTA
-  int chunk = (32768 + C - 1) / C;
+static int gn_geom(GnGeom& g, int HW, int C, int G, int* nchunk) {
+  if (C % 8 != 0 || C % G != 0 || G > GN_MAX_GROUPS || C > GN_MAX_C) {
+    set_error("GroupNorm: C=%d must be a multiple of 8 and of G=%d (G <= 32, C <= %d)", C, G, GN_MAX_C);
+    return MDM_E_ARG;
+  }
+  g.HW = HW; g.C = C; g.G = G; g.cpg = C / G;
+  g.L = C / 8;
+  if (g.L > GN_THREADS) { set_error("GroupNorm: C=%d too wide", C); return MDM_E_ARG; }
+  g.R = GN_THREADS / g.L;
+  // ~64K elements (128 KB of bf16) per CTA, a multiple of R pixels
+  int chunk = (65536 + C - 1) / C;
   chunk = ((chunk + g.R - 1) / g.R) * g.R;
   if (chunk > HW) chunk = HW;
   if (chunk < 1) chunk = 1;
@@ -577,15 +727,50 @@ __global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __rest
   if (i < n) dx[i] = __float2bfloat16(dy[i] * dsiluf_(x[i]));
 }
 
-// out[c] += sum over rows of dy[row][c]   (bias gradients); grid = (C/64.., row chunks)
-__global__ void colsum_kernel(const bf16* __restrict__ dy, long long ld, float* __restrict__ out, float* __restrict__ out2, long long rows, int C, int rows_per_cta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const long long r0 = (long long)blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
-  float s = 0.f;
-  for (long long r = r0; r < r1; ++r) s += __bfloat162float(dy[r * ld + c]);
-  atomicAdd(out + c, s);
-  if (out2) atomicAdd(out2 + c, s);
+// out[c] += sum over rows of dy[row][c]   (bias gradients).  thread <-> 8 channels (16-byte loads), CTA <-> a
+// run of rows, shared-memory reduction across the CTA's row threads, one global atomic per channel per CTA.
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, long long ld, float* __restrict__ out,
+                                                     float* __restrict__ out2, long long rows, int C, int L, int R,
+                                                     int rows_per_cta) {
+  extern __shared__ float cs_sm[];   // [Cb]: this CTA's column block (blockIdx.y, up to 2048 channels)
+  const int c_base = blockIdx.y * 2048;
+  const int Cb = min(2048, C - c_base);
+  out += c_base;
+  if (out2) out2 += c_base;
+  C = Cb;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) cs_sm[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x % L, r = threadIdx.x / L;
+  if (r < R && lane * 8 < Cb) {
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(r0 + (long long)rows_per_cta, rows);
+    const bf16* base = dy + c_base + lane * 8;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    for (long long p = r0 + r; p < r1; p += (long long)R * 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long pp = p + (long long)u * R;
+        v[u] = pp < r1 ? ldg16(base + pp * ld) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += f[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&cs_sm[lane * 8 + j], s[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = cs_sm[c];
+    atomicAdd(out + c, v);
+    if (out2) atomicAdd(out2 + c, v);
+  }
 }
 
 // out[n][c] (fp32, ld_out) = sum over the HW pixels of sample n of dy[(n*HW+p)][c]; optional dbias[c] += same
@@ -649,37 +834,42 @@ using namespace mdm;
 extern "C" {
 
 int64_t mdm_gn_ws_floats(int N, int HW, int C, int G) {
-  GnGeom g; int th, nc;
-  if (gn_geom(g, HW, C, G, &th, &nc)) return 0;
+  GnGeom g; int nc;
+  if (gn_geom(g, HW, C, G, &nc)) return 0;
   return (int64_t)N * nc * GN_MAX_GROUPS * 2;
 }
 
 int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma, const float* beta,
                     float* stats, float* ws, int N, int HW, int C, int G, float eps, int silu, void* stream) {
   MDM_CHECK_ARG(x && y && gamma && beta && ws, "gn_silu_fwd: NULL pointer");
-  MDM_CHECK_ARG(ld_x % 4 == 0 && ld_y % 4 == 0, "gn_silu_fwd: channel strides must be multiples of 4");
-  GnGeom g; int th, nc;
-  int rc = gn_geom(g, HW, C, G, &th, &nc);
+  MDM_CHECK_ARG(ld_x % 8 == 0 && ld_y % 8 == 0, "gn_silu_fwd: channel strides must be multiples of 8");
+  MDM_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0), "gn_silu_fwd: pointers must be 16-byte aligned");
+  GnGeom g; int nc;
+  int rc = gn_geom(g, HW, C, G, &nc);
   if (rc) return rc;
   dim3 grid(nc, N);
-  gn_stats_kernel<<<grid, th, 0, as_stream(stream)>>>((const bf16*)x, ld_x, ws, g);
+  gn_stats_kernel<4><<<grid, GN_THREADS, 0, as_stream(stream)>>>((const bf16*)x, ld_x, ws, g);
   MDM_LAUNCH_CHECK();
-  gn_apply_kernel<<<grid, th, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta, ws, stats, eps, silu, g);
+  gn_apply_kernel<4><<<grid, GN_THREADS, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta, ws, stats, eps, silu, g);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
 
 int mdm_gn_silu_bwd(const void* x, long long ld_x, const void* dy, long long ld_dy, const void* add, long long ld_add,
-                    const void* add2, long long ld_add2, void* dx, long long ld_dx, const float* gamma, const float* beta, const float* stats, float* dgamma,
-                    float* dbeta, float* ws, int N, int HW, int C, int G, int silu, void* stream) {
+                    const void* add2, long long ld_add2, void* dx, long long ld_dx, const float* gamma, const float* beta,
+                    const float* stats, float* dgamma, float* dbeta, float* ws, float* colsum, long long ld_colsum,
+                    float* dbias, int N, int HW, int C, int G, int silu, void* stream) {
   MDM_CHECK_ARG(x && dy && dx && gamma && beta && stats && ws, "gn_silu_bwd: NULL pointer");
-  GnGeom g; int th, nc;
-  int rc = gn_geom(g, HW, C, G, &th, &nc);
+  MDM_CHECK_ARG(ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0 && ld_add % 8 == 0 && ld_add2 % 8 == 0,
+                "gn_silu_bwd: channel strides must be multiples of 8");
+  GnGeom g; int nc;
+  int rc = gn_geom(g, HW, C, G, &nc);
   if (rc) return rc;
   dim3 grid(nc, N);
-  gn_bwd_stats_kernel<<<grid, th, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, gamma, beta, stats, ws, dgamma, dbeta, silu, g);
+  const size_t sm1 = (size_t)2 * C * sizeof(float), sm2 = (size_t)C * sizeof(float);
+  gn_bwd_stats_kernel<2><<<grid, GN_THREADS, sm1, as_stream(stream)>>>((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, gamma, beta, stats, ws, dgamma, dbeta, silu, g);
   MDM_LAUNCH_CHECK();
-  gn_bwd_apply_kernel<<<grid, th, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (const bf16*)add, ld_add, (const bf16*)add2, ld_add2, (bf16*)dx, ld_dx, gamma, beta, stats, ws, silu, g);
+  gn_bwd_apply_kernel<2><<<grid, GN_THREADS, sm2, as_stream(stream)>>>((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (const bf16*)add, ld_add, (const bf16*)add2, ld_add2, (bf16*)dx, ld_dx, gamma, beta, stats, ws, silu, colsum, ld_colsum, dbias, g);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -822,9 +1012,15 @@ int mdm_silu_bwd(const float* x, const float* dy, void* dx, int64_t n, void* str
 
 int mdm_colsum(const void* dy, long long ld, float* out, float* out2, int64_t rows, int C, void* stream) {
   MDM_CHECK_ARG(dy && out, "colsum: NULL pointer");
-  int rows_per_cta = 256;
-  dim3 grid(GRID1D(C, 128), (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
-  colsum_kernel<<<grid, 128, 0, as_stream(stream)>>>((const bf16*)dy, ld, out, out2, rows, C, rows_per_cta);
+  MDM_CHECK_ARG(C % 8 == 0 && ld % 8 == 0 && ((uintptr_t)dy % 16 == 0), "colsum: C %% 8, ld %% 8, 16-byte aligned (C=%d ld=%lld)", C, ld);
+  const int Cb = C < 2048 ? C : 2048;
+  const int L = Cb / 8, R = 256 / L;
+  // ~128 KB of bf16 per CTA, at least one pass of R rows
+  long long rpc = (65536 + Cb - 1) / Cb;
+  rpc = ((rpc + R - 1) / R) * R;
+  if (rpc > rows) rpc = rows;
+  const dim3 blocks((unsigned)((rows + rpc - 1) / rpc), (unsigned)((C + 2047) / 2048));
+  colsum_kernel<<<blocks, 256, (size_t)Cb * sizeof(float), as_stream(stream)>>>((const bf16*)dy, ld, out, out2, rows, C, L, R, (int)rpc);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }

@@ -674,9 +674,11 @@ class _Plan:
                     ops.colsum(d_out, m.g32(f"{p}.conv2.bias"), B * HW, r.cout, out2=m.g32(f"{p}.conv_shortcut.bias"))
                 else:
                     ops.colsum(d_out, m.g32(f"{p}.conv2.bias"), B * HW, r.cout)
+                # d_h1 plus, in the same pass, its per-sample column sums = d(time_emb_proj output) and conv1.bias grad
                 ops.gn_silu_bwd(h1, d_a2, d_h1, m.w32(f"{p}.norm2.weight"), m.w32(f"{p}.norm2.bias"), st2,
-                                m.g32(f"{p}.norm2.weight"), m.g32(f"{p}.norm2.bias"), ws2(), B, HW, r.cout, G, True)
-                ops.sample_colsum(d_h1, self.d_tproj[:, r.tproj_off:], self.d_tproj.shape[1], m.g32(f"{p}.conv1.bias"), B, HW, r.cout)
+                                m.g32(f"{p}.norm2.weight"), m.g32(f"{p}.norm2.bias"), ws2(), B, HW, r.cout, G, True,
+                                colsum=self.d_tproj[:, r.tproj_off:], ld_colsum=self.d_tproj.shape[1],
+                                dbias=m.g32(f"{p}.conv1.bias"))
                 ops.conv_dgrad(d_h1, m.w16(f"{p}.conv1.weight"), d_a1, B, H, H, 3)
                 ops.conv_wgrad(a1, d_h1, m.g32(f"{p}.conv1.weight"), B, H, H, 3, 1)
                 add = None
@@ -812,5 +814,6 @@ class _Plan:
 
     def run_backward(self, d_out):
         self.d_out.copy_(d_out)
+        self.d_tproj.zero_()          # accumulated by the fused column sums of the norm2 backward
         for op in self.bwd:
             op()

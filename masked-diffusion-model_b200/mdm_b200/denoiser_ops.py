@@ -25,6 +25,7 @@ class ConvArgs(Structure):
         ("y_f32", c_void_p),
         ("x2", c_void_p), ("ld_x2", c_longlong), ("cin2", c_int), ("w2", c_void_p),
         ("dw", c_void_p), ("w_col0", c_longlong), ("w_cols", c_int),
+        ("splitk_ws", c_void_p), ("splitk_ws_floats", c_longlong),
     ]
 
 
@@ -37,7 +38,7 @@ _lib.register({
     "mdm_conv_wgrad": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_gn_ws_floats": (_I64, [c_int, c_int, c_int, c_int]),
     "mdm_gn_silu_fwd": (c_int, [_P, _LL, _P, _LL, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
-    "mdm_gn_silu_bwd": (c_int, [_P, _LL, _P, _LL, _P, _LL, _P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P,
+    "mdm_gn_silu_bwd": (c_int, [_P, _LL, _P, _LL, _P, _LL, _P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _LL, _P,
                                 c_int, c_int, c_int, c_int, c_int, _P]),
     "mdm_conv_in_fwd": (c_int, [_P, _P, _P, _P, _LL, c_int, c_int, c_int, c_int, c_int, _P]),
     "mdm_conv_in_wgrad": (c_int, [_P, _P, _LL, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
@@ -60,6 +61,19 @@ _lib.register({
 
 def _dp(t):
     return t.data_ptr() if t is not None else None
+
+
+# zeroed fp32 scratch per device: small-M layers split their K loop over the SMs through it (the kernels
+# leave it zeroed again, and launches are stream-ordered, so one buffer serves every layer)
+SPLITK_WS_FLOATS = 1 << 20
+_splitk_ws = {}
+
+
+def _splitk(a, device):
+    ws = _splitk_ws.get(device)
+    if ws is None:
+        ws = _splitk_ws[device] = torch.zeros(SPLITK_WS_FLOATS, dtype=torch.float32, device=device)
+    a.splitk_ws, a.splitk_ws_floats = ws.data_ptr(), ws.numel()
 
 
 def pix_ld(t: torch.Tensor) -> int:
@@ -93,6 +107,7 @@ def conv_fprop(x, w, y, N, H, W, ksize=3, stride=1, bias=None, rowvec=None, resi
     a.y_f32 = _dp(y_f32)
     if x2 is not None:
         a.x2, a.ld_x2, a.cin2, a.w2 = _dp(x2), pix_ld(x2), x2.shape[-1], _dp(w2)
+    _splitk(a, x.device)
     check(lib().mdm_conv_fprop(ctypes.byref(a), stream_ptr(x.device)))
 
 
@@ -111,6 +126,7 @@ def conv_dgrad(dy, w, dx, N, H, W, ksize=3, resid=None, accumulate=False, dx_f32
     a.accumulate = int(accumulate)
     a.y_f32 = _dp(dx_f32)
     a.w_cols = w.shape[-1]
+    _splitk(a, dy.device)
     check(lib().mdm_conv_dgrad(ctypes.byref(a), stream_ptr(dy.device)))
 
 
@@ -150,12 +166,15 @@ def gn_silu_fwd(x, y, gamma, beta, stats, ws, N, HW, C, G=32, eps=1e-5, silu=Tru
                                 N, HW, C, G, eps, int(silu), _s(x)))
 
 
-def gn_silu_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, ws, N, HW, C, G=32, silu=True, add=None, add2=None):
+def gn_silu_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, ws, N, HW, C, G=32, silu=True, add=None, add2=None,
+                colsum=None, ld_colsum=0, dbias=None):
+    """dx = GroupNorm(+SiLU) backward (+ add + add2); optional fused per-sample column sums of the GroupNorm
+    part of dx: colsum[n, c] += ..., dbias[c] += ... (fp32, accumulated)"""
     check(lib().mdm_gn_silu_bwd(_dp(x), pix_ld(x), _dp(dy), pix_ld(dy),
                                 _dp(add), pix_ld(add) if add is not None else 0,
                                 _dp(add2), pix_ld(add2) if add2 is not None else 0,
                                 _dp(dx), pix_ld(dx), _dp(gamma), _dp(beta), _dp(stats), _dp(dgamma), _dp(dbeta),
-                                _dp(ws), N, HW, C, G, int(silu), _s(x)))
+                                _dp(ws), _dp(colsum), ld_colsum, _dp(dbias), N, HW, C, G, int(silu), _s(x)))
 
 
 def conv_in_fwd(img, w, bias, y, N, C, H, W, cout):

@@ -119,12 +119,13 @@ def test_graph_step_equals_eager_step(method):
 
 
 def test_training_reduces_loss_c1_shape():
-    """BASELINE c1 shape (64 x 1 x 32 x 32), base trainer: 12 steps on a fixed batch"""
+    """BASELINE c1 shape (64 x 1 x 32 x 32), base trainer: 24 steps on a fixed batch"""
     a, model, ema, opt, sched, tr = _b200_setup("base", C=1, S=32, B=64, graph=True, T=10)
     g = torch.Generator().manual_seed(6)
     x0 = (torch.rand(64, 1, 32, 32, generator=g) * 2 - 1).cuda()
     torch.manual_seed(0)
     tr.Scheduler.adopt_torch_rng("cuda")
-    ls = [tr._run_batch(i, (x0,), 0, 1, 0, None, None)[0] for i in range(12)]
+    ls = [tr._run_batch(i, (x0,), 0, 1, 0, None, None)[0] for i in range(24)]
     assert all(np.isfinite(ls)), ls
-    assert min(ls[-3:]) < 0.7 * ls[0], ls
+    # the timestep (hence the loss scale) is redrawn every step: compare averages
+    assert np.mean(ls[-6:]) < 0.8 * np.mean(ls[:6]), ls
