@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint32, c_void
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmdm_sm100.so")
+LIB_PATH = os.environ.get("MDM_LIB_PATH") or os.path.join(_HERE, "libmdm_sm100.so")   # override: A/B builds of the kernels
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "mdm.h"))
 
 MDM_F32, MDM_BF16 = 0, 1

@@ -26,23 +26,31 @@
 //   reduce: fp32 TMA reduce-add into global memory -- wgrad (split over pixels) and split-K partials of
 //           small-M fprop/dgrad layers (finished by splitk_finalize_kernel).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace mdm {
 
 constexpr int TILE_M = 128, TILE_N = 128, TILE_K = 64;
-constexpr int STAGES = 4;
-constexpr int A_BYTES = TILE_M * TILE_K * 2;   // 16 KB
+constexpr int A_BYTES = TILE_M * TILE_K * 2;   // 16 KB: one [128 pixel x 64 channel] operand tile
 constexpr int B_BYTES = TILE_N * TILE_K * 2;   // 16 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+// halo mode (3x3 stride-1 fprop / dgrad on maps >= 16 x 8): the M tile is an 8 (w) x 16 (h) pixel patch and
+// the A ring holds its zero-padded (16 w x 18 h) x 64 channel input halo, loaded ONCE per channel chunk;
+// the nine taps are nine shifted views of it (UMMA descriptor start offsets), a 4x cut of the A traffic.
+constexpr int HALO_W = 16, HALO_H = 18, PATCH_W = 8, PATCH_H = 16;
+constexpr int HALO_BYTES = HALO_W * HALO_H * 128;   // 36 KB
+constexpr int MAX_A_SLOTS = 4, MAX_B_SLOTS = 6;
 constexpr int EPI_BYTES = 32768;               // one staging tile: 128 x 128 bf16, or 2 boxes of 128 x 32 fp32
-constexpr int IGEMM_THREADS = 192;
-constexpr int SMEM_EPI_OFF = STAGES * STAGE_BYTES;
+constexpr int IGEMM_THREADS = 224;
+constexpr int RING_BYTES = 2 * HALO_BYTES + 5 * B_BYTES;    // halo: 2 A + 5 B slots; plain: 4 A + 4 B slots (128 KB)
+constexpr int SMEM_EPI_OFF = RING_BYTES;
 constexpr int SMEM_BIAS_OFF = SMEM_EPI_OFF + 2 * EPI_BYTES;   // 128 floats
 constexpr int SMEM_BAR_OFF = SMEM_BIAS_OFF + 512;
 constexpr int IGEMM_SMEM = SMEM_BAR_OFF + 256 + 1024 /*alignment slack*/;
 constexpr int TMEM_COLS = 256;                 // two 128-column fp32 accumulators
+static_assert(4 * A_BYTES + 4 * B_BYTES <= RING_BYTES, "plain ring must fit");
+static_assert(IGEMM_SMEM <= 232448, "shared memory budget");
 
 // ---- raw PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,6 +152,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 }
 // K-major tile [rows][64 bf16]: 8-row groups 1024 B apart; k-th 16-element slice = +32 B
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t base, int k) { return smem_desc(base + k * 32, 16, 1024); }
+// K-major view into the halo: 8-pixel row groups one halo row (16 pixels = 2048 B) apart, start shifted by whole
+// pixels (128 B).  The 128B swizzle is a function of the absolute shared-memory address bits (measured on
+// B200: the shifted views read back exactly what TMA wrote with base_offset = 0), so a shifted start needs
+// nothing but the new address.
+__device__ __forceinline__ uint64_t desc_halo(uint32_t addr) { return smem_desc(addr, 16, HALO_W * 128); }
 // MN-major tile: 64-wide MN atoms 8 KB apart (LBO), 8 K-rows per 1024 B group (SBO); k-th slice = +2 groups
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t base, int k) { return smem_desc(base + k * 2048, 8192, 1024); }
 
@@ -156,6 +169,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int a_mn, int b_mn) {
 struct IgemmArgs {
   int mode;   // 0: activation GEMM (fprop / dgrad), 1: wgrad
   int epi;    // 0: bf16 TMA store (+bias/rowvec/C tile), 1: fp32 TMA reduce-add
+  int halo;   // mode 0 only: A = input halo per channel chunk, taps = shifted views; M tile = 8 x 16 patch
+  int pw, ph, pn;       // wgrad: geometry of the 64-pixel K box
   int nseg;
   int seg_taps[2];
   int seg_kc[2];
@@ -208,6 +223,57 @@ __device__ __forceinline__ Work decode_work(const IgemmArgs& a, int w) {
   return k;
 }
 
+// pixel coordinates of an M tile: plain = 128 consecutive pixels of the flattened (n, h, w) raster;
+// halo = an 8 (w) x 16 (h) patch of one image
+__device__ __forceinline__ void tile_origin(const IgemmArgs& a, bool halo, int m_tile, int& w0, int& h0, int& n0) {
+  if (halo) {
+    const int tw = a.W / PATCH_W, th = a.H / PATCH_H;
+    w0 = (m_tile % tw) * PATCH_W;
+    h0 = ((m_tile / tw) % th) * PATCH_H;
+    n0 = m_tile / (tw * th);
+  } else {
+    const int p0 = m_tile * TILE_M;
+    w0 = p0 % a.W;
+    h0 = (p0 / a.W) % a.H;
+    n0 = p0 / (a.W * a.H);
+  }
+}
+
+// walks the (segment, tap, k-chunk) iteration space of an activation GEMM without integer division in the
+// steady state.  plain order: tap-major, k-chunk-minor; halo order (segment 0): k-chunk-major, tap-minor.
+template <bool kHalo>
+struct IterWalker {
+  int seg, tap, kc;
+  __device__ __forceinline__ void init(const IgemmArgs& a, int it) {
+    const int seg0_total = a.seg_taps[0] * a.seg_kc[0];
+    seg = it >= seg0_total ? 1 : 0;
+    if (seg) it -= seg0_total;
+    if (kHalo && seg == 0) { kc = it / a.seg_taps[0]; tap = it - kc * a.seg_taps[0]; }
+    else { tap = it / a.seg_kc[seg]; kc = it - tap * a.seg_kc[seg]; }
+  }
+  __device__ __forceinline__ bool halo_it() const { return kHalo && seg == 0; }
+  __device__ __forceinline__ void next(const IgemmArgs& a) {
+    if (kHalo && seg == 0) {
+      if (++tap == a.seg_taps[0]) { tap = 0; if (++kc == a.seg_kc[0]) { seg = 1; kc = 0; } }
+    } else {
+      if (++kc == a.seg_kc[seg]) { kc = 0; if (++tap == a.seg_taps[seg] && seg == 0) { seg = 1; tap = 0; } }
+    }
+  }
+};
+
+// descriptor words.  hi: SBO | version (bit 46) | SWIZZLE_128B (bits 61..63); lo: start address | LBO
+constexpr uint32_t DESC_HI_SBO1024 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t DESC_HI_HALO = ((uint32_t)(HALO_W * 128) >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t DESC_LO_KMAJOR = (16u >> 4) << 16;     // LBO (unused for swizzled K-major)
+constexpr uint32_t DESC_LO_MNMAJOR = (8192u >> 4) << 16;  // LBO = distance between the two 64-wide MN atoms
+__device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
+// kMode 0: activation GEMM (fprop / dgrad), 1: wgrad.  kHalo: see HALO_* above.  Template parameters keep the
+// single-thread producer / MMA-issue loops minimal: those loops pace the tensor pipe (4 MMAs = 256 cycles per
+// iteration), every extra instruction in them showed up 1:1 in the measured throughput.
+// Warp roles: 0 = TMA producer of the A operand, 6 = TMA producer of the B operand, 1 = MMA issuer (+TMEM
+// allocator), 2..5 = epilogue.
+template <int kMode, bool kHalo>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
              const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
@@ -215,20 +281,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
              const __grid_constant__ IgemmArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int kASlots = kHalo ? 2 : 0;
+  constexpr int kBSlots = kHalo ? 5 : 4;
+  constexpr int kBSlotBytes = kHalo ? B_BYTES : A_BYTES + B_BYTES;   // plain stage = [B tile][A tile]
+  uint8_t* a_ring = smem;                                   // halo slots (halo mode only)
+  uint8_t* b_ring = smem + kASlots * HALO_BYTES;
   float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS_OFF);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFF);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint64_t* c_full_bar = tmem_empty_bar + 2;      // [2]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFF);
+  uint64_t* a_empty = a_full + MAX_A_SLOTS;
+  uint64_t* b_full = a_empty + MAX_A_SLOTS;
+  uint64_t* b_empty = b_full + MAX_B_SLOTS;
+  uint64_t* tmem_full_bar = b_empty + MAX_B_SLOTS;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint64_t* c_full_bar = tmem_empty_bar + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_full_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < MAX_A_SLOTS; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < MAX_B_SLOTS; ++s) {
+      mbar_init(&b_full[s], kHalo ? 1 : 2);   // plain stage: the A and the B producer both arrive
+      mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
@@ -251,89 +328,170 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const int w_first = blockIdx.x, w_step = gridDim.x;
 
   if (warp == 0 && lane == 0) {
-    // ============================== TMA producer ==============================================
-    int g = 0;   // stage counter across work items
+    // ============================== TMA producer: A operand ==================================
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
     for (int w = w_first; w < args.num_work; w += w_step) {
       const Work k = decode_work(args, w);
-      if (args.mode == 0) {
-        const int p0 = k.m_tile * TILE_M;
-        const int w0 = p0 % args.W, h0 = (p0 / args.W) % args.H, n0 = p0 / (args.W * args.H);
-        const int ncol0 = k.n_tile * TILE_N;
-        const int seg0_total = args.seg_taps[0] * args.seg_kc[0];
-        for (int i = 0; i < k.nit; ++i, ++g) {
-          int it = k.it0 + i;
-          const int seg = it >= seg0_total ? 1 : 0;
-          if (seg) it -= seg0_total;
-          const int tap = it / args.seg_kc[seg], kc = it % args.seg_kc[seg];
-          const CUtensorMap* mA = seg == 0 ? &mapA0 : &mapA1;
-          const CUtensorMap* mB = seg == 0 ? &mapB0 : &mapB1;
-          const int st = args.a_stride[seg];
-          const int dh = args.tap_dh[seg][tap], dw = args.tap_dw[seg][tap], tb = args.tap_b[seg][tap];
-          const int s = g % STAGES;
-          const uint32_t ph = (g / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* a_dst = smem + s * STAGE_BYTES;
-          uint8_t* b_dst = a_dst + A_BYTES;
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-          tma_load_4d(mA, a_dst, &full_bar[s], kc * TILE_K, w0 * st + dw, h0 * st + dh, n0);
-          if (!args.b_mn_major) {
-            tma_load_3d(mB, b_dst, &full_bar[s], kc * TILE_K, tb, ncol0);
+      if (kMode == 0) {
+        int w0, h0, n0;
+        tile_origin(args, kHalo, k.m_tile, w0, h0, n0);
+        IterWalker<kHalo> it;
+        it.init(args, k.it0);
+        for (int i = 0; i < k.nit; ++i) {
+          if (kHalo) {
+            if (it.halo_it()) {
+              if (it.tap == 0) {   // one halo per channel chunk
+                mbar_wait(&a_empty[sa], pa ^ 1);
+                mbar_expect_tx(&a_full[sa], HALO_BYTES);
+                tma_load_4d(&mapA0, a_ring + sa * HALO_BYTES, &a_full[sa], it.kc * TILE_K, w0 - 1, h0 - 1, n0);
+                if (++sa == kASlots) { sa = 0; pa ^= 1; }
+              }
+            } else {               // fused 1x1 shortcut segment: a plain patch in a halo slot
+              mbar_wait(&a_empty[sa], pa ^ 1);
+              mbar_expect_tx(&a_full[sa], A_BYTES);
+              tma_load_4d(&mapA1, a_ring + sa * HALO_BYTES, &a_full[sa], it.kc * TILE_K, w0, h0, n0);
+              if (++sa == kASlots) { sa = 0; pa ^= 1; }
+            }
           } else {
-            tma_load_3d(mB, b_dst, &full_bar[s], ncol0, tb, kc * TILE_K);
-            tma_load_3d(mB, b_dst + 8192, &full_bar[s], ncol0 + 64, tb, kc * TILE_K);
+            const CUtensorMap* mA = it.seg == 0 ? &mapA0 : &mapA1;
+            const int st = args.a_stride[it.seg];
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_expect_tx(&b_full[sb], A_BYTES);
+            tma_load_4d(mA, b_ring + sb * kBSlotBytes + B_BYTES, &b_full[sb], it.kc * TILE_K,
+                        w0 * st + args.tap_dw[it.seg][it.tap], h0 * st + args.tap_dh[it.seg][it.tap], n0);
+            if (++sb == kBSlots) { sb = 0; pb ^= 1; }
           }
+          it.next(args);
         }
       } else {
-        // wgrad: A = dY (MN-major, M = co), B = X shifted by the tap (MN-major, N = ci)
-        const int co0 = k.m_tile * TILE_M, ci0 = k.n_tile * TILE_N;
+        // wgrad: A = dY (MN-major, M = co); 64 pixels (pw x ph x pn box) per iteration
+        const int co0 = k.m_tile * TILE_M;
+        const int hw = args.W * args.H;
+        const int p0 = k.it0 * TILE_K;
+        int n0 = p0 / hw;
+        const int rem = p0 - n0 * hw;
+        int h0 = rem / args.W, w0 = rem - h0 * args.W;
+        for (int i = 0; i < k.nit; ++i) {
+          mbar_wait(&b_empty[sb], pb ^ 1);
+          uint8_t* a_dst = b_ring + sb * kBSlotBytes + B_BYTES;
+          mbar_expect_tx(&b_full[sb], A_BYTES);
+          tma_load_4d(&mapA0, a_dst, &b_full[sb], co0, w0, h0, n0);
+          tma_load_4d(&mapA0, a_dst + 8192, &b_full[sb], co0 + 64, w0, h0, n0);
+          if (++sb == kBSlots) { sb = 0; pb ^= 1; }
+          w0 += args.pw;
+          if (w0 >= args.W) { w0 = 0; h0 += args.ph; if (h0 >= args.H) { h0 = 0; n0 += args.pn; } }
+        }
+      }
+    }
+  } else if (warp == 6 && lane == 0) {
+    // ============================== TMA producer: B operand ==================================
+    int sb = 0;
+    uint32_t pb = 0;
+    for (int w = w_first; w < args.num_work; w += w_step) {
+      const Work k = decode_work(args, w);
+      if (kMode == 0) {
+        const int ncol0 = k.n_tile * TILE_N;
+        IterWalker<kHalo> it;
+        it.init(args, k.it0);
+        for (int i = 0; i < k.nit; ++i) {
+          const CUtensorMap* mB = it.seg == 0 ? &mapB0 : &mapB1;
+          const int tb = args.tap_b[it.seg][it.tap];
+          mbar_wait(&b_empty[sb], pb ^ 1);
+          uint8_t* b_dst = b_ring + sb * kBSlotBytes;
+          mbar_expect_tx(&b_full[sb], B_BYTES);
+          if (!args.b_mn_major) {
+            tma_load_3d(mB, b_dst, &b_full[sb], it.kc * TILE_K, tb, ncol0);
+          } else {
+            tma_load_3d(mB, b_dst, &b_full[sb], ncol0, tb, it.kc * TILE_K);
+            tma_load_3d(mB, b_dst + 8192, &b_full[sb], ncol0 + 64, tb, it.kc * TILE_K);
+          }
+          if (++sb == kBSlots) { sb = 0; pb ^= 1; }
+          it.next(args);
+        }
+      } else {
+        // wgrad: B = X shifted by the tap (MN-major, N = ci)
+        const int ci0 = k.n_tile * TILE_N;
         const int dh = args.tap_dh[0][k.tap], dw = args.tap_dw[0][k.tap];
         const int st = args.a_stride[0];
-        for (int i = 0; i < k.nit; ++i, ++g) {
-          const int s = g % STAGES;
-          const uint32_t ph = (g / STAGES) & 1;
-          const int p0 = (k.it0 + i) * TILE_K;  // 64 pixels of dY
-          const int w0 = p0 % args.W, h0 = (p0 / args.W) % args.H, n0 = p0 / (args.W * args.H);
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* a_dst = smem + s * STAGE_BYTES;
-          uint8_t* b_dst = a_dst + A_BYTES;
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-          tma_load_4d(&mapA0, a_dst, &full_bar[s], co0, w0, h0, n0);
-          tma_load_4d(&mapA0, a_dst + 8192, &full_bar[s], co0 + 64, w0, h0, n0);
-          tma_load_4d(&mapB0, b_dst, &full_bar[s], ci0, w0 * st + dw, h0 * st + dh, n0);
-          tma_load_4d(&mapB0, b_dst + 8192, &full_bar[s], ci0 + 64, w0 * st + dw, h0 * st + dh, n0);
+        const int hw = args.W * args.H;
+        const int p0 = k.it0 * TILE_K;
+        int n0 = p0 / hw;
+        const int rem = p0 - n0 * hw;
+        int h0 = rem / args.W, w0 = rem - h0 * args.W;
+        for (int i = 0; i < k.nit; ++i) {
+          mbar_wait(&b_empty[sb], pb ^ 1);
+          uint8_t* b_dst = b_ring + sb * kBSlotBytes;
+          mbar_expect_tx(&b_full[sb], B_BYTES);
+          tma_load_4d(&mapB0, b_dst, &b_full[sb], ci0, w0 * st + dw, h0 * st + dh, n0);
+          tma_load_4d(&mapB0, b_dst + 8192, &b_full[sb], ci0 + 64, w0 * st + dw, h0 * st + dh, n0);
+          if (++sb == kBSlots) { sb = 0; pb ^= 1; }
+          w0 += args.pw;
+          if (w0 >= args.W) { w0 = 0; h0 += args.ph; if (h0 >= args.H) { h0 = 0; n0 += args.pn; } }
         }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ============================== MMA issuer ================================================
-    const int a_mn = args.mode == 1 ? 1 : 0;
-    const int b_mn = args.mode == 1 ? 1 : args.b_mn_major;
+    const int a_mn = kMode == 1 ? 1 : 0;
+    const int b_mn = kMode == 1 ? 1 : args.b_mn_major;
     const uint32_t idesc = make_idesc(a_mn, b_mn);
-    int g = 0, local = 0;
+    // descriptor low words of slot 0 and the per-16-element K step of each operand
+    const uint32_t lo_b0 = ((smem_u32(b_ring) >> 4) & 0x3FFF) | (b_mn ? DESC_LO_MNMAJOR : DESC_LO_KMAJOR);
+    const uint32_t lo_a0 = lo_b0 + (B_BYTES >> 4);   // plain stage: A tile behind the B tile (same LBO class in mode 1 / 0)
+    const uint32_t lo_a_plain0 = (kMode == 1 || !b_mn) ? lo_a0 : (((smem_u32(b_ring) + B_BYTES) >> 4) & 0x3FFF) | DESC_LO_KMAJOR;
+    const uint32_t kstep_a = a_mn ? (2048u >> 4) : (32u >> 4);
+    const uint32_t kstep_b = b_mn ? (2048u >> 4) : (32u >> 4);
+    const uint32_t lo_halo0 = ((smem_u32(a_ring) >> 4) & 0x3FFF) | DESC_LO_KMAJOR;
+    int sa = 0, sb = 0, local = 0;
+    uint32_t pa = 0, pb = 0;
     for (int w = w_first; w < args.num_work; w += w_step, ++local) {
       const Work k = decode_work(args, w);
       const int acc = local & 1;
       mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * TILE_N;
-      for (int i = 0; i < k.nit; ++i, ++g) {
-        const int s = g % STAGES;
-        const uint32_t ph = (g / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t lo_a = 0;
+      int sa_cur = 0, tap = 0;
+      const int n_halo = kHalo ? args.seg_taps[0] * args.seg_kc[0] : 0;   // halo iterations come first (no K split)
+      bool ready = mbar_try_wait(&b_full[sb], pb);
+      for (int i = 0; i < k.nit; ++i) {
+        const bool halo_it = kHalo && i < n_halo;
+        if (kHalo && (!halo_it || tap == 0)) {      // this iteration starts on a fresh A-ring slot
+          sa_cur = sa;
+          mbar_wait(&a_full[sa], pa);
+          lo_a = lo_halo0 + sa * (HALO_BYTES >> 4);
+          if (++sa == kASlots) { sa = 0; pa ^= 1; }
+        }
+        if (!ready) mbar_wait(&b_full[sb], pb);
         tcgen05_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_base = a_base + A_BYTES;
+        const uint32_t lo_b = lo_b0 + sb * (kBSlotBytes >> 4);
+        uint32_t lo_at;
+        if (kHalo) {
+          lo_at = lo_a;
+          if (halo_it) lo_at += (uint32_t)(((args.tap_dh[0][tap] + 1) * HALO_W + (args.tap_dw[0][tap] + 1)) * (128 >> 4));
+        } else {
+          lo_at = lo_a_plain0 + sb * (kBSlotBytes >> 4);
+        }
+        const uint32_t hi_a = halo_it ? DESC_HI_HALO : DESC_HI_SBO1024;
+        // look at the next stage's barrier now: its latency hides behind the MMA issue below
+        const int sb_cur = sb;
+        if (++sb == kBSlots) { sb = 0; pb ^= 1; }
+        ready = (i + 1 < k.nit) ? mbar_try_wait(&b_full[sb], pb) : false;
 #pragma unroll
         for (int kk = 0; kk < TILE_K / 16; ++kk) {
-          const uint64_t da = a_mn ? desc_mnmajor(a_base, kk) : desc_kmajor(a_base, kk);
-          const uint64_t db = b_mn ? desc_mnmajor(b_base, kk) : desc_kmajor(b_base, kk);
-          umma_bf16(tmem_d, da, db, idesc, (i | kk) != 0 ? 1u : 0u);
+          umma_bf16(tmem_d, make_desc(hi_a, lo_at + kk * kstep_a), make_desc(DESC_HI_SBO1024, lo_b + kk * kstep_b), idesc,
+                    (i | kk) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&b_empty[sb_cur]);
+        if (kHalo) {
+          if (!halo_it || tap == args.seg_taps[0] - 1) umma_commit(&a_empty[sa_cur]);
+          if (halo_it && ++tap == args.seg_taps[0]) tap = 0;
+        }
       }
       umma_commit(&tmem_full_bar[acc]);
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp <= 5) {
     // ============================== epilogue ==================================================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;          // row of the 128 x 128 tile held by this thread
@@ -342,12 +500,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     uint8_t* stg_base = smem + SMEM_EPI_OFF;
     uint32_t v[32];
     int local = 0;
-    if (args.has_c && et == 0 && w_first < args.num_work) {   // C tile of the first work item
-      const Work k = decode_work(args, w_first);
-      mbar_expect_tx(&c_full_bar[0], EPI_BYTES);
-      tma_load_2d(&mapC, stg_base, &c_full_bar[0], k.n_tile * TILE_N, k.m_tile * TILE_M);
-      tma_load_2d(&mapC, stg_base + 16384, &c_full_bar[0], k.n_tile * TILE_N + 64, k.m_tile * TILE_M);
-    }
+    // C / D tiles: plain = 2-D [pixel][channel] boxes {64, 128}; halo = 4-D NHWC boxes {64, 8, 16, 1}
+    auto load_c = [&](const Work& kk, int buf) {
+      uint8_t* so = stg_base + buf * EPI_BYTES;
+      mbar_expect_tx(&c_full_bar[buf], EPI_BYTES);
+      if (kHalo) {
+        int w0, h0, n0;
+        tile_origin(args, kHalo, kk.m_tile, w0, h0, n0);
+        tma_load_4d(&mapC, so, &c_full_bar[buf], kk.n_tile * TILE_N, w0, h0, n0);
+        tma_load_4d(&mapC, so + 16384, &c_full_bar[buf], kk.n_tile * TILE_N + 64, w0, h0, n0);
+      } else {
+        tma_load_2d(&mapC, so, &c_full_bar[buf], kk.n_tile * TILE_N, kk.m_tile * TILE_M);
+        tma_load_2d(&mapC, so + 16384, &c_full_bar[buf], kk.n_tile * TILE_N + 64, kk.m_tile * TILE_M);
+      }
+    };
+    if (args.has_c && et == 0 && w_first < args.num_work) load_c(decode_work(args, w_first), 0);
     for (int w = w_first; w < args.num_work; w += w_step, ++local) {
       const Work k = decode_work(args, w);
       const int acc = local & 1;
@@ -356,7 +523,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         const int buf = local & 1;
         uint8_t* stg = stg_base + buf * EPI_BYTES;
         const int ncol0 = k.n_tile * TILE_N;
-        const long long p = (long long)k.m_tile * TILE_M + row;
+        int w0, h0, n0;
+        tile_origin(args, kHalo, k.m_tile, w0, h0, n0);
+        long long p;       // flattened pixel of this thread's row
+        if (kHalo) p = ((long long)n0 * args.H + h0 + (row >> 3)) * args.W + w0 + (row & 7);
+        else p = (long long)k.m_tile * TILE_M + row;
         const bool valid = p < args.M_total;
         bias_s[et] = (args.bias ? __ldg(args.bias + ncol0 + et) : 0.f) + (args.bias2 ? __ldg(args.bias2 + ncol0 + et) : 0.f);
         const float* rv = (args.rowvec && valid) ? args.rowvec + (p / args.rows_per_vec) * args.ld_rowvec + ncol0 : nullptr;
@@ -423,18 +594,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
         epi_bar_sync();
         if (et == 0 && args.store_bf16) {
-          tma_store_2d(&mapD, stg, ncol0, k.m_tile * TILE_M);
-          tma_store_2d(&mapD, stg + 16384, ncol0 + 64, k.m_tile * TILE_M);
+          if (kHalo) {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"((uint64_t)&mapD), "r"(smem_u32(stg)), "r"(ncol0), "r"(w0), "r"(h0), "r"(n0) : "memory");
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"((uint64_t)&mapD), "r"(smem_u32(stg + 16384)), "r"(ncol0 + 64), "r"(w0), "r"(h0), "r"(n0) : "memory");
+          } else {
+            tma_store_2d(&mapD, stg, ncol0, k.m_tile * TILE_M);
+            tma_store_2d(&mapD, stg + 16384, ncol0 + 64, k.m_tile * TILE_M);
+          }
           bulk_commit();
           bulk_wait_read<1>();   // every store but the one just issued has read its smem: the OTHER tile is free
           const int wn = w + w_step;
-          if (args.has_c && wn < args.num_work) {
-            const Work kn = decode_work(args, wn);
-            uint8_t* so = stg_base + (buf ^ 1) * EPI_BYTES;
-            mbar_expect_tx(&c_full_bar[buf ^ 1], EPI_BYTES);
-            tma_load_2d(&mapC, so, &c_full_bar[buf ^ 1], kn.n_tile * TILE_N, kn.m_tile * TILE_M);
-            tma_load_2d(&mapC, so + 16384, &c_full_bar[buf ^ 1], kn.n_tile * TILE_N + 64, kn.m_tile * TILE_M);
-          }
+          if (args.has_c && wn < args.num_work) load_c(decode_work(args, wn), buf ^ 1);
         }
       } else {
         // fp32 reduce-add: 4 chunks of 32 columns -> 4 boxes {32 fp32, 128 rows} (2 per staging tile)
@@ -604,7 +776,9 @@ static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 static int ensure_smem_attr() {
   static bool done = false;
   if (!done) {
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     done = true;
   }
   return MDM_OK;
@@ -630,24 +804,56 @@ static void fill_taps(IgemmArgs& a, int seg, int ksize, bool flip, int H, int W,
   a.seg_taps[seg] = n;
 }
 
+
+static int env_flag(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CUtensorMap& mA1, const CUtensorMap& mB1,
-                        const CUtensorMap& mC, const CUtensorMap& mD, const IgemmArgs& a, void* stream) {
+                        const CUtensorMap& mC, const CUtensorMap& mD, IgemmArgs& a, void* stream) {
   const int grid = a.num_work < kNumSMs ? a.num_work : kNumSMs;
-  igemm_kernel<<<grid, IGEMM_THREADS, IGEMM_SMEM, as_stream(stream)>>>(mA0, mB0, mA1, mB1, mC, mD, a);
+  cudaStream_t st = as_stream(stream);
+  if (a.mode == 1) igemm_kernel<1, false><<<grid, IGEMM_THREADS, IGEMM_SMEM, st>>>(mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.halo) igemm_kernel<0, true><<<grid, IGEMM_THREADS, IGEMM_SMEM, st>>>(mA0, mB0, mA1, mB1, mC, mD, a);
+  else igemm_kernel<0, false><<<grid, IGEMM_THREADS, IGEMM_SMEM, st>>>(mA0, mB0, mA1, mB1, mC, mD, a);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
 
-// fprop / dgrad share this: choose a K split for small grids, launch, finish split-K partials
-static int run_activation_gemm(IgemmArgs& a, const CUtensorMap& mA0, const CUtensorMap& mB0, const CUtensorMap& mA1,
-                               const CUtensorMap& mB1, const mdm_conv_args* c, void* out, long long ld_out, void* stream) {
-  const int num_m = (a.M_total + TILE_M - 1) / TILE_M;
+// can this layer run in halo mode?  3x3, stride 1, map at least 16 (h) x 8 (w), bf16 output only
+static bool halo_ok(const mdm_conv_args* c, const void* out) {
+  static const int enabled = env_flag("MDM_IGEMM_HALO", 0);   // measured: plain stages are faster until the halo pipeline gets a 3rd slot
+  return enabled && c->ksize == 3 && c->stride == 1 && c->H % PATCH_H == 0 && c->W % PATCH_W == 0 && out != nullptr &&
+         c->y_f32 == nullptr;
+}
+
+// fprop / dgrad share this: build the operand / epilogue maps, choose a K split for small grids, launch,
+// finish split-K partials.  act = the A-side activation (x for fprop, dy for dgrad) with `act_c` channels.
+static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void* act, long long ld_act, int act_c,
+                               int act_stride, const CUtensorMap& mB0, const CUtensorMap* mB1, void* out, long long ld_out,
+                               void* stream) {
+  int rc;
+  CUtensorMap mA0, mA1, mC, mD;
+  a.halo = halo_ok(c, out) ? 1 : 0;
+  int bw, bh, bn;
+  if (a.halo) { bw = PATCH_W; bh = PATCH_H; bn = 1; }
+  else pixel_box(128, c->H, c->W, &bw, &bh, &bn);
+  if (a.halo) rc = make_act_map(&mA0, act, ld_act, act_c, c->W, c->H, c->N, HALO_W, HALO_H, 1, 1);
+  else rc = make_act_map(&mA0, act, ld_act, act_c, c->W * act_stride, c->H * act_stride, c->N, bw, bh, bn, act_stride);
+  if (rc) return rc;
+  mA1 = mA0;
+  if (mB1) {   // fused 1x1 shortcut segment: plain tiles (a patch in halo mode)
+    rc = make_act_map(&mA1, c->x2, c->ld_x2, c->cin2, c->W, c->H, c->N, bw, bh, bn, 1);
+    if (rc) return rc;
+  }
+  const int num_m = a.halo ? c->N * (c->H / PATCH_H) * (c->W / PATCH_W) : (a.M_total + TILE_M - 1) / TILE_M;
   a.num_n = a.N_total / TILE_N;
   const int tiles = num_m * a.num_n;
   a.iters_total = a.seg_taps[0] * a.seg_kc[0] + (a.nseg > 1 ? a.seg_taps[1] * a.seg_kc[1] : 0);
   int splits = 1;
   const long long ws_need = (long long)a.M_total * a.N_total;
-  if (c->splitk_ws && c->splitk_ws_floats >= ws_need && tiles * 2 <= kNumSMs && a.iters_total >= 8) {
+  if (!a.halo && c->splitk_ws && c->splitk_ws_floats >= ws_need && tiles * 2 <= kNumSMs && a.iters_total >= 8) {
     splits = kNumSMs / tiles;
     if (splits > a.iters_total / 4) splits = a.iters_total / 4;
     if (splits < 1) splits = 1;
@@ -657,23 +863,24 @@ static int run_activation_gemm(IgemmArgs& a, const CUtensorMap& mA0, const CUten
   a.num_work = tiles * a.splits;
   const void* c_ptr = c->accumulate ? out : c->resid;
   const long long c_ld = c->accumulate ? ld_out : c->ld_resid;
-  CUtensorMap mC, mD;
-  int rc;
+  const CUtensorMap& mB1r = mB1 ? *mB1 : mB0;
   if (a.splits == 1) {
     a.epi = 0;
     a.store_bf16 = out != nullptr ? 1 : 0;
     a.has_c = (c_ptr != nullptr && out != nullptr) ? 1 : 0;
     mD = mA0;   // placeholder when nothing is TMA-stored (fp32-only output of the tiny Linear layers)
     if (out) {
-      rc = make_tile_map(&mD, out, false, a.N_total, a.M_total, ld_out);
+      if (a.halo) rc = make_act_map(&mD, out, ld_out, a.N_total, c->W, c->H, c->N, PATCH_W, PATCH_H, 1, 1);
+      else rc = make_tile_map(&mD, out, false, a.N_total, a.M_total, ld_out);
       if (rc) return rc;
     }
     mC = mD;
     if (a.has_c) {
-      rc = make_tile_map(&mC, c_ptr, false, a.N_total, a.M_total, c_ld);
+      if (a.halo) rc = make_act_map(&mC, c_ptr, c_ld, a.N_total, c->W, c->H, c->N, PATCH_W, PATCH_H, 1, 1);
+      else rc = make_tile_map(&mC, c_ptr, false, a.N_total, a.M_total, c_ld);
       if (rc) return rc;
     }
-    return launch_igemm(mA0, mB0, mA1, mB1, mC, mD, a, stream);
+    return launch_igemm(mA0, mB0, mA1, mB1r, mC, mD, a, stream);
   }
   // split-K: fp32 partials reduce-added into the (zero) workspace, then one elementwise pass
   a.epi = 1;
@@ -681,12 +888,11 @@ static int run_activation_gemm(IgemmArgs& a, const CUtensorMap& mA0, const CUten
   rc = make_tile_map(&mD, c->splitk_ws, true, a.N_total, a.M_total, a.N_total);
   if (rc) return rc;
   mC = mD;
-  const float* bias = a.bias; const float* bias2 = a.bias2; const float* rowvec = a.rowvec;
-  rc = launch_igemm(mA0, mB0, mA1, mB1, mC, mD, a, stream);
+  rc = launch_igemm(mA0, mB0, mA1, mB1r, mC, mD, a, stream);
   if (rc) return rc;
   const long long total4 = ws_need / 4;
   const int blocks = (int)((total4 + 255) / 256 < 4 * kNumSMs ? (total4 + 255) / 256 : 4 * kNumSMs);
-  splitk_finalize_kernel<<<blocks, 256, 0, as_stream(stream)>>>(c->splitk_ws, a.M_total, a.N_total, bias, bias2, rowvec,
+  splitk_finalize_kernel<<<blocks, 256, 0, as_stream(stream)>>>(c->splitk_ws, a.M_total, a.N_total, a.bias, a.bias2, a.rowvec,
                                                                 a.ld_rowvec, a.rows_per_vec, (const __nv_bfloat16*)c_ptr, c_ld,
                                                                 (__nv_bfloat16*)out, ld_out, c->y_f32);
   MDM_LAUNCH_CHECK();
@@ -720,26 +926,19 @@ int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
   a.N_total = c->cout;
   a.bias = c->bias; a.bias2 = c->bias2; a.rowvec = c->rowvec; a.ld_rowvec = c->ld_rowvec; a.rows_per_vec = c->H * c->W;
   a.out_f32 = c->y_f32;
-  int bw, bh, bn;
-  pixel_box(128, c->H, c->W, &bw, &bh, &bn);
-  CUtensorMap mA0, mB0, mA1, mB1;
-  rc = make_act_map(&mA0, c->x, c->ld_x, c->cin, c->W * c->stride, c->H * c->stride, c->N, bw, bh, bn, c->stride);
-  if (rc) return rc;
+  CUtensorMap mB0, mB1;
   rc = make_w_map(&mB0, c->w, c->cin, c->ksize * c->ksize, c->cout, 128);
   if (rc) return rc;
-  mA1 = mA0; mB1 = mB0;
   if (c->x2) {  // fused 1x1 shortcut: extra K segment on a second activation / weight pair
     MDM_CHECK_ARG(c->w2 && c->cin2 % 64 == 0 && c->ld_x2 % 8 == 0, "conv_fprop: bad shortcut segment");
     a.nseg = 2;
     fill_taps(a, 1, 1, false, c->H, c->W, 1);
     a.seg_kc[1] = c->cin2 / 64;
     a.a_stride[1] = 1;
-    rc = make_act_map(&mA1, c->x2, c->ld_x2, c->cin2, c->W, c->H, c->N, bw, bh, bn, 1);
-    if (rc) return rc;
     rc = make_w_map(&mB1, c->w2, c->cin2, 1, c->cout, 128);
     if (rc) return rc;
   }
-  return run_activation_gemm(a, mA0, mB0, mA1, mB1, c, c->y, c->ld_y, stream);
+  return run_activation_gemm(a, c, c->x, c->ld_x, c->cin, c->stride, mB0, c->x2 ? &mB1 : nullptr, c->y, c->ld_y, stream);
 }
 
 // dgrad of a stride-1 conv: dx[pix][ci] (+)= sum_tap sum_co dy[pix - tap][co] * w[co][tap][ci]
@@ -766,16 +965,12 @@ int mdm_conv_dgrad(const mdm_conv_args* c, void* stream) {
   a.N_total = c->cin;
   a.out_f32 = c->y_f32;
   a.rows_per_vec = 1;
-  int bw, bh, bn;
-  pixel_box(128, c->H, c->W, &bw, &bh, &bn);
-  CUtensorMap mA0, mB0;
-  rc = make_act_map(&mA0, c->x, c->ld_x, c->cout, c->W, c->H, c->N, bw, bh, bn, 1);
-  if (rc) return rc;
+  CUtensorMap mB0;
   // weight viewed as [K = co][tap][N = ci] with ci contiguous: box {64 ci, 1, 64 co}
   // w_cols: full row length of the packed weight (>= cin when cin is a slice); w_col0 offsets the slice
   rc = make_w_map(&mB0, (const __nv_bfloat16*)c->w + c->w_col0, c->w_cols ? c->w_cols : c->cin, c->ksize * c->ksize, c->cout, 64);
   if (rc) return rc;
-  return run_activation_gemm(a, mA0, mB0, mA0, mB0, c, c->y, c->ld_y, stream);
+  return run_activation_gemm(a, c, c->x, c->ld_x, c->cout, 1, mB0, nullptr, c->y, c->ld_y, stream);
 }
 
 // wgrad: dw[co][tap][ci] += sum_pix dy[pix][co] * x[pix*stride + tap][ci]   (fp32, TMA reduce-add, split over pixels)
@@ -817,6 +1012,7 @@ int mdm_conv_wgrad(const mdm_conv_args* c, void* stream) {
   a.num_work = tiles * a.splits;
   int pw, ph, pn;
   pixel_box(64, c->H, c->W, &pw, &ph, &pn);
+  a.pw = pw; a.ph = ph; a.pn = pn;
   CUtensorMap mA0, mB0, mD;
   rc = make_act_map(&mA0, c->y, c->ld_y, c->cout, c->W, c->H, c->N, pw, ph, pn, 1);
   if (rc) return rc;
@@ -825,6 +1021,7 @@ int mdm_conv_wgrad(const mdm_conv_args* c, void* stream) {
   const long long row = (long long)c->ksize * c->ksize * a.ci_total;
   rc = make_tile_map(&mD, c->dw, true, row, c->cout, row);
   if (rc) return rc;
+  a.halo = 0;
   return launch_igemm(mA0, mB0, mA0, mB0, mD, mD, a, stream);
 }
 
