@@ -661,35 +661,35 @@ __global__ void splitk_finalize_kernel(float* __restrict__ ws, int M, int N, con
                                        const float* __restrict__ bias2, const float* __restrict__ rowvec, long long ld_rowvec,
                                        int rows_per_vec, const __nv_bfloat16* resid, long long ld_resid,
                                        __nv_bfloat16* out, long long ld_out, float* __restrict__ out_f32) {
-  const int n4 = N / 4;
-  const long long total = (long long)M * n4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / n4;
-    const int c = (int)(i % n4) * 4;
-    float4* wp = reinterpret_cast<float4*>(ws + r * N + c);
-    float4 a = *wp;
-    *wp = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias) { const float4 b = *reinterpret_cast<const float4*>(bias + c); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
-    if (bias2) { const float4 b = *reinterpret_cast<const float4*>(bias2 + c); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
-    if (rowvec) {
-      const float4 b = *reinterpret_cast<const float4*>(rowvec + (r / rows_per_vec) * ld_rowvec + c);
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-    }
-    if (resid) {
-      const uint2 u = *reinterpret_cast<const uint2*>(resid + r * ld_resid + c);
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-      const float2 t0 = __bfloat1622float2(h2[0]), t1 = __bfloat1622float2(h2[1]);
-      a.x += t0.x; a.y += t0.y; a.z += t1.x; a.w += t1.y;
-    }
-    if (out) {
-      uint2 u;
-      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-      h2[0] = __floats2bfloat162_rn(a.x, a.y);
-      h2[1] = __floats2bfloat162_rn(a.z, a.w);
-      *reinterpret_cast<uint2*>(out + r * ld_out + c) = u;
-    }
-    if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * N + c) = a;
+  // one thread per float4 (no loop: parallelism hides the latency), 32-bit index math
+  const uint32_t n4 = (uint32_t)N >> 2;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint32_t)M * n4) return;
+  const uint32_t r = i / n4;
+  const int c = (int)(i - r * n4) * 4;
+  float4* wp = reinterpret_cast<float4*>(ws + (size_t)r * N + c);
+  float4 a = *wp;
+  *wp = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c)); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+  if (bias2) { const float4 b = __ldg(reinterpret_cast<const float4*>(bias2 + c)); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+  if (rowvec) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(rowvec + (size_t)(r / (uint32_t)rows_per_vec) * ld_rowvec + c));
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
   }
+  if (resid) {
+    const uint2 u = *reinterpret_cast<const uint2*>(resid + (size_t)r * ld_resid + c);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const float2 t0 = __bfloat1622float2(h2[0]), t1 = __bfloat1622float2(h2[1]);
+    a.x += t0.x; a.y += t0.y; a.z += t1.x; a.w += t1.y;
+  }
+  if (out) {
+    uint2 u;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+    h2[0] = __floats2bfloat162_rn(a.x, a.y);
+    h2[1] = __floats2bfloat162_rn(a.z, a.w);
+    *reinterpret_cast<uint2*>(out + (size_t)r * ld_out + c) = u;
+  }
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)r * N + c) = a;
 }
 
 // ---- host side: tensor maps ----------------------------------------------------------------------
@@ -891,7 +891,7 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
   rc = launch_igemm(mA0, mB0, mA1, mB1r, mC, mD, a, stream);
   if (rc) return rc;
   const long long total4 = ws_need / 4;
-  const int blocks = (int)((total4 + 255) / 256 < 4 * kNumSMs ? (total4 + 255) / 256 : 4 * kNumSMs);
+  const int blocks = (int)((total4 + 255) / 256);
   splitk_finalize_kernel<<<blocks, 256, 0, as_stream(stream)>>>(c->splitk_ws, a.M_total, a.N_total, a.bias, a.bias2, a.rowvec,
                                                                 a.ld_rowvec, a.rows_per_vec, (const __nv_bfloat16*)c_ptr, c_ld,
                                                                 (__nv_bfloat16*)out, ld_out, c->y_f32);

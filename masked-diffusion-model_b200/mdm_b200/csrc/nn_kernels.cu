@@ -36,12 +36,17 @@ __device__ __forceinline__ float dsiluf_(float z) {
 }
 
 // =============================================================================================
-// K2: GroupNorm (+SiLU) forward / backward.  HBM-bound: every access is a 16-byte (8 x bf16) vector,
-// a thread keeps a FIXED 8-channel slice (its per-channel constants live in registers) and walks
-// pixels with GN_UNROLL independent loads in flight; grid = (pixel chunks, N).
-//   fwd : stats pass (per-chunk partial sums -> ws) + apply pass (the re-read hits the 126 MB L2)
-//   bwd : stats pass (per-channel dgamma/dbeta partials reduced in shared memory, ONE global atomic
-//         per channel per CTA; the two group sums follow from them: sum(d*gamma) = sum_c gamma_c dbeta_c,
+// K2: GroupNorm (+SiLU) forward / backward.  HBM-bound streaming kernels, built the same way:
+//   * a thread owns a FIXED 8-channel slice (16-byte vectors; its per-channel constants live in registers)
+//     and walks the pixels of its CTA's chunk with a pointer increment -- no index arithmetic, no bounds test
+//     in the main loop, UNROLL independent loads in flight per thread per tensor;
+//   * grid = (pixel chunks, N) with ~32K elements per CTA: a few hundred CTAs, long enough to amortise the
+//     per-thread set-up and the block reduction (measured: 8K-element chunks spent > 80 % of their
+//     instructions outside the streaming loop);
+//   * reductions: per-thread partials -> shared memory per CHANNEL (one smem atomic per channel per thread)
+//     -> per group / per channel results; global atomics only once per channel per CTA.
+//   fwd : stats pass (per-chunk group sums -> ws, deterministic) + apply pass (the re-read hits the 126 MB L2)
+//   bwd : stats pass (dgamma/dbeta; the two group sums follow from them: sum(d*gamma) = sum_c gamma_c dbeta_c,
 //         sum(d*gamma*xhat) = sum_c gamma_c dgamma_c) + apply pass, which can also emit the per-sample
 //         column sums of dx (the time-embedding / conv-bias gradients) so no separate reduction runs.
 // =============================================================================================
@@ -54,13 +59,11 @@ struct GnGeom {
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float2 t = __bfloat1622float2(h[e]);
-    f[2 * e] = t.x;
-    f[2 * e + 1] = t.y;
-  }
+  // bf16 -> fp32 is a 16-bit shift: even elements = low halves, odd = high halves
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 u;
@@ -71,60 +74,70 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 __device__ __forceinline__ uint4 ldg16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
-// add the 8 per-channel values of a thread into per-group shared accumulators (slot = 2*group + which)
-__device__ __forceinline__ void group_scatter(float* acc, int which, int c0, int cpg, const float (&v)[8]) {
-  int gcur = c0 / cpg;
-  float run = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int gj = (c0 + j) / cpg;
-    if (gj != gcur) {
-      atomicAdd(&acc[gcur * 2 + which], run);
-      run = 0.f;
-      gcur = gj;
-    }
-    run += v[j];
-  }
-  atomicAdd(&acc[gcur * 2 + which], run);
+// the pixels [p0, p1) of sample n handled by this thread: first pixel p0 + r, then every R-th
+struct GnWalk {
+  long long off;     // element offset of the first pixel's channel slice, for a tensor with pixel stride 1 (x ld)
+  int count;         // pixels this thread handles
+  int lane, r;
+};
+__device__ __forceinline__ GnWalk gn_walk(const GnGeom& g, int n, int chunk) {
+  GnWalk w;
+  w.lane = threadIdx.x % g.L;
+  w.r = threadIdx.x / g.L;
+  const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
+  w.count = (w.r < g.R && p0 + w.r < p1) ? (p1 - p0 - w.r + g.R - 1) / g.R : 0;
+  w.off = (long long)n * g.HW + p0 + w.r;
+  return w;
 }
 
 template <int UNROLL>
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __restrict__ x, long long ld,
                                                               float* __restrict__ ws, GnGeom g) {
-  __shared__ float acc[GN_MAX_GROUPS * 2];
+  extern __shared__ float gn_sm[];   // s[C], q[C]
   const int n = blockIdx.y, chunk = blockIdx.x;
-  if (threadIdx.x < GN_MAX_GROUPS * 2) acc[threadIdx.x] = 0.f;
+  for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) gn_sm[c] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x % g.L, r = threadIdx.x / g.L;
-  if (r < g.R) {
-    const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
-    const bf16* base = x + (long long)n * g.HW * ld + lane * 8;
+  const GnWalk w = gn_walk(g, n, chunk);
+  if (w.count > 0) {
+    const bf16* p = x + w.off * ld + w.lane * 8;
+    const long long step = (long long)g.R * ld;
     float s[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    for (int p = p0 + r; p < p1; p += g.R * UNROLL) {
+    int it = 0;
+    for (; it + UNROLL <= w.count; it += UNROLL) {
       uint4 v[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int pp = p + u * g.R;
-        v[u] = pp < p1 ? ldg16(base + (long long)pp * ld) : make_uint4(0, 0, 0, 0);
-      }
+      for (int u = 0; u < UNROLL; ++u) v[u] = ldg16(p + u * step);
+      p += UNROLL * step;
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         float f[8];
         unpack8(v[u], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s[j] += f[j];
-          q[j] = fmaf(f[j], f[j], q[j]);
-        }
+        for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
       }
     }
-    group_scatter(acc, 0, lane * 8, g.cpg, s);
-    group_scatter(acc, 1, lane * 8, g.cpg, q);
+    for (; it < w.count; ++it, p += step) {
+      float f[8];
+      unpack8(ldg16(p), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&gn_sm[w.lane * 8 + j], s[j]);
+      atomicAdd(&gn_sm[g.C + w.lane * 8 + j], q[j]);
+    }
   }
   __syncthreads();
-  if (threadIdx.x < g.G * 2) ws[((long long)(n * g.nchunk + chunk)) * GN_MAX_GROUPS * 2 + threadIdx.x] = acc[threadIdx.x];
+  if (threadIdx.x < g.G) {
+    float a = 0.f, b = 0.f;
+    for (int c = threadIdx.x * g.cpg; c < (threadIdx.x + 1) * g.cpg; ++c) { a += gn_sm[c]; b += gn_sm[g.C + c]; }
+    float* o = ws + ((long long)(n * g.nchunk + chunk)) * GN_MAX_GROUPS * 2 + threadIdx.x * 2;
+    o[0] = a;
+    o[1] = b;
+  }
 }
 
 template <int UNROLL>
@@ -154,9 +167,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
     }
   }
   __syncthreads();
-  const int lane = threadIdx.x % g.L, r = threadIdx.x / g.L;
-  if (r >= g.R) return;
-  const int c0 = lane * 8;
+  const GnWalk w = gn_walk(g, n, chunk);
+  if (w.count == 0) return;
+  const int c0 = w.lane * 8;
   float sc[8], sh[8];   // y = x * sc + sh
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -166,31 +179,38 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
     sc[j] = rstd * ga;
     sh[j] = be - mean * rstd * ga;
   }
-  const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
-  const bf16* xb = x + (long long)n * g.HW * ld + c0;
-  bf16* yb = y + (long long)n * g.HW * ldy + c0;
-  for (int p = p0 + r; p < p1; p += g.R * UNROLL) {
+  const bf16* p = x + w.off * ld + c0;
+  bf16* o = y + w.off * ldy + c0;
+  const long long step = (long long)g.R * ld, ostep = (long long)g.R * ldy;
+  auto body = [&](const uint4& v, bf16* dst) {
+    float f[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z = fmaf(f[j], sc[j], sh[j]);
+      if (silu) z = __fdividef(z, 1.0f + __expf(-z));
+      f[j] = z;
+    }
+    *reinterpret_cast<uint4*>(dst) = pack8(f);
+  };
+  int it = 0;
+  for (; it + UNROLL <= w.count; it += UNROLL) {
     uint4 v[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int pp = p + u * g.R;
-      if (pp < p1) v[u] = ldg16(xb + (long long)pp * ld);
-    }
+    for (int u = 0; u < UNROLL; ++u) v[u] = ldg16(p + u * step);
+    p += UNROLL * step;
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int pp = p + u * g.R;
-      if (pp >= p1) break;
-      float f[8];
-      unpack8(v[u], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float z = fmaf(f[j], sc[j], sh[j]);
-        if (silu) z = siluf_(z);
-        f[j] = z;
-      }
-      *reinterpret_cast<uint4*>(yb + (long long)pp * ldy) = pack8(f);
-    }
+    for (int u = 0; u < UNROLL; ++u) body(v[u], o + u * ostep);
+    o += UNROLL * ostep;
   }
+  for (; it < w.count; ++it, p += step, o += ostep) body(ldg16(p), o);
+}
+
+// d(silu(z))/dz with one exp and one fast division
+__device__ __forceinline__ float dsilu_fast(float z) {
+  const float e = __expf(-z);
+  const float s = __fdividef(1.0f, 1.0f + e);
+  return s * fmaf(z, 1.0f - s, 1.0f);
 }
 
 // backward pass 1: per-channel dgamma / dbeta partials; per (n, chunk, group) sums of d*gamma and d*gamma*xhat
@@ -207,9 +227,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
   const int n = blockIdx.y, chunk = blockIdx.x;
   for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) gn_sm[c] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x % g.L, r = threadIdx.x / g.L;
-  if (r < g.R) {
-    const int c0 = lane * 8;
+  const GnWalk w = gn_walk(g, n, chunk);
+  if (w.count > 0) {
+    const int c0 = w.lane * 8;
     float rs[8], mb[8], ga[8], be[8], dg[8], db[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -221,33 +241,33 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
       be[j] = beta[c0 + j];
       dg[j] = db[j] = 0.f;
     }
-    const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
-    const bf16* xb = x + (long long)n * g.HW * ld + c0;
-    const bf16* dbp = dy + (long long)n * g.HW * lddy + c0;
-    for (int p = p0 + r; p < p1; p += g.R * UNROLL) {
+    const bf16* px = x + w.off * ld + c0;
+    const bf16* pd = dy + w.off * lddy + c0;
+    const long long sx = (long long)g.R * ld, sd = (long long)g.R * lddy;
+    auto body = [&](const uint4& vx, const uint4& vd) {
+      float fx[8], fd[8];
+      unpack8(vx, fx);
+      unpack8(vd, fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(fx[j], rs[j], mb[j]);
+        float d = fd[j];
+        if (silu) d *= dsilu_fast(fmaf(xh, ga[j], be[j]));
+        dg[j] = fmaf(d, xh, dg[j]);
+        db[j] += d;
+      }
+    };
+    int it = 0;
+    for (; it + UNROLL <= w.count; it += UNROLL) {
       uint4 vx[UNROLL], vd[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int pp = p + u * g.R;
-        const bool ok = pp < p1;
-        vx[u] = ok ? ldg16(xb + (long long)pp * ld) : make_uint4(0, 0, 0, 0);
-        vd[u] = ok ? ldg16(dbp + (long long)pp * lddy) : make_uint4(0, 0, 0, 0);   // d = 0 -> no contribution
-      }
+      for (int u = 0; u < UNROLL; ++u) { vx[u] = ldg16(px + u * sx); vd[u] = ldg16(pd + u * sd); }
+      px += UNROLL * sx;
+      pd += UNROLL * sd;
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        float fx[8], fd[8];
-        unpack8(vx[u], fx);
-        unpack8(vd[u], fd);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = fmaf(fx[j], rs[j], mb[j]);
-          float d = fd[j];
-          if (silu) d *= dsiluf_(fmaf(xh, ga[j], be[j]));
-          dg[j] = fmaf(d, xh, dg[j]);
-          db[j] += d;
-        }
-      }
+      for (int u = 0; u < UNROLL; ++u) body(vx[u], vd[u]);
     }
+    for (; it < w.count; ++it, px += sx, pd += sd) body(ldg16(px), ldg16(pd));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       atomicAdd(&sdg[c0 + j], dg[j]);
@@ -268,16 +288,16 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
       s1 = fmaf(gm, sdb[c], s1);
       s2 = fmaf(gm, sdg[c], s2);
     }
-    float* w = ws + ((long long)(n * g.nchunk + chunk)) * GN_MAX_GROUPS * 2 + threadIdx.x * 2;
-    w[0] = s1;
-    w[1] = s2;
+    float* o = ws + ((long long)(n * g.nchunk + chunk)) * GN_MAX_GROUPS * 2 + threadIdx.x * 2;
+    o[0] = s1;
+    o[1] = s2;
   }
 }
 
 // backward pass 2: dx = rstd * (d*gamma - mean(d*gamma) - xhat * mean(d*gamma*xhat)) (+ add + add2);
 // optionally colsum[n][c] += sum_pixels dx and dbias[c] += the same (conv bias / time-embedding gradients)
-template <int UNROLL>
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(
+template <int UNROLL, bool HAS_ADD, bool HAS_ADD2>
+__global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(
     const bf16* __restrict__ x, long long ld, const bf16* __restrict__ dy, long long lddy, const bf16* add /* may alias dx */,
     long long ldadd, const bf16* __restrict__ add2, long long ldadd2, bf16* dx, long long lddx,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
@@ -301,73 +321,84 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(
     m12[threadIdx.x * 2 + 1] = (float)(s2 / cnt);
   }
   __syncthreads();
-  const int lane = threadIdx.x % g.L, r = threadIdx.x / g.L;
-  if (r < g.R) {
-    const int c0 = lane * 8;
-    float rs[8], mb[8], ga[8], be[8], m1[8], m2[8], cs[8];
+  const GnWalk w = gn_walk(g, n, chunk);
+  if (w.count > 0) {
+    const int c0 = w.lane * 8;
+    // dx = d * A + x * B + Cc   with d already multiplied by silu'(z):  A = rstd*gamma, B = -rstd^2*m2, Cc = -rstd*(m1 - mean*rstd*m2)
+    float rs[8], mb[8], ga[8], be[8], A[8], Bc[8], Cc[8], cs[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int grp = (c0 + j) / g.cpg;
       const float mean = stats[((long long)n * g.G + grp) * 2], rstd = stats[((long long)n * g.G + grp) * 2 + 1];
+      const float m1 = m12[grp * 2], m2 = m12[grp * 2 + 1];
       rs[j] = rstd;
       mb[j] = -mean * rstd;
       ga[j] = gamma[c0 + j];
       be[j] = beta[c0 + j];
-      m1[j] = m12[grp * 2];
-      m2[j] = m12[grp * 2 + 1];
+      A[j] = rstd * ga[j];
+      Bc[j] = -rstd * rstd * m2;
+      Cc[j] = -rstd * (m1 + mb[j] * m2);
       cs[j] = 0.f;
     }
-    const int p0 = chunk * g.chunk_pix, p1 = min(p0 + g.chunk_pix, g.HW);
-    const long long sample = (long long)n * g.HW;
-    const bf16* xb = x + sample * ld + c0;
-    const bf16* dbp = dy + sample * lddy + c0;
-    const bf16* ab = add ? add + sample * ldadd + c0 : nullptr;
-    const bf16* ab2 = add2 ? add2 + sample * ldadd2 + c0 : nullptr;
-    bf16* ob = dx + sample * lddx + c0;
-    for (int p = p0 + r; p < p1; p += g.R * UNROLL) {
+    const bf16* px = x + w.off * ld + c0;
+    const bf16* pd = dy + w.off * lddy + c0;
+    const bf16* pa = HAS_ADD ? add + w.off * ldadd + c0 : nullptr;
+    const bf16* pb = HAS_ADD2 ? add2 + w.off * ldadd2 + c0 : nullptr;
+    bf16* po = dx + w.off * lddx + c0;
+    const long long sx = (long long)g.R * ld, sd = (long long)g.R * lddy, sa = (long long)g.R * ldadd,
+                    sb = (long long)g.R * ldadd2, so = (long long)g.R * lddx;
+    auto body = [&](const uint4& vx, const uint4& vd, const uint4& va, const uint4& vb, bf16* dst) {
+      float fx[8], fd[8], o[8];
+      unpack8(vx, fx);
+      unpack8(vd, fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d = fd[j];
+        if (silu) d *= dsilu_fast(fmaf(fmaf(fx[j], rs[j], mb[j]), ga[j], be[j]));
+        o[j] = fmaf(d, A[j], fmaf(fx[j], Bc[j], Cc[j]));
+      }
+      if (want_cs) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[j] += o[j];
+      }
+      if (HAS_ADD) {
+        float fa[8];
+        unpack8(va, fa);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += fa[j];
+      }
+      if (HAS_ADD2) {
+        float fb[8];
+        unpack8(vb, fb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += fb[j];
+      }
+      *reinterpret_cast<uint4*>(dst) = pack8(o);
+    };
+    int it = 0;
+    for (; it + UNROLL <= w.count; it += UNROLL) {
       uint4 vx[UNROLL], vd[UNROLL], va[UNROLL], vb[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const int pp = p + u * g.R;
-        if (pp < p1) {
-          vx[u] = ldg16(xb + (long long)pp * ld);
-          vd[u] = ldg16(dbp + (long long)pp * lddy);
-          if (ab) va[u] = *reinterpret_cast<const uint4*>(ab + (long long)pp * ldadd);   // may alias dx: plain load
-          if (ab2) vb[u] = ldg16(ab2 + (long long)pp * ldadd2);
-        }
+        vx[u] = ldg16(px + u * sx);
+        vd[u] = ldg16(pd + u * sd);
+        if (HAS_ADD) va[u] = *reinterpret_cast<const uint4*>(pa + u * sa);   // may alias dx: plain load
+        if (HAS_ADD2) vb[u] = ldg16(pb + u * sb);
       }
+      px += UNROLL * sx;
+      pd += UNROLL * sd;
+      if (HAS_ADD) pa += UNROLL * sa;
+      if (HAS_ADD2) pb += UNROLL * sb;
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int pp = p + u * g.R;
-        if (pp >= p1) break;
-        float fx[8], fd[8], o[8];
-        unpack8(vx[u], fx);
-        unpack8(vd[u], fd);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = fmaf(fx[j], rs[j], mb[j]);
-          float d = fd[j];
-          if (silu) d *= dsiluf_(fmaf(xh, ga[j], be[j]));
-          o[j] = rs[j] * (d * ga[j] - m1[j] - xh * m2[j]);
-        }
-        if (want_cs) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) cs[j] += o[j];
-        }
-        if (ab) {
-          float fa[8];
-          unpack8(va[u], fa);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += fa[j];
-        }
-        if (ab2) {
-          float fb[8];
-          unpack8(vb[u], fb);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += fb[j];
-        }
-        *reinterpret_cast<uint4*>(ob + (long long)pp * lddx) = pack8(o);
-      }
+      for (int u = 0; u < UNROLL; ++u) body(vx[u], vd[u], va[u], vb[u], po + u * so);
+      po += UNROLL * so;
+    }
+    for (; it < w.count; ++it) {
+      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+      if (HAS_ADD) { va = *reinterpret_cast<const uint4*>(pa); pa += sa; }
+      if (HAS_ADD2) { vb = ldg16(pb); pb += sb; }
+      body(ldg16(px), ldg16(pd), va, vb, po);
+      px += sx; pd += sd; po += so;
     }
     if (want_cs) {
 #pragma unroll
@@ -393,8 +424,8 @@ static int gn_geom(GnGeom& g, int HW, int C, int G, int* nchunk) {
   g.L = C / 8;
   if (g.L > GN_THREADS) { set_error("GroupNorm: C=%d too wide", C); return MDM_E_ARG; }
   g.R = GN_THREADS / g.L;
-  // ~64K elements (128 KB of bf16) per CTA, a multiple of R pixels
-  int chunk = (65536 + C - 1) / C;
+  // ~32K elements (64 KB of bf16) per CTA, a multiple of R pixels
+  int chunk = (32768 + C - 1) / C;
   chunk = ((chunk + g.R - 1) / g.R) * g.R;
   if (chunk > HW) chunk = HW;
   if (chunk < 1) chunk = 1;
@@ -848,7 +879,7 @@ int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, cons
   int rc = gn_geom(g, HW, C, G, &nc);
   if (rc) return rc;
   dim3 grid(nc, N);
-  gn_stats_kernel<4><<<grid, GN_THREADS, 0, as_stream(stream)>>>((const bf16*)x, ld_x, ws, g);
+  gn_stats_kernel<8><<<grid, GN_THREADS, (size_t)2 * C * sizeof(float), as_stream(stream)>>>((const bf16*)x, ld_x, ws, g);
   MDM_LAUNCH_CHECK();
   gn_apply_kernel<4><<<grid, GN_THREADS, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta, ws, stats, eps, silu, g);
   MDM_LAUNCH_CHECK();
@@ -867,9 +898,17 @@ int mdm_gn_silu_bwd(const void* x, long long ld_x, const void* dy, long long ld_
   if (rc) return rc;
   dim3 grid(nc, N);
   const size_t sm1 = (size_t)2 * C * sizeof(float), sm2 = (size_t)C * sizeof(float);
-  gn_bwd_stats_kernel<2><<<grid, GN_THREADS, sm1, as_stream(stream)>>>((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, gamma, beta, stats, ws, dgamma, dbeta, silu, g);
+  gn_bwd_stats_kernel<4><<<grid, GN_THREADS, sm1, as_stream(stream)>>>((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, gamma, beta, stats, ws, dgamma, dbeta, silu, g);
   MDM_LAUNCH_CHECK();
-  gn_bwd_apply_kernel<2><<<grid, GN_THREADS, sm2, as_stream(stream)>>>((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (const bf16*)add, ld_add, (const bf16*)add2, ld_add2, (bf16*)dx, ld_dx, gamma, beta, stats, ws, silu, colsum, ld_colsum, dbias, g);
+#define GN_BWD_APPLY(A1, A2)                                                                                              \
+  gn_bwd_apply_kernel<2, A1, A2><<<grid, GN_THREADS, sm2, as_stream(stream)>>>(                                           \
+      (const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (const bf16*)add, ld_add, (const bf16*)add2, ld_add2, (bf16*)dx, ld_dx, \
+      gamma, beta, stats, ws, silu, colsum, ld_colsum, dbias, g)
+  if (add && add2) GN_BWD_APPLY(true, true);
+  else if (add) GN_BWD_APPLY(true, false);
+  else if (add2) GN_BWD_APPLY(false, true);
+  else GN_BWD_APPLY(false, false);
+#undef GN_BWD_APPLY
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -1015,8 +1054,8 @@ int mdm_colsum(const void* dy, long long ld, float* out, float* out2, int64_t ro
   MDM_CHECK_ARG(C % 8 == 0 && ld % 8 == 0 && ((uintptr_t)dy % 16 == 0), "colsum: C %% 8, ld %% 8, 16-byte aligned (C=%d ld=%lld)", C, ld);
   const int Cb = C < 2048 ? C : 2048;
   const int L = Cb / 8, R = 256 / L;
-  // ~128 KB of bf16 per CTA, at least one pass of R rows
-  long long rpc = (65536 + Cb - 1) / Cb;
+  // ~64 KB of bf16 per CTA, at least one pass of R rows
+  long long rpc = (32768 + Cb - 1) / Cb;
   rpc = ((rpc + R - 1) / R) * R;
   if (rpc > rows) rpc = rows;
   const dim3 blocks((unsigned)((rows + rpc - 1) / rpc), (unsigned)((C + 2047) / 2048));

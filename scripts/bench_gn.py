@@ -1,0 +1,30 @@
+"""micro-benchmark of the GroupNorm / colsum kernels: python scripts/bench_gn.py [iters]"""
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "masked-diffusion-model_b200"))
+from mdm_b200 import denoiser_ops as ops
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+SHAPES = [(128, 32, 128), (128, 32, 256), (128, 16, 128), (128, 8, 256), (128, 2, 512), (64, 128, 128), (64, 64, 256)]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+def timeit(fn):
+    for _ in range(2): fn()
+    tot = 0.0
+    for _ in range(iters):
+        flush.zero_()                      # evict L2 between iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters * 1e3
+for N, H, C in SHAPES:
+    x = torch.randn(N, H, H, C, device="cuda").to(torch.bfloat16)
+    dy = torch.randn(N, H, H, C, device="cuda").to(torch.bfloat16)
+    y = torch.empty_like(x); dx = torch.empty_like(x)
+    gamma = torch.ones(C, device="cuda"); beta = torch.zeros(C, device="cuda")
+    dg = torch.zeros(C, device="cuda"); db = torch.zeros(C, device="cuda")
+    stats = torch.empty(N, 32, 2, device="cuda")
+    ws = torch.empty(max(1, ops.gn_ws_floats(N, H * H, C)), device="cuda")
+    nb = x.numel() * 2
+    tf = timeit(lambda: ops.gn_silu_fwd(x, y, gamma, beta, stats, ws, N, H * H, C, 32, 1e-5, True))
+    tb = timeit(lambda: ops.gn_silu_bwd(x, dy, dx, gamma, beta, stats, dg, db, ws, N, H * H, C, 32, True, add2=y))
+    tc = timeit(lambda: ops.colsum(dy, dg, N * H * H, C))
+    print(f"N={N} H={H} C={C} ({nb/1e6:.1f} MB): fwd {tf:6.1f} us = {3*nb/tf/1e6:5.2f} TB/s(3 passes) | bwd {tb:6.1f} us = {6*nb/tb/1e6:5.2f} TB/s(6 passes) | colsum {tc:6.1f} us = {nb/tc/1e6:5.2f} TB/s", flush=True)
