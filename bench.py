@@ -205,7 +205,7 @@ def roofline_pass(tr, model, batch_dev, peaks):
         cin = dx.shape[-1] if dx is not None else kw.get("cin")
         return 2.0 * N * H * W * cin * ksize * ksize * dy.shape[-1]
 
-    def fl_wgrad(x, dy, dw, N, H, W, ksize=3, stride=1):
+    def fl_wgrad(x, dy, dw, N, H, W, ksize=3, stride=1, **kw):
         return 2.0 * N * H * W * dy.shape[-1] * ksize * ksize * x.shape[-1]
 
     wrap("conv_fprop", fl_fprop)

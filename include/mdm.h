@@ -166,6 +166,8 @@ typedef struct mdm_conv_args {
   float* dw;            /* wgrad output fp32 [cout][k*k][cin], accumulated atomically */
   long long w_col0;     /* dgrad/wgrad on a channel slice of a wider packed weight */
   int w_cols;
+  float* dbias;         /* wgrad only, optional: dbias[cout] += sum over pixels of dy (the bias gradient), computed by */
+  float* dbias2;        /* one extra N=16 MMA against a tile of ones inside the same kernel; dbias2 gets the same sums */
   float* splitk_ws;     /* optional ZEROED fp32 workspace: lets small-M fprop/dgrad layers split K over the SMs */
   long long splitk_ws_floats; /* (needs N*H*W*cout floats; left zeroed again on return) */
 } mdm_conv_args;

@@ -47,9 +47,12 @@ constexpr int RING_BYTES = 2 * HALO_BYTES + 5 * B_BYTES;    // halo: 2 A + 5 B s
 constexpr int SMEM_EPI_OFF = RING_BYTES;
 constexpr int SMEM_BIAS_OFF = SMEM_EPI_OFF + 2 * EPI_BYTES;   // 128 floats
 constexpr int SMEM_BAR_OFF = SMEM_BIAS_OFF + 512;
+constexpr int SMEM_ONES_OFF = 4 * (A_BYTES + B_BYTES);   // mode 1 only (plain ring = 128 KB): inside the unused ring tail
 constexpr int IGEMM_SMEM = SMEM_BAR_OFF + 256 + 1024 /*alignment slack*/;
-constexpr int TMEM_COLS = 256;                 // two 128-column fp32 accumulators
-static_assert(4 * A_BYTES + 4 * B_BYTES <= RING_BYTES, "plain ring must fit");
+constexpr int TMEM_COLS = 512;                 // two 128-column fp32 accumulators + two 16-column bias-gradient ones
+constexpr int TMEM_BIAS_COL = 256;             // wgrad bias gradient: D2[co][0..15] = sum_pix dY[pix][co] * 1
+constexpr int ONES_BYTES = 8192;               // [64 K-rows][64 bf16] of 1.0: the B operand of that extra MMA
+static_assert(4 * A_BYTES + 4 * B_BYTES + ONES_BYTES <= RING_BYTES, "plain ring + ones tile must fit");
 static_assert(IGEMM_SMEM <= 232448, "shared memory budget");
 
 // ---- raw PTX wrappers ------------------------------------------------------------------------
@@ -171,6 +174,8 @@ struct IgemmArgs {
   int epi;    // 0: bf16 TMA store (+bias/rowvec/C tile), 1: fp32 TMA reduce-add
   int halo;   // mode 0 only: A = input halo per channel chunk, taps = shifted views; M tile = 8 x 16 patch
   int pw, ph, pn;       // wgrad: geometry of the 64-pixel K box
+  float* dbias;         // wgrad: bias gradient dbias[co] += sum_pix dY[pix][co] (one extra N=16 MMA against a ones tile)
+  float* dbias2;
   int nseg;
   int seg_taps[2];
   int seg_kc[2];
@@ -321,6 +326,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (kMode == 1 && args.dbias != nullptr && warp >= 2 && warp <= 5) {   // ones tile (bf16 1.0 = 0x3F80) for the bias-gradient MMA
+    uint4* o = reinterpret_cast<uint4*>(smem + SMEM_ONES_OFF);
+    for (int i = threadIdx.x - 64; i < ONES_BYTES / 16; i += 128) o[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -453,6 +463,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       const uint32_t tmem_d = tmem_base + acc * TILE_N;
       uint32_t lo_a = 0;
       int sa_cur = 0, tap = 0;
+      // wgrad work items (ci tile 0, first tap) also accumulate the bias gradient: A = dY tile, B = ones, N = 16
+      const bool bias_item = kMode == 1 && args.dbias != nullptr && k.n_tile == 0 && k.tap == 0;
+      const uint32_t idesc16 = (idesc & ~(0x3Fu << 17)) | ((16u >> 3) << 17);
+      const uint32_t lo_ones = ((smem_u32(smem + SMEM_ONES_OFF) >> 4) & 0x3FFF) | DESC_LO_MNMAJOR;
       const int n_halo = kHalo ? args.seg_taps[0] * args.seg_kc[0] : 0;   // halo iterations come first (no K split)
       bool ready = mbar_try_wait(&b_full[sb], pb);
       for (int i = 0; i < k.nit; ++i) {
@@ -482,6 +496,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         for (int kk = 0; kk < TILE_K / 16; ++kk) {
           umma_bf16(tmem_d, make_desc(hi_a, lo_at + kk * kstep_a), make_desc(DESC_HI_SBO1024, lo_b + kk * kstep_b), idesc,
                     (i | kk) != 0 ? 1u : 0u);
+        }
+        if (bias_item) {
+#pragma unroll
+          for (int kk = 0; kk < TILE_K / 16; ++kk)
+            umma_bf16(tmem_base + TMEM_BIAS_COL + acc * 16, make_desc(hi_a, lo_at + kk * kstep_a),
+                      make_desc(DESC_HI_SBO1024, lo_ones + kk * (2048u >> 4)), idesc16, (i | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&b_empty[sb_cur]);
         if (kHalo) {
@@ -622,6 +642,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         epi_bar_sync();
         mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1);
         tcgen05_fence_after();
+        if (kMode == 1 && args.dbias != nullptr && k.n_tile == 0 && k.tap == 0) {
+          uint32_t b0, b1, b2, b3, b4, b5, b6, b7;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3), "=r"(b4), "=r"(b5), "=r"(b6), "=r"(b7)
+                       : "r"(tmem_base + TMEM_BIAS_COL + acc * 16 + ((uint32_t)(q * 32) << 16)) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int co = k.m_tile * TILE_M + row;
+          if (co < args.M_total) {
+            atomicAdd(args.dbias + co, __uint_as_float(b0));
+            if (args.dbias2) atomicAdd(args.dbias2 + co, __uint_as_float(b0));
+          }
+        }
 #pragma unroll 1
         for (int cc = 0; cc < TILE_N / 32; ++cc) {
           tmem_ld32(tmem_acc + cc * 32, v);
@@ -996,6 +1028,8 @@ int mdm_conv_wgrad(const mdm_conv_args* c, void* stream) {
   a.N_total = c->cin;
   a.ci_total = c->w_cols ? c->w_cols : c->cin;
   a.w_col0 = (int)c->w_col0;
+  a.dbias = c->dbias;
+  a.dbias2 = c->dbias2;
   a.num_co = c->cout / TILE_M;
   a.num_n = c->cin / TILE_N;
   const long long pixels = (long long)c->N * c->H * c->W;

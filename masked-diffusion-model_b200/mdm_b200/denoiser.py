@@ -530,15 +530,14 @@ class _Plan:
             def temb_bwd():
                 ops.cast_f32_bf16(self.d_tproj, d_tproj16)
                 ops.conv_dgrad(d_tproj16, w_tp, None, B, 1, 1, 1, dx_f32=d_e2act, cin=temb)
-                ops.conv_wgrad(e2_act, d_tproj16, g_tp, B, 1, 1, 1, 1)
-                ops.colsum(d_tproj16, gb_tp, B, L.tproj_total)
+                ops.conv_wgrad(e2_act, d_tproj16, g_tp, B, 1, 1, 1, 1, dbias=gb_tp)
                 ops.silu_bwd(e2_f32, d_e2act, d_e2)
                 ops.conv_dgrad(d_e2, m.w16("time_embedding.linear_2.weight"), None, B, 1, 1, 1, dx_f32=d_e1act, cin=temb)
-                ops.conv_wgrad(e1_act, d_e2, m.g32("time_embedding.linear_2.weight").view(temb, 1, temb), B, 1, 1, 1, 1)
-                ops.colsum(d_e2, m.g32("time_embedding.linear_2.bias"), B, temb)
+                ops.conv_wgrad(e1_act, d_e2, m.g32("time_embedding.linear_2.weight").view(temb, 1, temb), B, 1, 1, 1, 1,
+                               dbias=m.g32("time_embedding.linear_2.bias"))
                 ops.silu_bwd(e1_f32, d_e1act, d_e1)
-                ops.conv_wgrad(te0, d_e1, m.g32("time_embedding.linear_1.weight").view(temb, 1, boc[0]), B, 1, 1, 1, 1)
-                ops.colsum(d_e1, m.g32("time_embedding.linear_1.bias"), B, temb)
+                ops.conv_wgrad(te0, d_e1, m.g32("time_embedding.linear_1.weight").view(temb, 1, boc[0]), B, 1, 1, 1, 1,
+                               dbias=m.g32("time_embedding.linear_1.bias"))
             self._temb_bwd = temb_bwd
 
         # ---- symbolic pass -------------------------------------------------------------------------
@@ -668,12 +667,11 @@ class _Plan:
                 d_out = out.grad
                 d_a2, d_h1, d_a1 = self.sget(rd_a2), self.sget(rd_h1), self.sget(rd_a1)
                 ops.conv_dgrad(d_out, m.w16(f"{p}.conv2.weight"), d_a2, B, H, H, 3)
-                ops.conv_wgrad(a2, d_out, m.g32(f"{p}.conv2.weight"), B, H, H, 3, 1)
+                # weight gradients; the bias gradients (column sums of d_out) ride in the same kernel
+                ops.conv_wgrad(a2, d_out, m.g32(f"{p}.conv2.weight"), B, H, H, 3, 1, dbias=m.g32(f"{p}.conv2.bias"),
+                               dbias2=m.g32(f"{p}.conv_shortcut.bias") if r.shortcut else None)
                 if r.shortcut:
                     ops.conv_wgrad(x.val, d_out, m.g32(f"{p}.conv_shortcut.weight"), B, H, H, 1, 1)
-                    ops.colsum(d_out, m.g32(f"{p}.conv2.bias"), B * HW, r.cout, out2=m.g32(f"{p}.conv_shortcut.bias"))
-                else:
-                    ops.colsum(d_out, m.g32(f"{p}.conv2.bias"), B * HW, r.cout)
                 # d_h1 plus, in the same pass, its per-sample column sums = d(time_emb_proj output) and conv1.bias grad
                 ops.gn_silu_bwd(h1, d_a2, d_h1, m.w32(f"{p}.norm2.weight"), m.w32(f"{p}.norm2.bias"), st2,
                                 m.g32(f"{p}.norm2.weight"), m.g32(f"{p}.norm2.bias"), ws2(), B, HW, r.cout, G, True,
@@ -726,12 +724,11 @@ class _Plan:
                 d_out = out.grad
                 d_att, d_qkv, d_y = self.sget(rd_att), self.sget(rd_qkv), self.sget(rd_y)
                 ops.conv_dgrad(d_out, m.w16(f"{p}.to_out.0.weight"), d_att, B * L_, 1, 1, 1)
-                ops.conv_wgrad(att, d_out, m.g32(f"{p}.to_out.0.weight").view(C, 1, C), B * L_, 1, 1, 1, 1)
-                ops.colsum(d_out, m.g32(f"{p}.to_out.0.bias"), B * L_, C)
+                ops.conv_wgrad(att, d_out, m.g32(f"{p}.to_out.0.weight").view(C, 1, C), B * L_, 1, 1, 1, 1,
+                               dbias=m.g32(f"{p}.to_out.0.bias"))
                 ops.attention_bwd(qkv, d_att, d_qkv, B, L_, C)
                 ops.conv_dgrad(d_qkv, w_qkv, d_y, B * L_, 1, 1, 1)
-                ops.conv_wgrad(y, d_qkv, g_qkv, B * L_, 1, 1, 1, 1)
-                ops.colsum(d_qkv, gb_qkv, B * L_, 3 * C)
+                ops.conv_wgrad(y, d_qkv, g_qkv, B * L_, 1, 1, 1, 1, dbias=gb_qkv)
                 ops.gn_silu_bwd(x.val, d_y, x.grad, m.w32(f"{p}.group_norm.weight"), m.w32(f"{p}.group_norm.bias"), st,
                                 m.g32(f"{p}.group_norm.weight"), m.g32(f"{p}.group_norm.bias"), ws(), B, L_, C, G, False,
                                 add=x.grad if has_up else None, add2=d_out)
@@ -751,8 +748,7 @@ class _Plan:
                 z = self.sget(rz)
                 ops.zero_insert2x(out.grad, z, B, H, H, C)
                 ops.conv_dgrad(z, m.w16(name + ".weight"), x.grad, B, 2 * H, 2 * H, 3, accumulate=has_up)
-                ops.conv_wgrad(x.val, out.grad, m.g32(name + ".weight"), B, H, H, 3, 2)
-                ops.colsum(out.grad, m.g32(name + ".bias"), B * H * H, C)
+                ops.conv_wgrad(x.val, out.grad, m.g32(name + ".weight"), B, H, H, 3, 2, dbias=m.g32(name + ".bias"))
             bw = [backward]
         return fw, bw
 
@@ -774,8 +770,7 @@ class _Plan:
             def backward():
                 du = self.sget(rdu)
                 ops.conv_dgrad(out.grad, m.w16(name + ".weight"), du, B, 2 * H, 2 * H, 3)
-                ops.conv_wgrad(u, out.grad, m.g32(name + ".weight"), B, 2 * H, 2 * H, 3, 1)
-                ops.colsum(out.grad, m.g32(name + ".bias"), B * 4 * H * H, C)
+                ops.conv_wgrad(u, out.grad, m.g32(name + ".weight"), B, 2 * H, 2 * H, 3, 1, dbias=m.g32(name + ".bias"))
                 ops.upsample2x_bwd(du, x.grad, B, H, H, C)
             bw = [backward]
         return fw, bw

@@ -25,6 +25,7 @@ class ConvArgs(Structure):
         ("y_f32", c_void_p),
         ("x2", c_void_p), ("ld_x2", c_longlong), ("cin2", c_int), ("w2", c_void_p),
         ("dw", c_void_p), ("w_col0", c_longlong), ("w_cols", c_int),
+        ("dbias", c_void_p), ("dbias2", c_void_p),
         ("splitk_ws", c_void_p), ("splitk_ws_floats", c_longlong),
     ]
 
@@ -130,13 +131,15 @@ def conv_dgrad(dy, w, dx, N, H, W, ksize=3, resid=None, accumulate=False, dx_f32
     check(lib().mdm_conv_dgrad(ctypes.byref(a), stream_ptr(dy.device)))
 
 
-def conv_wgrad(x, dy, dw, N, H, W, ksize=3, stride=1):
-    """dw[cout,k*k,cin] (fp32) += wgrad(x[N,H*s,W*s,cin], dy[N,H,W,cout])"""
+def conv_wgrad(x, dy, dw, N, H, W, ksize=3, stride=1, dbias=None, dbias2=None):
+    """dw[cout,k*k,cin] (fp32) += wgrad(x[N,H*s,W*s,cin], dy[N,H,W,cout]); optional dbias[cout] (+dbias2) += column
+    sums of dy (bias gradient), fused into the same kernel"""
     a = ConvArgs()
     a.x, a.ld_x, a.cin = _dp(x), pix_ld(x), x.shape[-1]
     a.y, a.ld_y, a.cout = _dp(dy), pix_ld(dy), dy.shape[-1]
     a.N, a.H, a.W, a.ksize, a.stride = N, H, W, ksize, stride
     a.dw = _dp(dw)
+    a.dbias, a.dbias2 = _dp(dbias), _dp(dbias2)
     a.w_cols = dw.shape[-1]
     check(lib().mdm_conv_wgrad(ctypes.byref(a), stream_ptr(dw.device)))
 

@@ -98,7 +98,13 @@ def test_wgrad(N, H, cin, cout, k, stride):
     dy = torch.randn(N, cout, H, H, device="cuda", generator=g)
     xb, dyb = nhwc(x), nhwc(dy)
     dw = torch.zeros(cout, k * k, cin, device="cuda")
-    ops.conv_wgrad(xb, dyb, dw, N, H, H, k, stride)
+    db = torch.full((cout,), 0.5, device="cuda")
+    db2 = torch.zeros(cout, device="cuda")
+    ops.conv_wgrad(xb, dyb, dw, N, H, H, k, stride, dbias=db, dbias2=db2)
     ref = torch.nn.grad.conv2d_weight(nchw(xb), (cout, cin, k, k), nchw(dyb), stride=stride, padding=k // 2)
     err = (ops.unpack_conv_weight(dw, k) - ref).abs().max().item()
     assert err <= 2e-3 * ref.abs().max().item() + 1e-4, err
+    # bias gradient fused into the same kernel (one N=16 MMA against a tile of ones): accumulates into dbias
+    ref_b = dyb.float().sum(dim=(0, 1, 2))
+    tol = 2e-3 * ref_b.abs().max().item() + 1e-3
+    assert (db - 0.5 - ref_b).abs().max().item() <= tol and (db2 - ref_b).abs().max().item() <= tol
