@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../../include/mdm.h"
 
@@ -38,6 +39,36 @@ extern long long g_launch_count;
   } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Programmatic dependent launch: every kernel of this library is launched with the stream-serialization
+// attribute relaxed and opens with MDM_PDL_ENTER(): `launch_dependents` lets the NEXT kernel of the stream be
+// scheduled (its launch latency and prologue overlap this kernel's tail), `wait` blocks until the PREVIOUS grid
+// has completed and its writes are visible -- so no global memory may be touched before it.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define MDM_PDL_ENTER()               \
+  do {                                \
+    ::mdm::pdl_launch_dependents();   \
+    ::mdm::pdl_wait();                \
+  } while (0)
+
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  static const int pdl_on = [] { const char* v = getenv("MDM_PDL"); return v ? atoi(v) : 0; }();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_on ? 1 : 0;   // measured on B200 (round 1): PDL edges made the captured step ~4 % SLOWER -> off by default
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);   // errors surface through MDM_LAUNCH_CHECK (cudaGetLastError)
+}
+#endif
 
 constexpr int kNumSMs = 148;  // B200
 

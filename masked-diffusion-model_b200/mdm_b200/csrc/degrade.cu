@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_stats_kernel(const T* __re
                                                                    const uint8_t* __restrict__ mask,
                                                                    int mask_ch, float* __restrict__ ws,
                                                                    int C, int hw, int nchunk) {
+  MDM_PDL_ENTER();
   __shared__ float red[32];
   const int chunk = blockIdx.x, plane = blockIdx.y;  // plane = b*C + c
   const int b = plane / C, c = plane % C;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_apply_kernel(
     float fill_const, int mean_area, const float* __restrict__ ws, float* __restrict__ x_t,
     float* __restrict__ mask_f32, float* __restrict__ degrade_mask, float* __restrict__ fill_out,
     int C, int hw, int nchunk) {
+  MDM_PDL_ENTER();
   const int chunk = blockIdx.x, plane = blockIdx.y;
   const int b = plane / C, c = plane % C;
   const float fill = fill_value(ws + (int64_t)b * C * nchunk * 3, c, C, nchunk, fill_mode, fill_const, mean_area);
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(DG_THREADS) sampler_stats_kernel(
     const float* __restrict__ x_t, const float* __restrict__ net, Shift shift,
     const uint8_t* __restrict__ mask_t, const uint8_t* __restrict__ mask_n, int mask_ch,
     float* __restrict__ ws_t, float* __restrict__ ws_n, int C, int hw, int nchunk) {
+  MDM_PDL_ENTER();
   __shared__ float red[32];
   const int chunk = blockIdx.x, plane = blockIdx.y;
   const int b = plane / C, c = plane % C;
@@ -178,6 +181,7 @@ __global__ void __launch_bounds__(DG_THREADS) sampler_update_kernel(
     float fill_const, int mean_area, int momentum, int update, Shift shift_next,
     const float* __restrict__ ws_t, const float* __restrict__ ws_n, float* __restrict__ x_next,
     float* __restrict__ x_in_next, float* __restrict__ s0_out, int C, int hw, int nchunk) {
+  MDM_PDL_ENTER();
   const int chunk = blockIdx.x, plane = blockIdx.y;
   const int b = plane / C, c = plane % C;
   const int64_t po = (int64_t)plane * hw;
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(DG_THREADS) sampler_update_kernel(
 
 __global__ void __launch_bounds__(DG_THREADS) add_shift_kernel(const float* __restrict__ x, Shift shift,
                                                                float* __restrict__ out, int C, int hw) {
+  MDM_PDL_ENTER();
   const int plane = blockIdx.y, b = plane / C, c = plane % C;
   const int64_t po = (int64_t)plane * hw;
   const int base = blockIdx.x * DG_CHUNK;
@@ -239,15 +244,15 @@ int mdm_degrade(const void* img, int img_dtype, const uint8_t* mask, int mask_ch
   cudaStream_t st = as_stream(stream);
   if (fill_mode != MDM_FILL_CONST) {
     if (img_dtype == MDM_F32)
-      degrade_stats_kernel<float><<<grid, DG_THREADS, 0, st>>>((const float*)img, mask, mask_ch, ws, channels, hw, nc);
+      launch_pdl(degrade_stats_kernel<float>, dim3(grid), dim3(DG_THREADS), 0, st, (const float*)img, mask, mask_ch, ws, channels, hw, nc);
     else
-      degrade_stats_kernel<__nv_bfloat16><<<grid, DG_THREADS, 0, st>>>((const __nv_bfloat16*)img, mask, mask_ch, ws, channels, hw, nc);
+      launch_pdl(degrade_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(DG_THREADS), 0, st, (const __nv_bfloat16*)img, mask, mask_ch, ws, channels, hw, nc);
     MDM_LAUNCH_CHECK();
   }
   if (img_dtype == MDM_F32)
-    degrade_apply_kernel<float><<<grid, DG_THREADS, 0, st>>>((const float*)img, mask, mask_ch, fill_mode, fill_const, mean_area, ws, x_t, mask_f32, degrade_mask, fill_out, channels, hw, nc);
+    launch_pdl(degrade_apply_kernel<float>, dim3(grid), dim3(DG_THREADS), 0, st, (const float*)img, mask, mask_ch, fill_mode, fill_const, mean_area, ws, x_t, mask_f32, degrade_mask, fill_out, channels, hw, nc);
   else
-    degrade_apply_kernel<__nv_bfloat16><<<grid, DG_THREADS, 0, st>>>((const __nv_bfloat16*)img, mask, mask_ch, fill_mode, fill_const, mean_area, ws, x_t, mask_f32, degrade_mask, fill_out, channels, hw, nc);
+    launch_pdl(degrade_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(DG_THREADS), 0, st, (const __nv_bfloat16*)img, mask, mask_ch, fill_mode, fill_const, mean_area, ws, x_t, mask_f32, degrade_mask, fill_out, channels, hw, nc);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -272,10 +277,10 @@ int mdm_sampler_step(const float* x_t, const float* net, const float* shift, int
   float* ws_n = ws ? ws + mdm_degrade_ws_floats(batch, channels, hw) : nullptr;
   if (update && fill_mode != MDM_FILL_CONST) {
     MDM_CHECK_ARG(ws, "workspace is NULL");
-    sampler_stats_kernel<<<grid, DG_THREADS, 0, st>>>(x_t, net, s, mask_t, mask_next, mask_ch, ws_t, ws_n, channels, hw, nc);
+    launch_pdl(sampler_stats_kernel, dim3(grid), dim3(DG_THREADS), 0, st, x_t, net, s, mask_t, mask_next, mask_ch, ws_t, ws_n, channels, hw, nc);
     MDM_LAUNCH_CHECK();
   }
-  sampler_update_kernel<<<grid, DG_THREADS, 0, st>>>(x_t, net, s, mask_t, mask_next, mask_ch, fill_mode, fill_const, mean_area, momentum, update, sn, ws_t, ws_n, x_next, x_in_next, s0_out, channels, hw, nc);
+  launch_pdl(sampler_update_kernel, dim3(grid), dim3(DG_THREADS), 0, st, x_t, net, s, mask_t, mask_next, mask_ch, fill_mode, fill_const, mean_area, momentum, update, sn, ws_t, ws_n, x_next, x_in_next, s0_out, channels, hw, nc);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -285,7 +290,7 @@ int mdm_add_shift(const float* x, const float* shift, int64_t sb, int64_t sc, in
   MDM_CHECK_ARG(x && out, "x/out is NULL");
   MDM_CHECK_ARG(batch > 0 && channels > 0 && hw > 0, "empty image batch");
   dim3 grid(nchunks(hw), batch * channels);
-  add_shift_kernel<<<grid, DG_THREADS, 0, as_stream(stream)>>>(x, Shift{shift, sb, sc, sp}, out, channels, hw);
+  launch_pdl(add_shift_kernel, dim3(grid), dim3(DG_THREADS), 0, as_stream(stream), x, Shift{shift, sb, sc, sp}, out, channels, hw);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }

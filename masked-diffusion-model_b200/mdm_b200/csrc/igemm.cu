@@ -284,6 +284,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
              const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
              const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapD,
              const __grid_constant__ IgemmArgs args) {
+  pdl_launch_dependents();   // the next kernel may be scheduled as SMs drain; it blocks in its own pdl_wait()
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int kASlots = kHalo ? 2 : 0;
@@ -336,6 +337,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int w_first = blockIdx.x, w_step = gridDim.x;
+  pdl_wait();   // barrier init, TMEM allocation and descriptor prefetch above overlapped the previous kernel's tail
 
   if (warp == 0 && lane == 0) {
     // ============================== TMA producer: A operand ==================================
@@ -693,6 +695,7 @@ __global__ void splitk_finalize_kernel(float* __restrict__ ws, int M, int N, con
                                        const float* __restrict__ bias2, const float* __restrict__ rowvec, long long ld_rowvec,
                                        int rows_per_vec, const __nv_bfloat16* resid, long long ld_resid,
                                        __nv_bfloat16* out, long long ld_out, float* __restrict__ out_f32) {
+  MDM_PDL_ENTER();
   // one thread per float4 (no loop: parallelism hides the latency), 32-bit index math
   const uint32_t n4 = (uint32_t)N >> 2;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -846,9 +849,9 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
                         const CUtensorMap& mC, const CUtensorMap& mD, IgemmArgs& a, void* stream) {
   const int grid = a.num_work < kNumSMs ? a.num_work : kNumSMs;
   cudaStream_t st = as_stream(stream);
-  if (a.mode == 1) igemm_kernel<1, false><<<grid, IGEMM_THREADS, IGEMM_SMEM, st>>>(mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.halo) igemm_kernel<0, true><<<grid, IGEMM_THREADS, IGEMM_SMEM, st>>>(mA0, mB0, mA1, mB1, mC, mD, a);
-  else igemm_kernel<0, false><<<grid, IGEMM_THREADS, IGEMM_SMEM, st>>>(mA0, mB0, mA1, mB1, mC, mD, a);
+  if (a.mode == 1) launch_pdl(igemm_kernel<1, false>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.halo) launch_pdl(igemm_kernel<0, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else launch_pdl(igemm_kernel<0, false>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -924,7 +927,7 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
   if (rc) return rc;
   const long long total4 = ws_need / 4;
   const int blocks = (int)((total4 + 255) / 256);
-  splitk_finalize_kernel<<<blocks, 256, 0, as_stream(stream)>>>(c->splitk_ws, a.M_total, a.N_total, a.bias, a.bias2, a.rowvec,
+  launch_pdl(splitk_finalize_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), c->splitk_ws, a.M_total, a.N_total, a.bias, a.bias2, a.rowvec,
                                                                 a.ld_rowvec, a.rows_per_vec, (const __nv_bfloat16*)c_ptr, c_ld,
                                                                 (__nv_bfloat16*)out, ld_out, c->y_f32);
   MDM_LAUNCH_CHECK();

@@ -93,6 +93,7 @@ __device__ __forceinline__ GnWalk gn_walk(const GnGeom& g, int n, int chunk) {
 template <int UNROLL>
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __restrict__ x, long long ld,
                                                               float* __restrict__ ws, GnGeom g) {
+  MDM_PDL_ENTER();
   extern __shared__ float gn_sm[];   // s[C], q[C]
   const int n = blockIdx.y, chunk = blockIdx.x;
   for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) gn_sm[c] = 0.f;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
                                                               long long ldy, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const float* __restrict__ ws,
                                                               float* __restrict__ stats, float eps, int silu, GnGeom g) {
+  MDM_PDL_ENTER();
   __shared__ float mr[GN_MAX_GROUPS * 2];
   const int n = blockIdx.y, chunk = blockIdx.x;
   if (threadIdx.x < g.G) {
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
                                                                   const float* __restrict__ stats, float* __restrict__ ws,
                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                   int silu, GnGeom g) {
+  MDM_PDL_ENTER();
   extern __shared__ float gn_sm[];   // sdg[C], sdb[C]
   float* sdg = gn_sm;
   float* sdb = gn_sm + g.C;
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
     const float* __restrict__ ws, int silu, float* __restrict__ colsum, long long ld_colsum, float* __restrict__ dbias,
     GnGeom g) {
+  MDM_PDL_ENTER();
   extern __shared__ float gn_sm[];   // scs[C] when colsum
   __shared__ float m12[GN_MAX_GROUPS * 2];
   const int n = blockIdx.y, chunk = blockIdx.x;
@@ -447,6 +451,7 @@ template <int FLIP_T>
 __global__ void planar_to_nhwc_conv_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                            const float* __restrict__ bias, bf16* __restrict__ y, long long ldy,
                                            int C, int H, int W, int cout, int w_is_out_layout) {
+  MDM_PDL_ENTER();
   // tile: one image row h, PL_TW pixels
   __shared__ float tile[PL_MAXC][3][PL_TW + 2];
   const int tiles_w = (W + PL_TW - 1) / PL_TW;
@@ -488,6 +493,7 @@ template <int FLIP_T>
 __global__ void planar_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ t, long long ldt,
                                     float* __restrict__ dw, float* __restrict__ dbias, int C, int H, int W, int cout,
                                     int w_is_out_layout, int rows_per_cta) {
+  MDM_PDL_ENTER();
   __shared__ float tile[PL_MAXC][3][PL_TW + 2];
   const int tiles_w = (W + PL_TW - 1) / PL_TW;
   const int n = blockIdx.y;
@@ -538,6 +544,7 @@ __global__ void planar_wgrad_kernel(const float* __restrict__ img, const bf16* _
 // last conv forward: NHWC bf16 [.,cin] -> planar fp32 [N][C][H][W]; thread <-> pixel
 __global__ void nhwc_to_planar_conv_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ w,
                                            const float* __restrict__ bias, float* __restrict__ y, int C, int H, int W, int cin) {
+  MDM_PDL_ENTER();
   extern __shared__ float wsm[];  // [9][cin][4]
   for (int i = threadIdx.x; i < 9 * cin * 4; i += blockDim.x) {
     const int c = i & 3, ci = (i >> 2) % cin, t = (i >> 2) / cin;
@@ -571,6 +578,7 @@ __global__ void nhwc_to_planar_conv_kernel(const bf16* __restrict__ x, long long
 }
 
 __global__ void planar_sum_kernel(const float* __restrict__ img, float* __restrict__ out, int C, long long hw) {
+  MDM_PDL_ENTER();
   // out[c] += sum over n, hw of img[n][c][:]
   __shared__ float red[32];
   const int c = blockIdx.y % C, n = blockIdx.y / C;
@@ -586,6 +594,7 @@ __global__ void planar_sum_kernel(const float* __restrict__ img, float* __restri
 // =============================================================================================
 __global__ void upsample2x_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
                                   int H, int W, int C, long long total_vec) {
+  MDM_PDL_ENTER();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total_vec) return;
   const int V = C / 8;
@@ -599,6 +608,7 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ x, long long ldx, bf1
 
 __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, long long ldy, bf16* __restrict__ dx, long long ldx,
                                       int H, int W, int C, long long total_vec) {
+  MDM_PDL_ENTER();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total_vec) return;
   const int V = C / 4;
@@ -617,6 +627,7 @@ __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, long long ldy
 
 __global__ void zero_insert2x_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
                                      int H, int W, int C, long long total_vec) {
+  MDM_PDL_ENTER();
   // y[n][2h][2w] = x[n][h][w], zero elsewhere; y is [N][2H][2W][C]
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total_vec) return;
@@ -638,6 +649,7 @@ __global__ void zero_insert2x_kernel(const bf16* __restrict__ x, long long ldx, 
 // =============================================================================================
 constexpr int ATT_D = 8;
 __global__ void attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int C, float scale) {
+  MDM_PDL_ENTER();
   extern __shared__ float att_sm[];  // K[L][8], V[L][8]
   float* Ks = att_sm;
   float* Vs = att_sm + L * ATT_D;
@@ -671,6 +683,7 @@ __global__ void attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restr
 
 __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
                                      int L, int C, float scale) {
+  MDM_PDL_ENTER();
   extern __shared__ float att_sm[];  // K, V, dK, dV : 4 * L * 8
   float* Ks = att_sm;
   float* Vs = Ks + L * ATT_D;
@@ -738,6 +751,7 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
 // =============================================================================================
 // diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): [cos(t f_k), sin(t f_k)], f_k = exp(-ln(1e4) k / half)
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, bf16* __restrict__ out, int N, int dim) {
+  MDM_PDL_ENTER();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * dim) return;
   const int n = i / dim, k = i % dim, half = dim / 2;
@@ -749,11 +763,13 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, bf16* __r
 
 // y = silu(x) elementwise; x fp32 [rows][C] -> y bf16  (time-embedding MLP; tiny)
 __global__ void silu_f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  MDM_PDL_ENTER();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = __float2bfloat16(siluf_(x[i]));
 }
 // dx = dy * silu'(x): dy fp32, x fp32 -> dx bf16
 __global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, bf16* __restrict__ dx, long long n) {
+  MDM_PDL_ENTER();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dx[i] = __float2bfloat16(dy[i] * dsiluf_(x[i]));
 }
@@ -763,6 +779,7 @@ __global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __rest
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, long long ld, float* __restrict__ out,
                                                      float* __restrict__ out2, long long rows, int C, int L, int R,
                                                      int rows_per_cta) {
+  MDM_PDL_ENTER();
   extern __shared__ float cs_sm[];   // [Cb]: this CTA's column block (blockIdx.y, up to 2048 channels)
   const int c_base = blockIdx.y * 2048;
   const int Cb = min(2048, C - c_base);
@@ -807,6 +824,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
 // out[n][c] (fp32, ld_out) = sum over the HW pixels of sample n of dy[(n*HW+p)][c]; optional dbias[c] += same
 __global__ void sample_colsum_kernel(const bf16* __restrict__ dy, long long ld, float* __restrict__ out, long long ld_out,
                                      float* __restrict__ dbias, int HW, int C) {
+  MDM_PDL_ENTER();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (c >= C) return;
@@ -824,6 +842,7 @@ __global__ void mse_residual_kernel(const float* __restrict__ x_in, const float*
                                     const float* __restrict__ weight, float* __restrict__ dnet,
                                     float* __restrict__ recon_out, float* __restrict__ partial, long long per_sample,
                                     long long total, float inv_total) {
+  MDM_PDL_ENTER();
   __shared__ float red[32];
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -839,6 +858,7 @@ __global__ void mse_residual_kernel(const float* __restrict__ x_in, const float*
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 __global__ void mse_finalize_kernel(const float* __restrict__ partial, int n, float inv_total, float* __restrict__ loss) {
+  MDM_PDL_ENTER();
   __shared__ float red[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
@@ -847,6 +867,7 @@ __global__ void mse_finalize_kernel(const float* __restrict__ partial, int n, fl
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  MDM_PDL_ENTER();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(x + i);
@@ -879,9 +900,9 @@ int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, cons
   int rc = gn_geom(g, HW, C, G, &nc);
   if (rc) return rc;
   dim3 grid(nc, N);
-  gn_stats_kernel<8><<<grid, GN_THREADS, (size_t)2 * C * sizeof(float), as_stream(stream)>>>((const bf16*)x, ld_x, ws, g);
+  launch_pdl(gn_stats_kernel<8>, dim3(grid), dim3(GN_THREADS), (size_t)2 * C * sizeof(float), as_stream(stream), (const bf16*)x, ld_x, ws, g);
   MDM_LAUNCH_CHECK();
-  gn_apply_kernel<4><<<grid, GN_THREADS, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta, ws, stats, eps, silu, g);
+  launch_pdl(gn_apply_kernel<4>, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), (const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta, ws, stats, eps, silu, g);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -898,10 +919,10 @@ int mdm_gn_silu_bwd(const void* x, long long ld_x, const void* dy, long long ld_
   if (rc) return rc;
   dim3 grid(nc, N);
   const size_t sm1 = (size_t)2 * C * sizeof(float), sm2 = (size_t)C * sizeof(float);
-  gn_bwd_stats_kernel<4><<<grid, GN_THREADS, sm1, as_stream(stream)>>>((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, gamma, beta, stats, ws, dgamma, dbeta, silu, g);
+  launch_pdl(gn_bwd_stats_kernel<4>, dim3(grid), dim3(GN_THREADS), sm1, as_stream(stream), (const bf16*)x, ld_x, (const bf16*)dy, ld_dy, gamma, beta, stats, ws, dgamma, dbeta, silu, g);
   MDM_LAUNCH_CHECK();
 #define GN_BWD_APPLY(A1, A2)                                                                                              \
-  gn_bwd_apply_kernel<2, A1, A2><<<grid, GN_THREADS, sm2, as_stream(stream)>>>(                                           \
+  launch_pdl(gn_bwd_apply_kernel<2, A1, A2>, dim3(grid), dim3(GN_THREADS), sm2, as_stream(stream),                                            \
       (const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (const bf16*)add, ld_add, (const bf16*)add2, ld_add2, (bf16*)dx, ld_dx, \
       gamma, beta, stats, ws, silu, colsum, ld_colsum, dbias, g)
   if (add && add2) GN_BWD_APPLY(true, true);
@@ -918,7 +939,7 @@ int mdm_conv_in_fwd(const float* img, const float* w, const float* bias, void* y
   MDM_CHECK_ARG(img && w && y, "conv_in_fwd: NULL pointer");
   MDM_CHECK_ARG(C >= 1 && C <= PL_MAXC, "conv_in_fwd: image channels must be 1..4 (got %d)", C);
   dim3 grid(H * ((W + PL_TW - 1) / PL_TW), N);
-  planar_to_nhwc_conv_kernel<0><<<grid, 128, 0, as_stream(stream)>>>(img, w, bias, (bf16*)y, ld_y, C, H, W, cout, 0);
+  launch_pdl(planar_to_nhwc_conv_kernel<0>, dim3(grid), dim3(128), 0, as_stream(stream), img, w, bias, (bf16*)y, ld_y, C, H, W, cout, 0);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -931,7 +952,7 @@ int mdm_conv_in_wgrad(const float* img, const void* dy, long long ld_dy, float* 
   const int rows_per_cta = 8;
   dim3 grid((jobs + rows_per_cta - 1) / rows_per_cta, N);
   const int th = ((cout + 31) / 32) * 32;
-  planar_wgrad_kernel<0><<<grid, th, 0, as_stream(stream)>>>(img, (const bf16*)dy, ld_dy, dw, dbias, C, H, W, cout, 0, rows_per_cta);
+  launch_pdl(planar_wgrad_kernel<0>, dim3(grid), dim3(th), 0, as_stream(stream), img, (const bf16*)dy, ld_dy, dw, dbias, C, H, W, cout, 0, rows_per_cta);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -947,7 +968,7 @@ int mdm_conv_out_fwd(const void* x, long long ld_x, const float* w, const float*
     smem_set = smem;
   }
   dim3 grid(GRID1D((long long)H * W, 128), N);
-  nhwc_to_planar_conv_kernel<<<grid, 128, smem, as_stream(stream)>>>((const bf16*)x, ld_x, w, bias, y, C, H, W, cin);
+  launch_pdl(nhwc_to_planar_conv_kernel, dim3(grid), dim3(128), smem, as_stream(stream), (const bf16*)x, ld_x, w, bias, y, C, H, W, cin);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -960,7 +981,7 @@ int mdm_conv_out_bwd(const void* x, long long ld_x, const float* w, const float*
   cudaStream_t st = as_stream(stream);
   if (dx) {
     dim3 grid(H * ((W + PL_TW - 1) / PL_TW), N);
-    planar_to_nhwc_conv_kernel<1><<<grid, 128, 0, st>>>(dy, w, nullptr, (bf16*)dx, ld_dx, C, H, W, cin, 1);
+    launch_pdl(planar_to_nhwc_conv_kernel<1>, dim3(grid), dim3(128), 0, st, dy, w, nullptr, (bf16*)dx, ld_dx, C, H, W, cin, 1);
     MDM_LAUNCH_CHECK();
   }
   if (dw) {
@@ -968,12 +989,12 @@ int mdm_conv_out_bwd(const void* x, long long ld_x, const float* w, const float*
     const int rows_per_cta = 8;
     dim3 grid((jobs + rows_per_cta - 1) / rows_per_cta, N);
     const int th = ((cin + 31) / 32) * 32;
-    planar_wgrad_kernel<1><<<grid, th, 0, st>>>(dy, (const bf16*)x, ld_x, dw, nullptr, C, H, W, cin, 1, rows_per_cta);
+    launch_pdl(planar_wgrad_kernel<1>, dim3(grid), dim3(th), 0, st, dy, (const bf16*)x, ld_x, dw, nullptr, C, H, W, cin, 1, rows_per_cta);
     MDM_LAUNCH_CHECK();
   }
   if (dbias) {
     dim3 grid(8, N * C);
-    planar_sum_kernel<<<grid, 256, 0, st>>>(dy, dbias, C, (long long)H * W);
+    launch_pdl(planar_sum_kernel, dim3(grid), dim3(256), 0, st, dy, dbias, C, (long long)H * W);
     MDM_LAUNCH_CHECK();
   }
   return MDM_OK;
@@ -982,7 +1003,7 @@ int mdm_conv_out_bwd(const void* x, long long ld_x, const float* w, const float*
 int mdm_upsample2x_fwd(const void* x, long long ld_x, void* y, long long ld_y, int N, int H, int W, int C, void* stream) {
   MDM_CHECK_ARG(x && y && C % 8 == 0, "upsample2x_fwd: bad arguments");
   const long long total = (long long)N * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<GRID1D(total, 256), 256, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (bf16*)y, ld_y, H, W, C, total);
+  launch_pdl(upsample2x_kernel, dim3(GRID1D(total, 256)), dim3(256), 0, as_stream(stream), (const bf16*)x, ld_x, (bf16*)y, ld_y, H, W, C, total);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -990,7 +1011,7 @@ int mdm_upsample2x_fwd(const void* x, long long ld_x, void* y, long long ld_y, i
 int mdm_upsample2x_bwd(const void* dy, long long ld_dy, void* dx, long long ld_dx, int N, int H, int W, int C, void* stream) {
   MDM_CHECK_ARG(dy && dx && C % 4 == 0, "upsample2x_bwd: bad arguments");
   const long long total = (long long)N * H * W * (C / 4);
-  upsample2x_bwd_kernel<<<GRID1D(total, 256), 256, 0, as_stream(stream)>>>((const bf16*)dy, ld_dy, (bf16*)dx, ld_dx, H, W, C, total);
+  launch_pdl(upsample2x_bwd_kernel, dim3(GRID1D(total, 256)), dim3(256), 0, as_stream(stream), (const bf16*)dy, ld_dy, (bf16*)dx, ld_dx, H, W, C, total);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -998,7 +1019,7 @@ int mdm_upsample2x_bwd(const void* dy, long long ld_dy, void* dx, long long ld_d
 int mdm_zero_insert2x(const void* x, long long ld_x, void* y, long long ld_y, int N, int H, int W, int C, void* stream) {
   MDM_CHECK_ARG(x && y && C % 8 == 0, "zero_insert2x: bad arguments");
   const long long total = (long long)N * 4 * H * W * (C / 8);
-  zero_insert2x_kernel<<<GRID1D(total, 256), 256, 0, as_stream(stream)>>>((const bf16*)x, ld_x, (bf16*)y, ld_y, H, W, C, total);
+  launch_pdl(zero_insert2x_kernel, dim3(GRID1D(total, 256)), dim3(256), 0, as_stream(stream), (const bf16*)x, ld_x, (bf16*)y, ld_y, H, W, C, total);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -1008,7 +1029,7 @@ int mdm_attention_fwd(const void* qkv, void* out, int N, int L, int C, void* str
   const int th = L < 32 ? 32 : (L > 256 ? 256 : ((L + 31) / 32) * 32);
   const size_t smem = (size_t)2 * L * ATT_D * sizeof(float);
   dim3 grid(C / ATT_D, N);
-  attention_fwd_kernel<<<grid, th, smem, as_stream(stream)>>>((const bf16*)qkv, (bf16*)out, L, C, 1.0f / sqrtf((float)ATT_D));
+  launch_pdl(attention_fwd_kernel, dim3(grid), dim3(th), smem, as_stream(stream), (const bf16*)qkv, (bf16*)out, L, C, 1.0f / sqrtf((float)ATT_D));
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -1023,28 +1044,28 @@ int mdm_attention_bwd(const void* qkv, const void* dout, void* dqkv, int N, int 
     smem_set = smem;
   }
   dim3 grid(C / ATT_D, N);
-  attention_bwd_kernel<<<grid, th, smem, as_stream(stream)>>>((const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, L, C, 1.0f / sqrtf((float)ATT_D));
+  launch_pdl(attention_bwd_kernel, dim3(grid), dim3(th), smem, as_stream(stream), (const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, L, C, 1.0f / sqrtf((float)ATT_D));
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
 
 int mdm_timestep_embedding(const float* t, void* out, int N, int dim, void* stream) {
   MDM_CHECK_ARG(t && out && dim % 2 == 0, "timestep_embedding: bad arguments");
-  timestep_embedding_kernel<<<GRID1D(N * dim, 256), 256, 0, as_stream(stream)>>>(t, (bf16*)out, N, dim);
+  launch_pdl(timestep_embedding_kernel, dim3(GRID1D(N * dim, 256)), dim3(256), 0, as_stream(stream), t, (bf16*)out, N, dim);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
 
 int mdm_silu_fwd(const float* x, void* y, int64_t n, void* stream) {
   MDM_CHECK_ARG(x && y, "silu_fwd: NULL pointer");
-  silu_f32_to_bf16_kernel<<<GRID1D(n, 256), 256, 0, as_stream(stream)>>>(x, (bf16*)y, n);
+  launch_pdl(silu_f32_to_bf16_kernel, dim3(GRID1D(n, 256)), dim3(256), 0, as_stream(stream), x, (bf16*)y, n);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
 
 int mdm_silu_bwd(const float* x, const float* dy, void* dx, int64_t n, void* stream) {
   MDM_CHECK_ARG(x && dy && dx, "silu_bwd: NULL pointer");
-  silu_bwd_kernel<<<GRID1D(n, 256), 256, 0, as_stream(stream)>>>(x, dy, (bf16*)dx, n);
+  launch_pdl(silu_bwd_kernel, dim3(GRID1D(n, 256)), dim3(256), 0, as_stream(stream), x, dy, (bf16*)dx, n);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -1059,7 +1080,7 @@ int mdm_colsum(const void* dy, long long ld, float* out, float* out2, int64_t ro
   rpc = ((rpc + R - 1) / R) * R;
   if (rpc > rows) rpc = rows;
   const dim3 blocks((unsigned)((rows + rpc - 1) / rpc), (unsigned)((C + 2047) / 2048));
-  colsum_kernel<<<blocks, 256, (size_t)Cb * sizeof(float), as_stream(stream)>>>((const bf16*)dy, ld, out, out2, rows, C, L, R, (int)rpc);
+  launch_pdl(colsum_kernel, dim3(blocks), dim3(256), (size_t)Cb * sizeof(float), as_stream(stream), (const bf16*)dy, ld, out, out2, rows, C, L, R, (int)rpc);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -1067,7 +1088,7 @@ int mdm_colsum(const void* dy, long long ld, float* out, float* out2, int64_t ro
 int mdm_sample_colsum(const void* dy, long long ld, float* out, long long ld_out, float* dbias, int N, int HW, int C, void* stream) {
   MDM_CHECK_ARG(dy && out, "sample_colsum: NULL pointer");
   dim3 grid(GRID1D(C, 128), N);
-  sample_colsum_kernel<<<grid, 128, 0, as_stream(stream)>>>((const bf16*)dy, ld, out, ld_out, dbias, HW, C);
+  launch_pdl(sample_colsum_kernel, dim3(grid), dim3(128), 0, as_stream(stream), (const bf16*)dy, ld, out, ld_out, dbias, HW, C);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -1077,16 +1098,16 @@ int mdm_mse_residual(const float* x_in, const float* net, const float* shift, co
   MDM_CHECK_ARG(x_in && net && x0 && loss && ws, "mse_residual: NULL pointer");
   const int blocks = (int)((total + 256 * 8 - 1) / (256 * 8) < 1024 ? (total + 256 * 8 - 1) / (256 * 8) : 1024);
   const float inv = 1.0f / (float)total;
-  mse_residual_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x_in, net, shift, x0, weight, dnet, recon, ws, per_sample, total, inv);
+  launch_pdl(mse_residual_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), x_in, net, shift, x0, weight, dnet, recon, ws, per_sample, total, inv);
   MDM_LAUNCH_CHECK();
-  mse_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(ws, blocks, inv, loss);
+  launch_pdl(mse_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), ws, blocks, inv, loss);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
 
 int mdm_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
   MDM_CHECK_ARG(x && y, "cast: NULL pointer");
-  f32_to_bf16_kernel<<<GRID1D((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(x, (bf16*)y, n);
+  launch_pdl(f32_to_bf16_kernel, dim3(GRID1D((n + 3) / 4, 256)), dim3(256), 0, as_stream(stream), x, (bf16*)y, n);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }

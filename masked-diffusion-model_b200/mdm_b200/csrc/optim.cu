@@ -9,6 +9,7 @@
 namespace mdm {
 
 __global__ void sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
+  MDM_PDL_ENTER();
   __shared__ float red[32];
   float s = 0.f;
   const long long n4 = n / 4;
@@ -24,6 +25,7 @@ __global__ void sumsq_partial_kernel(const float* __restrict__ g, long long n, f
 }
 
 __global__ void sumsq_final_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  MDM_PDL_ENTER();
   __shared__ double red[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partial[i];
@@ -45,6 +47,7 @@ struct AdamArgs {
 __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, float* __restrict__ ema, __nv_bfloat16* __restrict__ p16,
                                 long long n, const float* __restrict__ gnorm_sq, const float* __restrict__ hyper, AdamArgs a) {
+  MDM_PDL_ENTER();
   if (hyper) {  // per-step scalars read from device memory so that a captured CUDA graph can be replayed
     a.lr = hyper[0]; a.bias_c1 = hyper[1]; a.bias_c2 = hyper[2]; a.ema_decay = hyper[3];
   }
@@ -94,6 +97,7 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ ema,
                            __nv_bfloat16* __restrict__ p16, long long n, const float* __restrict__ gnorm_sq,
                            const float* __restrict__ hyper, AdamArgs a) {
+  MDM_PDL_ENTER();
   if (hyper) { a.lr = hyper[0]; a.ema_decay = hyper[3]; }
   float coef = a.grad_scale;
   if (gnorm_sq && a.max_norm > 0.f) coef *= fminf(1.0f, a.max_norm / (sqrtf(*gnorm_sq) * a.grad_scale + 1e-6f));
@@ -114,9 +118,9 @@ extern "C" {
 int mdm_grad_sumsq(const float* g, int64_t n, float* ws, float* out, void* stream) {
   MDM_CHECK_ARG(g && ws && out && n > 0, "grad_sumsq: bad arguments");
   const int blocks = 1024;
-  sumsq_partial_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, n, ws);
+  launch_pdl(sumsq_partial_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), g, n, ws);
   MDM_LAUNCH_CHECK();
-  sumsq_final_kernel<<<1, 1024, 0, as_stream(stream)>>>(ws, blocks, out);
+  launch_pdl(sumsq_final_kernel, dim3(1), dim3(1024), 0, as_stream(stream), ws, blocks, out);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -130,10 +134,10 @@ static int adam_launch(float* p, const float* g, float* m, float* v, float* ema,
   AdamArgs a{lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2, max_norm, ema_decay, grad_scale, mode == 1};
   const int blocks = kNumSMs * 8;
   if (mode == 2) {
-    sgd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, ema, (__nv_bfloat16*)p_bf16, n, gnorm_sq, hyper, a);
+    launch_pdl(sgd_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), p, g, ema, (__nv_bfloat16*)p_bf16, n, gnorm_sq, hyper, a);
   } else {
     MDM_CHECK_ARG(m && v, "adam_ema_step: moment buffers are NULL");
-    adam_ema_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, ema, (__nv_bfloat16*)p_bf16, n, gnorm_sq, hyper, a);
+    launch_pdl(adam_ema_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), p, g, m, v, ema, (__nv_bfloat16*)p_bf16, n, gnorm_sq, hyper, a);
   }
   MDM_LAUNCH_CHECK();
   return MDM_OK;

@@ -46,6 +46,7 @@ __device__ __forceinline__ uint32_t mt_next_word(const uint32_t* s, int k) {
 
 template <class Emit>
 __global__ void __launch_bounds__(MT_THREADS, 1) mt_stream_kernel(uint32_t* rng, int64_t n, Emit emit) {
+  MDM_PDL_ENTER();
   __shared__ uint32_t st[2][MT_N];
   const int k = threadIdx.x;
   int cur = 0;
@@ -117,7 +118,7 @@ static int launch_stream(uint32_t* rng, int64_t n, Emit e, void* stream) {
   MDM_CHECK_ARG(rng != nullptr, "rng state is NULL");
   MDM_CHECK_ARG(n >= 0, "negative draw count");
   if (n == 0) return MDM_OK;
-  mt_stream_kernel<Emit><<<1, MT_THREADS, 0, as_stream(stream)>>>(rng, n, e);
+  launch_pdl(mt_stream_kernel<Emit>, dim3(1), dim3(MT_THREADS), 0, as_stream(stream), rng, n, e);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -125,6 +126,7 @@ static int launch_stream(uint32_t* rng, int64_t n, Emit e, void* stream) {
 // ---- normal_: in-place 16-wide Box-Muller over a buffer of uniforms ---------------------------
 __global__ void boxmuller16_kernel(float* data, int64_t npairs, float mean, float std,
                                    const double* ratio, int64_t per_sample) {
+  MDM_PDL_ENTER();
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npairs) return;
   const int64_t i0 = (p >> 3) * 16 + (p & 7);
@@ -151,6 +153,7 @@ constexpr int FY_ZCHUNK = 8192;
 __global__ void __launch_bounds__(256) fy_mask_kernel(const uint32_t* __restrict__ words,
                                                       const int64_t* __restrict__ count,
                                                       uint8_t* __restrict__ mask, int hw) {
+  MDM_PDL_ENTER();
   extern __shared__ uint16_t fy_sm[];
   uint16_t* perm = fy_sm;
   uint16_t* z = fy_sm + hw;
@@ -225,7 +228,7 @@ int mdm_rng_normal(uint32_t* rng, float* out, int batch, int64_t per_sample, flo
   const int64_t npairs = n / 2;
   const int threads = 256;
   const int64_t blocks = (npairs + threads - 1) / threads;
-  boxmuller16_kernel<<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(out, npairs, mean, std, ratio, per_sample);
+  launch_pdl(boxmuller16_kernel, dim3((unsigned)blocks), dim3(threads), 0, as_stream(stream), out, npairs, mean, std, ratio, per_sample);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -251,7 +254,7 @@ int mdm_rng_randperm_mask(uint32_t* rng, const int64_t* count, uint8_t* mask, ui
     MDM_CUDA(cudaFuncSetAttribute(fy_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (65536 + FY_ZCHUNK) * 2));
     attr_set = true;
   }
-  fy_mask_kernel<<<batch, 256, smem, as_stream(stream)>>>(words_ws, count, mask, hw);
+  launch_pdl(fy_mask_kernel, dim3(batch), dim3(256), smem, as_stream(stream), words_ws, count, mask, hw);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
