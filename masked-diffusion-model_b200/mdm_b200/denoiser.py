@@ -446,6 +446,10 @@ class _Plan:
         self.fwd, self.bwd = [], []
         self.acts = []
         self._scratch = {}
+        # weight-gradient GEMMs only feed the optimiser: they run on a side stream, concurrently with the
+        # dgrad / GroupNorm chain of the main stream (small layers leave most SMs idle otherwise)
+        self.side = torch.cuda.Stream(device=self.dev) if need_grad else None
+        self._side_readers = {}        # scratch tag -> event recorded after its last side-stream reader
         self._build()
 
     # -- storage helpers ---------------------------------------------------------------------------
@@ -469,6 +473,38 @@ class _Plan:
     def sget(self, ref):
         tag, dtype, shape = ref
         return self._scratch[(tag, dtype)][:math.prod(shape)].view(shape)
+
+    # -- side stream (wgrad) ---------------------------------------------------------------------------
+    def on_side(self, fn, reads=()):
+        """run `fn` (weight-gradient launches) on the side stream after everything enqueued so far on the
+        main stream; `reads` = scratch tags the launches read (guarded against the next main-stream writer)"""
+        if not getattr(self.m, "wgrad_side_stream", True):
+            fn()
+            return
+        main = torch.cuda.current_stream(self.dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            fn()
+            if reads:
+                done = torch.cuda.Event()
+                done.record(self.side)
+                for tag in reads:
+                    self._side_readers[tag] = done
+
+    def before_write(self, *tags):
+        """main stream is about to overwrite these scratch buffers: wait for their side-stream readers"""
+        main = torch.cuda.current_stream(self.dev)
+        for tag in tags:
+            ev = self._side_readers.pop(tag, None)
+            if ev is not None:
+                main.wait_event(ev)
+
+    def join_side(self):
+        if self.side is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(self.side)
+            self._side_readers.clear()
 
     def _materialise(self):
         for a in self.acts:
@@ -529,15 +565,15 @@ class _Plan:
 
             def temb_bwd():
                 ops.cast_f32_bf16(self.d_tproj, d_tproj16)
+                self.on_side(lambda: ops.conv_wgrad(e2_act, d_tproj16, g_tp, B, 1, 1, 1, 1, dbias=gb_tp))
                 ops.conv_dgrad(d_tproj16, w_tp, None, B, 1, 1, 1, dx_f32=d_e2act, cin=temb)
-                ops.conv_wgrad(e2_act, d_tproj16, g_tp, B, 1, 1, 1, 1, dbias=gb_tp)
                 ops.silu_bwd(e2_f32, d_e2act, d_e2)
+                self.on_side(lambda: ops.conv_wgrad(e1_act, d_e2, m.g32("time_embedding.linear_2.weight").view(temb, 1, temb),
+                                                    B, 1, 1, 1, 1, dbias=m.g32("time_embedding.linear_2.bias")))
                 ops.conv_dgrad(d_e2, m.w16("time_embedding.linear_2.weight"), None, B, 1, 1, 1, dx_f32=d_e1act, cin=temb)
-                ops.conv_wgrad(e1_act, d_e2, m.g32("time_embedding.linear_2.weight").view(temb, 1, temb), B, 1, 1, 1, 1,
-                               dbias=m.g32("time_embedding.linear_2.bias"))
                 ops.silu_bwd(e1_f32, d_e1act, d_e1)
-                ops.conv_wgrad(te0, d_e1, m.g32("time_embedding.linear_1.weight").view(temb, 1, boc[0]), B, 1, 1, 1, 1,
-                               dbias=m.g32("time_embedding.linear_1.bias"))
+                self.on_side(lambda: ops.conv_wgrad(te0, d_e1, m.g32("time_embedding.linear_1.weight").view(temb, 1, boc[0]),
+                                                    B, 1, 1, 1, 1, dbias=m.g32("time_embedding.linear_1.bias")))
             self._temb_bwd = temb_bwd
 
         # ---- symbolic pass -------------------------------------------------------------------------
@@ -663,22 +699,27 @@ class _Plan:
             rd_a1 = self.scratch("d_a1", (B, H, H, r.cin))
             has_up = x.has_upstream_grad
 
-            def backward():
+            def wgrad_out():
                 d_out = out.grad
-                d_a2, d_h1, d_a1 = self.sget(rd_a2), self.sget(rd_h1), self.sget(rd_a1)
-                ops.conv_dgrad(d_out, m.w16(f"{p}.conv2.weight"), d_a2, B, H, H, 3)
                 # weight gradients; the bias gradients (column sums of d_out) ride in the same kernel
                 ops.conv_wgrad(a2, d_out, m.g32(f"{p}.conv2.weight"), B, H, H, 3, 1, dbias=m.g32(f"{p}.conv2.bias"),
                                dbias2=m.g32(f"{p}.conv_shortcut.bias") if r.shortcut else None)
                 if r.shortcut:
                     ops.conv_wgrad(x.val, d_out, m.g32(f"{p}.conv_shortcut.weight"), B, H, H, 1, 1)
+
+            def backward():
+                d_out = out.grad
+                d_a2, d_h1, d_a1 = self.sget(rd_a2), self.sget(rd_h1), self.sget(rd_a1)
+                self.on_side(wgrad_out)
+                ops.conv_dgrad(d_out, m.w16(f"{p}.conv2.weight"), d_a2, B, H, H, 3)
+                self.before_write("d_h1")
                 # d_h1 plus, in the same pass, its per-sample column sums = d(time_emb_proj output) and conv1.bias grad
                 ops.gn_silu_bwd(h1, d_a2, d_h1, m.w32(f"{p}.norm2.weight"), m.w32(f"{p}.norm2.bias"), st2,
                                 m.g32(f"{p}.norm2.weight"), m.g32(f"{p}.norm2.bias"), ws2(), B, HW, r.cout, G, True,
                                 colsum=self.d_tproj[:, r.tproj_off:], ld_colsum=self.d_tproj.shape[1],
                                 dbias=m.g32(f"{p}.conv1.bias"))
+                self.on_side(lambda: ops.conv_wgrad(a1, d_h1, m.g32(f"{p}.conv1.weight"), B, H, H, 3, 1), reads=("d_h1",))
                 ops.conv_dgrad(d_h1, m.w16(f"{p}.conv1.weight"), d_a1, B, H, H, 3)
-                ops.conv_wgrad(a1, d_h1, m.g32(f"{p}.conv1.weight"), B, H, H, 3, 1)
                 add = None
                 if r.shortcut:
                     ops.conv_dgrad(d_out, m.w16(f"{p}.conv_shortcut.weight"), x.grad, B, H, H, 1, accumulate=has_up)
@@ -723,12 +764,13 @@ class _Plan:
             def backward():
                 d_out = out.grad
                 d_att, d_qkv, d_y = self.sget(rd_att), self.sget(rd_qkv), self.sget(rd_y)
+                self.on_side(lambda: ops.conv_wgrad(att, d_out, m.g32(f"{p}.to_out.0.weight").view(C, 1, C), B * L_, 1, 1, 1, 1,
+                                                    dbias=m.g32(f"{p}.to_out.0.bias")))
                 ops.conv_dgrad(d_out, m.w16(f"{p}.to_out.0.weight"), d_att, B * L_, 1, 1, 1)
-                ops.conv_wgrad(att, d_out, m.g32(f"{p}.to_out.0.weight").view(C, 1, C), B * L_, 1, 1, 1, 1,
-                               dbias=m.g32(f"{p}.to_out.0.bias"))
+                self.before_write("d_qkv")
                 ops.attention_bwd(qkv, d_att, d_qkv, B, L_, C)
+                self.on_side(lambda: ops.conv_wgrad(y, d_qkv, g_qkv, B * L_, 1, 1, 1, 1, dbias=gb_qkv), reads=("d_qkv",))
                 ops.conv_dgrad(d_qkv, w_qkv, d_y, B * L_, 1, 1, 1)
-                ops.conv_wgrad(y, d_qkv, g_qkv, B * L_, 1, 1, 1, 1, dbias=gb_qkv)
                 ops.gn_silu_bwd(x.val, d_y, x.grad, m.w32(f"{p}.group_norm.weight"), m.w32(f"{p}.group_norm.bias"), st,
                                 m.g32(f"{p}.group_norm.weight"), m.g32(f"{p}.group_norm.bias"), ws(), B, L_, C, G, False,
                                 add=x.grad if has_up else None, add2=d_out)
@@ -747,8 +789,8 @@ class _Plan:
             def backward():
                 z = self.sget(rz)
                 ops.zero_insert2x(out.grad, z, B, H, H, C)
+                self.on_side(lambda: ops.conv_wgrad(x.val, out.grad, m.g32(name + ".weight"), B, H, H, 3, 2, dbias=m.g32(name + ".bias")))
                 ops.conv_dgrad(z, m.w16(name + ".weight"), x.grad, B, 2 * H, 2 * H, 3, accumulate=has_up)
-                ops.conv_wgrad(x.val, out.grad, m.g32(name + ".weight"), B, H, H, 3, 2, dbias=m.g32(name + ".bias"))
             bw = [backward]
         return fw, bw
 
@@ -769,8 +811,8 @@ class _Plan:
 
             def backward():
                 du = self.sget(rdu)
+                self.on_side(lambda: ops.conv_wgrad(u, out.grad, m.g32(name + ".weight"), B, 2 * H, 2 * H, 3, 1, dbias=m.g32(name + ".bias")))
                 ops.conv_dgrad(out.grad, m.w16(name + ".weight"), du, B, 2 * H, 2 * H, 3)
-                ops.conv_wgrad(u, out.grad, m.g32(name + ".weight"), B, 2 * H, 2 * H, 3, 1, dbias=m.g32(name + ".bias"))
                 ops.upsample2x_bwd(du, x.grad, B, H, H, C)
             bw = [backward]
         return fw, bw
@@ -812,3 +854,4 @@ class _Plan:
         self.d_tproj.zero_()          # accumulated by the fused column sums of the norm2 backward
         for op in self.bwd:
             op()
+        self.join_side()              # every weight gradient has landed before the caller (optimiser / all-reduce) runs
