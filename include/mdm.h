@@ -205,6 +205,13 @@ int mdm_conv_out_bwd(const void* x, long long ld_x, const float* w, const float*
                      long long ld_dx, float* dw, float* dbias, int N, int C, int H, int W, int cin,
                      void* stream);
 
+/* first / last convolution as tensor-core GEMMs (round 1b): gather the 3x3 neighbourhood of the C-channel planar fp32
+ * image into a [N*H*W][64] bf16 matrix, column tap*C + c (zero padded; flip = taps mirrored, for the adjoint), and
+ * the 9-tap scatter-sum that finishes the last conv: out[n][c][h][w] = bias[c] + sum_tap z[(n,h+dh,w+dw)][tap*C+c]
+ * with z fp32 [N*H*W][32].  The GEMMs themselves are mdm_conv_fprop / mdm_conv_wgrad with ksize 1. */
+int mdm_im2col3x3(const float* img, void* out_bf16, int N, int C, int H, int W, int flip, void* stream);
+int mdm_tapsum3x3(const float* z, const float* bias, float* out, int N, int C, int H, int W, void* stream);
+
 /* nearest 2x upsample, its adjoint, and zero insertion (turns a stride-2 dgrad into a stride-1 one) */
 int mdm_upsample2x_fwd(const void* x, long long ld_x, void* y, long long ld_y, int N, int H, int W, int C, void* stream);
 int mdm_upsample2x_bwd(const void* dy, long long ld_dy, void* dx, long long ld_dx, int N, int H, int W, int C, void* stream);

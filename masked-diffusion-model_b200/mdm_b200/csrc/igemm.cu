@@ -551,7 +551,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         if (kHalo) p = ((long long)n0 * args.H + h0 + (row >> 3)) * args.W + w0 + (row & 7);
         else p = (long long)k.m_tile * TILE_M + row;
         const bool valid = p < args.M_total;
-        bias_s[et] = (args.bias ? __ldg(args.bias + ncol0 + et) : 0.f) + (args.bias2 ? __ldg(args.bias2 + ncol0 + et) : 0.f);
+        const bool col_ok = ncol0 + et < args.N_total;
+        bias_s[et] = ((args.bias && col_ok) ? __ldg(args.bias + ncol0 + et) : 0.f) + ((args.bias2 && col_ok) ? __ldg(args.bias2 + ncol0 + et) : 0.f);
         const float* rv = (args.rowvec && valid) ? args.rowvec + (p / args.rows_per_vec) * args.ld_rowvec + ncol0 : nullptr;
         if (args.has_c) mbar_wait(&c_full_bar[buf], (local >> 1) & 1);
         epi_bar_sync();   // bias_s visible; staging[buf] is free (thread 0 waited for its last TMA store below)
@@ -574,7 +575,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             f[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
             f[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
           }
-          if (rv) {
+          const bool chunk_ok = ncol0 + cc * 32 < args.N_total;   // N_total is a multiple of 32
+          if (rv && chunk_ok) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 r4 = __ldg(reinterpret_cast<const float4*>(rv + cc * 32) + j4);
@@ -597,7 +599,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               }
             }
           }
-          if (args.out_f32 && valid) {
+          if (args.out_f32 && valid && chunk_ok) {
             float4* o = reinterpret_cast<float4*>(args.out_f32 + p * (long long)args.N_total + ncol0 + cc * 32);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) o[j4] = make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
@@ -883,7 +885,7 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
     if (rc) return rc;
   }
   const int num_m = a.halo ? c->N * (c->H / PATCH_H) * (c->W / PATCH_W) : (a.M_total + TILE_M - 1) / TILE_M;
-  a.num_n = a.N_total / TILE_N;
+  a.num_n = (a.N_total + TILE_N - 1) / TILE_N;   // a narrow last tile is clipped by the TMA store / guarded in the epilogue
   const int tiles = num_m * a.num_n;
   a.iters_total = a.seg_taps[0] * a.seg_kc[0] + (a.nseg > 1 ? a.seg_taps[1] * a.seg_kc[1] : 0);
   int splits = 1;
@@ -944,7 +946,7 @@ int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
   MDM_CHECK_ARG(c && c->x && c->w && (c->y || c->y_f32), "conv_fprop: NULL pointer");
   MDM_CHECK_ARG(c->ksize == 1 || c->ksize == 3, "conv_fprop: ksize must be 1 or 3");
   MDM_CHECK_ARG(c->stride == 1 || c->stride == 2, "conv_fprop: stride must be 1 or 2");
-  MDM_CHECK_ARG(c->cin % 64 == 0 && c->cout % 128 == 0, "conv_fprop: cin %% 64 / cout %% 128 (got %d, %d)", c->cin, c->cout);
+  MDM_CHECK_ARG(c->cin % 64 == 0 && c->cout % 32 == 0, "conv_fprop: cin %% 64 / cout %% 32 (got %d, %d)", c->cin, c->cout);
   MDM_CHECK_ARG(is_pow2(c->H) && is_pow2(c->W), "conv_fprop: output H, W must be powers of two (got %d x %d)", c->H, c->W);
   MDM_CHECK_ARG(c->ld_x % 8 == 0 && c->ld_y % 8 == 0, "conv_fprop: channel strides must be multiples of 8");
   int rc = ensure_smem_attr();
@@ -1013,7 +1015,7 @@ int mdm_conv_wgrad(const mdm_conv_args* c, void* stream) {
   MDM_CHECK_ARG(c && c->x && c->y && c->dw, "conv_wgrad: NULL pointer");
   MDM_CHECK_ARG(c->ksize == 1 || c->ksize == 3, "conv_wgrad: ksize must be 1 or 3");
   MDM_CHECK_ARG(c->stride == 1 || c->stride == 2, "conv_wgrad: stride must be 1 or 2");
-  MDM_CHECK_ARG(c->cin % 128 == 0 && c->cout % 128 == 0, "conv_wgrad: cin, cout %% 128 (got %d, %d)", c->cin, c->cout);
+  MDM_CHECK_ARG(c->cin % 64 == 0 && c->cout % 64 == 0, "conv_wgrad: cin, cout %% 64 (got %d, %d)", c->cin, c->cout);
   MDM_CHECK_ARG(is_pow2(c->H) && is_pow2(c->W), "conv_wgrad: H, W must be powers of two");
   MDM_CHECK_ARG(c->w_col0 % 4 == 0, "conv_wgrad: w_col0 must be a multiple of 4");
   int rc = ensure_smem_attr();
@@ -1033,8 +1035,8 @@ int mdm_conv_wgrad(const mdm_conv_args* c, void* stream) {
   a.w_col0 = (int)c->w_col0;
   a.dbias = c->dbias;
   a.dbias2 = c->dbias2;
-  a.num_co = c->cout / TILE_M;
-  a.num_n = c->cin / TILE_N;
+  a.num_co = (c->cout + TILE_M - 1) / TILE_M;   // partial tiles: TMA zero-fills the loads and clips the reduce-add
+  a.num_n = (c->cin + TILE_N - 1) / TILE_N;
   const long long pixels = (long long)c->N * c->H * c->W;
   a.iters_total = (int)((pixels + 63) / 64);
   // split the pixel (K) range so that ~2 work items per SM exist, at least 4 chunks each

@@ -590,6 +590,62 @@ __global__ void planar_sum_kernel(const float* __restrict__ img, float* __restri
 }
 
 // =============================================================================================
+// First / last convolution as tensor-core GEMMs.  The 3x3 neighbourhood of the (1..4)-channel image is
+// gathered into a [pixel][64] bf16 matrix (column tap*C + c, zero padded): the first conv is then a 1x1
+// GEMM [pix][64] x W'[cout][64], its wgrad the matching wgrad GEMM; the last conv is a 1x1 GEMM producing
+// the 9*C per-tap partial outputs z[pix][32] (fp32) followed by the 9-tap scatter-sum below, its backward
+// the same gather (flipped) feeding a dgrad-as-fprop GEMM and a wgrad GEMM.  (csrc/igemm.cu does the GEMMs.)
+// =============================================================================================
+__global__ void im2col3x3_kernel(const float* __restrict__ img, bf16* __restrict__ out, int C, int H, int W, int flip,
+                                 long long total) {
+  MDM_PDL_ENTER();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (pixel, 8-column chunk)
+  if (i >= total) return;
+  const int chunk = (int)(i & 7);
+  long long p = i >> 3;
+  const int w = (int)(p % W); p /= W;
+  const int h = (int)(p % H); const long long n = p / H;
+  float f[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int j = chunk * 8 + e;
+    float v = 0.f;
+    if (j < 9 * C) {
+      const int tap = j / C, c = j - tap * C;
+      const int dh = flip ? 1 - tap / 3 : tap / 3 - 1, dw = flip ? 1 - tap % 3 : tap % 3 - 1;
+      const int hh = h + dh, ww = w + dw;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(img + ((n * C + c) * H + hh) * W + ww);
+    }
+    f[e] = v;
+  }
+  *reinterpret_cast<uint4*>(out + (i << 3)) = pack8(f);
+}
+
+// out[n][c][h][w] = bias[c] + sum_tap z[(n, h+dh, w+dw)][tap*C + c]   (z: fp32 [N*H*W][32])
+__global__ void tapsum3x3_kernel(const float* __restrict__ z, const float* __restrict__ bias, float* __restrict__ out, int C,
+                                 int H, int W, long long total) {
+  MDM_PDL_ENTER();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // output pixel
+  if (i >= total) return;
+  long long p = i;
+  const int w = (int)(p % W); p /= W;
+  const int h = (int)(p % H); const long long n = p / H;
+  float acc[PL_MAXC];
+#pragma unroll
+  for (int c = 0; c < PL_MAXC; ++c) acc[c] = (bias && c < C) ? bias[c] : 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    const float* zp = z + ((n * H + hh) * W + ww) * 32 + tap * C;
+#pragma unroll
+    for (int c = 0; c < PL_MAXC; ++c)
+      if (c < C) acc[c] += __ldg(zp + c);
+  }
+  for (int c = 0; c < C; ++c) out[((n * C + c) * H + h) * W + w] = acc[c];
+}
+
+// =============================================================================================
 // nearest 2x upsample (fwd), its adjoint (sum of the 2x2 block), zero insertion (stride-2 dgrad)
 // =============================================================================================
 __global__ void upsample2x_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
@@ -997,6 +1053,22 @@ int mdm_conv_out_bwd(const void* x, long long ld_x, const float* w, const float*
     launch_pdl(planar_sum_kernel, dim3(grid), dim3(256), 0, st, dy, dbias, C, (long long)H * W);
     MDM_LAUNCH_CHECK();
   }
+  return MDM_OK;
+}
+
+int mdm_im2col3x3(const float* img, void* out, int N, int C, int H, int W, int flip, void* stream) {
+  MDM_CHECK_ARG(img && out && C >= 1 && C <= PL_MAXC, "im2col3x3: bad arguments (C=%d)", C);
+  const long long total = (long long)N * H * W * 8;
+  launch_pdl(im2col3x3_kernel, dim3(GRID1D(total, 256)), dim3(256), 0, as_stream(stream), img, (bf16*)out, C, H, W, flip, total);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_tapsum3x3(const float* z, const float* bias, float* out, int N, int C, int H, int W, void* stream) {
+  MDM_CHECK_ARG(z && out && C >= 1 && C <= 3, "tapsum3x3: bad arguments (C=%d; 9*C must fit 32 columns)", C);
+  const long long total = (long long)N * H * W;
+  launch_pdl(tapsum3x3_kernel, dim3(GRID1D(total, 256)), dim3(256), 0, as_stream(stream), z, bias, out, C, H, W, total);
+  MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
 

@@ -648,10 +648,27 @@ class _Plan:
         return lambda: self._gnws
 
     def _emit_conv_in(self, out):
+        """first conv as a tensor-core GEMM: gather the 3x3 neighbourhood of the C-channel image into a
+        [pixel][64] bf16 matrix (im2col3x3), then a 1x1 GEMM against W'[cout][tap*C + c]"""
         m, B, S = self.m, self.B, self.S
-        C = m._cfg["in_channels"]
-        fw = [lambda: ops.conv_in_fwd(self.x_in, m.w32("conv_in.weight"), m.w32("conv_in.bias"), out.val, B, C, S, S, out.C)]
-        bw = [lambda: ops.conv_in_wgrad(self.x_in, out.grad, m.g32("conv_in.weight"), m.g32("conv_in.bias"), B, C, S, S, out.C)]
+        C, co = m._cfg["in_channels"], out.C
+        g_in = self.new((B, S, S, 64))
+        wq = self.new((co, 1, 64), zero=True)
+
+        def prep_w():
+            wq[:, 0, :9 * C].copy_(m.w32("conv_in.weight").view(co, C, 9).permute(0, 2, 1).reshape(co, 9 * C))
+        fw = [prep_w,
+              lambda: ops.im2col3x3(self.x_in, g_in, B, C, S, S),
+              lambda: ops.conv_fprop(g_in, wq, out.val, B, S, S, 1, 1, bias=m.w32("conv_in.bias"))]
+        bw = []
+        if self.need_grad:
+            dwq = self.new((co, 1, 64), torch.float32)
+
+            def backward():
+                dwq.zero_()
+                ops.conv_wgrad(g_in, out.grad, dwq, B, S, S, 1, 1, dbias=m.g32("conv_in.bias"))
+                m.g32("conv_in.weight").add_(dwq[:, 0, :9 * C].view(co, 9, C).permute(0, 2, 1).reshape(co, C, 3, 3))
+            bw = [backward]
         return fw, bw
 
     def _emit_resnet(self, r, x, out, H):
@@ -818,22 +835,41 @@ class _Plan:
         return fw, bw
 
     def _emit_head(self, x):
+        """GroupNorm + SiLU + last conv.  The conv is a 1x1 GEMM producing the 9*Co per-tap partial outputs
+        z[pixel][tap*Co + c] (fp32) followed by the 9-tap scatter-sum; its backward is the flipped gather of
+        d_out feeding a GEMM (dgrad) and a wgrad GEMM."""
         m, B, S = self.m, self.B, self.S
         C, Co = x.C, m._cfg["out_channels"]
         a = self.new((B, S, S, C))
         st = self.new((B, G, 2), torch.float32)
         ws = self._gn_ws(S * S, C)
         eps = self.eps
+        w2 = self.new((32, 1, C), zero=True)
+        z = self.new((B * S * S, 32), torch.float32)
+
+        def prep_w2():
+            w2[:9 * Co, 0, :].copy_(m.w32("conv_out.weight").view(Co, C, 9).permute(2, 0, 1).reshape(9 * Co, C))
         fw = [lambda: ops.gn_silu_fwd(x.val, a, m.w32("conv_norm_out.weight"), m.w32("conv_norm_out.bias"), st, ws(), B, S * S, C, G, eps, True),
-              lambda: ops.conv_out_fwd(a, m.w32("conv_out.weight"), m.w32("conv_out.bias"), self.out, B, Co, S, S, C)]
+              prep_w2,
+              lambda: ops.conv_fprop(a, w2, None, B, S, S, 1, 1, y_f32=z, cout=32),
+              lambda: ops.tapsum3x3(z, m.w32("conv_out.bias"), self.out, B, Co, S, S)]
         bw = []
         if self.need_grad:
             rda = self.scratch("d_head", (B, S, S, C))
             self.d_out = self.new((B, Co, S, S), torch.float32)
+            g_out = self.new((B, S, S, 64))
+            w3 = self.new((C, 1, 64), zero=True)
+            dw2 = self.new((64, 1, C), torch.float32)
 
             def backward():
                 da = self.sget(rda)
-                ops.conv_out_bwd(a, m.w32("conv_out.weight"), self.d_out, da, m.g32("conv_out.weight"), m.g32("conv_out.bias"), B, Co, S, S, C)
+                ops.im2col3x3(self.d_out, g_out, B, Co, S, S, flip=True)
+                w3[:, 0, :9 * Co].copy_(m.w32("conv_out.weight").view(Co, C, 9).permute(1, 2, 0).reshape(C, 9 * Co))
+                ops.conv_fprop(g_out, w3, da, B, S, S, 1, 1)
+                dw2.zero_()
+                ops.conv_wgrad(a, g_out, dw2, B, S, S, 1, 1)
+                m.g32("conv_out.weight").add_(dw2[:9 * Co, 0, :].view(9, Co, C).permute(1, 2, 0).reshape(Co, C, 3, 3))
+                m.g32("conv_out.bias").add_(self.d_out.sum(dim=(0, 2, 3)))
                 ops.gn_silu_bwd(x.val, da, x.grad, m.w32("conv_norm_out.weight"), m.w32("conv_norm_out.bias"), st,
                                 m.g32("conv_norm_out.weight"), m.g32("conv_norm_out.bias"), ws(), B, S * S, C, G, True)
             bw = [backward]

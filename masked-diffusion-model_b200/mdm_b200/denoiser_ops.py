@@ -45,6 +45,8 @@ _lib.register({
     "mdm_conv_in_wgrad": (c_int, [_P, _P, _LL, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "mdm_conv_out_fwd": (c_int, [_P, _LL, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "mdm_conv_out_bwd": (c_int, [_P, _LL, _P, _P, _P, _LL, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mdm_im2col3x3": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mdm_tapsum3x3": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "mdm_upsample2x_fwd": (c_int, [_P, _LL, _P, _LL, c_int, c_int, c_int, c_int, _P]),
     "mdm_upsample2x_bwd": (c_int, [_P, _LL, _P, _LL, c_int, c_int, c_int, c_int, _P]),
     "mdm_zero_insert2x": (c_int, [_P, _LL, _P, _LL, c_int, c_int, c_int, c_int, _P]),
@@ -195,6 +197,16 @@ def conv_out_fwd(x, w, bias, y, N, C, H, W, cin):
 def conv_out_bwd(x, w, dy, dx, dw, dbias, N, C, H, W, cin):
     check(lib().mdm_conv_out_bwd(_dp(x), pix_ld(x), _dp(w), _dp(dy), _dp(dx), pix_ld(dx) if dx is not None else 0,
                                  _dp(dw), _dp(dbias), N, C, H, W, cin, _s(x)))
+
+
+def im2col3x3(img, out, N, C, H, W, flip=False):
+    """planar fp32 [N,C,H,W] -> bf16 [N*H*W, 64], column tap*C + c (zero padded); flip mirrors the taps"""
+    check(lib().mdm_im2col3x3(_dp(img), _dp(out), N, C, H, W, int(flip), _s(img)))
+
+
+def tapsum3x3(z, bias, out, N, C, H, W):
+    """out[n,c,h,w] = bias[c] + sum_tap z[(n,h+dh,w+dw), tap*C + c]; z fp32 [N*H*W, 32]"""
+    check(lib().mdm_tapsum3x3(_dp(z), _dp(bias), _dp(out), N, C, H, W, _s(z)))
 
 
 def upsample2x_fwd(x, y, N, H, W, C):
