@@ -214,6 +214,7 @@ def roofline_pass(tr, model, batch_dev, peaks):
     saved = tr.args.cuda_graph
     tr.args.cuda_graph = False
     tr._graphs.clear()
+    model.wgrad_side_stream = False     # serialise wgrad with the main chain: each event pair then times ONE kernel
     try:
         torch.cuda.synchronize()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -227,6 +228,7 @@ def roofline_pass(tr, model, batch_dev, peaks):
     finally:
         for k, f in orig.items():
             setattr(ops, k, f)
+        model.wgrad_side_stream = True
         tr.args.cuda_graph = saved
         tr._graphs.clear()
     total_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in rec)

@@ -173,6 +173,7 @@ struct IgemmArgs {
   int mode;   // 0: activation GEMM (fprop / dgrad), 1: wgrad
   int epi;    // 0: bf16 TMA store (+bias/rowvec/C tile), 1: fp32 TMA reduce-add
   int halo;   // mode 0 only: A = input halo per channel chunk, taps = shifted views; M tile = 8 x 16 patch
+  int mt;     // 128-row sub-tiles per work item (2: 256 x 128 output tiles)
   int pw, ph, pn;       // wgrad: geometry of the 64-pixel K box
   float* dbias;         // wgrad: bias gradient dbias[co] += sum_pix dY[pix][co] (one extra N=16 MMA against a ones tile)
   float* dbias2;
@@ -278,7 +279,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return
 // iteration), every extra instruction in them showed up 1:1 in the measured throughput.
 // Warp roles: 0 = TMA producer of the A operand, 6 = TMA producer of the B operand, 1 = MMA issuer (+TMEM
 // allocator), 2..5 = epilogue.
-template <int kMode, bool kHalo>
+// kMT: 128-row sub-tiles per work item (2 = a 256 x 128 output tile: both halves share every B tile, which cuts the
+// L2 -> SM operand traffic per FLOP by 25 %; 3 stages of [B][A0][A1] = 48 KB; the two TMEM stages hold 256 columns each)
+template <int kMode, bool kHalo, int kMT>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
              const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
@@ -288,8 +291,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int kASlots = kHalo ? 2 : 0;
-  constexpr int kBSlots = kHalo ? 5 : 4;
-  constexpr int kBSlotBytes = kHalo ? B_BYTES : A_BYTES + B_BYTES;   // plain stage = [B tile][A tile]
+  constexpr int kBSlots = kHalo ? 5 : (kMT == 2 ? 3 : 4);
+  constexpr int kBSlotBytes = kHalo ? B_BYTES : kMT * A_BYTES + B_BYTES;   // plain stage = [B tile][A tile(s)]
+  constexpr int kAccCols = TILE_N * kMT;
+  static_assert(kMT == 1 || (kMode == 0 && !kHalo), "256-row tiles: plain activation GEMM only");
   uint8_t* a_ring = smem;                                   // halo slots (halo mode only)
   uint8_t* b_ring = smem + kASlots * HALO_BYTES;
   float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS_OFF);
@@ -346,8 +351,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     for (int w = w_first; w < args.num_work; w += w_step) {
       const Work k = decode_work(args, w);
       if (kMode == 0) {
-        int w0, h0, n0;
-        tile_origin(args, kHalo, k.m_tile, w0, h0, n0);
+        int w0, h0, n0, w1 = 0, h1 = 0, n1 = 0;
+        tile_origin(args, kHalo, k.m_tile * kMT, w0, h0, n0);
+        if (kMT == 2) tile_origin(args, kHalo, k.m_tile * kMT + 1, w1, h1, n1);
         IterWalker<kHalo> it;
         it.init(args, k.it0);
         for (int i = 0; i < k.nit; ++i) {
@@ -368,10 +374,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           } else {
             const CUtensorMap* mA = it.seg == 0 ? &mapA0 : &mapA1;
             const int st = args.a_stride[it.seg];
+            const int dw = args.tap_dw[it.seg][it.tap], dh = args.tap_dh[it.seg][it.tap];
             mbar_wait(&b_empty[sb], pb ^ 1);
-            mbar_expect_tx(&b_full[sb], A_BYTES);
-            tma_load_4d(mA, b_ring + sb * kBSlotBytes + B_BYTES, &b_full[sb], it.kc * TILE_K,
-                        w0 * st + args.tap_dw[it.seg][it.tap], h0 * st + args.tap_dh[it.seg][it.tap], n0);
+            mbar_expect_tx(&b_full[sb], kMT * A_BYTES);
+            tma_load_4d(mA, b_ring + sb * kBSlotBytes + B_BYTES, &b_full[sb], it.kc * TILE_K, w0 * st + dw, h0 * st + dh, n0);
+            if (kMT == 2)
+              tma_load_4d(mA, b_ring + sb * kBSlotBytes + B_BYTES + A_BYTES, &b_full[sb], it.kc * TILE_K, w1 * st + dw,
+                          h1 * st + dh, n1);
             if (++sb == kBSlots) { sb = 0; pb ^= 1; }
           }
           it.next(args);
@@ -462,7 +471,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       const int acc = local & 1;
       mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
       tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * TILE_N;
+      const uint32_t tmem_d = tmem_base + acc * kAccCols;
       uint32_t lo_a = 0;
       int sa_cur = 0, tap = 0;
       // wgrad work items (ci tile 0, first tap) also accumulate the bias gradient: A = dY tile, B = ones, N = 16
@@ -495,9 +504,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         if (++sb == kBSlots) { sb = 0; pb ^= 1; }
         ready = (i + 1 < k.nit) ? mbar_try_wait(&b_full[sb], pb) : false;
 #pragma unroll
-        for (int kk = 0; kk < TILE_K / 16; ++kk) {
-          umma_bf16(tmem_d, make_desc(hi_a, lo_at + kk * kstep_a), make_desc(DESC_HI_SBO1024, lo_b + kk * kstep_b), idesc,
-                    (i | kk) != 0 ? 1u : 0u);
+        for (int half = 0; half < kMT; ++half) {
+#pragma unroll
+          for (int kk = 0; kk < TILE_K / 16; ++kk) {
+            umma_bf16(tmem_d + half * TILE_N, make_desc(hi_a, lo_at + half * (A_BYTES >> 4) + kk * kstep_a),
+                      make_desc(DESC_HI_SBO1024, lo_b + kk * kstep_b), idesc, (i | kk) != 0 ? 1u : 0u);
+          }
         }
         if (bias_item) {
 #pragma unroll
@@ -523,45 +535,51 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     uint32_t v[32];
     int local = 0;
     // C / D tiles: plain = 2-D [pixel][channel] boxes {64, 128}; halo = 4-D NHWC boxes {64, 8, 16, 1}
-    auto load_c = [&](const Work& kk, int buf) {
+    auto load_c = [&](int m128, int n_tile, int buf) {   // residual / accumulate tile of one 128 x 128 output tile
       uint8_t* so = stg_base + buf * EPI_BYTES;
       mbar_expect_tx(&c_full_bar[buf], EPI_BYTES);
       if (kHalo) {
         int w0, h0, n0;
-        tile_origin(args, kHalo, kk.m_tile, w0, h0, n0);
-        tma_load_4d(&mapC, so, &c_full_bar[buf], kk.n_tile * TILE_N, w0, h0, n0);
-        tma_load_4d(&mapC, so + 16384, &c_full_bar[buf], kk.n_tile * TILE_N + 64, w0, h0, n0);
+        tile_origin(args, kHalo, m128, w0, h0, n0);
+        tma_load_4d(&mapC, so, &c_full_bar[buf], n_tile * TILE_N, w0, h0, n0);
+        tma_load_4d(&mapC, so + 16384, &c_full_bar[buf], n_tile * TILE_N + 64, w0, h0, n0);
       } else {
-        tma_load_2d(&mapC, so, &c_full_bar[buf], kk.n_tile * TILE_N, kk.m_tile * TILE_M);
-        tma_load_2d(&mapC, so + 16384, &c_full_bar[buf], kk.n_tile * TILE_N + 64, kk.m_tile * TILE_M);
+        tma_load_2d(&mapC, so, &c_full_bar[buf], n_tile * TILE_N, m128 * TILE_M);
+        tma_load_2d(&mapC, so + 16384, &c_full_bar[buf], n_tile * TILE_N + 64, m128 * TILE_M);
       }
     };
-    if (args.has_c && et == 0 && w_first < args.num_work) load_c(decode_work(args, w_first), 0);
+    if (args.has_c && et == 0 && w_first < args.num_work) {
+      const Work k0 = decode_work(args, w_first);
+      load_c(k0.m_tile * kMT, k0.n_tile, 0);
+    }
+    int hl = 0;   // 128 x 128 tiles finished by this CTA (staging buffer / C-tile barrier parity)
     for (int w = w_first; w < args.num_work; w += w_step, ++local) {
       const Work k = decode_work(args, w);
       const int acc = local & 1;
-      const uint32_t tmem_acc = tmem_base + acc * TILE_N + ((uint32_t)(q * 32) << 16);
       if (args.epi == 0) {
-        const int buf = local & 1;
+       for (int half = 0; half < kMT; ++half, ++hl) {
+        const uint32_t tmem_acc = tmem_base + acc * kAccCols + half * TILE_N + ((uint32_t)(q * 32) << 16);
+        const int m128 = k.m_tile * kMT + half;
+        const int buf = hl & 1;
         uint8_t* stg = stg_base + buf * EPI_BYTES;
         const int ncol0 = k.n_tile * TILE_N;
         int w0, h0, n0;
-        tile_origin(args, kHalo, k.m_tile, w0, h0, n0);
+        tile_origin(args, kHalo, m128, w0, h0, n0);
         long long p;       // flattened pixel of this thread's row
         if (kHalo) p = ((long long)n0 * args.H + h0 + (row >> 3)) * args.W + w0 + (row & 7);
-        else p = (long long)k.m_tile * TILE_M + row;
+        else p = (long long)m128 * TILE_M + row;
         const bool valid = p < args.M_total;
         const bool col_ok = ncol0 + et < args.N_total;
         bias_s[et] = ((args.bias && col_ok) ? __ldg(args.bias + ncol0 + et) : 0.f) + ((args.bias2 && col_ok) ? __ldg(args.bias2 + ncol0 + et) : 0.f);
         const float* rv = (args.rowvec && valid) ? args.rowvec + (p / args.rows_per_vec) * args.ld_rowvec + ncol0 : nullptr;
-        if (args.has_c) mbar_wait(&c_full_bar[buf], (local >> 1) & 1);
+        if (args.has_c) mbar_wait(&c_full_bar[buf], (hl >> 1) & 1);
         epi_bar_sync();   // bias_s visible; staging[buf] is free (thread 0 waited for its last TMA store below)
-        mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1);
+        if (half == 0) mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1);
         tcgen05_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < TILE_N / 32; ++cc) {
           tmem_ld32(tmem_acc + cc * 32, v);
-          if (cc == TILE_N / 32 - 1) {      // accumulator fully read: hand it back to the MMA warp
+          if (cc == TILE_N / 32 - 1 && half == kMT - 1) {      // accumulator fully read: hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -624,15 +642,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                          ::"l"((uint64_t)&mapD), "r"(smem_u32(stg + 16384)), "r"(ncol0 + 64), "r"(w0), "r"(h0), "r"(n0) : "memory");
           } else {
-            tma_store_2d(&mapD, stg, ncol0, k.m_tile * TILE_M);
-            tma_store_2d(&mapD, stg + 16384, ncol0 + 64, k.m_tile * TILE_M);
+            tma_store_2d(&mapD, stg, ncol0, m128 * TILE_M);
+            tma_store_2d(&mapD, stg + 16384, ncol0 + 64, m128 * TILE_M);
           }
           bulk_commit();
           bulk_wait_read<1>();   // every store but the one just issued has read its smem: the OTHER tile is free
-          const int wn = w + w_step;
-          if (args.has_c && wn < args.num_work) load_c(decode_work(args, wn), buf ^ 1);
+          if (args.has_c) {      // prefetch the C tile of the next 128 x 128 tile into the other staging buffer
+            if (half + 1 < kMT) {
+              load_c(m128 + 1, k.n_tile, buf ^ 1);
+            } else if (w + w_step < args.num_work) {
+              const Work kn = decode_work(args, w + w_step);
+              load_c(kn.m_tile * kMT, kn.n_tile, buf ^ 1);
+            }
+          }
         }
+       }
       } else {
+        const uint32_t tmem_acc = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
         // fp32 reduce-add: 4 chunks of 32 columns -> 4 boxes {32 fp32, 128 rows} (2 per staging tile)
         int x0, y0;
         if (args.mode == 1) {
@@ -813,9 +839,10 @@ static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 static int ensure_smem_attr() {
   static bool done = false;
   if (!done) {
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     done = true;
   }
   return MDM_OK;
@@ -851,9 +878,10 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
                         const CUtensorMap& mC, const CUtensorMap& mD, IgemmArgs& a, void* stream) {
   const int grid = a.num_work < kNumSMs ? a.num_work : kNumSMs;
   cudaStream_t st = as_stream(stream);
-  if (a.mode == 1) launch_pdl(igemm_kernel<1, false>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.halo) launch_pdl(igemm_kernel<0, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else launch_pdl(igemm_kernel<0, false>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  if (a.mode == 1) launch_pdl(igemm_kernel<1, false, 1>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.halo) launch_pdl(igemm_kernel<0, true, 1>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.mt == 2) launch_pdl(igemm_kernel<0, false, 2>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else launch_pdl(igemm_kernel<0, false, 1>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -884,8 +912,15 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
     rc = make_act_map(&mA1, c->x2, c->ld_x2, c->cin2, c->W, c->H, c->N, bw, bh, bn, 1);
     if (rc) return rc;
   }
-  const int num_m = a.halo ? c->N * (c->H / PATCH_H) * (c->W / PATCH_W) : (a.M_total + TILE_M - 1) / TILE_M;
+  int num_m = a.halo ? c->N * (c->H / PATCH_H) * (c->W / PATCH_W) : (a.M_total + TILE_M - 1) / TILE_M;
   a.num_n = (a.N_total + TILE_N - 1) / TILE_N;   // a narrow last tile is clipped by the TMA store / guarded in the epilogue
+  // 256-row tiles once they still fill every SM (both halves share each weight tile: 25 % less operand traffic)
+  static const int mt2_enabled = env_flag("MDM_IGEMM_M256", 1);
+  a.mt = 1;
+  if (mt2_enabled && !a.halo && out != nullptr && ((num_m + 1) / 2) * a.num_n >= kNumSMs) {
+    a.mt = 2;
+    num_m = (num_m + 1) / 2;
+  }
   const int tiles = num_m * a.num_n;
   a.iters_total = a.seg_taps[0] * a.seg_kc[0] + (a.nseg > 1 ? a.seg_taps[1] * a.seg_kc[1] : 0);
   int splits = 1;
