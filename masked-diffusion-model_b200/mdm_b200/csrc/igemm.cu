@@ -47,12 +47,12 @@ constexpr int RING_BYTES = 2 * HALO_BYTES + 5 * B_BYTES;    // halo: 2 A + 5 B s
 constexpr int SMEM_EPI_OFF = RING_BYTES;
 constexpr int SMEM_BIAS_OFF = SMEM_EPI_OFF + 2 * EPI_BYTES;   // 128 floats
 constexpr int SMEM_BAR_OFF = SMEM_BIAS_OFF + 512;
-constexpr int SMEM_ONES_OFF = 4 * (A_BYTES + B_BYTES);   // mode 1 only (plain ring = 128 KB): inside the unused ring tail
+constexpr int SMEM_ONES_OFF = 3 * (A_BYTES + 2 * B_BYTES);   // mode 1 only (ring = 3 x 48 KB): the unused ring tail
 constexpr int IGEMM_SMEM = SMEM_BAR_OFF + 256 + 1024 /*alignment slack*/;
 constexpr int TMEM_COLS = 512;                 // two 128-column fp32 accumulators + two 16-column bias-gradient ones
 constexpr int TMEM_BIAS_COL = 256;             // wgrad bias gradient: D2[co][0..15] = sum_pix dY[pix][co] * 1
 constexpr int ONES_BYTES = 8192;               // [64 K-rows][64 bf16] of 1.0: the B operand of that extra MMA
-static_assert(4 * A_BYTES + 4 * B_BYTES + ONES_BYTES <= RING_BYTES, "plain ring + ones tile must fit");
+static_assert(4 * A_BYTES + 4 * B_BYTES <= RING_BYTES && SMEM_ONES_OFF + ONES_BYTES <= RING_BYTES, "plain ring / wgrad ring + ones tile must fit");
 static_assert(IGEMM_SMEM <= 232448, "shared memory budget");
 
 // ---- raw PTX wrappers ------------------------------------------------------------------------
@@ -205,10 +205,16 @@ struct IgemmArgs {
 };
 
 struct Work {
-  int m_tile, n_tile;   // mode 0: pixel tile, cout tile;  mode 1: cout tile, cin tile
-  int tap;              // mode 1
+  int m_tile, n_tile;   // mode 0: pixel tile, cout tile;  mode 1: cout tile, -
+  int y0;               // mode 1: first of the (up to two) consecutive (cin tile, tap) entries sharing this item's dY tiles
   int it0, nit;         // iteration range
 };
+// wgrad entry y -> (cin tile, tap index); entries y >= num_n * taps do not exist
+__device__ __forceinline__ bool wg_entry(const IgemmArgs& a, int y, int& n_tile, int& tap) {
+  n_tile = y / a.taps;
+  tap = y - n_tile * a.taps;
+  return y < a.num_n * a.taps;
+}
 
 __device__ __forceinline__ Work decode_work(const IgemmArgs& a, int w) {
   Work k;
@@ -217,12 +223,11 @@ __device__ __forceinline__ Work decode_work(const IgemmArgs& a, int w) {
   if (a.mode == 0) {
     k.n_tile = t % a.num_n;
     k.m_tile = t / a.num_n;
-    k.tap = 0;
+    k.y0 = 0;
   } else {
     k.m_tile = t % a.num_co;
-    const int y = t / a.num_co;
-    k.tap = y % a.taps;
-    k.n_tile = y / a.taps;
+    k.y0 = (t / a.num_co) * a.mt;
+    k.n_tile = 0;
   }
   k.it0 = z * a.iters_per_split;
   k.nit = min(a.iters_per_split, a.iters_total - k.it0);
@@ -292,9 +297,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int kASlots = kHalo ? 2 : 0;
   constexpr int kBSlots = kHalo ? 5 : (kMT == 2 ? 3 : 4);
-  constexpr int kBSlotBytes = kHalo ? B_BYTES : kMT * A_BYTES + B_BYTES;   // plain stage = [B tile][A tile(s)]
+  // plain stage: mode 0 = [B][A0](A1) (two pixel sub-tiles share the weight tile); mode 1 = [B0](B1)[A] (two
+  // (cin tile, tap) entries share the dY tile)
+  constexpr int kBSlotBytes = kHalo ? B_BYTES : (kMT + 1) * A_BYTES;
+  constexpr int kAOff = kMode == 1 ? kMT * B_BYTES : B_BYTES;
   constexpr int kAccCols = TILE_N * kMT;
-  static_assert(kMT == 1 || (kMode == 0 && !kHalo), "256-row tiles: plain activation GEMM only");
+  constexpr int kAccStages = (kMode == 1 && kMT == 2) ? 1 : 2;   // wgrad pairs: 256 + 16 (bias) columns, long K loops
+  static_assert(kMT == 1 || !kHalo, "two sub-tiles: plain stages only");
   uint8_t* a_ring = smem;                                   // halo slots (halo mode only)
   uint8_t* b_ring = smem + kASlots * HALO_BYTES;
   float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS_OFF);
@@ -377,9 +386,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             const int dw = args.tap_dw[it.seg][it.tap], dh = args.tap_dh[it.seg][it.tap];
             mbar_wait(&b_empty[sb], pb ^ 1);
             mbar_expect_tx(&b_full[sb], kMT * A_BYTES);
-            tma_load_4d(mA, b_ring + sb * kBSlotBytes + B_BYTES, &b_full[sb], it.kc * TILE_K, w0 * st + dw, h0 * st + dh, n0);
+            tma_load_4d(mA, b_ring + sb * kBSlotBytes + kAOff, &b_full[sb], it.kc * TILE_K, w0 * st + dw, h0 * st + dh, n0);
             if (kMT == 2)
-              tma_load_4d(mA, b_ring + sb * kBSlotBytes + B_BYTES + A_BYTES, &b_full[sb], it.kc * TILE_K, w1 * st + dw,
+              tma_load_4d(mA, b_ring + sb * kBSlotBytes + kAOff + A_BYTES, &b_full[sb], it.kc * TILE_K, w1 * st + dw,
                           h1 * st + dh, n1);
             if (++sb == kBSlots) { sb = 0; pb ^= 1; }
           }
@@ -395,7 +404,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         int h0 = rem / args.W, w0 = rem - h0 * args.W;
         for (int i = 0; i < k.nit; ++i) {
           mbar_wait(&b_empty[sb], pb ^ 1);
-          uint8_t* a_dst = b_ring + sb * kBSlotBytes + B_BYTES;
+          uint8_t* a_dst = b_ring + sb * kBSlotBytes + kAOff;
           mbar_expect_tx(&b_full[sb], A_BYTES);
           tma_load_4d(&mapA0, a_dst, &b_full[sb], co0, w0, h0, n0);
           tma_load_4d(&mapA0, a_dst + 8192, &b_full[sb], co0 + 64, w0, h0, n0);
@@ -431,9 +440,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           it.next(args);
         }
       } else {
-        // wgrad: B = X shifted by the tap (MN-major, N = ci)
-        const int ci0 = k.n_tile * TILE_N;
-        const int dh = args.tap_dh[0][k.tap], dw = args.tap_dw[0][k.tap];
+        // wgrad: B = X shifted by the tap (MN-major, N = ci); up to kMT (cin tile, tap) entries per item
+        int ci0[kMT], dh[kMT], dw[kMT];
+        int nvalid = 0;
+#pragma unroll
+        for (int half = 0; half < kMT; ++half) {
+          int nt, tp;
+          if (wg_entry(args, k.y0 + half, nt, tp)) ++nvalid;
+          else tp = 0;
+          ci0[half] = nt * TILE_N;
+          dh[half] = args.tap_dh[0][tp];
+          dw[half] = args.tap_dw[0][tp];
+        }
         const int st = args.a_stride[0];
         const int hw = args.W * args.H;
         const int p0 = k.it0 * TILE_K;
@@ -443,9 +461,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         for (int i = 0; i < k.nit; ++i) {
           mbar_wait(&b_empty[sb], pb ^ 1);
           uint8_t* b_dst = b_ring + sb * kBSlotBytes;
-          mbar_expect_tx(&b_full[sb], B_BYTES);
-          tma_load_4d(&mapB0, b_dst, &b_full[sb], ci0, w0 * st + dw, h0 * st + dh, n0);
-          tma_load_4d(&mapB0, b_dst + 8192, &b_full[sb], ci0 + 64, w0 * st + dw, h0 * st + dh, n0);
+          mbar_expect_tx(&b_full[sb], nvalid * B_BYTES);
+#pragma unroll
+          for (int half = 0; half < kMT; ++half) {
+            if (half < nvalid) {
+              tma_load_4d(&mapB0, b_dst + half * B_BYTES, &b_full[sb], ci0[half], w0 * st + dw[half], h0 * st + dh[half], n0);
+              tma_load_4d(&mapB0, b_dst + half * B_BYTES + 8192, &b_full[sb], ci0[half] + 64, w0 * st + dw[half], h0 * st + dh[half], n0);
+            }
+          }
           if (++sb == kBSlots) { sb = 0; pb ^= 1; }
           w0 += args.pw;
           if (w0 >= args.W) { w0 = 0; h0 += args.ph; if (h0 >= args.H) { h0 = 0; n0 += args.pn; } }
@@ -459,8 +482,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     const uint32_t idesc = make_idesc(a_mn, b_mn);
     // descriptor low words of slot 0 and the per-16-element K step of each operand
     const uint32_t lo_b0 = ((smem_u32(b_ring) >> 4) & 0x3FFF) | (b_mn ? DESC_LO_MNMAJOR : DESC_LO_KMAJOR);
-    const uint32_t lo_a0 = lo_b0 + (B_BYTES >> 4);   // plain stage: A tile behind the B tile (same LBO class in mode 1 / 0)
-    const uint32_t lo_a_plain0 = (kMode == 1 || !b_mn) ? lo_a0 : (((smem_u32(b_ring) + B_BYTES) >> 4) & 0x3FFF) | DESC_LO_KMAJOR;
+    const uint32_t lo_a0 = lo_b0 + (kAOff >> 4);   // plain stage: A tile(s) behind the B tile(s) (same LBO class in mode 1 / 0)
+    const uint32_t lo_a_plain0 = (kMode == 1 || !b_mn) ? lo_a0 : (((smem_u32(b_ring) + kAOff) >> 4) & 0x3FFF) | DESC_LO_KMAJOR;
     const uint32_t kstep_a = a_mn ? (2048u >> 4) : (32u >> 4);
     const uint32_t kstep_b = b_mn ? (2048u >> 4) : (32u >> 4);
     const uint32_t lo_halo0 = ((smem_u32(a_ring) >> 4) & 0x3FFF) | DESC_LO_KMAJOR;
@@ -468,14 +491,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     uint32_t pa = 0, pb = 0;
     for (int w = w_first; w < args.num_work; w += w_step, ++local) {
       const Work k = decode_work(args, w);
-      const int acc = local & 1;
-      mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+      const int acc = local % kAccStages;
+      mbar_wait(&tmem_empty_bar[acc], ((local / kAccStages) & 1) ^ 1);   // the epilogue has drained this accumulator
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * kAccCols;
+      int nhalf = kMT;                                          // wgrad: the second entry of the pair may not exist
+      if (kMode == 1) { int nt, tp; nhalf = 0; for (int h = 0; h < kMT; ++h) nhalf += wg_entry(args, k.y0 + h, nt, tp) ? 1 : 0; }
       uint32_t lo_a = 0;
       int sa_cur = 0, tap = 0;
       // wgrad work items (ci tile 0, first tap) also accumulate the bias gradient: A = dY tile, B = ones, N = 16
-      const bool bias_item = kMode == 1 && args.dbias != nullptr && k.n_tile == 0 && k.tap == 0;
+      const bool bias_item = kMode == 1 && args.dbias != nullptr && k.y0 == 0;
       const uint32_t idesc16 = (idesc & ~(0x3Fu << 17)) | ((16u >> 3) << 17);
       const uint32_t lo_ones = ((smem_u32(smem + SMEM_ONES_OFF) >> 4) & 0x3FFF) | DESC_LO_MNMAJOR;
       const int n_halo = kHalo ? args.seg_taps[0] * args.seg_kc[0] : 0;   // halo iterations come first (no K split)
@@ -505,10 +530,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         ready = (i + 1 < k.nit) ? mbar_try_wait(&b_full[sb], pb) : false;
 #pragma unroll
         for (int half = 0; half < kMT; ++half) {
+          if (half < nhalf) {
+            // mode 0: the halves are two A (pixel) sub-tiles against one B; mode 1: two B tiles against one A
+            const uint32_t la = lo_at + (kMode == 0 ? half * (A_BYTES >> 4) : 0);
+            const uint32_t lb = lo_b + (kMode == 1 ? half * (B_BYTES >> 4) : 0);
 #pragma unroll
-          for (int kk = 0; kk < TILE_K / 16; ++kk) {
-            umma_bf16(tmem_d + half * TILE_N, make_desc(hi_a, lo_at + half * (A_BYTES >> 4) + kk * kstep_a),
-                      make_desc(DESC_HI_SBO1024, lo_b + kk * kstep_b), idesc, (i | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < TILE_K / 16; ++kk) {
+              umma_bf16(tmem_d + half * TILE_N, make_desc(hi_a, la + kk * kstep_a), make_desc(DESC_HI_SBO1024, lb + kk * kstep_b),
+                        idesc, (i | kk) != 0 ? 1u : 0u);
+            }
           }
         }
         if (bias_item) {
@@ -555,7 +585,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     int hl = 0;   // 128 x 128 tiles finished by this CTA (staging buffer / C-tile barrier parity)
     for (int w = w_first; w < args.num_work; w += w_step, ++local) {
       const Work k = decode_work(args, w);
-      const int acc = local & 1;
+      const int acc = local % kAccStages;
+      const uint32_t acc_parity = (local / kAccStages) & 1;
       if (args.epi == 0) {
        for (int half = 0; half < kMT; ++half, ++hl) {
         const uint32_t tmem_acc = tmem_base + acc * kAccCols + half * TILE_N + ((uint32_t)(q * 32) << 16);
@@ -574,7 +605,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         const float* rv = (args.rowvec && valid) ? args.rowvec + (p / args.rows_per_vec) * args.ld_rowvec + ncol0 : nullptr;
         if (args.has_c) mbar_wait(&c_full_bar[buf], (hl >> 1) & 1);
         epi_bar_sync();   // bias_s visible; staging[buf] is free (thread 0 waited for its last TMA store below)
-        if (half == 0) mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1);
+        if (half == 0) mbar_wait(&tmem_full_bar[acc], acc_parity);
         tcgen05_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < TILE_N / 32; ++cc) {
@@ -658,51 +689,59 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         }
        }
       } else {
-        const uint32_t tmem_acc = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
-        // fp32 reduce-add: 4 chunks of 32 columns -> 4 boxes {32 fp32, 128 rows} (2 per staging tile)
-        int x0, y0;
-        if (args.mode == 1) {
-          x0 = args.tap_b[0][k.tap] * args.ci_total + args.w_col0 + k.n_tile * TILE_N;
-          y0 = k.m_tile * TILE_M;
-        } else {
-          x0 = k.n_tile * TILE_N;
-          y0 = k.m_tile * TILE_M;
-        }
-        if (et == 0) bulk_wait_read<0>();   // the previous item's reductions have read the staging tiles
-        epi_bar_sync();
-        mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1);
-        tcgen05_fence_after();
-        if (kMode == 1 && args.dbias != nullptr && k.n_tile == 0 && k.tap == 0) {
-          uint32_t b0, b1, b2, b3, b4, b5, b6, b7;
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                       : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3), "=r"(b4), "=r"(b5), "=r"(b6), "=r"(b7)
-                       : "r"(tmem_base + TMEM_BIAS_COL + acc * 16 + ((uint32_t)(q * 32) << 16)) : "memory");
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const int co = k.m_tile * TILE_M + row;
-          if (co < args.M_total) {
-            atomicAdd(args.dbias + co, __uint_as_float(b0));
-            if (args.dbias2) atomicAdd(args.dbias2 + co, __uint_as_float(b0));
+        // fp32 reduce-add: per (sub-)tile 4 chunks of 32 columns -> 4 boxes {32 fp32, 128 rows} in the two staging tiles
+        int nhalf = 1;
+        if (kMode == 1) { int nt, tp; nhalf = 0; for (int h = 0; h < kMT; ++h) nhalf += wg_entry(args, k.y0 + h, nt, tp) ? 1 : 0; }
+        for (int half = 0; half < nhalf; ++half) {
+          const uint32_t tmem_acc = tmem_base + acc * kAccCols + half * TILE_N + ((uint32_t)(q * 32) << 16);
+          int x0, y0;
+          if (kMode == 1) {
+            int nt, tp;
+            wg_entry(args, k.y0 + half, nt, tp);
+            x0 = args.tap_b[0][tp] * args.ci_total + args.w_col0 + nt * TILE_N;
+            y0 = k.m_tile * TILE_M;
+          } else {
+            x0 = k.n_tile * TILE_N;
+            y0 = k.m_tile * TILE_M;
           }
-        }
+          if (et == 0) bulk_wait_read<0>();   // the previous reductions have read the staging tiles
+          epi_bar_sync();
+          if (half == 0) {
+            mbar_wait(&tmem_full_bar[acc], acc_parity);
+            tcgen05_fence_after();
+            if (kMode == 1 && args.dbias != nullptr && k.y0 == 0) {
+              uint32_t b0, b1, b2, b3, b4, b5, b6, b7;
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                           : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3), "=r"(b4), "=r"(b5), "=r"(b6), "=r"(b7)
+                           : "r"(tmem_base + TMEM_BIAS_COL + acc * 16 + ((uint32_t)(q * 32) << 16)) : "memory");
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              const int co = k.m_tile * TILE_M + row;
+              if (co < args.M_total) {
+                atomicAdd(args.dbias + co, __uint_as_float(b0));
+                if (args.dbias2) atomicAdd(args.dbias2 + co, __uint_as_float(b0));
+              }
+            }
+          }
 #pragma unroll 1
-        for (int cc = 0; cc < TILE_N / 32; ++cc) {
-          tmem_ld32(tmem_acc + cc * 32, v);
-          if (cc == TILE_N / 32 - 1) {
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          for (int cc = 0; cc < TILE_N / 32; ++cc) {
+            tmem_ld32(tmem_acc + cc * 32, v);
+            if (cc == TILE_N / 32 - 1 && half == nhalf - 1) {
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            }
+            uint8_t* rowp = stg_base + cc * 16384 + row * 128;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<uint4*>(rowp + (((uint32_t)j4 ^ sw) << 4)) = make_uint4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
           }
-          uint8_t* rowp = stg_base + cc * 16384 + row * 128;
+          fence_proxy_async();
+          epi_bar_sync();
+          if (et == 0) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            *reinterpret_cast<uint4*>(rowp + (((uint32_t)j4 ^ sw) << 4)) = make_uint4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-        }
-        fence_proxy_async();
-        epi_bar_sync();
-        if (et == 0) {
-#pragma unroll
-          for (int cc = 0; cc < TILE_N / 32; ++cc) tma_reduce_add_2d(&mapD, stg_base + cc * 16384, x0 + cc * 32, y0);
-          bulk_commit();
+            for (int cc = 0; cc < TILE_N / 32; ++cc) tma_reduce_add_2d(&mapD, stg_base + cc * 16384, x0 + cc * 32, y0);
+            bulk_commit();
+          }
         }
       }
     }
@@ -842,7 +881,7 @@ static int ensure_smem_attr() {
     MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     done = true;
   }
   return MDM_OK;
@@ -878,7 +917,7 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
                         const CUtensorMap& mC, const CUtensorMap& mD, IgemmArgs& a, void* stream) {
   const int grid = a.num_work < kNumSMs ? a.num_work : kNumSMs;
   cudaStream_t st = as_stream(stream);
-  if (a.mode == 1) launch_pdl(igemm_kernel<1, false, 1>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  if (a.mode == 1) launch_pdl(igemm_kernel<1, false, 2>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
   else if (a.halo) launch_pdl(igemm_kernel<0, true, 1>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
   else if (a.mt == 2) launch_pdl(igemm_kernel<0, false, 2>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
   else launch_pdl(igemm_kernel<0, false, 1>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
@@ -1075,7 +1114,8 @@ int mdm_conv_wgrad(const mdm_conv_args* c, void* stream) {
   const long long pixels = (long long)c->N * c->H * c->W;
   a.iters_total = (int)((pixels + 63) / 64);
   // split the pixel (K) range so that ~2 work items per SM exist, at least 4 chunks each
-  const int tiles = a.num_co * a.num_n * a.taps;
+  a.mt = 2;   // work item = two consecutive (cin tile, tap) entries sharing the dY tiles
+  const int tiles = a.num_co * ((a.num_n * a.taps + 1) / 2);
   int split = (2 * kNumSMs + tiles - 1) / tiles;
   if (split < 1) split = 1;
   int per = (a.iters_total + split - 1) / split;
