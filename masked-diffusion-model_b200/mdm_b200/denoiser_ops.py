@@ -73,9 +73,11 @@ _splitk_ws = {}
 
 
 def _splitk(a, device):
-    ws = _splitk_ws.get(device)
+    # one workspace per (device, stream): GEMMs on different streams may run concurrently
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _splitk_ws.get(key)
     if ws is None:
-        ws = _splitk_ws[device] = torch.zeros(SPLITK_WS_FLOATS, dtype=torch.float32, device=device)
+        ws = _splitk_ws[key] = torch.zeros(SPLITK_WS_FLOATS, dtype=torch.float32, device=device)
     a.splitk_ws, a.splitk_ws_floats = ws.data_ptr(), ws.numel()
 
 
