@@ -419,6 +419,234 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(
   }
 }
 
+// ---- small maps: one CTA per sample keeps the whole sample in registers -> ONE kernel, one read ------------
+// (low-resolution levels of the U-Net: <= 32K elements per sample forward, <= 16K backward)
+template <int MAXV>
+__global__ void __launch_bounds__(GN_THREADS) gn_small_fwd_kernel(const bf16* __restrict__ x, long long ld, bf16* __restrict__ y,
+                                                                  long long ldy, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float* __restrict__ stats,
+                                                                  float eps, int silu, GnGeom g) {
+  MDM_PDL_ENTER();
+  extern __shared__ float gn_sm[];   // s[C], q[C]
+  __shared__ float mr[GN_MAX_GROUPS * 2];
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) gn_sm[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x % g.L, r = threadIdx.x / g.L;
+  const int count = (r < g.R && r < g.HW) ? (g.HW - r + g.R - 1) / g.R : 0;
+  const int c0 = lane * 8;
+  const bf16* p = x + ((long long)n * g.HW + r) * ld + c0;
+  const long long step = (long long)g.R * ld;
+  uint4 v[MAXV];
+  if (count > 0) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) v[i] = i < count ? ldg16(p + i * step) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      float f[8];
+      unpack8(v[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&gn_sm[c0 + j], s[j]);
+      atomicAdd(&gn_sm[g.C + c0 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < g.G) {
+    double a = 0.0, b = 0.0;
+    for (int c = threadIdx.x * g.cpg; c < (threadIdx.x + 1) * g.cpg; ++c) { a += gn_sm[c]; b += gn_sm[g.C + c]; }
+    const double cnt = (double)g.HW * g.cpg;
+    const double mean = a / cnt;
+    double var = b / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    mr[threadIdx.x * 2] = (float)mean;
+    mr[threadIdx.x * 2 + 1] = rstd;
+    if (stats) {
+      stats[((long long)n * g.G + threadIdx.x) * 2] = (float)mean;
+      stats[((long long)n * g.G + threadIdx.x) * 2 + 1] = rstd;
+    }
+  }
+  __syncthreads();
+  if (count == 0) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int grp = (c0 + j) / g.cpg;
+    const float mean = mr[grp * 2], rstd = mr[grp * 2 + 1];
+    const float ga = gamma[c0 + j], be = beta[c0 + j];
+    sc[j] = rstd * ga;
+    sh[j] = be - mean * rstd * ga;
+  }
+  bf16* o = y + ((long long)n * g.HW + r) * ldy + c0;
+  const long long ostep = (long long)g.R * ldy;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < count) {
+      float f[8];
+      unpack8(v[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float z = fmaf(f[j], sc[j], sh[j]);
+        if (silu) z = __fdividef(z, 1.0f + __expf(-z));
+        f[j] = z;
+      }
+      *reinterpret_cast<uint4*>(o + i * ostep) = pack8(f);
+    }
+  }
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(GN_THREADS, 1) gn_small_bwd_kernel(
+    const bf16* __restrict__ x, long long ld, const bf16* __restrict__ dy, long long lddy, const bf16* add /* may alias dx */,
+    long long ldadd, const bf16* __restrict__ add2, long long ldadd2, bf16* dx, long long lddx,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int silu, float* __restrict__ colsum, long long ld_colsum,
+    float* __restrict__ dbias, GnGeom g) {
+  MDM_PDL_ENTER();
+  extern __shared__ float gn_sm[];   // sdg[C], sdb[C]; reused as scs[C]
+  __shared__ float m12[GN_MAX_GROUPS * 2];
+  float* sdg = gn_sm;
+  float* sdb = gn_sm + g.C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) gn_sm[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x % g.L, r = threadIdx.x / g.L;
+  const int count = (r < g.R && r < g.HW) ? (g.HW - r + g.R - 1) / g.R : 0;
+  const int c0 = lane * 8;
+  const long long first = (long long)n * g.HW + r;
+  uint4 vx[MAXV], vd[MAXV];
+  float rs[8], mb[8], ga[8], be[8];
+  if (count > 0) {
+    float dg[8], db[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int grp = (c0 + j) / g.cpg;
+      const float mean = stats[((long long)n * g.G + grp) * 2], rstd = stats[((long long)n * g.G + grp) * 2 + 1];
+      rs[j] = rstd;
+      mb[j] = -mean * rstd;
+      ga[j] = gamma[c0 + j];
+      be[j] = beta[c0 + j];
+      dg[j] = db[j] = 0.f;
+    }
+    const bf16* px = x + first * ld + c0;
+    const bf16* pd = dy + first * lddy + c0;
+    const long long sx = (long long)g.R * ld, sd = (long long)g.R * lddy;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      vx[i] = i < count ? ldg16(px + i * sx) : make_uint4(0, 0, 0, 0);
+      vd[i] = i < count ? ldg16(pd + i * sd) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      float fx[8], fd[8];
+      unpack8(vx[i], fx);
+      unpack8(vd[i], fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(fx[j], rs[j], mb[j]);
+        float d = fd[j];
+        if (silu) d *= dsilu_fast(fmaf(xh, ga[j], be[j]));
+        dg[j] = fmaf(d, xh, dg[j]);
+        db[j] += d;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sdg[c0 + j], dg[j]);
+      atomicAdd(&sdb[c0 + j], db[j]);
+    }
+  }
+  __syncthreads();
+  if (dgamma) {
+    for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+      atomicAdd(dgamma + c, sdg[c]);
+      atomicAdd(dbeta + c, sdb[c]);
+    }
+  }
+  if (threadIdx.x < g.G) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = threadIdx.x * g.cpg; c < (threadIdx.x + 1) * g.cpg; ++c) {
+      const float gm = gamma[c];
+      s1 = fmaf(gm, sdb[c], s1);
+      s2 = fmaf(gm, sdg[c], s2);
+    }
+    const float cnt = (float)g.HW * g.cpg;
+    m12[threadIdx.x * 2] = s1 / cnt;
+    m12[threadIdx.x * 2 + 1] = s2 / cnt;
+  }
+  __syncthreads();
+  const bool want_cs = colsum != nullptr || dbias != nullptr;
+  if (want_cs)
+    for (int c = threadIdx.x; c < g.C; c += blockDim.x) gn_sm[c] = 0.f;   // sdg no longer needed
+  if (want_cs) __syncthreads();
+  if (count > 0) {
+    float A[8], Bc[8], Cc[8], cs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int grp = (c0 + j) / g.cpg;
+      const float m1 = m12[grp * 2], m2 = m12[grp * 2 + 1];
+      A[j] = rs[j] * ga[j];
+      Bc[j] = -rs[j] * rs[j] * m2;
+      Cc[j] = -rs[j] * (m1 + mb[j] * m2);
+      cs[j] = 0.f;
+    }
+    const bf16* pa = add ? add + first * ldadd + c0 : nullptr;
+    const bf16* pb = add2 ? add2 + first * ldadd2 + c0 : nullptr;
+    bf16* po = dx + first * lddx + c0;
+    const long long sa = (long long)g.R * ldadd, sb = (long long)g.R * ldadd2, so = (long long)g.R * lddx;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (i < count) {
+        float fx[8], fd[8], o[8];
+        unpack8(vx[i], fx);
+        unpack8(vd[i], fd);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float d = fd[j];
+          if (silu) d *= dsilu_fast(fmaf(fmaf(fx[j], rs[j], mb[j]), ga[j], be[j]));
+          o[j] = fmaf(d, A[j], fmaf(fx[j], Bc[j], Cc[j]));
+        }
+        if (want_cs) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cs[j] += o[j];
+        }
+        if (pa) {
+          float fa[8];
+          unpack8(*reinterpret_cast<const uint4*>(pa + i * sa), fa);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += fa[j];
+        }
+        if (pb) {
+          float fb[8];
+          unpack8(ldg16(pb + i * sb), fb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += fb[j];
+        }
+        *reinterpret_cast<uint4*>(po + i * so) = pack8(o);
+      }
+    }
+    if (want_cs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&gn_sm[c0 + j], cs[j]);
+    }
+  }
+  if (want_cs) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+      const float v = gn_sm[c];
+      if (colsum) atomicAdd(colsum + (long long)n * ld_colsum + c, v);
+      if (dbias) atomicAdd(dbias + c, v);
+    }
+  }
+}
+
 static int gn_geom(GnGeom& g, int HW, int C, int G, int* nchunk) {
   if (C % 8 != 0 || C % G != 0 || G > GN_MAX_GROUPS || C > GN_MAX_C) {
     set_error("GroupNorm: C=%d must be a multiple of 8 and of G=%d (G <= 32, C <= %d)", C, G, GN_MAX_C);
@@ -955,6 +1183,14 @@ int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, cons
   GnGeom g; int nc;
   int rc = gn_geom(g, HW, C, G, &nc);
   if (rc) return rc;
+  if ((long long)HW * C <= 32768) {   // small map: one CTA per sample, single pass over registers
+    const int per_thread = (HW + g.R - 1) / g.R;
+    const size_t sm = (size_t)2 * C * sizeof(float);
+    if (per_thread <= 4) launch_pdl(gn_small_fwd_kernel<4>, dim3(N), dim3(GN_THREADS), sm, as_stream(stream), (const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta, stats, eps, silu, g);
+    else launch_pdl(gn_small_fwd_kernel<16>, dim3(N), dim3(GN_THREADS), sm, as_stream(stream), (const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta, stats, eps, silu, g);
+    MDM_LAUNCH_CHECK();
+    return MDM_OK;
+  }
   dim3 grid(nc, N);
   launch_pdl(gn_stats_kernel<8>, dim3(grid), dim3(GN_THREADS), (size_t)2 * C * sizeof(float), as_stream(stream), (const bf16*)x, ld_x, ws, g);
   MDM_LAUNCH_CHECK();
@@ -973,6 +1209,14 @@ int mdm_gn_silu_bwd(const void* x, long long ld_x, const void* dy, long long ld_
   GnGeom g; int nc;
   int rc = gn_geom(g, HW, C, G, &nc);
   if (rc) return rc;
+  if ((long long)HW * C <= 16384) {   // small map: one CTA per sample, x and dy stay in registers across both phases
+    const int per_thread = (HW + g.R - 1) / g.R;
+    const size_t sm = (size_t)2 * C * sizeof(float);
+    if (per_thread <= 2) launch_pdl(gn_small_bwd_kernel<2>, dim3(N), dim3(GN_THREADS), sm, as_stream(stream), (const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (const bf16*)add, ld_add, (const bf16*)add2, ld_add2, (bf16*)dx, ld_dx, gamma, beta, stats, dgamma, dbeta, silu, colsum, ld_colsum, dbias, g);
+    else launch_pdl(gn_small_bwd_kernel<8>, dim3(N), dim3(GN_THREADS), sm, as_stream(stream), (const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (const bf16*)add, ld_add, (const bf16*)add2, ld_add2, (bf16*)dx, ld_dx, gamma, beta, stats, dgamma, dbeta, silu, colsum, ld_colsum, dbias, g);
+    MDM_LAUNCH_CHECK();
+    return MDM_OK;
+  }
   dim3 grid(nc, N);
   const size_t sm1 = (size_t)2 * C * sizeof(float), sm2 = (size_t)C * sizeof(float);
   launch_pdl(gn_bwd_stats_kernel<4>, dim3(grid), dim3(GN_THREADS), sm1, as_stream(stream), (const bf16*)x, ld_x, (const bf16*)dy, ld_dy, gamma, beta, stats, ws, dgamma, dbeta, silu, g);
