@@ -432,8 +432,12 @@ def run_b200(a):
         "loss": round(float(loss_last), 5),
         "clocks": clk.summary(),
     }
-    if rank == 0 and not a.no_roofline:
-        line["roofline"] = roofline_pass(tr, model, devb[0], peaks)
+    if not a.no_roofline:
+        # every rank runs the instrumented step (it contains the gradient all-reduce: a collective must not be
+        # entered by rank 0 alone); rank 0's numbers are reported
+        rl = roofline_pass(tr, model, devb[0], peaks)
+        if rank == 0:
+            line["roofline"] = rl
     if world > 1:
         dist.barrier()
     if not a.no_sampling:
