@@ -214,6 +214,13 @@ class UNet2DModelB200:
     def num_parameters(self):
         return sum(s.numel for s in self._specs)
 
+    def late_grad_range(self):
+        """[lo, hi) of the flat buffers holding mid_block, up_blocks, conv_norm_out and conv_out (contiguous in the
+        layout order): the parameters whose gradients the backward pass finishes FIRST"""
+        lo = self._by_name["mid_block.resnets.0.norm1.weight"].offset
+        last = self._by_name["conv_out.bias"]
+        return lo, (last.offset + last.numel + 63) // 64 * 64
+
     # views ------------------------------------------------------------------------------------
     def w32(self, name):
         s = self._by_name[name]
@@ -659,14 +666,28 @@ class _Plan:
         emit = dict(conv_in=self._emit_conv_in, resnet=self._emit_resnet, attn=self._emit_attn, down=self._emit_down,
                     up=self._emit_up, head=self._emit_head)
         bw_chunks = []
-        for kind, d in self._ops:
+        first_mid = None
+        for i, (kind, d) in enumerate(self._ops):
+            if first_mid is None and kind == "resnet" and d["r"].prefix == "mid_block.resnets.0":
+                first_mid = i
             fw, bw = emit[kind](**d)
             self.fwd += fw
             bw_chunks.append(bw)
         if ng:
-            for bw in reversed(bw_chunks):
-                self.bwd += bw
+            for i in range(len(bw_chunks) - 1, -1, -1):
+                self.bwd += bw_chunks[i]
+                if i == first_mid:
+                    # the head, the whole up path and the mid block are done: their gradients -- one contiguous
+                    # range of the flat buffer -- are final; data-parallel runs start reducing them now
+                    self.bwd.append(self._grads_ready_mid)
             self.bwd.append(self._temb_bwd)
+
+    def _grads_ready_mid(self):
+        hook = getattr(self.m, "grad_ready_hook", None)
+        if hook is not None:
+            self.join_side()                     # the weight gradients of that range ran on the side stream
+            lo, hi = self.m.late_grad_range()
+            hook(lo, hi)
 
     def _sym_resnet(self, r, x, res):
         out = self.act(res, r.cout, r.prefix)

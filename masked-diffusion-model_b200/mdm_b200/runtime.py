@@ -433,6 +433,24 @@ class Accelerator:
                         dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
                         p.grad.mul_(1.0 / self.num_processes)
 
+    # -- overlapped all-reduce of the flat gradient (B200 denoiser): the range finished first by the backward pass
+    #    is reduced asynchronously while the rest of the backward still runs
+    def start_late_all_reduce(self, model, lo, hi):
+        self._late = (model, lo, hi, dist.all_reduce(model.flat_grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+
+    def finish_all_reduce(self, model):
+        late = getattr(self, "_late", None)
+        if late is None or late[0] is not model:
+            dist.all_reduce(model.flat_grad, op=dist.ReduceOp.SUM)
+            return
+        _, lo, hi, work = late
+        self._late = None
+        if lo > 0:
+            dist.all_reduce(model.flat_grad[:lo], op=dist.ReduceOp.SUM)
+        if hi < model.flat_grad.numel():
+            dist.all_reduce(model.flat_grad[hi:], op=dist.ReduceOp.SUM)
+        work.wait()
+
     def clip_grad_norm_(self, parameters, max_norm, norm_type=2):
         for o in self._optimizers:
             if isinstance(o, FusedOptimizer):

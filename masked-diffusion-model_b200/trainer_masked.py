@@ -150,7 +150,10 @@ class Trainer:
                     return stats
                 g = (train_ops.GraphedCallable(body, enabled=use_graph), None)
             else:
-                # data parallel: graph(fwd+bwd) -> NCCL all-reduce of the flat gradient -> graph(optimiser tail)
+                # data parallel: graph(fwd+bwd) -> NCCL all-reduce of the flat gradient -> graph(optimiser tail).
+                # (Capturing the all-reduce inside one graph, started mid-backward through
+                # `model.grad_ready_hook` / `Accelerator.start_late_all_reduce`, hung on 2 GPUs in round 1: the
+                # plumbing stays, the trainer uses the validated three-piece sequence.)
                 g = (train_ops.GraphedCallable(self._forward_backward, enabled=use_graph),
                      train_ops.GraphedCallable(self._optimizer_tail_device, enabled=use_graph))
             self._graphs[key] = g
@@ -160,8 +163,10 @@ class Trainer:
             stats = g[0]()
         else:
             acc._defer_all_reduce = True        # the all-reduce runs between the two graphs
-            stats = g[0]()
-            acc._defer_all_reduce = False
+            try:
+                stats = g[0]()
+            finally:
+                acc._defer_all_reduce = False
             acc.all_reduce_gradients()
             g[1]()
         return stats
