@@ -49,8 +49,9 @@ constexpr int SMEM_BIAS_OFF = SMEM_EPI_OFF + 2 * EPI_BYTES;   // 128 floats
 constexpr int SMEM_BAR_OFF = SMEM_BIAS_OFF + 512;
 constexpr int SMEM_ONES_OFF = 3 * (A_BYTES + 2 * B_BYTES);   // mode 1 only (ring = 3 x 48 KB): the unused ring tail
 constexpr int IGEMM_SMEM = SMEM_BAR_OFF + 256 + 1024 /*alignment slack*/;
-constexpr int TMEM_COLS = 512;                 // two 128-column fp32 accumulators + two 16-column bias-gradient ones
-constexpr int TMEM_BIAS_COL = 256;             // wgrad bias gradient: D2[co][0..15] = sum_pix dY[pix][co] * 1
+constexpr int TMEM_COLS = 512;                 // two accumulator stages of 256 fp32 columns
+// wgrad bias gradient: D2[co][0..15] = sum_pix dY[pix][co] * 1 lives in the (unused) second half of the stage of a
+// single-entry work item (the first item of every cout tile), so both stages stay 256 columns wide
 constexpr int ONES_BYTES = 8192;               // [64 K-rows][64 bf16] of 1.0: the B operand of that extra MMA
 static_assert(4 * A_BYTES + 4 * B_BYTES <= RING_BYTES && SMEM_ONES_OFF + ONES_BYTES <= RING_BYTES, "plain ring / wgrad ring + ones tile must fit");
 static_assert(IGEMM_SMEM <= 232448, "shared memory budget");
@@ -207,13 +208,13 @@ struct IgemmArgs {
 struct Work {
   int m_tile, n_tile;   // mode 0: pixel tile, cout tile;  mode 1: cout tile, -
   int y0;               // mode 1: first of the (up to two) consecutive (cin tile, tap) entries sharing this item's dY tiles
+  int nh;               // mode 1: entries of this item (item 0 of a cout tile: entry 0 alone + the bias gradient)
   int it0, nit;         // iteration range
 };
-// wgrad entry y -> (cin tile, tap index); entries y >= num_n * taps do not exist
-__device__ __forceinline__ bool wg_entry(const IgemmArgs& a, int y, int& n_tile, int& tap) {
+// wgrad entry y -> (cin tile, tap index)
+__device__ __forceinline__ void wg_entry(const IgemmArgs& a, int y, int& n_tile, int& tap) {
   n_tile = y / a.taps;
   tap = y - n_tile * a.taps;
-  return y < a.num_n * a.taps;
 }
 
 __device__ __forceinline__ Work decode_work(const IgemmArgs& a, int w) {
@@ -224,9 +225,13 @@ __device__ __forceinline__ Work decode_work(const IgemmArgs& a, int w) {
     k.n_tile = t % a.num_n;
     k.m_tile = t / a.num_n;
     k.y0 = 0;
+    k.nh = a.mt;
   } else {
+    // items of a cout tile: {entry 0 (+ bias gradient)}, {1, 2}, {3, 4}, ...
     k.m_tile = t % a.num_co;
-    k.y0 = (t / a.num_co) * a.mt;
+    const int j = t / a.num_co;
+    k.y0 = j == 0 ? 0 : 2 * j - 1;
+    k.nh = j == 0 ? 1 : min(2, a.num_n * a.taps - k.y0);
     k.n_tile = 0;
   }
   k.it0 = z * a.iters_per_split;
@@ -302,7 +307,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   constexpr int kBSlotBytes = kHalo ? B_BYTES : (kMT + 1) * A_BYTES;
   constexpr int kAOff = kMode == 1 ? kMT * B_BYTES : B_BYTES;
   constexpr int kAccCols = TILE_N * kMT;
-  constexpr int kAccStages = (kMode == 1 && kMT == 2) ? 1 : 2;   // wgrad pairs: 256 + 16 (bias) columns, long K loops
+  constexpr int kAccStages = 2;
   static_assert(kMT == 1 || !kHalo, "two sub-tiles: plain stages only");
   uint8_t* a_ring = smem;                                   // halo slots (halo mode only)
   uint8_t* b_ring = smem + kASlots * HALO_BYTES;
@@ -442,12 +447,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       } else {
         // wgrad: B = X shifted by the tap (MN-major, N = ci); up to kMT (cin tile, tap) entries per item
         int ci0[kMT], dh[kMT], dw[kMT];
-        int nvalid = 0;
+        const int nvalid = k.nh;
 #pragma unroll
         for (int half = 0; half < kMT; ++half) {
           int nt, tp;
-          if (wg_entry(args, k.y0 + half, nt, tp)) ++nvalid;
-          else tp = 0;
+          wg_entry(args, half < nvalid ? k.y0 + half : k.y0, nt, tp);
           ci0[half] = nt * TILE_N;
           dh[half] = args.tap_dh[0][tp];
           dw[half] = args.tap_dw[0][tp];
@@ -495,8 +499,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       mbar_wait(&tmem_empty_bar[acc], ((local / kAccStages) & 1) ^ 1);   // the epilogue has drained this accumulator
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * kAccCols;
-      int nhalf = kMT;                                          // wgrad: the second entry of the pair may not exist
-      if (kMode == 1) { int nt, tp; nhalf = 0; for (int h = 0; h < kMT; ++h) nhalf += wg_entry(args, k.y0 + h, nt, tp) ? 1 : 0; }
+      const int nhalf = kMode == 1 ? k.nh : kMT;                // wgrad: the second entry of the pair may not exist
       uint32_t lo_a = 0;
       int sa_cur = 0, tap = 0;
       // wgrad work items (ci tile 0, first tap) also accumulate the bias gradient: A = dY tile, B = ones, N = 16
@@ -544,7 +547,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         if (bias_item) {
 #pragma unroll
           for (int kk = 0; kk < TILE_K / 16; ++kk)
-            umma_bf16(tmem_base + TMEM_BIAS_COL + acc * 16, make_desc(hi_a, lo_at + kk * kstep_a),
+            umma_bf16(tmem_d + TILE_N, make_desc(hi_a, lo_at + kk * kstep_a),
                       make_desc(DESC_HI_SBO1024, lo_ones + kk * (2048u >> 4)), idesc16, (i | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&b_empty[sb_cur]);
@@ -690,8 +693,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
        }
       } else {
         // fp32 reduce-add: per (sub-)tile 4 chunks of 32 columns -> 4 boxes {32 fp32, 128 rows} in the two staging tiles
-        int nhalf = 1;
-        if (kMode == 1) { int nt, tp; nhalf = 0; for (int h = 0; h < kMT; ++h) nhalf += wg_entry(args, k.y0 + h, nt, tp) ? 1 : 0; }
+        const int nhalf = kMode == 1 ? k.nh : 1;
         for (int half = 0; half < nhalf; ++half) {
           const uint32_t tmem_acc = tmem_base + acc * kAccCols + half * TILE_N + ((uint32_t)(q * 32) << 16);
           int x0, y0;
@@ -713,7 +715,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               uint32_t b0, b1, b2, b3, b4, b5, b6, b7;
               asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                            : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3), "=r"(b4), "=r"(b5), "=r"(b6), "=r"(b7)
-                           : "r"(tmem_base + TMEM_BIAS_COL + acc * 16 + ((uint32_t)(q * 32) << 16)) : "memory");
+                           : "r"(tmem_base + acc * kAccCols + TILE_N + ((uint32_t)(q * 32) << 16)) : "memory");
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
               const int co = k.m_tile * TILE_M + row;
               if (co < args.M_total) {
@@ -1113,17 +1115,30 @@ int mdm_conv_wgrad(const mdm_conv_args* c, void* stream) {
   a.num_n = (c->cin + TILE_N - 1) / TILE_N;
   const long long pixels = (long long)c->N * c->H * c->W;
   a.iters_total = (int)((pixels + 63) / 64);
-  // split the pixel (K) range so that ~2 work items per SM exist, at least 4 chunks each
-  a.mt = 2;   // work item = two consecutive (cin tile, tap) entries sharing the dY tiles
-  const int tiles = a.num_co * ((a.num_n * a.taps + 1) / 2);
-  int split = (2 * kNumSMs + tiles - 1) / tiles;
-  if (split < 1) split = 1;
-  int per = (a.iters_total + split - 1) / split;
-  if (per < 4) per = 4;
-  if (per > a.iters_total) per = a.iters_total;
-  a.iters_per_split = per;
-  a.splits = (a.iters_total + per - 1) / per;
-  a.num_work = tiles * a.splits;
+  // work item = (cout tile, up to two consecutive (cin tile, tap) entries sharing the dY tiles, K split); the first
+  // item of every cout tile holds entry 0 alone plus the bias gradient.  The K (pixel) split is chosen by a cost
+  // model of the static persistent schedule: waves x max(main loop, epilogue) -- never one item over a wave.
+  a.mt = 2;
+  const int tiles = a.num_co * (1 + (a.num_n * a.taps) / 2);
+  {
+    long long best = -1;
+    int best_per = a.iters_total;
+    const int max_split = a.iters_total;
+    for (int split = 1; split <= max_split; ++split) {
+      const int per = (a.iters_total + split - 1) / split;
+      const int sp = (a.iters_total + per - 1) / per;
+      if (sp != split) continue;                     // same schedule as a smaller split count
+      if (per < 4 && split > 1) break;
+      const long long waves = ((long long)tiles * sp + kNumSMs - 1) / kNumSMs;
+      const long long item = per * 512LL > 4000 ? per * 512LL : 4000;   // cycles: 8 MMAs per chunk vs the reduce-add epilogue
+      const long long cost = waves * item + 16LL * sp;
+      if (best < 0 || cost < best) { best = cost; best_per = per; }
+      if (waves > 8) break;
+    }
+    a.iters_per_split = best_per;
+    a.splits = (a.iters_total + best_per - 1) / best_per;
+    a.num_work = tiles * a.splits;
+  }
   int pw, ph, pn;
   pixel_box(64, c->H, c->W, &pw, &ph, &pn);
   a.pw = pw; a.ph = ph; a.pn = pn;
