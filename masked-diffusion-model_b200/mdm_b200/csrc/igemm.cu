@@ -40,10 +40,17 @@ constexpr int B_BYTES = TILE_N * TILE_K * 2;   // 16 KB
 // the nine taps are nine shifted views of it (UMMA descriptor start offsets), a 4x cut of the A traffic.
 constexpr int HALO_W = 16, HALO_H = 18, PATCH_W = 8, PATCH_H = 16;
 constexpr int HALO_BYTES = HALO_W * HALO_H * 128;   // 36 KB
+// halo mode with 256-row work items: the M tile is a 16 x 16 patch = two 8-wide sub-tiles sharing ONE 18 x 18 halo
+// and every weight tile: (41.5 KB + 9 x 16 KB) per 18 x 256-cycle MMA groups = 10.3 KB / 256 cycles, under the
+// ~42.6 B/cycle/SM the L2 can deliver (plain 256-row stages need 24 KB / 256 cycles: the tensor pipe idles > 50 %)
+constexpr int HALO2_W = 18, HALO2_H = 18;
+constexpr int HALO2_BYTES = HALO2_W * HALO2_H * 128;   // 41472
+constexpr int HALO2_SLOT = 41 * 1024;                   // slot pitch, 1024-aligned (swizzle atom)
 constexpr int MAX_A_SLOTS = 4, MAX_B_SLOTS = 6;
 constexpr int EPI_BYTES = 32768;               // one staging tile: 128 x 128 bf16, or 2 boxes of 128 x 32 fp32
 constexpr int IGEMM_THREADS = 224;
-constexpr int RING_BYTES = 2 * HALO_BYTES + 5 * B_BYTES;    // halo: 2 A + 5 B slots; plain: 4 A + 4 B slots (128 KB)
+constexpr int RING_BYTES = 2 * HALO_BYTES + 5 * B_BYTES;    // halo: 2 A + 5 B slots (256-row: 2 x 41 KB + 4 B); plain: 4 A + 4 B slots (128 KB)
+static_assert(2 * HALO2_SLOT + 4 * B_BYTES <= RING_BYTES, "256-row halo ring must fit");
 constexpr int SMEM_EPI_OFF = RING_BYTES;
 constexpr int SMEM_BIAS_OFF = SMEM_EPI_OFF + 2 * EPI_BYTES;   // 128 floats
 constexpr int SMEM_BAR_OFF = SMEM_BIAS_OFF + 512;
@@ -280,6 +287,7 @@ struct IterWalker {
 // descriptor words.  hi: SBO | version (bit 46) | SWIZZLE_128B (bits 61..63); lo: start address | LBO
 constexpr uint32_t DESC_HI_SBO1024 = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr uint32_t DESC_HI_HALO = ((uint32_t)(HALO_W * 128) >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t DESC_HI_HALO2 = ((uint32_t)(HALO2_W * 128) >> 4) | (1u << 14) | (2u << 29);
 constexpr uint32_t DESC_LO_KMAJOR = (16u >> 4) << 16;     // LBO (unused for swizzled K-major)
 constexpr uint32_t DESC_LO_MNMAJOR = (8192u >> 4) << 16;  // LBO = distance between the two 64-wide MN atoms
 __device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
@@ -301,16 +309,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int kASlots = kHalo ? 2 : 0;
-  constexpr int kBSlots = kHalo ? 5 : (kMT == 2 ? 3 : 4);
+  constexpr int kBSlots = kHalo ? (kMT == 2 ? 4 : 5) : (kMT == 2 ? 3 : 4);
+  constexpr int kHaloW = kMT == 2 ? HALO2_W : HALO_W;             // halo row pitch (pixels)
+  constexpr int kHaloBytes = kMT == 2 ? HALO2_BYTES : HALO_BYTES;  // bytes of one halo box
+  constexpr int kHaloSlot = kMT == 2 ? HALO2_SLOT : HALO_BYTES;    // A-ring slot pitch
+  constexpr uint32_t kDescHiHalo = kMT == 2 ? DESC_HI_HALO2 : DESC_HI_HALO;
   // plain stage: mode 0 = [B][A0](A1) (two pixel sub-tiles share the weight tile); mode 1 = [B0](B1)[A] (two
   // (cin tile, tap) entries share the dY tile)
   constexpr int kBSlotBytes = kHalo ? B_BYTES : (kMT + 1) * A_BYTES;
   constexpr int kAOff = kMode == 1 ? kMT * B_BYTES : B_BYTES;
   constexpr int kAccCols = TILE_N * kMT;
   constexpr int kAccStages = 2;
-  static_assert(kMT == 1 || !kHalo, "two sub-tiles: plain stages only");
   uint8_t* a_ring = smem;                                   // halo slots (halo mode only)
-  uint8_t* b_ring = smem + kASlots * HALO_BYTES;
+  uint8_t* b_ring = smem + kASlots * kHaloSlot;
   float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS_OFF);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFF);
   uint64_t* a_empty = a_full + MAX_A_SLOTS;
@@ -375,14 +386,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             if (it.halo_it()) {
               if (it.tap == 0) {   // one halo per channel chunk
                 mbar_wait(&a_empty[sa], pa ^ 1);
-                mbar_expect_tx(&a_full[sa], HALO_BYTES);
-                tma_load_4d(&mapA0, a_ring + sa * HALO_BYTES, &a_full[sa], it.kc * TILE_K, w0 - 1, h0 - 1, n0);
+                mbar_expect_tx(&a_full[sa], kHaloBytes);
+                tma_load_4d(&mapA0, a_ring + sa * kHaloSlot, &a_full[sa], it.kc * TILE_K, w0 - 1, h0 - 1, n0);
                 if (++sa == kASlots) { sa = 0; pa ^= 1; }
               }
             } else {               // fused 1x1 shortcut segment: a plain patch in a halo slot
               mbar_wait(&a_empty[sa], pa ^ 1);
-              mbar_expect_tx(&a_full[sa], A_BYTES);
-              tma_load_4d(&mapA1, a_ring + sa * HALO_BYTES, &a_full[sa], it.kc * TILE_K, w0, h0, n0);
+              mbar_expect_tx(&a_full[sa], kMT * A_BYTES);
+              tma_load_4d(&mapA1, a_ring + sa * kHaloSlot, &a_full[sa], it.kc * TILE_K, w0, h0, n0);
+              if (kMT == 2) tma_load_4d(&mapA1, a_ring + sa * kHaloSlot + A_BYTES, &a_full[sa], it.kc * TILE_K, w1, h1, n1);
               if (++sa == kASlots) { sa = 0; pa ^= 1; }
             }
           } else {
@@ -513,7 +525,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         if (kHalo && (!halo_it || tap == 0)) {      // this iteration starts on a fresh A-ring slot
           sa_cur = sa;
           mbar_wait(&a_full[sa], pa);
-          lo_a = lo_halo0 + sa * (HALO_BYTES >> 4);
+          lo_a = lo_halo0 + sa * (kHaloSlot >> 4);
           if (++sa == kASlots) { sa = 0; pa ^= 1; }
         }
         if (!ready) mbar_wait(&b_full[sb], pb);
@@ -522,11 +534,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         uint32_t lo_at;
         if (kHalo) {
           lo_at = lo_a;
-          if (halo_it) lo_at += (uint32_t)(((args.tap_dh[0][tap] + 1) * HALO_W + (args.tap_dw[0][tap] + 1)) * (128 >> 4));
+          if (halo_it) lo_at += (uint32_t)(((args.tap_dh[0][tap] + 1) * kHaloW + (args.tap_dw[0][tap] + 1)) * (128 >> 4));
         } else {
           lo_at = lo_a_plain0 + sb * (kBSlotBytes >> 4);
         }
-        const uint32_t hi_a = halo_it ? DESC_HI_HALO : DESC_HI_SBO1024;
+        const uint32_t hi_a = halo_it ? kDescHiHalo : DESC_HI_SBO1024;
+        // second 128-row sub-tile: the 8 pixels to the right inside the halo, or the second plain patch
+        const uint32_t half_a = halo_it ? (uint32_t)((8 * 128) >> 4) : (uint32_t)(A_BYTES >> 4);
         // look at the next stage's barrier now: its latency hides behind the MMA issue below
         const int sb_cur = sb;
         if (++sb == kBSlots) { sb = 0; pb ^= 1; }
@@ -535,7 +549,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         for (int half = 0; half < kMT; ++half) {
           if (half < nhalf) {
             // mode 0: the halves are two A (pixel) sub-tiles against one B; mode 1: two B tiles against one A
-            const uint32_t la = lo_at + (kMode == 0 ? half * (A_BYTES >> 4) : 0);
+            const uint32_t la = lo_at + (kMode == 0 ? half * half_a : 0);
             const uint32_t lb = lo_b + (kMode == 1 ? half * (B_BYTES >> 4) : 0);
 #pragma unroll
             for (int kk = 0; kk < TILE_K / 16; ++kk) {
@@ -883,6 +897,7 @@ static int ensure_smem_attr() {
     MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     done = true;
   }
@@ -920,6 +935,7 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
   const int grid = a.num_work < kNumSMs ? a.num_work : kNumSMs;
   cudaStream_t st = as_stream(stream);
   if (a.mode == 1) launch_pdl(igemm_kernel<1, false, 2>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.halo && a.mt == 2) launch_pdl(igemm_kernel<0, true, 2>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
   else if (a.halo) launch_pdl(igemm_kernel<0, true, 1>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
   else if (a.mt == 2) launch_pdl(igemm_kernel<0, false, 2>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
   else launch_pdl(igemm_kernel<0, false, 1>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
@@ -927,11 +943,23 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
   return MDM_OK;
 }
 
-// can this layer run in halo mode?  3x3, stride 1, map at least 16 (h) x 8 (w), bf16 output only
-static bool halo_ok(const mdm_conv_args* c, const void* out) {
-  static const int enabled = env_flag("MDM_IGEMM_HALO", 0);   // measured: plain stages are faster until the halo pipeline gets a 3rd slot
-  return enabled && c->ksize == 3 && c->stride == 1 && c->H % PATCH_H == 0 && c->W % PATCH_W == 0 && out != nullptr &&
-         c->y_f32 == nullptr;
+// can this layer run in halo mode?  3x3, stride 1, bf16 output only.  returns 2: 16 x 16 patches (256-row work
+// items), 1: 8 x 16 patches, 0: plain stages.
+// MDM_IGEMM_HALO: 0 = never, 1 = 8 x 16 patches wherever possible, 2 (default) = 16 x 16 patches where they measured
+// faster than plain 256-row stages (bench_conv.py, B200): layers with >= 4 channel chunks and >= 2 cout tiles
+// (+14..23 %), and single-cout-tile layers with >= 1024 work items (+3..10 %); elsewhere the wait for a whole
+// 41 KB halo before the first MMA of an item costs more than the 2.3x cut in L2 -> SM operand traffic returns.
+static int halo_ok(const mdm_conv_args* c, const void* out, int n_total, int k_chunks) {
+  const int enabled = env_flag("MDM_IGEMM_HALO", 2);                   // read per call: the tests switch modes
+  const int force = env_flag("MDM_IGEMM_HALO_FORCE", 0);               // tests: every eligible layer
+  if (!enabled || c->ksize != 3 || c->stride != 1 || out == nullptr || c->y_f32 != nullptr) return 0;
+  if (enabled == 1) return (c->H % PATCH_H == 0 && c->W % PATCH_W == 0) ? 1 : 0;
+  if (c->H % 16 == 0 && c->W % 16 == 0) {
+    const int num_n = (n_total + TILE_N - 1) / TILE_N;
+    const long long items = (long long)c->N * (c->H / 16) * (c->W / 16) * num_n;
+    if (force || (k_chunks >= 4 && num_n >= 2 && items >= 96) || (num_n == 1 && items >= 1024)) return 2;
+  }
+  return 0;
 }
 
 // fprop / dgrad share this: build the operand / epilogue maps, choose a K split for small grids, launch,
@@ -941,26 +969,31 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
                                void* stream) {
   int rc;
   CUtensorMap mA0, mA1, mC, mD;
-  a.halo = halo_ok(c, out) ? 1 : 0;
+  const int halo_kind = halo_ok(c, out, a.N_total, a.seg_kc[0]);   // 0: plain, 1: 8 x 16 patches, 2: 16 x 16 patches (256-row items)
+  a.halo = halo_kind ? 1 : 0;
+  a.num_n = (a.N_total + TILE_N - 1) / TILE_N;   // a narrow last tile is clipped by the TMA store / guarded in the epilogue
+  int num_m = a.halo ? c->N * (c->H / PATCH_H) * (c->W / PATCH_W) : (a.M_total + TILE_M - 1) / TILE_M;
+  // 256-row tiles once they still fill every SM (both halves share each weight tile: 25 % less operand traffic)
+  static const int mt2_enabled = env_flag("MDM_IGEMM_M256", 1);
+  a.mt = 1;
+  if (halo_kind == 2) {
+    a.mt = 2;
+    num_m /= 2;
+  } else if (mt2_enabled && !a.halo && out != nullptr && ((num_m + 1) / 2) * a.num_n >= kNumSMs) {
+    a.mt = 2;
+    num_m = (num_m + 1) / 2;
+  }
   int bw, bh, bn;
   if (a.halo) { bw = PATCH_W; bh = PATCH_H; bn = 1; }
   else pixel_box(128, c->H, c->W, &bw, &bh, &bn);
-  if (a.halo) rc = make_act_map(&mA0, act, ld_act, act_c, c->W, c->H, c->N, HALO_W, HALO_H, 1, 1);
+  if (halo_kind == 2) rc = make_act_map(&mA0, act, ld_act, act_c, c->W, c->H, c->N, HALO2_W, HALO2_H, 1, 1);
+  else if (a.halo) rc = make_act_map(&mA0, act, ld_act, act_c, c->W, c->H, c->N, HALO_W, HALO_H, 1, 1);
   else rc = make_act_map(&mA0, act, ld_act, act_c, c->W * act_stride, c->H * act_stride, c->N, bw, bh, bn, act_stride);
   if (rc) return rc;
   mA1 = mA0;
   if (mB1) {   // fused 1x1 shortcut segment: plain tiles (a patch in halo mode)
     rc = make_act_map(&mA1, c->x2, c->ld_x2, c->cin2, c->W, c->H, c->N, bw, bh, bn, 1);
     if (rc) return rc;
-  }
-  int num_m = a.halo ? c->N * (c->H / PATCH_H) * (c->W / PATCH_W) : (a.M_total + TILE_M - 1) / TILE_M;
-  a.num_n = (a.N_total + TILE_N - 1) / TILE_N;   // a narrow last tile is clipped by the TMA store / guarded in the epilogue
-  // 256-row tiles once they still fill every SM (both halves share each weight tile: 25 % less operand traffic)
-  static const int mt2_enabled = env_flag("MDM_IGEMM_M256", 1);
-  a.mt = 1;
-  if (mt2_enabled && !a.halo && out != nullptr && ((num_m + 1) / 2) * a.num_n >= kNumSMs) {
-    a.mt = 2;
-    num_m = (num_m + 1) / 2;
   }
   const int tiles = num_m * a.num_n;
   a.iters_total = a.seg_taps[0] * a.seg_kc[0] + (a.nseg > 1 ? a.seg_taps[1] * a.seg_kc[1] : 0);

@@ -50,6 +50,14 @@ __device__ __forceinline__ float dsiluf_(float z) {
 //         sum(d*gamma*xhat) = sum_c gamma_c dgamma_c) + apply pass, which can also emit the per-sample
 //         column sums of dx (the time-embedding / conv-bias gradients) so no separate reduction runs.
 // =============================================================================================
+// sigmoid with ONE special-function op (tanh.approx, |rel err| <= 2^-11 -- far below the bf16 output rounding);
+// exp + reciprocal costs two, and these kernels sit close to the MUFU rate on B200 (16 / clk / SM)
+__device__ __forceinline__ float sigmoid_fast(float z) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float silu_fast(float z) { return z * sigmoid_fast(z); }
 constexpr int GN_MAX_GROUPS = 32;
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_C = 2048;
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float z = fmaf(f[j], sc[j], sh[j]);
-      if (silu) z = __fdividef(z, 1.0f + __expf(-z));
+      if (silu) z = silu_fast(z);
       f[j] = z;
     }
     *reinterpret_cast<uint4*>(dst) = pack8(f);
@@ -210,8 +218,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
 
 // d(silu(z))/dz with one exp and one fast division
 __device__ __forceinline__ float dsilu_fast(float z) {
-  const float e = __expf(-z);
-  const float s = __fdividef(1.0f, 1.0f + e);
+  const float s = sigmoid_fast(z);
   return s * fmaf(z, 1.0f - s, 1.0f);
 }
 
@@ -494,7 +501,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_small_fwd_kernel(const bf16* __
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float z = fmaf(f[j], sc[j], sh[j]);
-        if (silu) z = __fdividef(z, 1.0f + __expf(-z));
+        if (silu) z = silu_fast(z);
         f[j] = z;
       }
       *reinterpret_cast<uint4*>(o + i * ostep) = pack8(f);
@@ -645,6 +652,356 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_small_bwd_kernel(
       if (dbias) atomicAdd(dbias + c, v);
     }
   }
+}
+
+// ---- medium maps: ONE kernel, one HBM read -- a thread-block CLUSTER per sample --------------------------------
+// The sample (up to 16 x 32K elements forward, 16 x 16K backward) is split by pixel range over the K CTAs of a
+// cluster.  Every thread copies its vectors with cp.async into thread-private shared-memory slots (slot i of
+// thread t at [i][t]: conflict-free, no register cost -> 3 CTAs per SM overlap one CTA's load phase with another's
+// store phase), the per-group partial sums are PUSHED into every peer's shared memory (DSMEM stores) before one
+// cluster barrier, and the normalisation runs from the staged copy: x (and dy) cross HBM/L2 exactly once.
+constexpr int GN_MAX_CLUSTER = 16;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store two floats into the same shared-memory offset of CTA `rank` of this cluster
+__device__ __forceinline__ void dsmem_store2(float* local_ptr, uint32_t rank, float a, float b) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(local_ptr)), "r"(rank));
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_cluster_fwd_kernel(const bf16* __restrict__ x, long long ld, bf16* __restrict__ y,
+                                                                       long long ldy, const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta, float* __restrict__ stats,
+                                                                       float eps, int silu, GnGeom g, int K) {
+  MDM_PDL_ENTER();
+  extern __shared__ __align__(16) uint8_t gn_dyn[];
+  uint4* slots = reinterpret_cast<uint4*>(gn_dyn);                               // [MAXV][GN_THREADS]
+  float* ch = reinterpret_cast<float*>(gn_dyn + (size_t)MAXV * GN_THREADS * 16);  // s[C], q[C]
+  __shared__ __align__(8) float recv[GN_MAX_CLUSTER * GN_MAX_GROUPS * 2];         // [rank][group]{sum, sumsq}
+  __shared__ float mr[GN_MAX_GROUPS * 2];
+  const uint32_t rank = cluster_ctarank();
+  const int n = blockIdx.x / K;
+  const int HWp = g.HW / K, p0 = (int)rank * HWp;
+  const int lane = threadIdx.x % g.L, r = threadIdx.x / g.L;
+  const int count = (r < g.R && r < HWp) ? (HWp - r + g.R - 1) / g.R : 0;
+  const int c0 = lane * 8;
+  {
+    const bf16* p = x + ((long long)n * g.HW + p0 + r) * ld + c0;
+    const long long step = (long long)g.R * ld;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (i < count) cp_async16(&slots[i * GN_THREADS + threadIdx.x], p + i * step);
+  }
+  for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) ch[c] = 0.f;
+  cp_async_wait_all();
+  __syncthreads();
+  if (count > 0) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < count; ++i) {
+      float f[8];
+      unpack8(slots[i * GN_THREADS + threadIdx.x], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&ch[c0 + j], s[j]);
+      atomicAdd(&ch[g.C + c0 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < g.G) {
+    float a = 0.f, b = 0.f;
+    for (int c = threadIdx.x * g.cpg; c < (threadIdx.x + 1) * g.cpg; ++c) { a += ch[c]; b += ch[g.C + c]; }
+    float* slot = &recv[(rank * GN_MAX_GROUPS + threadIdx.x) * 2];
+    for (int peer = 0; peer < K; ++peer) dsmem_store2(slot, (uint32_t)peer, a, b);
+  }
+  cluster_sync_all();
+  if (threadIdx.x < g.G) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < K; ++k) { a += recv[(k * GN_MAX_GROUPS + threadIdx.x) * 2]; b += recv[(k * GN_MAX_GROUPS + threadIdx.x) * 2 + 1]; }
+    const double cnt = (double)g.HW * g.cpg;
+    const double mean = a / cnt;
+    double var = b / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    mr[threadIdx.x * 2] = (float)mean;
+    mr[threadIdx.x * 2 + 1] = rstd;
+    if (rank == 0 && stats) {
+      stats[((long long)n * g.G + threadIdx.x) * 2] = (float)mean;
+      stats[((long long)n * g.G + threadIdx.x) * 2 + 1] = rstd;
+    }
+  }
+  __syncthreads();
+  if (count == 0) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int grp = (c0 + j) / g.cpg;
+    const float mean = mr[grp * 2], rstd = mr[grp * 2 + 1];
+    const float ga = gamma[c0 + j], be = beta[c0 + j];
+    sc[j] = rstd * ga;
+    sh[j] = be - mean * rstd * ga;
+  }
+  bf16* o = y + ((long long)n * g.HW + p0 + r) * ldy + c0;
+  const long long ostep = (long long)g.R * ldy;
+#pragma unroll 4
+  for (int i = 0; i < count; ++i) {
+    float f[8];
+    unpack8(slots[i * GN_THREADS + threadIdx.x], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z = fmaf(f[j], sc[j], sh[j]);
+      if (silu) z = silu_fast(z);
+      f[j] = z;
+    }
+    *reinterpret_cast<uint4*>(o + i * ostep) = pack8(f);
+  }
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_cluster_bwd_kernel(
+    const bf16* __restrict__ x, long long ld, const bf16* __restrict__ dy, long long lddy, const bf16* add /* may alias dx */,
+    long long ldadd, const bf16* __restrict__ add2, long long ldadd2, bf16* dx, long long lddx,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int silu, float* __restrict__ colsum, long long ld_colsum,
+    float* __restrict__ dbias, GnGeom g, int K) {
+  MDM_PDL_ENTER();
+  extern __shared__ __align__(16) uint8_t gn_dyn[];
+  uint4* sx = reinterpret_cast<uint4*>(gn_dyn);                                    // [MAXV][GN_THREADS]
+  uint4* sdy = sx + MAXV * GN_THREADS;                                             // [MAXV][GN_THREADS]
+  float* sdg = reinterpret_cast<float*>(gn_dyn + (size_t)2 * MAXV * GN_THREADS * 16);   // [C]; reused for the column sums
+  float* sdb = sdg + g.C;
+  __shared__ __align__(8) float recv[GN_MAX_CLUSTER * GN_MAX_GROUPS * 2];
+  __shared__ float m12[GN_MAX_GROUPS * 2];
+  const uint32_t rank = cluster_ctarank();
+  const int n = blockIdx.x / K;
+  const int HWp = g.HW / K, p0 = (int)rank * HWp;
+  const int lane = threadIdx.x % g.L, r = threadIdx.x / g.L;
+  const int count = (r < g.R && r < HWp) ? (HWp - r + g.R - 1) / g.R : 0;
+  const int c0 = lane * 8;
+  const long long first = (long long)n * g.HW + p0 + r;
+  {
+    const bf16* px = x + first * ld + c0;
+    const bf16* pd = dy + first * lddy + c0;
+    const long long stx = (long long)g.R * ld, std_ = (long long)g.R * lddy;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (i < count) {
+        cp_async16(&sx[i * GN_THREADS + threadIdx.x], px + i * stx);
+        cp_async16(&sdy[i * GN_THREADS + threadIdx.x], pd + i * std_);
+      }
+  }
+  for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) sdg[c] = 0.f;
+  float rs[8], mb[8], ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int grp = (c0 + j) / g.cpg;
+    const float mean = stats[((long long)n * g.G + grp) * 2], rstd = stats[((long long)n * g.G + grp) * 2 + 1];
+    rs[j] = rstd;
+    mb[j] = -mean * rstd;
+    ga[j] = gamma[c0 + j];
+    be[j] = beta[c0 + j];
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (count > 0) {
+    float dg[8], db[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dg[j] = db[j] = 0.f;
+#pragma unroll 2
+    for (int i = 0; i < count; ++i) {
+      float fx[8], fd[8];
+      unpack8(sx[i * GN_THREADS + threadIdx.x], fx);
+      unpack8(sdy[i * GN_THREADS + threadIdx.x], fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(fx[j], rs[j], mb[j]);
+        float d = fd[j];
+        if (silu) d *= dsilu_fast(fmaf(xh, ga[j], be[j]));
+        dg[j] = fmaf(d, xh, dg[j]);
+        db[j] += d;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sdg[c0 + j], dg[j]);
+      atomicAdd(&sdb[c0 + j], db[j]);
+    }
+  }
+  __syncthreads();
+  if (dgamma) {
+    for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+      atomicAdd(dgamma + c, sdg[c]);
+      atomicAdd(dbeta + c, sdb[c]);
+    }
+  }
+  if (threadIdx.x < g.G) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = threadIdx.x * g.cpg; c < (threadIdx.x + 1) * g.cpg; ++c) {
+      const float gm = gamma[c];
+      s1 = fmaf(gm, sdb[c], s1);
+      s2 = fmaf(gm, sdg[c], s2);
+    }
+    float* slot = &recv[(rank * GN_MAX_GROUPS + threadIdx.x) * 2];
+    for (int peer = 0; peer < K; ++peer) dsmem_store2(slot, (uint32_t)peer, s1, s2);
+  }
+  cluster_sync_all();   // (also a CTA barrier: sdg / sdb are free again)
+  if (threadIdx.x < g.G) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < K; ++k) { s1 += recv[(k * GN_MAX_GROUPS + threadIdx.x) * 2]; s2 += recv[(k * GN_MAX_GROUPS + threadIdx.x) * 2 + 1]; }
+    const double cnt = (double)g.HW * g.cpg;
+    m12[threadIdx.x * 2] = (float)(s1 / cnt);
+    m12[threadIdx.x * 2 + 1] = (float)(s2 / cnt);
+  }
+  const bool want_cs = colsum != nullptr || dbias != nullptr;
+  if (want_cs)
+    for (int c = threadIdx.x; c < g.C; c += blockDim.x) sdg[c] = 0.f;
+  __syncthreads();
+  if (count > 0) {
+    float A[8], Bc[8], Cc[8], cs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int grp = (c0 + j) / g.cpg;
+      const float m1 = m12[grp * 2], m2 = m12[grp * 2 + 1];
+      A[j] = rs[j] * ga[j];
+      Bc[j] = -rs[j] * rs[j] * m2;
+      Cc[j] = -rs[j] * (m1 + mb[j] * m2);
+      cs[j] = 0.f;
+    }
+    const bf16* pa = add ? add + first * ldadd + c0 : nullptr;
+    const bf16* pb = add2 ? add2 + first * ldadd2 + c0 : nullptr;
+    bf16* po = dx + first * lddx + c0;
+    const long long sa = (long long)g.R * ldadd, sb = (long long)g.R * ldadd2, so = (long long)g.R * lddx;
+#pragma unroll 2
+    for (int i = 0; i < count; ++i) {
+      float fx[8], fd[8], o[8];
+      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+      if (pa) va = *reinterpret_cast<const uint4*>(pa + i * sa);
+      if (pb) vb = ldg16(pb + i * sb);
+      unpack8(sx[i * GN_THREADS + threadIdx.x], fx);
+      unpack8(sdy[i * GN_THREADS + threadIdx.x], fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d = fd[j];
+        if (silu) d *= dsilu_fast(fmaf(fmaf(fx[j], rs[j], mb[j]), ga[j], be[j]));
+        o[j] = fmaf(d, A[j], fmaf(fx[j], Bc[j], Cc[j]));
+      }
+      if (want_cs) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[j] += o[j];
+      }
+      if (pa) {
+        float fa[8];
+        unpack8(va, fa);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += fa[j];
+      }
+      if (pb) {
+        float fb[8];
+        unpack8(vb, fb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += fb[j];
+      }
+      *reinterpret_cast<uint4*>(po + i * so) = pack8(o);
+    }
+    if (want_cs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sdg[c0 + j], cs[j]);
+    }
+  }
+  if (want_cs) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+      const float v = sdg[c];
+      if (colsum) atomicAdd(colsum + (long long)n * ld_colsum + c, v);
+      if (dbias) atomicAdd(dbias + c, v);
+    }
+  }
+}
+
+template <typename... KArgs, typename... Args>
+static inline void launch_cluster(void (*kernel)(KArgs...), int grid, int cluster, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+constexpr int GN_CL_FWD_V = 16, GN_CL_BWD_V = 8;   // 16-byte vectors per thread held in the staged copy
+static size_t gn_cluster_smem(int C, bool bwd) {
+  return (size_t)(bwd ? 2 * GN_CL_BWD_V : GN_CL_FWD_V) * GN_THREADS * 16 + (size_t)2 * C * sizeof(float);
+}
+// largest usable cluster size (16 needs the non-portable opt-in and enough co-schedulable SMs per GPC)
+static int gn_cluster_limit() {
+  static int limit = -1;
+  if (limit >= 0) return limit;
+  limit = 0;
+  const char* v = getenv("MDM_GN_CLUSTER");
+  const int want = v ? atoi(v) : 16;
+  if (want < 2) return limit;
+  const size_t sm_max = gn_cluster_smem(GN_MAX_C, false);
+  if (cudaFuncSetAttribute(gn_cluster_fwd_kernel<GN_CL_FWD_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_max) != cudaSuccess ||
+      cudaFuncSetAttribute(gn_cluster_bwd_kernel<GN_CL_BWD_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_max) != cudaSuccess) {
+    cudaGetLastError();
+    return limit;
+  }
+  limit = 8;
+  if (want >= 16 &&
+      cudaFuncSetAttribute(gn_cluster_fwd_kernel<GN_CL_FWD_V>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+      cudaFuncSetAttribute(gn_cluster_bwd_kernel<GN_CL_BWD_V>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16);
+    cfg.blockDim = dim3(GN_THREADS);
+    cfg.dynamicSmemBytes = gn_cluster_smem(512, true);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 16; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, gn_cluster_bwd_kernel<GN_CL_BWD_V>, &cfg) == cudaSuccess && nclusters >= 4) limit = 16;
+  }
+  cudaGetLastError();
+  if (want < limit) limit = want >= 8 ? 8 : (want >= 4 ? 4 : 2);
+  return limit;
+}
+// cluster size for a sample of HW x C elements with `maxv` vectors per thread; 0: does not fit
+static int gn_cluster_size(const GnGeom& g, int maxv) {
+  const int limit = gn_cluster_limit();
+  for (int K = 2; K <= limit; K *= 2) {
+    if (g.HW % K) return 0;
+    const int HWp = g.HW / K;
+    if ((HWp + g.R - 1) / g.R <= maxv) return K;
+  }
+  return 0;
 }
 
 static int gn_geom(GnGeom& g, int HW, int C, int G, int* nchunk) {
@@ -1191,6 +1548,11 @@ int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, cons
     MDM_LAUNCH_CHECK();
     return MDM_OK;
   }
+  if (const int K = gn_cluster_size(g, GN_CL_FWD_V)) {   // medium map: one cluster per sample, one pass
+    launch_cluster(gn_cluster_fwd_kernel<GN_CL_FWD_V>, N * K, K, gn_cluster_smem(C, false), as_stream(stream), (const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta, stats, eps, silu, g, K);
+    MDM_LAUNCH_CHECK();
+    return MDM_OK;
+  }
   dim3 grid(nc, N);
   launch_pdl(gn_stats_kernel<8>, dim3(grid), dim3(GN_THREADS), (size_t)2 * C * sizeof(float), as_stream(stream), (const bf16*)x, ld_x, ws, g);
   MDM_LAUNCH_CHECK();
@@ -1214,6 +1576,15 @@ int mdm_gn_silu_bwd(const void* x, long long ld_x, const void* dy, long long ld_
     const size_t sm = (size_t)2 * C * sizeof(float);
     if (per_thread <= 2) launch_pdl(gn_small_bwd_kernel<2>, dim3(N), dim3(GN_THREADS), sm, as_stream(stream), (const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (const bf16*)add, ld_add, (const bf16*)add2, ld_add2, (bf16*)dx, ld_dx, gamma, beta, stats, dgamma, dbeta, silu, colsum, ld_colsum, dbias, g);
     else launch_pdl(gn_small_bwd_kernel<8>, dim3(N), dim3(GN_THREADS), sm, as_stream(stream), (const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (const bf16*)add, ld_add, (const bf16*)add2, ld_add2, (bf16*)dx, ld_dx, gamma, beta, stats, dgamma, dbeta, silu, colsum, ld_colsum, dbias, g);
+    MDM_LAUNCH_CHECK();
+    return MDM_OK;
+  }
+  // measured (bench_gn.py, B200): the single-pass cluster backward is SLOWER than the two-pass kernels (its second phase
+  // waits on the add / add2 loads with few warps per SM): opt-in until those loads are staged too
+  const char* clb = getenv("MDM_GN_CLUSTER_BWD");
+  const int K_bwd = (clb && atoi(clb)) ? gn_cluster_size(g, GN_CL_BWD_V) : 0;
+  if (const int K = K_bwd) {   // medium map: one cluster per sample, x and dy read once
+    launch_cluster(gn_cluster_bwd_kernel<GN_CL_BWD_V>, N * K, K, gn_cluster_smem(C, true), as_stream(stream), (const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (const bf16*)add, ld_add, (const bf16*)add2, ld_add2, (bf16*)dx, ld_dx, gamma, beta, stats, dgamma, dbeta, silu, colsum, ld_colsum, dbias, g, K);
     MDM_LAUNCH_CHECK();
     return MDM_OK;
   }

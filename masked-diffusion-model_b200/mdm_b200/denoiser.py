@@ -457,7 +457,22 @@ class UNet2DModelB200:
     def _backward_plans(self, plans, d_out):
         n = len(plans)
         h = d_out.shape[0] // n
-        self._run_plans(plans, lambda p, i: p.run_backward(d_out[i * h:(i + 1) * h]))
+        seg = 0 if (getattr(self, "bwd_segmented", False) and n == 1) else None
+        self._run_plans(plans, lambda p, i: p.run_backward(d_out[i * h:(i + 1) * h], seg))
+
+    def backward_segment(self, k):
+        """segment k >= 1 of the last backward (after `bwd_segmented = True` made loss.backward() stop at segment 0)"""
+        self._last_plans[0].run_backward(None, k)
+
+    def grad_segment_ranges(self):
+        """[(lo, hi)] of the flat gradient finished by backward segment 0, 1, ...; the last segment finishes the
+        complement.  Matches `_Plan.bwd_marks`."""
+        lo0, hi0 = self.late_grad_range()
+        out = [(lo0, hi0)]
+        d2 = self._by_name.get("down_blocks.2.resnets.0.norm1.weight")
+        if d2 is not None and len(self._cfg["block_out_channels"]) > 3:
+            out.append((d2.offset, lo0))
+        return out
 
     def backward(self, d_out: torch.Tensor):
         """Backpropagate d(loss)/d(sample output) (NCHW fp32) through the last training forward;
@@ -666,20 +681,27 @@ class _Plan:
         emit = dict(conv_in=self._emit_conv_in, resnet=self._emit_resnet, attn=self._emit_attn, down=self._emit_down,
                     up=self._emit_up, head=self._emit_head)
         bw_chunks = []
-        first_mid = None
+        first_mid = first_d2 = None
         for i, (kind, d) in enumerate(self._ops):
             if first_mid is None and kind == "resnet" and d["r"].prefix == "mid_block.resnets.0":
                 first_mid = i
+            if first_d2 is None and kind == "resnet" and d["r"].prefix == "down_blocks.2.resnets.0":
+                first_d2 = i
             fw, bw = emit[kind](**d)
             self.fwd += fw
             bw_chunks.append(bw)
+        # backward segments for data-parallel overlap: the gradients of a contiguous range of the flat buffer are
+        # final at the end of each segment (UNet2DModelB200.grad_segment_ranges), so their all-reduce runs while
+        # the next segment computes.  segment 0: head, up path, mid block; 1: down blocks 5..2; 2: the rest.
+        self.bwd_marks = []
         if ng:
             for i in range(len(bw_chunks) - 1, -1, -1):
                 self.bwd += bw_chunks[i]
                 if i == first_mid:
-                    # the head, the whole up path and the mid block are done: their gradients -- one contiguous
-                    # range of the flat buffer -- are final; data-parallel runs start reducing them now
                     self.bwd.append(self._grads_ready_mid)
+                    self.bwd_marks.append(len(self.bwd))
+                elif i == first_d2 and first_mid is not None and len(self.m._cfg["block_out_channels"]) > 3:
+                    self.bwd_marks.append(len(self.bwd))
             self.bwd.append(self._temb_bwd)
 
     def _grads_ready_mid(self):
@@ -945,9 +967,15 @@ class _Plan:
             op()
         return self.out
 
-    def run_backward(self, d_out):
-        self.d_out.copy_(d_out)
-        self.d_tproj.zero_()          # accumulated by the fused column sums of the norm2 backward
-        for op in self.bwd:
+    def run_backward(self, d_out, seg=None):
+        """the whole backward program (seg None) or one of its segments (see `bwd_marks`)"""
+        if seg is None or seg == 0:
+            self.d_out.copy_(d_out)
+            self.d_tproj.zero_()      # accumulated by the fused column sums of the norm2 backward
+        prog = self.bwd
+        if seg is not None:
+            bounds = [0] + self.bwd_marks + [len(self.bwd)]
+            prog = self.bwd[bounds[seg]:bounds[seg + 1]]
+        for op in prog:
             op()
         self.join_side()              # every weight gradient has landed before the caller (optimiser / all-reduce) runs

@@ -433,6 +433,10 @@ class Accelerator:
                         dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
                         p.grad.mul_(1.0 / self.num_processes)
 
+    def all_reduce_async(self, t):
+        """SUM all-reduce of a slice of the flat gradient on NCCL's stream; `.wait()` orders the current stream after it"""
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
+
     # -- overlapped all-reduce of the flat gradient (B200 denoiser): the range finished first by the backward pass
     #    is reduced asynchronously while the rest of the backward still runs
     def start_late_all_reduce(self, model, lo, hi):

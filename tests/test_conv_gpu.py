@@ -108,3 +108,65 @@ def test_wgrad(N, H, cin, cout, k, stride):
     ref_b = dyb.float().sum(dim=(0, 1, 2))
     tol = 2e-3 * ref_b.abs().max().item() + 1e-3
     assert (db - 0.5 - ref_b).abs().max().item() <= tol and (db2 - ref_b).abs().max().item() <= tol
+
+
+# ---- halo mode: the M tile is a pixel patch whose zero-padded input halo is TMA-loaded once per channel chunk;
+# the nine taps are shifted UMMA views of it.  kind 2 = 16x16 patches (256-row work items, the default for big
+# layers), kind 1 = 8x16 patches.  The small test shapes are forced into halo mode through the environment.
+HALO_CASES = [
+    # N, H, cin, cout
+    (2, 32, 128, 128),
+    (3, 16, 128, 256),
+    (1, 64, 192, 160),      # narrow last cout tile, 3 channel chunks
+    (150, 16, 64, 128),     # more work items than SMs: several items per CTA (ring / accumulator parities wrap)
+]
+
+
+@pytest.fixture(params=[2, 1], ids=["halo256", "halo128"])
+def halo_env(request, monkeypatch):
+    monkeypatch.setenv("MDM_IGEMM_HALO", "1" if request.param == 1 else "2")
+    monkeypatch.setenv("MDM_IGEMM_HALO_FORCE", "1")
+    return request.param
+
+
+@pytest.mark.parametrize("N,H,cin,cout", HALO_CASES)
+def test_halo_fprop_dgrad(halo_env, N, H, cin, cout):
+    from mdm_b200 import denoiser_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(N, cin, H, H, device="cuda", generator=g)
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g)
+    rv = torch.randn(N, cout, device="cuda", generator=g)
+    res = torch.randn(N, cout, H, H, device="cuda", generator=g)
+    xb, wb, resb = nhwc(x), ops.pack_conv_weight(w).to(torch.bfloat16), nhwc(res)
+    y = torch.empty(N, H, H, cout, device="cuda", dtype=torch.bfloat16)
+    ops.conv_fprop(xb, wb, y, N, H, H, 3, 1, bias=b, rowvec=rv, resid=resb)
+    ref = F.conv2d(nchw(xb), ops.unpack_conv_weight(wb.float(), 3), b, padding=1) + rv[:, :, None, None] + nchw(resb)
+    assert (nchw(y) - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    if cin % 128 == 0 and cout % 64 == 0:
+        dyb = nhwc(torch.randn(N, cout, H, H, device="cuda", generator=g))
+        dx = torch.empty(N, H, H, cin, device="cuda", dtype=torch.bfloat16)
+        ops.conv_dgrad(dyb, wb, dx, N, H, H, 3)
+        refd = torch.nn.grad.conv2d_input((N, cin, H, H), ops.unpack_conv_weight(wb.float(), 3), nchw(dyb), padding=1)
+        assert (nchw(dx) - refd).abs().max().item() <= 1e-2 * refd.abs().max().item()
+        ops.conv_dgrad(dyb, wb, dx, N, H, H, 3, accumulate=True)
+        assert (nchw(dx) - 2 * refd).abs().max().item() <= 2.5e-2 * refd.abs().max().item()
+
+
+def test_halo_fused_shortcut_slices(halo_env):
+    """conv3x3(a) + conv1x1(x) in one accumulator in halo mode; operands are channel slices of wider buffers."""
+    from mdm_b200 import denoiser_ops as ops
+    N, H, cin, cout, cx = 3, 16, 256, 256, 384
+    g = torch.Generator(device="cuda").manual_seed(6)
+    abuf = torch.randn(N, H, H, cin + 64, device="cuda", generator=g).to(torch.bfloat16)
+    xbuf = torch.randn(N, H, H, cx + 128, device="cuda", generator=g).to(torch.bfloat16)
+    a, x = abuf[..., 64:], xbuf[..., :cx]
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (9 * cin) ** 0.5)
+    ws = (torch.randn(cout, cx, 1, 1, device="cuda", generator=g) / cx ** 0.5)
+    wb, wsb = ops.pack_conv_weight(w).to(torch.bfloat16), ops.pack_conv_weight(ws).to(torch.bfloat16)
+    ybuf = torch.zeros(N, H, H, cout + 256, device="cuda", dtype=torch.bfloat16)
+    y = ybuf[..., 256:]
+    ops.conv_fprop(a, wb, y, N, H, H, 3, 1, x2=x, w2=wsb)
+    ref = F.conv2d(nchw(a), ops.unpack_conv_weight(wb.float(), 3), padding=1) + F.conv2d(nchw(x), ops.unpack_conv_weight(wsb.float(), 1))
+    assert (nchw(y) - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert ybuf[..., :256].abs().max().item() == 0

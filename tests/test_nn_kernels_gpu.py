@@ -17,11 +17,15 @@ def _nhwc_view(N, H, W, C, c_total=None, c_off=0, seed=0, scale=1.0):
     return buf[..., c_off:c_off + C]
 
 
+@pytest.mark.parametrize("cluster_bwd", ["0", "1"], ids=["bwd2pass", "bwdcluster"])
 @pytest.mark.parametrize("N,H,C,c_total,c_off,silu", [
     (4, 32, 128, None, 0, True), (3, 16, 256, 384, 128, True), (2, 8, 384, None, 0, True), (5, 4, 512, 1024, 512, False),
-    (2, 2, 768, None, 0, True), (7, 1, 1024, None, 0, True), (2, 64, 128, 256, 0, True)])
-def test_groupnorm_silu_fwd_bwd(N, H, C, c_total, c_off, silu):
+    (2, 2, 768, None, 0, True), (7, 1, 1024, None, 0, True), (2, 64, 128, 256, 0, True),
+    # cluster-per-sample single-pass kernels: 16-CTA clusters (fwd 384 ch: ragged 5-pixel rows; bwd 256 ch)
+    (2, 32, 384, None, 0, True), (3, 32, 256, 512, 256, True), (150, 16, 128, None, 0, True)])
+def test_groupnorm_silu_fwd_bwd(N, H, C, c_total, c_off, silu, cluster_bwd, monkeypatch):
     from mdm_b200 import denoiser_ops as ops
+    monkeypatch.setenv("MDM_GN_CLUSTER_BWD", cluster_bwd)
     G, eps = 32, 1e-5
     x = _nhwc_view(N, H, H, C, c_total, c_off, seed=1)
     dy = _nhwc_view(N, H, H, C, seed=2)
