@@ -60,12 +60,16 @@ static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  static const int pdl_on = [] { const char* v = getenv("MDM_PDL"); return v ? atoi(v) : 0; }();
+  // MDM_PDL: 0 = never, 1 = every launch, 2 (default) = only launches of at most MDM_PDL_MAX_CTAS CTAs: the
+  // launch-latency-bound low-resolution layers, whose grids leave most SMs idle anyway.  Measured on B200 (3x32x32
+  // batch 128, captured step): off 8.84 ms, <= 64 CTAs 8.59, <= 148..1200 CTAs 8.33, every launch 8.39.
+  static const int pdl_on = [] { const char* v = getenv("MDM_PDL"); return v ? atoi(v) : 2; }();
+  static const unsigned pdl_max = [] { const char* v = getenv("MDM_PDL_MAX_CTAS"); return v ? (unsigned)atoi(v) : 300u; }();
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_on ? 1 : 0;   // measured on B200 (round 1): PDL edges made the captured step ~4 % SLOWER -> off by default
+  cfg.numAttrs = (pdl_on == 1 || (pdl_on == 2 && grid.x * grid.y * grid.z <= pdl_max)) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);   // errors surface through MDM_LAUNCH_CHECK (cudaGetLastError)
 }
 #endif

@@ -98,6 +98,26 @@ __device__ __forceinline__ GnWalk gn_walk(const GnGeom& g, int n, int chunk) {
   return w;
 }
 
+// add this thread's 8-channel partials into the per-channel shared accumulators dst[C].  Threads of a warp that own
+// the SAME channel slice (L = C/8 < 32 lanes per pixel, i.e. 32/L pixels per warp) are combined with shuffles first:
+// shared-memory float atomics are CAS loops, and same-address lanes of one warp serialise and retry (ncu: the
+// short-scoreboard stall of these kernels).  Must be reached by ALL threads of the CTA; threads without data pass zeros.
+__device__ __forceinline__ void gn_reduce8(float (&v)[8], float* dst, int lane, int L, bool has_data) {
+  if (L < 32 && (32 % L) == 0) {
+    for (int o = L; o < 32; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+    }
+    if ((int)(threadIdx.x & 31) < L) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&dst[lane * 8 + j], v[j]);
+    }
+  } else if (has_data) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&dst[lane * 8 + j], v[j]);
+  }
+}
+
 template <int UNROLL>
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __restrict__ x, long long ld,
                                                               float* __restrict__ ws, GnGeom g) {
@@ -107,12 +127,12 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __rest
   for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) gn_sm[c] = 0.f;
   __syncthreads();
   const GnWalk w = gn_walk(g, n, chunk);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   if (w.count > 0) {
     const bf16* p = x + w.off * ld + w.lane * 8;
     const long long step = (long long)g.R * ld;
-    float s[8], q[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
     int it = 0;
     for (; it + UNROLL <= w.count; it += UNROLL) {
       uint4 v[UNROLL];
@@ -133,12 +153,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __rest
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&gn_sm[w.lane * 8 + j], s[j]);
-      atomicAdd(&gn_sm[g.C + w.lane * 8 + j], q[j]);
-    }
   }
+  gn_reduce8(s, gn_sm, w.lane, g.L, w.count > 0);
+  gn_reduce8(q, gn_sm + g.C, w.lane, g.L, w.count > 0);
   __syncthreads();
   if (threadIdx.x < g.G) {
     float a = 0.f, b = 0.f;
@@ -238,9 +255,12 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
   for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) gn_sm[c] = 0.f;
   __syncthreads();
   const GnWalk w = gn_walk(g, n, chunk);
+  float dg[8], db[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dg[j] = db[j] = 0.f;
   if (w.count > 0) {
     const int c0 = w.lane * 8;
-    float rs[8], mb[8], ga[8], be[8], dg[8], db[8];
+    float rs[8], mb[8], ga[8], be[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int grp = (c0 + j) / g.cpg;
@@ -249,7 +269,6 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
       mb[j] = -mean * rstd;
       ga[j] = gamma[c0 + j];
       be[j] = beta[c0 + j];
-      dg[j] = db[j] = 0.f;
     }
     const bf16* px = x + w.off * ld + c0;
     const bf16* pd = dy + w.off * lddy + c0;
@@ -278,12 +297,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
       for (int u = 0; u < UNROLL; ++u) body(vx[u], vd[u]);
     }
     for (; it < w.count; ++it, px += sx, pd += sd) body(ldg16(px), ldg16(pd));
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sdg[c0 + j], dg[j]);
-      atomicAdd(&sdb[c0 + j], db[j]);
-    }
   }
+  gn_reduce8(dg, sdg, w.lane, g.L, w.count > 0);
+  gn_reduce8(db, sdb, w.lane, g.L, w.count > 0);
   __syncthreads();
   if (dgamma) {
     for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
@@ -333,10 +349,13 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(
   }
   __syncthreads();
   const GnWalk w = gn_walk(g, n, chunk);
+  float cs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cs[j] = 0.f;
   if (w.count > 0) {
     const int c0 = w.lane * 8;
     // dx = d * A + x * B + Cc   with d already multiplied by silu'(z):  A = rstd*gamma, B = -rstd^2*m2, Cc = -rstd*(m1 - mean*rstd*m2)
-    float rs[8], mb[8], ga[8], be[8], A[8], Bc[8], Cc[8], cs[8];
+    float rs[8], mb[8], ga[8], be[8], A[8], Bc[8], Cc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int grp = (c0 + j) / g.cpg;
@@ -349,7 +368,6 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(
       A[j] = rstd * ga[j];
       Bc[j] = -rstd * rstd * m2;
       Cc[j] = -rstd * (m1 + mb[j] * m2);
-      cs[j] = 0.f;
     }
     const bf16* px = x + w.off * ld + c0;
     const bf16* pd = dy + w.off * lddy + c0;
@@ -411,12 +429,9 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(
       body(ldg16(px), ldg16(pd), va, vb, po);
       px += sx; pd += sd; po += so;
     }
-    if (want_cs) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&gn_sm[c0 + j], cs[j]);
-    }
   }
   if (want_cs) {
+    gn_reduce8(cs, gn_sm, w.lane, g.L, w.count > 0);
     __syncthreads();
     for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
       const float v = gn_sm[c];
@@ -445,24 +460,23 @@ __global__ void __launch_bounds__(GN_THREADS) gn_small_fwd_kernel(const bf16* __
   const bf16* p = x + ((long long)n * g.HW + r) * ld + c0;
   const long long step = (long long)g.R * ld;
   uint4 v[MAXV];
-  if (count > 0) {
+  {
     float s[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    if (count > 0) {
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) v[i] = i < count ? ldg16(p + i * step) : make_uint4(0, 0, 0, 0);
+      for (int i = 0; i < MAXV; ++i) v[i] = i < count ? ldg16(p + i * step) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      float f[8];
-      unpack8(v[i], f);
+      for (int i = 0; i < MAXV; ++i) {
+        float f[8];
+        unpack8(v[i], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+        for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+      }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&gn_sm[c0 + j], s[j]);
-      atomicAdd(&gn_sm[g.C + c0 + j], q[j]);
-    }
+    gn_reduce8(s, gn_sm, lane, g.L, count > 0);
+    gn_reduce8(q, gn_sm + g.C, lane, g.L, count > 0);
   }
   __syncthreads();
   if (threadIdx.x < g.G) {
@@ -530,8 +544,10 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_small_bwd_kernel(
   const long long first = (long long)n * g.HW + r;
   uint4 vx[MAXV], vd[MAXV];
   float rs[8], mb[8], ga[8], be[8];
+  float dg[8], db[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dg[j] = db[j] = 0.f;
   if (count > 0) {
-    float dg[8], db[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int grp = (c0 + j) / g.cpg;
@@ -540,7 +556,6 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_small_bwd_kernel(
       mb[j] = -mean * rstd;
       ga[j] = gamma[c0 + j];
       be[j] = beta[c0 + j];
-      dg[j] = db[j] = 0.f;
     }
     const bf16* px = x + first * ld + c0;
     const bf16* pd = dy + first * lddy + c0;
@@ -564,12 +579,9 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_small_bwd_kernel(
         db[j] += d;
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sdg[c0 + j], dg[j]);
-      atomicAdd(&sdb[c0 + j], db[j]);
-    }
   }
+  gn_reduce8(dg, sdg, lane, g.L, count > 0);
+  gn_reduce8(db, sdb, lane, g.L, count > 0);
   __syncthreads();
   if (dgamma) {
     for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
@@ -593,8 +605,11 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_small_bwd_kernel(
   if (want_cs)
     for (int c = threadIdx.x; c < g.C; c += blockDim.x) gn_sm[c] = 0.f;   // sdg no longer needed
   if (want_cs) __syncthreads();
+  float cs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cs[j] = 0.f;
   if (count > 0) {
-    float A[8], Bc[8], Cc[8], cs[8];
+    float A[8], Bc[8], Cc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int grp = (c0 + j) / g.cpg;
@@ -602,7 +617,6 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_small_bwd_kernel(
       A[j] = rs[j] * ga[j];
       Bc[j] = -rs[j] * rs[j] * m2;
       Cc[j] = -rs[j] * (m1 + mb[j] * m2);
-      cs[j] = 0.f;
     }
     const bf16* pa = add ? add + first * ldadd + c0 : nullptr;
     const bf16* pb = add2 ? add2 + first * ldadd2 + c0 : nullptr;
@@ -639,12 +653,9 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_small_bwd_kernel(
         *reinterpret_cast<uint4*>(po + i * so) = pack8(o);
       }
     }
-    if (want_cs) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&gn_sm[c0 + j], cs[j]);
-    }
   }
   if (want_cs) {
+    gn_reduce8(cs, gn_sm, lane, g.L, count > 0);
     __syncthreads();
     for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
       const float v = gn_sm[c];
@@ -710,7 +721,7 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_cluster_fwd_kernel(const bf1
   for (int c = threadIdx.x; c < 2 * g.C; c += blockDim.x) ch[c] = 0.f;
   cp_async_wait_all();
   __syncthreads();
-  if (count > 0) {
+  {
     float s[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
@@ -721,11 +732,8 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_cluster_fwd_kernel(const bf1
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&ch[c0 + j], s[j]);
-      atomicAdd(&ch[g.C + c0 + j], q[j]);
-    }
+    gn_reduce8(s, ch, lane, g.L, count > 0);
+    gn_reduce8(q, ch + g.C, lane, g.L, count > 0);
   }
   __syncthreads();
   if (threadIdx.x < g.G) {
@@ -823,7 +831,7 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_cluster_bwd_kernel(
   }
   cp_async_wait_all();
   __syncthreads();
-  if (count > 0) {
+  {
     float dg[8], db[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) dg[j] = db[j] = 0.f;
@@ -841,11 +849,8 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_cluster_bwd_kernel(
         db[j] += d;
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sdg[c0 + j], dg[j]);
-      atomicAdd(&sdb[c0 + j], db[j]);
-    }
+    gn_reduce8(dg, sdg, lane, g.L, count > 0);
+    gn_reduce8(db, sdb, lane, g.L, count > 0);
   }
   __syncthreads();
   if (dgamma) {
@@ -876,8 +881,11 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_cluster_bwd_kernel(
   if (want_cs)
     for (int c = threadIdx.x; c < g.C; c += blockDim.x) sdg[c] = 0.f;
   __syncthreads();
+  float cs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cs[j] = 0.f;
   if (count > 0) {
-    float A[8], Bc[8], Cc[8], cs[8];
+    float A[8], Bc[8], Cc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int grp = (c0 + j) / g.cpg;
@@ -885,7 +893,6 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_cluster_bwd_kernel(
       A[j] = rs[j] * ga[j];
       Bc[j] = -rs[j] * rs[j] * m2;
       Cc[j] = -rs[j] * (m1 + mb[j] * m2);
-      cs[j] = 0.f;
     }
     const bf16* pa = add ? add + first * ldadd + c0 : nullptr;
     const bf16* pb = add2 ? add2 + first * ldadd2 + c0 : nullptr;
@@ -923,12 +930,9 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_cluster_bwd_kernel(
       }
       *reinterpret_cast<uint4*>(po + i * so) = pack8(o);
     }
-    if (want_cs) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&sdg[c0 + j], cs[j]);
-    }
   }
   if (want_cs) {
+    gn_reduce8(cs, sdg, lane, g.L, count > 0);
     __syncthreads();
     for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
       const float v = sdg[c];
