@@ -761,7 +761,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         }
       }
     }
-    if (et == 0) bulk_wait_all();   // global writes of this CTA complete before it exits
+    // the staging tiles must stay valid until the bulk stores have READ them; completion of the global writes
+    // themselves is implied by grid completion (what the next kernel / griddepcontrol.wait orders against)
+    if (et == 0) bulk_wait_read<0>();
     tcgen05_fence_before();
   }
 
@@ -979,7 +981,7 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
   if (halo_kind == 2) {
     a.mt = 2;
     num_m /= 2;
-  } else if (mt2_enabled && !a.halo && out != nullptr && ((num_m + 1) / 2) * a.num_n >= kNumSMs) {
+  } else if (mt2_enabled && !a.halo && out != nullptr && ((num_m + 1) / 2) * a.num_n >= env_flag("MDM_IGEMM_M256_MIN", kNumSMs)) {
     a.mt = 2;
     num_m = (num_m + 1) / 2;
   }

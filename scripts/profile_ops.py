@@ -14,6 +14,7 @@ ap.add_argument("--out", default="gpurun_out/ops_profile.json")
 pa = ap.parse_args()
 a = argparse.Namespace(batch=pa.batch, size=pa.size, channels=pa.channels, method=pa.method, no_graph=True)
 tr, model, acc = bench.build_trainer(a, bench.workload_args(a))
+model.wgrad_side_stream = False      # serialise the weight-gradient GEMMs with the main chain: one kernel at a time under every event pair
 dev = torch.device("cuda", 0)
 x = (torch.rand(pa.batch, pa.channels, pa.size, pa.size) * 2 - 1).to(dev)
 torch.manual_seed(0); tr.Scheduler.adopt_torch_rng(dev)
@@ -56,7 +57,7 @@ agg2 = collections.defaultdict(lambda: [0, 0.0])
 for n, d, us in rows:
     agg2[(n, d)][0] += 1; agg2[(n, d)][1] += us
 print("--- by shape (top 60)")
-for (n, d), (c, us) in sorted(agg2.items(), key=lambda kv: -kv[1][1])[:60]:
+for (n, d), (c, us) in sorted(agg2.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get("TOP", 60))]:
     print(f"{us:9.0f} us {100*us/tot:5.1f}%  n={c:3d}  avg={us/c:7.1f}  {n}  {d}")
 os.makedirs(os.path.dirname(pa.out), exist_ok=True)
 json.dump(rows, open(pa.out, "w"))
