@@ -208,7 +208,9 @@ int mdm_conv_out_bwd(const void* x, long long ld_x, const float* w, const float*
 /* first / last convolution as tensor-core GEMMs (round 1b): gather the 3x3 neighbourhood of the C-channel planar fp32
  * image into a [N*H*W][64] bf16 matrix, column tap*C + c (zero padded; flip = taps mirrored, for the adjoint), and
  * the 9-tap scatter-sum that finishes the last conv: out[n][c][h][w] = bias[c] + sum_tap z[(n,h+dh,w+dw)][tap*C+c]
- * with z fp32 [N*H*W][32].  The GEMMs themselves are mdm_conv_fprop / mdm_conv_wgrad with ksize 1. */
+ * with z fp32 [N*H*W][32].  The GEMMs themselves are mdm_conv_fprop / mdm_conv_wgrad with ksize 1.
+ * mdm_im2col3x3 writes columns [0, 8*ceil(9C/8)) only: the caller zero-fills the matrix once (the padding columns
+ * never change between calls). */
 int mdm_im2col3x3(const float* img, void* out_bf16, int N, int C, int H, int W, int flip, void* stream);
 int mdm_tapsum3x3(const float* z, const float* bias, float* out, int N, int C, int H, int W, void* stream);
 

@@ -1008,7 +1008,7 @@ static int gn_cluster_size(const GnGeom& g, int maxv) {
   return 0;
 }
 
-static int gn_geom(GnGeom& g, int HW, int C, int G, int* nchunk) {
+static int gn_geom(GnGeom& g, int HW, int C, int G, int* nchunk, int nbatch = 0) {
   if (C % 8 != 0 || C % G != 0 || G > GN_MAX_GROUPS || C > GN_MAX_C) {
     set_error("GroupNorm: C=%d must be a multiple of 8 and of G=%d (G <= 32, C <= %d)", C, G, GN_MAX_C);
     return MDM_E_ARG;
@@ -1017,8 +1017,14 @@ static int gn_geom(GnGeom& g, int HW, int C, int G, int* nchunk) {
   g.L = C / 8;
   if (g.L > GN_THREADS) { set_error("GroupNorm: C=%d too wide", C); return MDM_E_ARG; }
   g.R = GN_THREADS / g.L;
-  // ~32K elements (64 KB of bf16) per CTA, a multiple of R pixels
-  int chunk = (32768 + C - 1) / C;
+  // ~32K elements (64 KB of bf16) per CTA, a multiple of R pixels; big tensors get longer chunks (about 8 CTAs
+  // per SM in total) so the per-CTA set-up / reduction / tail is amortised over more streaming
+  long long per_cta = 32768;
+  if (nbatch > 0) {
+    const long long want = ((long long)nbatch * HW * C) / (kNumSMs * 8);
+    if (want > per_cta) per_cta = want;
+  }
+  int chunk = (int)((per_cta + C - 1) / C);
   chunk = ((chunk + g.R - 1) / g.R) * g.R;
   if (chunk > HW) chunk = HW;
   if (chunk < 1) chunk = 1;
@@ -1185,13 +1191,19 @@ __global__ void planar_sum_kernel(const float* __restrict__ img, float* __restri
 // the 9*C per-tap partial outputs z[pix][32] (fp32) followed by the 9-tap scatter-sum below, its backward
 // the same gather (flipped) feeding a dgrad-as-fprop GEMM and a wgrad GEMM.  (csrc/igemm.cu does the GEMMs.)
 // =============================================================================================
-__global__ void im2col3x3_kernel(const float* __restrict__ img, bf16* __restrict__ out, int C, int H, int W, int flip,
+// thread <-> (pixel, 8-column chunk); only the ceil(9C/8) chunks that hold data are written: the caller zero-fills
+// the [pixel][64] matrix ONCE (its columns >= 8*ceil(9C/8) never change).  C is a template parameter: every
+// division below has a constant divisor.
+template <int C>
+__global__ void im2col3x3_kernel(const float* __restrict__ img, bf16* __restrict__ out, int H, int W, int flip,
                                  long long total) {
   MDM_PDL_ENTER();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (pixel, 8-column chunk)
+  constexpr int NCH = (9 * C + 7) / 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (pixel, chunk)
   if (i >= total) return;
-  const int chunk = (int)(i & 7);
-  long long p = i >> 3;
+  long long p = i / NCH;
+  const int chunk = (int)(i - p * NCH);
+  const long long pix = p;
   const int w = (int)(p % W); p /= W;
   const int h = (int)(p % H); const long long n = p / H;
   float f[8];
@@ -1201,35 +1213,54 @@ __global__ void im2col3x3_kernel(const float* __restrict__ img, bf16* __restrict
     float v = 0.f;
     if (j < 9 * C) {
       const int tap = j / C, c = j - tap * C;
-      const int dh = flip ? 1 - tap / 3 : tap / 3 - 1, dw = flip ? 1 - tap % 3 : tap % 3 - 1;
+      const int r = tap / 3, q = tap - r * 3;
+      const int dh = flip ? 1 - r : r - 1, dw = flip ? 1 - q : q - 1;
       const int hh = h + dh, ww = w + dw;
       if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(img + ((n * C + c) * H + hh) * W + ww);
     }
     f[e] = v;
   }
-  *reinterpret_cast<uint4*>(out + (i << 3)) = pack8(f);
+  *reinterpret_cast<uint4*>(out + pix * 64 + chunk * 8) = pack8(f);
 }
 
 // out[n][c][h][w] = bias[c] + sum_tap z[(n, h+dh, w+dw)][tap*C + c]   (z: fp32 [N*H*W][32])
-__global__ void tapsum3x3_kernel(const float* __restrict__ z, const float* __restrict__ bias, float* __restrict__ out, int C,
-                                 int H, int W, long long total) {
+// CTA <-> a 16 x 16 pixel tile of one image: the 18 x 18 z rows it needs are staged in shared memory with fully
+// coalesced float4 loads (a row = 128 contiguous bytes), then thread <-> pixel sums its nine taps from the tile.
+constexpr int TS_T = 16;
+__global__ void __launch_bounds__(256) tapsum3x3_kernel(const float* __restrict__ z, const float* __restrict__ bias,
+                                                        float* __restrict__ out, int C, int H, int W) {
   MDM_PDL_ENTER();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // output pixel
-  if (i >= total) return;
-  long long p = i;
-  const int w = (int)(p % W); p /= W;
-  const int h = (int)(p % H); const long long n = p / H;
+  extern __shared__ float4 ts_sm[];   // [(TS_T+2)^2][8] float4, chunk index XOR-swizzled by the pixel (bank spread)
+  const int tiles_w = (W + TS_T - 1) / TS_T, tiles_h = (H + TS_T - 1) / TS_T;
+  int t = blockIdx.x;
+  const int tw = t % tiles_w; t /= tiles_w;
+  const int th = t % tiles_h; const long long n = t / tiles_h;
+  const int h0 = th * TS_T, w0 = tw * TS_T;
+  constexpr int HP = TS_T + 2;
+  for (int i = threadIdx.x; i < HP * HP * 8; i += blockDim.x) {
+    const int q = i & 7, pp = i >> 3;
+    const int hh = h0 + pp / HP - 1, ww = w0 + pp % HP - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(reinterpret_cast<const float4*>(z + ((n * H + hh) * W + ww) * 32) + q);
+    ts_sm[pp * 8 + (q ^ (pp & 7))] = v;
+  }
+  __syncthreads();
+  const int lh = threadIdx.x / TS_T, lw = threadIdx.x % TS_T;
+  const int h = h0 + lh, w = w0 + lw;
+  if (h >= H || w >= W) return;
+  const float* sm = reinterpret_cast<const float*>(ts_sm);
   float acc[PL_MAXC];
 #pragma unroll
   for (int c = 0; c < PL_MAXC; ++c) acc[c] = (bias && c < C) ? bias[c] : 0.f;
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
-    const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    const float* zp = z + ((n * H + hh) * W + ww) * 32 + tap * C;
+    const int pp = (lh + tap / 3) * HP + lw + tap % 3;    // (+1 halo, -1 tap offset)
 #pragma unroll
     for (int c = 0; c < PL_MAXC; ++c)
-      if (c < C) acc[c] += __ldg(zp + c);
+      if (c < C) {
+        const int col = tap * C + c;
+        acc[c] += sm[(pp * 8 + ((col >> 2) ^ (pp & 7))) * 4 + (col & 3)];
+      }
   }
   for (int c = 0; c < C; ++c) out[((n * C + c) * H + h) * W + w] = acc[c];
 }
@@ -1532,7 +1563,7 @@ extern "C" {
 
 int64_t mdm_gn_ws_floats(int N, int HW, int C, int G) {
   GnGeom g; int nc;
-  if (gn_geom(g, HW, C, G, &nc)) return 0;
+  if (gn_geom(g, HW, C, G, &nc, N)) return 0;
   return (int64_t)N * nc * GN_MAX_GROUPS * 2;
 }
 
@@ -1542,7 +1573,7 @@ int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, cons
   MDM_CHECK_ARG(ld_x % 8 == 0 && ld_y % 8 == 0, "gn_silu_fwd: channel strides must be multiples of 8");
   MDM_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0), "gn_silu_fwd: pointers must be 16-byte aligned");
   GnGeom g; int nc;
-  int rc = gn_geom(g, HW, C, G, &nc);
+  int rc = gn_geom(g, HW, C, G, &nc, N);
   if (rc) return rc;
   if ((long long)HW * C <= 32768) {   // small map: one CTA per sample, single pass over registers
     const int per_thread = (HW + g.R - 1) / g.R;
@@ -1573,7 +1604,7 @@ int mdm_gn_silu_bwd(const void* x, long long ld_x, const void* dy, long long ld_
   MDM_CHECK_ARG(ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0 && ld_add % 8 == 0 && ld_add2 % 8 == 0,
                 "gn_silu_bwd: channel strides must be multiples of 8");
   GnGeom g; int nc;
-  int rc = gn_geom(g, HW, C, G, &nc);
+  int rc = gn_geom(g, HW, C, G, &nc, N);
   if (rc) return rc;
   if ((long long)HW * C <= 16384) {   // small map: one CTA per sample, x and dy stay in registers across both phases
     const int per_thread = (HW + g.R - 1) / g.R;
@@ -1677,16 +1708,24 @@ int mdm_conv_out_bwd(const void* x, long long ld_x, const float* w, const float*
 
 int mdm_im2col3x3(const float* img, void* out, int N, int C, int H, int W, int flip, void* stream) {
   MDM_CHECK_ARG(img && out && C >= 1 && C <= PL_MAXC, "im2col3x3: bad arguments (C=%d)", C);
-  const long long total = (long long)N * H * W * 8;
-  launch_pdl(im2col3x3_kernel, dim3(GRID1D(total, 256)), dim3(256), 0, as_stream(stream), img, (bf16*)out, C, H, W, flip, total);
+  const long long total = (long long)N * H * W * ((9 * C + 7) / 8);
+#define MDM_IM2COL(CC) launch_pdl(im2col3x3_kernel<CC>, dim3(GRID1D(total, 256)), dim3(256), 0, as_stream(stream), img, (bf16*)out, H, W, flip, total)
+  switch (C) {
+    case 1: MDM_IM2COL(1); break;
+    case 2: MDM_IM2COL(2); break;
+    case 3: MDM_IM2COL(3); break;
+    default: MDM_IM2COL(4); break;
+  }
+#undef MDM_IM2COL
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
 
 int mdm_tapsum3x3(const float* z, const float* bias, float* out, int N, int C, int H, int W, void* stream) {
   MDM_CHECK_ARG(z && out && C >= 1 && C <= 3, "tapsum3x3: bad arguments (C=%d; 9*C must fit 32 columns)", C);
-  const long long total = (long long)N * H * W;
-  launch_pdl(tapsum3x3_kernel, dim3(GRID1D(total, 256)), dim3(256), 0, as_stream(stream), z, bias, out, C, H, W, total);
+  const long long tiles = (long long)N * ((H + TS_T - 1) / TS_T) * ((W + TS_T - 1) / TS_T);
+  const size_t sm = (size_t)(TS_T + 2) * (TS_T + 2) * 8 * sizeof(float4);   // 41472 B
+  launch_pdl(tapsum3x3_kernel, dim3((unsigned)tiles), dim3(256), sm, as_stream(stream), z, bias, out, C, H, W);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }

@@ -830,7 +830,7 @@ class _Plan:
         [pixel][64] bf16 matrix (im2col3x3), then a 1x1 GEMM against W'[cout][tap*C + c]"""
         m, B, S = self.m, self.B, self.S
         C, co = m._cfg["in_channels"], out.C
-        g_in = self.new((B, S, S, 64))
+        g_in = self.new((B, S, S, 64), zero=True)      # im2col3x3 only rewrites the data columns
         wq = self.new((co, 1, 64), zero=True)
 
         def prep_w():
@@ -1047,7 +1047,7 @@ class _Plan:
         if self.need_grad:
             rda = self.scratch("d_head", (B, S, S, C))
             self.d_out = self.new((B, Co, S, S), torch.float32)
-            g_out = self.new((B, S, S, 64))
+            g_out = self.new((B, S, S, 64), zero=True)
             w3 = self.new((C, 1, 64), zero=True)
             dw2 = self.new((64, 1, C), torch.float32)
 

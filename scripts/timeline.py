@@ -10,19 +10,39 @@ from torch.profiler import profile, ProfilerActivity
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=128); ap.add_argument("--size", type=int, default=32)
 ap.add_argument("--steps", type=int, default=3); ap.add_argument("--method", default="base")
+ap.add_argument("--sample", action="store_true", help="profile the sampler.py restoration loop (inference) instead of training steps")
 pa = ap.parse_args()
-a = argparse.Namespace(batch=pa.batch, size=pa.size, channels=3, method=pa.method, no_graph=False)
-tr, model, acc = bench.build_trainer(a, bench.workload_args(a))
 dev = torch.device("cuda", 0)
-x = (torch.rand(pa.batch, 3, pa.size, pa.size) * 2 - 1).to(dev)
-torch.manual_seed(0); tr.Scheduler.adopt_torch_rng(dev)
-for i in range(6):
-    tr._run_batch(i, (x,), 0, 1, 0, None, None)
-torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for i in range(pa.steps):
+if pa.sample:
+    import sampler as sampler_mod, scheduler as scheduler_mod
+    from mdm_b200.config import default_args
+    from mdm_b200.denoiser import UNet2DModelB200, default_config
+    S, N = pa.size, pa.batch
+    sa = default_args(data_size=S, in_channel=3, out_channel=3, ddpm_num_steps=1000, ddpm_schedule="linear",
+                      select_degrade_pixel="thresholding", degrade_channel="1-channel", mean_option="0", mean_area="image-wise",
+                      method="base", shift_type="noise_with_perturbation", sample_latent_shape="zero",
+                      momentum_adaptive="base_momentum", sampling_mask_dependency="independent", sample_num=N)
+    sa.weight_dtype = torch.float32
+    m = UNet2DModelB200(device=dev, **default_config(3, S)); m.reset_parameters(seed=0); m.eval()
+    Sch = scheduler_mod.Scheduler(sa); Sch.update_ddpm_num_steps(1000); ts = Sch.get_timesteps_epoch(0, 1)
+    smp = sampler_mod.Sampler(None, sa, Sch, [None, None, None])
+    torch.manual_seed(0)
+    smp.sample(m, ts[-2:]); torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        smp.sample(m, ts[-pa.steps:])
+        torch.cuda.synchronize()
+else:
+    a = argparse.Namespace(batch=pa.batch, size=pa.size, channels=3, method=pa.method, no_graph=False)
+    tr, model, acc = bench.build_trainer(a, bench.workload_args(a))
+    x = (torch.rand(pa.batch, 3, pa.size, pa.size) * 2 - 1).to(dev)
+    torch.manual_seed(0); tr.Scheduler.adopt_torch_rng(dev)
+    for i in range(6):
         tr._run_batch(i, (x,), 0, 1, 0, None, None)
     torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for i in range(pa.steps):
+            tr._run_batch(i, (x,), 0, 1, 0, None, None)
+        torch.cuda.synchronize()
 os.makedirs("gpurun_out", exist_ok=True)
 path = "gpurun_out/timeline_trace.json"
 prof.export_chrome_trace(path)
