@@ -170,6 +170,10 @@ typedef struct mdm_conv_args {
   float* dbias2;        /* one extra N=16 MMA against a tile of ones inside the same kernel; dbias2 gets the same sums */
   float* splitk_ws;     /* optional ZEROED fp32 workspace: lets small-M fprop/dgrad layers split K over the SMs */
   long long splitk_ws_floats; /* (needs N*H*W*cout floats; left zeroed again on return) */
+  float* qsum;          /* fprop only, optional: GroupNorm statistics of the output fused into the store epilogue:
+                         * qsum[n][cout/4][2] += (sum, sum of squares) over the pixels of sample n of every 4-channel
+                         * quad (fp32 atomics into a buffer the caller zeroed); needs H*W % 128 == 0.  Consumed by
+                         * mdm_gn_silu_fwd_q, which then reads the activation once instead of twice. */
 } mdm_conv_args;
 
 /* tcgen05/TMEM implicit GEMM fed by TMA (csrc/igemm.cu) */
@@ -187,6 +191,15 @@ int64_t mdm_gn_ws_floats(int N, int HW, int C, int G);
 int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma,
                     const float* beta, float* stats, float* ws, int N, int HW, int C, int G,
                     float eps, int silu, void* stream);
+/* forward with precomputed statistics: qa / qb hold the quad sums (see mdm_conv_args.qsum) of channels [0, 4*qa_quads)
+ * and [4*qa_quads, C) -- two producers when x is a channel concatenation; qb may be NULL when qa covers all of C.
+ * C/G must be a multiple of 4. */
+int mdm_gn_silu_fwd_q(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma, const float* beta,
+                      float* stats, const float* qa, int qa_quads, const float* qb, int N, int HW, int C, int G,
+                      float eps, int silu, void* stream);
+/* which forward kernel family mdm_gn_silu_fwd picks: 0 = one CTA per sample, 1 = one cluster per sample,
+ * 2 = statistics pass + apply pass (the case fused statistics save a pass) */
+int mdm_gn_fwd_kind(int N, int HW, int C, int G);
 int mdm_gn_silu_bwd(const void* x, long long ld_x, const void* dy, long long ld_dy, const void* add,
                     long long ld_add, const void* add2, long long ld_add2, void* dx, long long ld_dx, const float* gamma,
                     const float* beta, const float* stats, float* dgamma, float* dbeta, float* ws,

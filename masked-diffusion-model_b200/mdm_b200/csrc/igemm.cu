@@ -53,7 +53,8 @@ constexpr int RING_BYTES = 2 * HALO_BYTES + 5 * B_BYTES;    // halo: 2 A + 5 B s
 static_assert(2 * HALO2_SLOT + 4 * B_BYTES <= RING_BYTES, "256-row halo ring must fit");
 constexpr int SMEM_EPI_OFF = RING_BYTES;
 constexpr int SMEM_BIAS_OFF = SMEM_EPI_OFF + 2 * EPI_BYTES;   // 128 floats
-constexpr int SMEM_BAR_OFF = SMEM_BIAS_OFF + 512;
+constexpr int SMEM_QACC_OFF = SMEM_BIAS_OFF + 512;            // [4 epilogue warps][64] floats: per-tile quad (sum, sumsq) partials
+constexpr int SMEM_BAR_OFF = SMEM_QACC_OFF + 1024;
 constexpr int SMEM_ONES_OFF = 3 * (A_BYTES + 2 * B_BYTES);   // mode 1 only (ring = 3 x 48 KB): the unused ring tail
 constexpr int IGEMM_SMEM = SMEM_BAR_OFF + 256 + 1024 /*alignment slack*/;
 constexpr int TMEM_COLS = 512;                 // two accumulator stages of 256 fp32 columns
@@ -205,6 +206,10 @@ struct IgemmArgs {
   int has_c;            // a [128 x 128] bf16 tile of mapC (residual, or the output itself) is added
   int store_bf16;       // 0: no bf16 output (fp32 copy only)
   float* out_f32;       // optional fp32 copy [M][N_total] (row-major, ld = N_total)
+  // GroupNorm statistics of the OUTPUT, fused into the store epilogue: qsum[n][N_total/4][2] += (sum, sum of
+  // squares) of every 4-channel quad of sample n (fp32 atomics; the consumer combines cpg/4 quads per group).
+  // Needs H*W % 128 == 0: the 128 rows of a tile belong to one sample.
+  float* qsum;
   // wgrad
   int taps;             // valid taps
   int ci_total;
@@ -299,7 +304,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return
 // allocator), 2..5 = epilogue.
 // kMT: 128-row sub-tiles per work item (2 = a 256 x 128 output tile: both halves share every B tile, which cuts the
 // L2 -> SM operand traffic per FLOP by 25 %; 3 stages of [B][A0][A1] = 48 KB; the two TMEM stages hold 256 columns each)
-template <int kMode, bool kHalo, int kMT>
+// kStats: the store epilogue also accumulates GroupNorm quad sums of the output (IgemmArgs::qsum); a template
+// parameter so that the plain instantiations carry none of that code (measured: +4 % on the level-0 convolutions when
+// it was a run-time branch -- the store epilogue of a 256 x 128 item is as long as its main loop).
+template <int kMode, bool kHalo, int kMT, bool kStats = false>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
              const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
@@ -323,6 +331,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   uint8_t* a_ring = smem;                                   // halo slots (halo mode only)
   uint8_t* b_ring = smem + kASlots * kHaloSlot;
   float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS_OFF);
+  float* qacc = reinterpret_cast<float*>(smem + SMEM_QACC_OFF);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFF);
   uint64_t* a_empty = a_full + MAX_A_SLOTS;
   uint64_t* b_full = a_empty + MAX_A_SLOTS;
@@ -665,6 +674,32 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               }
             }
           }
+          if (kStats) {
+            // quad sums of this row's 32 columns, then a transposing butterfly over the warp's 32 rows: 16 shuffles
+            // leave the warp total of value (lane >> 1) -- sums of quads 0..7, then their sums of squares -- in each lane
+            float t[16];
+#pragma unroll
+            for (int qd = 0; qd < 8; ++qd) {
+              const float a0 = f[qd * 4], a1 = f[qd * 4 + 1], a2 = f[qd * 4 + 2], a3 = f[qd * 4 + 3];
+              const bool ok = valid && chunk_ok;
+              t[qd] = ok ? (a0 + a1) + (a2 + a3) : 0.f;
+              t[8 + qd] = ok ? fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, a3 * a3))) : 0.f;
+            }
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+            float u8[8], u4[4], u2[2];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u8[i] = (b4 ? t[8 + i] : t[i]) + __shfl_xor_sync(0xffffffffu, b4 ? t[i] : t[8 + i], 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) u4[i] = (b3 ? u8[4 + i] : u8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? u8[i] : u8[4 + i], 8);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) u2[i] = (b2 ? u4[2 + i] : u4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? u4[i] : u4[2 + i], 4);
+            float u1 = (b1 ? u2[1] : u2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? u2[0] : u2[1], 2);
+            u1 += __shfl_xor_sync(0xffffffffu, u1, 1);
+            if (!(lane & 1)) {
+              const int idx = lane >> 1;                      // 0..7: sum of quad idx, 8..15: sum of squares of quad idx - 8
+              qacc[q * 64 + (cc * 8 + (idx & 7)) * 2 + (idx >> 3)] = u1;   // this warp's slot: written once per tile, no atomics
+            }
+          }
           if (args.out_f32 && valid && chunk_ok) {
             float4* o = reinterpret_cast<float4*>(args.out_f32 + p * (long long)args.N_total + ncol0 + cc * 32);
 #pragma unroll
@@ -683,6 +718,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         }
         fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
         epi_bar_sync();
+        if (kStats && et < 64) {
+          const int quad = (ncol0 >> 2) + (et >> 1);
+          if (quad < (args.N_total >> 2))
+            atomicAdd(args.qsum + ((long long)n0 * (args.N_total >> 2) + quad) * 2 + (et & 1),
+                      (qacc[et] + qacc[64 + et]) + (qacc[128 + et] + qacc[192 + et]));
+        }
         if (et == 0 && args.store_bf16) {
           if (kHalo) {
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -901,6 +942,9 @@ static int ensure_smem_attr() {
     MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     done = true;
   }
   return MDM_OK;
@@ -937,6 +981,9 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
   const int grid = a.num_work < kNumSMs ? a.num_work : kNumSMs;
   cudaStream_t st = as_stream(stream);
   if (a.mode == 1) launch_pdl(igemm_kernel<1, false, 2>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.qsum && a.halo) launch_pdl(igemm_kernel<0, true, 2, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.qsum && a.mt == 2) launch_pdl(igemm_kernel<0, false, 2, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.qsum) launch_pdl(igemm_kernel<0, false, 1, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
   else if (a.halo && a.mt == 2) launch_pdl(igemm_kernel<0, true, 2>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
   else if (a.halo) launch_pdl(igemm_kernel<0, true, 1>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
   else if (a.mt == 2) launch_pdl(igemm_kernel<0, false, 2>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
@@ -971,7 +1018,8 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
                                void* stream) {
   int rc;
   CUtensorMap mA0, mA1, mC, mD;
-  const int halo_kind = halo_ok(c, out, a.N_total, a.seg_kc[0]);   // 0: plain, 1: 8 x 16 patches, 2: 16 x 16 patches (256-row items)
+  int halo_kind = halo_ok(c, out, a.N_total, a.seg_kc[0]);   // 0: plain, 1: 8 x 16 patches, 2: 16 x 16 patches (256-row items)
+  if (a.qsum && halo_kind == 1) halo_kind = 0;                 // (no statistics instantiation of the 8 x 16 patch kernel)
   a.halo = halo_kind ? 1 : 0;
   a.num_n = (a.N_total + TILE_N - 1) / TILE_N;   // a narrow last tile is clipped by the TMA store / guarded in the epilogue
   int num_m = a.halo ? c->N * (c->H / PATCH_H) * (c->W / PATCH_W) : (a.M_total + TILE_M - 1) / TILE_M;
@@ -1001,7 +1049,7 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
   a.iters_total = a.seg_taps[0] * a.seg_kc[0] + (a.nseg > 1 ? a.seg_taps[1] * a.seg_kc[1] : 0);
   int splits = 1;
   const long long ws_need = (long long)a.M_total * a.N_total;
-  if (!a.halo && c->splitk_ws && c->splitk_ws_floats >= ws_need && tiles * 2 <= kNumSMs && a.iters_total >= 8) {
+  if (!a.halo && !a.qsum && c->splitk_ws && c->splitk_ws_floats >= ws_need && tiles * 2 <= kNumSMs && a.iters_total >= 8) {
     splits = kNumSMs / tiles;
     if (splits > a.iters_total / 4) splits = a.iters_total / 4;
     if (splits < 1) splits = 1;
@@ -1074,6 +1122,11 @@ int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
   a.N_total = c->cout;
   a.bias = c->bias; a.bias2 = c->bias2; a.rowvec = c->rowvec; a.ld_rowvec = c->ld_rowvec; a.rows_per_vec = c->H * c->W;
   a.out_f32 = c->y_f32;
+  if (c->qsum) {
+    MDM_CHECK_ARG(c->y != nullptr && ((long long)c->H * c->W) % 128 == 0,
+                  "conv_fprop: fused GroupNorm statistics need a bf16 output and H*W %% 128 == 0 (got %d x %d)", c->H, c->W);
+    a.qsum = c->qsum;
+  }
   CUtensorMap mB0, mB1;
   rc = make_w_map(&mB0, c->w, c->cin, c->ksize * c->ksize, c->cout, 128);
   if (rc) return rc;

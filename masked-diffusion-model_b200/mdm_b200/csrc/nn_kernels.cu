@@ -170,12 +170,25 @@ template <int UNROLL>
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __restrict__ x, long long ld, bf16* __restrict__ y,
                                                               long long ldy, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const float* __restrict__ ws,
-                                                              float* __restrict__ stats, float eps, int silu, GnGeom g) {
+                                                              float* __restrict__ stats, float eps, int silu, GnGeom g,
+                                                              const float* __restrict__ qa, int qa_quads,
+                                                              const float* __restrict__ qb) {
   MDM_PDL_ENTER();
   __shared__ float mr[GN_MAX_GROUPS * 2];
   const int n = blockIdx.y, chunk = blockIdx.x;
   if (threadIdx.x < g.G) {
     double s = 0.0, ss = 0.0;
+    if (qa != nullptr) {
+      // statistics fused into the producing convolutions' epilogues: (sum, sumsq) per 4-channel quad
+      const int qpg = g.cpg >> 2, qb_quads = (g.C >> 2) - qa_quads;
+      for (int k = 0; k < qpg; ++k) {
+        const int quad = threadIdx.x * qpg + k;
+        const float* w = quad < qa_quads ? qa + ((long long)n * qa_quads + quad) * 2
+                                         : qb + ((long long)n * qb_quads + (quad - qa_quads)) * 2;
+        s += w[0];
+        ss += w[1];
+      }
+    } else
     for (int k = 0; k < g.nchunk; ++k) {
       const float* w = ws + ((long long)(n * g.nchunk + k)) * GN_MAX_GROUPS * 2 + threadIdx.x * 2;
       s += w[0];
@@ -968,9 +981,7 @@ static int gn_cluster_limit() {
   static int limit = -1;
   if (limit >= 0) return limit;
   limit = 0;
-  const char* v = getenv("MDM_GN_CLUSTER");
-  const int want = v ? atoi(v) : 16;
-  if (want < 2) return limit;
+  const int want = 16;   // (the MDM_GN_CLUSTER cap is applied per call in gn_cluster_size)
   const size_t sm_max = gn_cluster_smem(GN_MAX_C, false);
   if (cudaFuncSetAttribute(gn_cluster_fwd_kernel<GN_CL_FWD_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_max) != cudaSuccess ||
       cudaFuncSetAttribute(gn_cluster_bwd_kernel<GN_CL_BWD_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_max) != cudaSuccess) {
@@ -999,7 +1010,11 @@ static int gn_cluster_limit() {
 }
 // cluster size for a sample of HW x C elements with `maxv` vectors per thread; 0: does not fit
 static int gn_cluster_size(const GnGeom& g, int maxv) {
-  const int limit = gn_cluster_limit();
+  int limit = gn_cluster_limit();
+  if (const char* v = getenv("MDM_GN_CLUSTER")) {        // read per call: tests switch the kernel family
+    const int want = atoi(v);
+    if (want < limit) limit = want;
+  }
   for (int K = 2; K <= limit; K *= 2) {
     if (g.HW % K) return 0;
     const int HWp = g.HW / K;
@@ -1591,9 +1606,33 @@ int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, cons
   dim3 grid(nc, N);
   launch_pdl(gn_stats_kernel<8>, dim3(grid), dim3(GN_THREADS), (size_t)2 * C * sizeof(float), as_stream(stream), (const bf16*)x, ld_x, ws, g);
   MDM_LAUNCH_CHECK();
-  launch_pdl(gn_apply_kernel<4>, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), (const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta, ws, stats, eps, silu, g);
+  launch_pdl(gn_apply_kernel<4>, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), (const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta, ws, stats, eps, silu, g, (const float*)nullptr, 0, (const float*)nullptr);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
+}
+
+int mdm_gn_silu_fwd_q(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma, const float* beta,
+                      float* stats, const float* qa, int qa_quads, const float* qb, int N, int HW, int C, int G,
+                      float eps, int silu, void* stream) {
+  MDM_CHECK_ARG(x && y && gamma && beta && qa, "gn_silu_fwd_q: NULL pointer");
+  MDM_CHECK_ARG(ld_x % 8 == 0 && ld_y % 8 == 0, "gn_silu_fwd_q: channel strides must be multiples of 8");
+  GnGeom g; int nc;
+  int rc = gn_geom(g, HW, C, G, &nc, N);
+  if (rc) return rc;
+  MDM_CHECK_ARG(g.cpg % 4 == 0, "gn_silu_fwd_q: C/G = %d must be a multiple of 4 (quad sums)", g.cpg);
+  MDM_CHECK_ARG(qa_quads > 0 && qa_quads <= C / 4 && (qa_quads == C / 4 || qb != nullptr), "gn_silu_fwd_q: bad quad split %d of %d", qa_quads, C / 4);
+  dim3 grid(nc, N);
+  launch_pdl(gn_apply_kernel<4>, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), (const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta,
+             (const float*)nullptr, stats, eps, silu, g, qa, qa_quads, qb);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_gn_fwd_kind(int N, int HW, int C, int G) {
+  GnGeom g; int nc;
+  if (gn_geom(g, HW, C, G, &nc, N)) return -1;
+  if ((long long)HW * C <= 32768) return 0;
+  return gn_cluster_size(g, GN_CL_FWD_V) ? 1 : 2;
 }
 
 int mdm_gn_silu_bwd(const void* x, long long ld_x, const void* dy, long long ld_dy, const void* add, long long ld_add,

@@ -70,7 +70,7 @@ class ParamSpec:
 
 class Act:
     """symbolic NHWC activation; storage assigned after the graph is known"""
-    __slots__ = ("N", "H", "W", "C", "alias", "val", "grad", "has_upstream_grad", "name")
+    __slots__ = ("N", "H", "W", "C", "alias", "val", "grad", "has_upstream_grad", "name", "q", "no_q", "parts")
 
     def __init__(self, N, H, W, C, name=""):
         self.N, self.H, self.W, self.C = N, H, W, C
@@ -79,6 +79,17 @@ class Act:
         self.grad = None
         self.has_upstream_grad = False   # a later consumer (the up path) already wrote into .grad
         self.name = name
+        self.q = None              # _QBuf: GroupNorm quad sums of this tensor, written by its producer's conv epilogue
+        self.no_q = False          # producer cannot emit them (attention output projection)
+        self.parts = None          # channel concatenation: (first Act, second Act)
+
+
+class _QBuf:
+    """[N][C/4][2] fp32 slice of the plan's statistics arena (allocated after every emitter has asked)"""
+    __slots__ = ("N", "C", "t")
+
+    def __init__(self, N, C):
+        self.N, self.C, self.t = N, C, None
 
 
 class _Win:
@@ -543,6 +554,8 @@ class _Plan:
         self.lane_sides = [torch.cuda.Stream(device=self.dev) for _ in range(self.lanes)] if (self.lanes > 1 and need_grad) else []
         self._cur_lane = None
         self._lane_side_used = [False] * max(1, self.lanes)
+        self._qbufs = []
+        self.fused_stats = bool(int(os.environ.get("MDM_GN_FUSED_STATS", "1")))
         self._build()
 
     # -- storage helpers ---------------------------------------------------------------------------
@@ -721,6 +734,7 @@ class _Plan:
                 assert h.alias is None and s.alias is None
                 h.alias = (cat, 0)
                 s.alias = (cat, h.C)
+                cat.parts = (h, s)
                 s.has_upstream_grad = True
                 h = self._sym_resnet(r, cat, res)
                 if blk.attns:
@@ -732,6 +746,14 @@ class _Plan:
                 h = o
         self._ops.append(("head", dict(x=h)))
         self._materialise()
+        # GroupNorm sites fed by convolution epilogues (decided before emission: producers come first)
+        for kind, d in self._ops:
+            if kind == "resnet":
+                HW = d["H"] * d["H"]
+                d["q1"] = self._fused_stats_ok(HW, d["r"].cin) and self._want_q(d["x"])
+                d["q2"] = self._fused_stats_ok(HW, d["r"].cout)
+            elif kind == "head":
+                d["q"] = self._fused_stats_ok(S * S, d["x"].C) and self._want_q(d["x"])
         # ---- emit programs ---------------------------------------------------------------------------
         emit = dict(conv_in=self._emit_conv_in, resnet=self._emit_resnet, attn=self._emit_attn, down=self._emit_down,
                     up=self._emit_up, head=self._emit_head)
@@ -766,6 +788,7 @@ class _Plan:
                 region = None
                 self.fwd += fw
         bw_chunks = [(k, bw) for k, _, bw in entries]
+        self._alloc_q()
         # backward segments for data-parallel overlap: the gradients of a contiguous range of the flat buffer are
         # final at the end of each segment (UNet2DModelB200.grad_segment_ranges), so their all-reduce runs while
         # the next segment computes.  segment 0: head, up path, mid block; 1: down blocks 5..2; 2: the rest.
@@ -806,6 +829,7 @@ class _Plan:
 
     def _sym_attn(self, a, x, res):
         out = self.act(res, a.c, a.prefix)
+        out.no_q = True
         self._ops.append(("attn", dict(a=a, x=x, out=out, H=res)))
         return out
 
@@ -825,6 +849,44 @@ class _Plan:
         b0, nb, l = win
         return nb, b0, l, f"@{l}"
 
+    # -- GroupNorm statistics fused into the producing convolution's epilogue ------------------------------
+    def qbuf(self, N, C):
+        q = _QBuf(N, C)
+        self._qbufs.append(q)
+        return q
+
+    def _fused_stats_ok(self, HW, C):
+        """a GroupNorm site whose forward would need the statistics pass + apply pass (big maps): its producers'
+        store epilogues accumulate the statistics instead and the activation is read once"""
+        if not self.fused_stats or HW % 128 != 0 or (C // G) % 4 != 0:
+            return False
+        return ops.gn_fwd_kind(self.B, HW, C, G) == 2
+
+    def _want_q(self, x):
+        """mark the producers of x (both halves of a concatenation) to emit quad sums; False if one of them cannot"""
+        parts = x.parts or (x,)
+        if any(p.no_q or p.parts is not None for p in parts):
+            return False
+        for p in parts:
+            if p.q is None:
+                p.q = self.qbuf(self.B, p.C)
+        return True
+
+    def _q_of(self, x):
+        parts = x.parts or (x,)
+        return parts[0].q, (parts[1].q if len(parts) > 1 else None)
+
+    def _alloc_q(self):
+        total = sum(q.N * (q.C // 4) * 2 for q in self._qbufs)
+        self.q_arena = torch.zeros(max(1, total), dtype=torch.float32, device=self.dev)
+        off = 0
+        for q in self._qbufs:
+            n = q.N * (q.C // 4) * 2
+            q.t = self.q_arena[off:off + n].view(q.N, q.C // 4, 2)
+            off += n
+        if self._qbufs:
+            self.fwd.insert(0, lambda: self.q_arena.zero_())     # one memset per forward for every site
+
     def _emit_conv_in(self, out):
         """first conv as a tensor-core GEMM: gather the 3x3 neighbourhood of the C-channel image into a
         [pixel][64] bf16 matrix (im2col3x3), then a 1x1 GEMM against W'[cout][tap*C + c]"""
@@ -837,7 +899,8 @@ class _Plan:
             wq[:, 0, :9 * C].copy_(m.w32("conv_in.weight").view(co, C, 9).permute(0, 2, 1).reshape(co, 9 * C))
         fw = [prep_w,
               lambda: ops.im2col3x3(self.x_in, g_in, B, C, S, S),
-              lambda: ops.conv_fprop(g_in, wq, out.val, B, S, S, 1, 1, bias=m.w32("conv_in.bias"))]
+              lambda: ops.conv_fprop(g_in, wq, out.val, B, S, S, 1, 1, bias=m.w32("conv_in.bias"),
+                                     qsum=out.q.t if out.q is not None else None)]
         bw = []
         if self.need_grad:
             dwq = self.new((co, 1, 64), torch.float32)
@@ -849,9 +912,12 @@ class _Plan:
             bw = [backward]
         return fw, bw
 
-    def _emit_resnet(self, r, x, out, H, win=None):
+    def _emit_resnet(self, r, x, out, H, win=None, q1=False, q2=False):
         m = self.m
         B, b0, lane, sfx = self._lane(win)
+        q_in = self._q_of(x) if (q1 and win is None) else None            # statistics of x from its producers
+        q_h1 = self.qbuf(B, r.cout) if (q2 and win is None) else None      # statistics of h1 from conv1's epilogue
+        q_out = out.q if win is None else None
         if win is not None:
             x, out = _Win(x, b0, B), _Win(out, b0, B)
         HW = H * H
@@ -880,16 +946,35 @@ class _Plan:
         def A2():
             return a2 if ng else self.sget(ra2)
 
+        def qt(q):
+            return q.t if q is not None else None
+
+        def norm1():
+            if q_in is not None:
+                ops.gn_silu_fwd_q(x.val, A1(), m.w32(f"{p}.norm1.weight"), m.w32(f"{p}.norm1.bias"), st1, q_in[0].t, qt(q_in[1]),
+                                  B, HW, r.cin, G, eps, True)
+            else:
+                ops.gn_silu_fwd(x.val, A1(), m.w32(f"{p}.norm1.weight"), m.w32(f"{p}.norm1.bias"), st1, ws1(), B, HW, r.cin, G, eps, True)
+
+        def norm2():
+            if q_h1 is not None:
+                ops.gn_silu_fwd_q(H1(), A2(), m.w32(f"{p}.norm2.weight"), m.w32(f"{p}.norm2.bias"), st2, q_h1.t, None,
+                                  B, HW, r.cout, G, eps, True)
+            else:
+                ops.gn_silu_fwd(H1(), A2(), m.w32(f"{p}.norm2.weight"), m.w32(f"{p}.norm2.bias"), st2, ws2(), B, HW, r.cout, G, eps, True)
         fw = [
-            lambda: ops.gn_silu_fwd(x.val, A1(), m.w32(f"{p}.norm1.weight"), m.w32(f"{p}.norm1.bias"), st1, ws1(), B, HW, r.cin, G, eps, True),
-            lambda: ops.conv_fprop(A1(), m.w16(f"{p}.conv1.weight"), H1(), B, H, H, 3, 1, bias=m.w32(f"{p}.conv1.bias"), rowvec=tp, ld_rowvec=ld_tp),
-            lambda: ops.gn_silu_fwd(H1(), A2(), m.w32(f"{p}.norm2.weight"), m.w32(f"{p}.norm2.bias"), st2, ws2(), B, HW, r.cout, G, eps, True),
+            norm1,
+            lambda: ops.conv_fprop(A1(), m.w16(f"{p}.conv1.weight"), H1(), B, H, H, 3, 1, bias=m.w32(f"{p}.conv1.bias"), rowvec=tp,
+                                   ld_rowvec=ld_tp, qsum=qt(q_h1)),
+            norm2,
         ]
         if r.shortcut:
             fw.append(lambda: ops.conv_fprop(A2(), m.w16(f"{p}.conv2.weight"), out.val, B, H, H, 3, 1, bias=m.w32(f"{p}.conv2.bias"),
-                                             bias2=m.w32(f"{p}.conv_shortcut.bias"), x2=x.val, w2=m.w16(f"{p}.conv_shortcut.weight")))
+                                             bias2=m.w32(f"{p}.conv_shortcut.bias"), x2=x.val, w2=m.w16(f"{p}.conv_shortcut.weight"),
+                                             qsum=qt(q_out)))
         else:
-            fw.append(lambda: ops.conv_fprop(A2(), m.w16(f"{p}.conv2.weight"), out.val, B, H, H, 3, 1, bias=m.w32(f"{p}.conv2.bias"), resid=x.val))
+            fw.append(lambda: ops.conv_fprop(A2(), m.w16(f"{p}.conv2.weight"), out.val, B, H, H, 3, 1, bias=m.w32(f"{p}.conv2.bias"),
+                                             resid=x.val, qsum=qt(q_out)))
         bw = []
         if ng:
             rd_a2 = self.scratch("d_a2" + sfx, (B, H, H, r.cout))
@@ -984,7 +1069,9 @@ class _Plan:
         if win is not None:
             x, out = _Win(x, b0, B), _Win(out, b0, B)
         C = x.C
-        fw = [lambda: ops.conv_fprop(x.val, m.w16(name + ".weight"), out.val, B, H, H, 3, 2, bias=m.w32(name + ".bias"))]
+        q_out = out.q if win is None else None
+        fw = [lambda: ops.conv_fprop(x.val, m.w16(name + ".weight"), out.val, B, H, H, 3, 2, bias=m.w32(name + ".bias"),
+                                     qsum=q_out.t if q_out is not None else None)]
         bw = []
         if self.need_grad:
             rz = self.scratch("zins" + sfx, (B, 2 * H, 2 * H, C))
@@ -1010,8 +1097,10 @@ class _Plan:
 
         def U():
             return u if ng else self.sget(ru)
+        q_out = out.q if win is None else None
         fw = [lambda: ops.upsample2x_fwd(x.val, U(), B, H, H, C),
-              lambda: ops.conv_fprop(U(), m.w16(name + ".weight"), out.val, B, 2 * H, 2 * H, 3, 1, bias=m.w32(name + ".bias"))]
+              lambda: ops.conv_fprop(U(), m.w16(name + ".weight"), out.val, B, 2 * H, 2 * H, 3, 1, bias=m.w32(name + ".bias"),
+                                     qsum=q_out.t if q_out is not None else None)]
         bw = []
         if ng:
             rdu = self.scratch("d_ups" + sfx, (B, 2 * H, 2 * H, C))
@@ -1024,7 +1113,7 @@ class _Plan:
             bw = [backward]
         return fw, bw
 
-    def _emit_head(self, x):
+    def _emit_head(self, x, q=False):
         """GroupNorm + SiLU + last conv.  The conv is a 1x1 GEMM producing the 9*Co per-tap partial outputs
         z[pixel][tap*Co + c] (fp32) followed by the 9-tap scatter-sum; its backward is the flipped gather of
         d_out feeding a GEMM (dgrad) and a wgrad GEMM."""
@@ -1039,7 +1128,15 @@ class _Plan:
 
         def prep_w2():
             w2[:9 * Co, 0, :].copy_(m.w32("conv_out.weight").view(Co, C, 9).permute(2, 0, 1).reshape(9 * Co, C))
-        fw = [lambda: ops.gn_silu_fwd(x.val, a, m.w32("conv_norm_out.weight"), m.w32("conv_norm_out.bias"), st, ws(), B, S * S, C, G, eps, True),
+        q_in = self._q_of(x) if q else None
+
+        def norm():
+            if q_in is not None:
+                ops.gn_silu_fwd_q(x.val, a, m.w32("conv_norm_out.weight"), m.w32("conv_norm_out.bias"), st, q_in[0].t,
+                                  q_in[1].t if q_in[1] is not None else None, B, S * S, C, G, eps, True)
+            else:
+                ops.gn_silu_fwd(x.val, a, m.w32("conv_norm_out.weight"), m.w32("conv_norm_out.bias"), st, ws(), B, S * S, C, G, eps, True)
+        fw = [norm,
               prep_w2,
               lambda: ops.conv_fprop(a, w2, None, B, S, S, 1, 1, y_f32=z, cout=32),
               lambda: ops.tapsum3x3(z, m.w32("conv_out.bias"), self.out, B, Co, S, S)]

@@ -27,6 +27,7 @@ class ConvArgs(Structure):
         ("dw", c_void_p), ("w_col0", c_longlong), ("w_cols", c_int),
         ("dbias", c_void_p), ("dbias2", c_void_p),
         ("splitk_ws", c_void_p), ("splitk_ws_floats", c_longlong),
+        ("qsum", c_void_p),
     ]
 
 
@@ -38,6 +39,8 @@ _lib.register({
     "mdm_conv_dgrad": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_conv_wgrad": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_gn_ws_floats": (_I64, [c_int, c_int, c_int, c_int]),
+    "mdm_gn_fwd_kind": (c_int, [c_int, c_int, c_int, c_int]),
+    "mdm_gn_silu_fwd_q": (c_int, [_P, _LL, _P, _LL, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
     "mdm_gn_silu_fwd": (c_int, [_P, _LL, _P, _LL, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
     "mdm_gn_silu_bwd": (c_int, [_P, _LL, _P, _LL, _P, _LL, _P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _LL, _P,
                                 c_int, c_int, c_int, c_int, c_int, _P]),
@@ -91,7 +94,7 @@ def pix_ld(t: torch.Tensor) -> int:
 
 
 def conv_fprop(x, w, y, N, H, W, ksize=3, stride=1, bias=None, rowvec=None, resid=None, accumulate=False,
-               y_f32=None, x2=None, w2=None, bias2=None, cout=None, ld_rowvec=None):
+               y_f32=None, x2=None, w2=None, bias2=None, cout=None, ld_rowvec=None, qsum=None):
     """y[N,H,W,cout] = conv(x, w) (+bias +rowvec[n] +resid) ; x: [N,H*s,W*s,cin] view, w packed
     bf16 [cout, k*k, cin]; optional fused 1x1 shortcut (x2, w2)."""
     a = ConvArgs()
@@ -112,6 +115,7 @@ def conv_fprop(x, w, y, N, H, W, ksize=3, stride=1, bias=None, rowvec=None, resi
     a.y_f32 = _dp(y_f32)
     if x2 is not None:
         a.x2, a.ld_x2, a.cin2, a.w2 = _dp(x2), pix_ld(x2), x2.shape[-1], _dp(w2)
+    a.qsum = _dp(qsum)          # fused GroupNorm statistics of the output: qsum[N, cout/4, 2] += quad (sum, sumsq)
     _splitk(a, x.device)
     check(lib().mdm_conv_fprop(ctypes.byref(a), stream_ptr(x.device)))
 
@@ -171,6 +175,18 @@ def gn_ws_floats(N, HW, C, G=32):
 def gn_silu_fwd(x, y, gamma, beta, stats, ws, N, HW, C, G=32, eps=1e-5, silu=True):
     check(lib().mdm_gn_silu_fwd(_dp(x), pix_ld(x), _dp(y), pix_ld(y), _dp(gamma), _dp(beta), _dp(stats), _dp(ws),
                                 N, HW, C, G, eps, int(silu), _s(x)))
+
+
+def gn_fwd_kind(N, HW, C, G=32):
+    """0: one CTA per sample, 1: one cluster per sample, 2: statistics pass + apply pass (fused statistics save a pass)"""
+    return lib().mdm_gn_fwd_kind(N, HW, C, G)
+
+
+def gn_silu_fwd_q(x, y, gamma, beta, stats, qa, qb, N, HW, C, G=32, eps=1e-5, silu=True):
+    """GroupNorm(+SiLU) forward from quad sums produced by the convolutions that wrote x (qa: the first qa.shape[1]
+    quads, qb: the rest, None when qa covers all channels): x is read once"""
+    check(lib().mdm_gn_silu_fwd_q(_dp(x), pix_ld(x), _dp(y), pix_ld(y), _dp(gamma), _dp(beta), _dp(stats), _dp(qa),
+                                  qa.shape[1], _dp(qb), N, HW, C, G, eps, int(silu), _s(x)))
 
 
 def gn_silu_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, ws, N, HW, C, G=32, silu=True, add=None, add2=None,

@@ -98,3 +98,27 @@ def test_backward_matches_fp32_oracle():
     assert total <= 3e-2, total
     for e, ea, name in worst:
         assert e <= 7e-2 and e <= 2.0 * ea + 1e-2, (name, e, ea)
+
+
+def test_fused_groupnorm_statistics_match_unfused(monkeypatch):
+    """big-map GroupNorm sites take their statistics from the producing convolutions' epilogues; forcing the
+    two-pass kernel family at 32x32 (MDM_GN_CLUSTER=0) exercises that path on a small case: same output as the
+    plan built without the fusion, and as the fp32 oracle"""
+    monkeypatch.setenv("MDM_GN_CLUSTER", "0")
+    ref, mine = build_pair(3, 32)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.rand(4, 3, 32, 32, device="cuda", generator=g) * 2 - 1
+    t = torch.tensor([1.0, 250.0, 999.0, 37.0], device="cuda")
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MDM_GN_FUSED_STATS", flag)
+        mine._plans.clear()
+        mine.eval()
+        with torch.no_grad():
+            outs[flag] = mine(x, t).sample.clone()
+        plan = next(iter(mine._plans.values()))
+        assert bool(plan._qbufs) == (flag == "1")          # the fused plan really has statistics buffers
+    with torch.no_grad():
+        want = ref(x, t).sample
+    assert rel_l2(outs["1"], outs["0"]) <= 1.5e-2       # two bf16 evaluations of the same network
+    assert rel_l2(outs["1"], want) <= 2e-2

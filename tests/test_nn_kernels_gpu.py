@@ -127,3 +127,37 @@ def test_attention_core(N, L, C):
     ops.attention_bwd(qkv, dout, dqkv, N, L, C)
     want_d = torch.cat([t.grad.transpose(1, 2).reshape(N * L, C) for t in (q, k, v)], dim=1)
     assert torch.allclose(dqkv.float(), want_d, atol=3e-2 * max(1.0, want_d.abs().max().item()), rtol=3e-2)
+
+
+@pytest.mark.parametrize("N,H,cin,cout,halo", [(3, 16, 128, 128, 0), (2, 32, 64, 256, 0), (2, 32, 128, 160, 1), (5, 16, 128, 384, 0)])
+def test_conv_epilogue_groupnorm_statistics(N, H, cin, cout, halo, monkeypatch):
+    """GroupNorm statistics fused into the conv store epilogue (quad sums) + the apply-only forward
+    (mdm_gn_silu_fwd_q) == the stand-alone two-kernel forward on the conv's bf16 output"""
+    from mdm_b200 import denoiser_ops as ops
+    if halo:
+        monkeypatch.setenv("MDM_IGEMM_HALO_FORCE", "1")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(N, H, H, cin, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(cout, 9, cin, device="cuda", generator=g) / (9 * cin) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(cout, device="cuda", generator=g)
+    res = torch.randn(N, H, H, cout, device="cuda", generator=g).to(torch.bfloat16)
+    y = torch.empty(N, H, H, cout, device="cuda", dtype=torch.bfloat16)
+    q = torch.zeros(N, cout // 4, 2, device="cuda")
+    ops.conv_fprop(x, w, y, N, H, H, 3, 1, bias=b, resid=res, qsum=q)
+    yf = y.float().view(N, H * H, cout // 4, 4)
+    want_s, want_q = yf.sum(dim=(1, 3)), (yf * yf).sum(dim=(1, 3))
+    # the epilogue sums the fp32 values BEFORE the bf16 rounding of the store: agreement to bf16 rounding noise
+    assert torch.allclose(q[..., 0], want_s, atol=2e-2 * H, rtol=1e-2)
+    assert torch.allclose(q[..., 1], want_q, atol=2e-2 * H, rtol=1e-2)
+    if (cout // 32) % 4 == 0:
+        gamma = 1 + 0.2 * torch.randn(cout, device="cuda", generator=g)
+        beta = 0.2 * torch.randn(cout, device="cuda", generator=g)
+        o1, o2 = torch.empty_like(y), torch.empty_like(y)
+        st1, st2 = torch.empty(N, 32, 2, device="cuda"), torch.empty(N, 32, 2, device="cuda")
+        ws = torch.empty(max(1, ops.gn_ws_floats(N, H * H, cout)), device="cuda")
+        ops.gn_silu_fwd(y, o1, gamma, beta, st1, ws, N, H * H, cout, 32, 1e-5, True)
+        half = (cout // 4) // 2
+        qa, qb = q[:, :half].contiguous(), q[:, half:].contiguous()        # as if two producers had written a concatenation
+        ops.gn_silu_fwd_q(y, o2, gamma, beta, st2, qa, qb, N, H * H, cout, 32, 1e-5, True)
+        assert torch.allclose(st1, st2, atol=2e-3, rtol=2e-3)
+        assert torch.allclose(o1.float(), o2.float(), atol=3e-2, rtol=2e-2)
