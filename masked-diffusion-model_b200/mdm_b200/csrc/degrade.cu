@@ -21,8 +21,24 @@
 namespace mdm {
 
 constexpr int DG_THREADS = 256;
-constexpr int DG_VEC_PER_THREAD = 4;                              // 4 x float4 per thread
-constexpr int DG_CHUNK = DG_THREADS * DG_VEC_PER_THREAD * 4;      // 4096 elements
+constexpr int DG_VEC_PER_THREAD = 4;                              // K1: 4 x float4 per thread and tensor in flight
+constexpr int K5_VEC_PER_THREAD = 2;                              // K5 reads five tensors: 2 x float4 each keeps 4 CTAs / SM
+constexpr int DG_CHUNK = 8192;                                    // elements of a plane per CTA
+
+// sum of N values over the CTA with ONE shared-memory round (every thread gets the results)
+template <int N>
+__device__ __forceinline__ void block_sum_n(float (&v)[N], float* red /* >= N * 32 floats */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) red[k * 32 + wid] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = warp_sum(lane < nw ? red[k * 32 + lane] : 0.f);
+}
 
 struct Shift {
   const float* p;
@@ -30,7 +46,20 @@ struct Shift {
   __device__ __forceinline__ float at(int b, int c, int i) const {
     return p ? p[b * sb + c * sc + (int64_t)i * sp] : 0.0f;
   }
+  // four consecutive pixels (vector path: sp is 0 (broadcast) or 1 with 16-byte aligned rows, checked on the host)
+  __device__ __forceinline__ float4 at4(int b, int c, int i) const {
+    if (!p) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sp == 0) { const float v = p[b * sb + c * sc]; return make_float4(v, v, v, v); }
+    return *reinterpret_cast<const float4*>(p + b * sb + c * sc + i);
+  }
 };
+static bool shift_vec_ok(const float* p, int64_t sb, int64_t sc, int64_t sp) {
+  return p == nullptr || sp == 0 || (sp == 1 && (sb & 3) == 0 && (sc & 3) == 0 && ((uintptr_t)p & 15) == 0);
+}
+__device__ __forceinline__ float4 mask4(const uint8_t* m, int64_t i) {
+  const uchar4 k = *reinterpret_cast<const uchar4*>(m + i);
+  return make_float4((float)k.x, (float)k.y, (float)k.z, (float)k.w);
+}
 
 // partials layout per sample: [C][nchunk][3] = {sum img*(1-m), sum img*m, sum (1-m)}
 __device__ __forceinline__ float fill_value(const float* part, int c, int C, int nchunk, int fill_mode,
@@ -68,7 +97,7 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_stats_kernel(const T* __re
                                                                    int mask_ch, float* __restrict__ ws,
                                                                    int C, int hw, int nchunk) {
   MDM_PDL_ENTER();
-  __shared__ float red[32];
+  __shared__ float red[3 * 32];
   const int chunk = blockIdx.x, plane = blockIdx.y;  // plane = b*C + c
   const int b = plane / C, c = plane % C;
   const T* x = img + (int64_t)plane * hw;
@@ -76,6 +105,29 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_stats_kernel(const T* __re
   float s0 = 0.f, s1 = 0.f, n0 = 0.f;
   const int base = chunk * DG_CHUNK;
   const int end = min(base + DG_CHUNK, hw);
+  if (sizeof(T) == 4 && (hw & 3) == 0 && ((uintptr_t)img & 15) == 0 && ((uintptr_t)mask & 3) == 0) {
+    // all of this thread's 16-byte loads are issued before the first use (4 image + 4 mask vectors in flight)
+    for (int g0 = base; g0 < end; g0 += DG_THREADS * 4 * DG_VEC_PER_THREAD) {
+      float4 v[DG_VEC_PER_THREAD], k[DG_VEC_PER_THREAD];
+#pragma unroll
+      for (int u = 0; u < DG_VEC_PER_THREAD; ++u) {
+        const int i = g0 + (u * DG_THREADS + threadIdx.x) * 4;
+        const bool ok = i < end;
+        v[u] = ok ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        k[u] = ok ? mask4(m, i) : make_float4(1.f, 1.f, 1.f, 1.f);      // mask 1, value 0: contributes nothing
+      }
+#pragma unroll
+      for (int u = 0; u < DG_VEC_PER_THREAD; ++u) {
+        const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, kk[4] = {k[u].x, k[u].y, k[u].z, k[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s0 += __fmul_rn(vv[e], __fsub_rn(1.0f, kk[e]));
+          s1 += __fmul_rn(vv[e], kk[e]);
+          n0 += __fsub_rn(1.0f, kk[e]);
+        }
+      }
+    }
+  } else
   for (int i = base + threadIdx.x; i < end; i += DG_THREADS) {
     const float v = ld_as_float(x, i);
     const float mk = (float)m[i];
@@ -83,12 +135,11 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_stats_kernel(const T* __re
     s1 += __fmul_rn(v, mk);
     n0 += __fsub_rn(1.0f, mk);
   }
-  s0 = block_sum(s0, red);
-  s1 = block_sum(s1, red);
-  n0 = block_sum(n0, red);
+  float r3[3] = {s0, s1, n0};
+  block_sum_n(r3, red);
   if (threadIdx.x == 0) {
     float* o = ws + ((int64_t)plane * nchunk + chunk) * 3;
-    o[0] = s0; o[1] = s1; o[2] = n0;
+    o[0] = r3[0]; o[1] = r3[1]; o[2] = r3[2];
   }
 }
 
@@ -112,10 +163,22 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_apply_kernel(
   const int base = chunk * DG_CHUNK;
   const int end = min(base + DG_CHUNK, hw);
   if ((hw & 3) == 0 && sizeof(T) == 4) {
-    for (int i = base + threadIdx.x * 4; i < end; i += DG_THREADS * 4) {
-      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i);
-      const uchar4 mk = *reinterpret_cast<const uchar4*>(m + i);
-      const float m0 = mk.x, m1 = mk.y, m2 = mk.z, m3 = mk.w;
+   for (int g0 = base; g0 < end; g0 += DG_THREADS * 4 * DG_VEC_PER_THREAD) {
+    float4 vv[DG_VEC_PER_THREAD], kk[DG_VEC_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < DG_VEC_PER_THREAD; ++u) {
+      const int i = g0 + (u * DG_THREADS + threadIdx.x) * 4;
+      if (i < end) {
+        vv[u] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i);
+        kk[u] = mask4(m, i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < DG_VEC_PER_THREAD; ++u) {
+      const int i = g0 + (u * DG_THREADS + threadIdx.x) * 4;
+      if (i >= end) break;
+      const float4 v = vv[u];
+      const float m0 = kk[u].x, m1 = kk[u].y, m2 = kk[u].z, m3 = kk[u].w;
       float4 r;
       r.x = composite(m0, fill, v.x); r.y = composite(m1, fill, v.y);
       r.z = composite(m2, fill, v.z); r.w = composite(m3, fill, v.w);
@@ -128,6 +191,7 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_apply_kernel(
       }
       if (mf) *reinterpret_cast<float4*>(mf + i) = make_float4(m0, m1, m2, m3);
     }
+   }
   } else {
     for (int i = base + threadIdx.x; i < end; i += DG_THREADS) {
       const float v = ld_as_float(x, i);
@@ -148,9 +212,9 @@ __device__ __forceinline__ float x0_hat(float xt, float net, float sh) {
 __global__ void __launch_bounds__(DG_THREADS) sampler_stats_kernel(
     const float* __restrict__ x_t, const float* __restrict__ net, Shift shift,
     const uint8_t* __restrict__ mask_t, const uint8_t* __restrict__ mask_n, int mask_ch,
-    float* __restrict__ ws_t, float* __restrict__ ws_n, int C, int hw, int nchunk) {
+    float* __restrict__ ws_t, float* __restrict__ ws_n, int C, int hw, int nchunk, int vec) {
   MDM_PDL_ENTER();
-  __shared__ float red[32];
+  __shared__ float red[6 * 32];
   const int chunk = blockIdx.x, plane = blockIdx.y;
   const int b = plane / C, c = plane % C;
   const int64_t po = (int64_t)plane * hw;
@@ -158,19 +222,49 @@ __global__ void __launch_bounds__(DG_THREADS) sampler_stats_kernel(
   float a0 = 0.f, a1 = 0.f, an = 0.f, b0 = 0.f, b1 = 0.f, bn = 0.f;
   const int base = chunk * DG_CHUNK;
   const int end = min(base + DG_CHUNK, hw);
+  if (vec) {
+   for (int g0 = base; g0 < end; g0 += DG_THREADS * 4 * K5_VEC_PER_THREAD) {
+    float4 xv[K5_VEC_PER_THREAD], nv[K5_VEC_PER_THREAD], sv[K5_VEC_PER_THREAD], mt4[K5_VEC_PER_THREAD], mn4[K5_VEC_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < K5_VEC_PER_THREAD; ++u) {
+      const int i = g0 + (u * DG_THREADS + threadIdx.x) * 4;
+      if (i < end) {
+        xv[u] = *reinterpret_cast<const float4*>(x_t + po + i);
+        nv[u] = *reinterpret_cast<const float4*>(net + po + i);
+        sv[u] = shift.at4(b, c, i);
+        mt4[u] = mask4(mask_t + mo, i);
+        mn4[u] = mask4(mask_n + mo, i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < K5_VEC_PER_THREAD; ++u) {
+      const int i = g0 + (u * DG_THREADS + threadIdx.x) * 4;
+      if (i >= end) break;
+      const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, ns[4] = {nv[u].x, nv[u].y, nv[u].z, nv[u].w};
+      const float ss[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
+      const float ts[4] = {mt4[u].x, mt4[u].y, mt4[u].z, mt4[u].w}, ms[4] = {mn4[u].x, mn4[u].y, mn4[u].z, mn4[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v = x0_hat(xs[e], ns[e], ss[e]);
+        a0 += __fmul_rn(v, __fsub_rn(1.0f, ts[e])); a1 += __fmul_rn(v, ts[e]); an += __fsub_rn(1.0f, ts[e]);
+        b0 += __fmul_rn(v, __fsub_rn(1.0f, ms[e])); b1 += __fmul_rn(v, ms[e]); bn += __fsub_rn(1.0f, ms[e]);
+      }
+    }
+   }
+  } else
   for (int i = base + threadIdx.x; i < end; i += DG_THREADS) {
     const float v = x0_hat(x_t[po + i], net[po + i], shift.at(b, c, i));
     const float mt = (float)mask_t[mo + i], mn = (float)mask_n[mo + i];
     a0 += __fmul_rn(v, __fsub_rn(1.0f, mt)); a1 += __fmul_rn(v, mt); an += __fsub_rn(1.0f, mt);
     b0 += __fmul_rn(v, __fsub_rn(1.0f, mn)); b1 += __fmul_rn(v, mn); bn += __fsub_rn(1.0f, mn);
   }
-  a0 = block_sum(a0, red); a1 = block_sum(a1, red); an = block_sum(an, red);
-  b0 = block_sum(b0, red); b1 = block_sum(b1, red); bn = block_sum(bn, red);
+  float r6[6] = {a0, a1, an, b0, b1, bn};
+  block_sum_n(r6, red);
   if (threadIdx.x == 0) {
     float* o = ws_t + ((int64_t)plane * nchunk + chunk) * 3;
-    o[0] = a0; o[1] = a1; o[2] = an;
+    o[0] = r6[0]; o[1] = r6[1]; o[2] = r6[2];
     o = ws_n + ((int64_t)plane * nchunk + chunk) * 3;
-    o[0] = b0; o[1] = b1; o[2] = bn;
+    o[0] = r6[3]; o[1] = r6[4]; o[2] = r6[5];
   }
 }
 
@@ -180,7 +274,7 @@ __global__ void __launch_bounds__(DG_THREADS) sampler_update_kernel(
     const uint8_t* __restrict__ mask_t, const uint8_t* __restrict__ mask_n, int mask_ch, int fill_mode,
     float fill_const, int mean_area, int momentum, int update, Shift shift_next,
     const float* __restrict__ ws_t, const float* __restrict__ ws_n, float* __restrict__ x_next,
-    float* __restrict__ x_in_next, float* __restrict__ s0_out, int C, int hw, int nchunk) {
+    float* __restrict__ x_in_next, float* __restrict__ s0_out, int C, int hw, int nchunk, int vec) {
   MDM_PDL_ENTER();
   const int chunk = blockIdx.x, plane = blockIdx.y;
   const int b = plane / C, c = plane % C;
@@ -191,6 +285,48 @@ __global__ void __launch_bounds__(DG_THREADS) sampler_update_kernel(
   const float f_n = update ? fill_value(ws_n + wo, c, C, nchunk, fill_mode, fill_const, mean_area) : 0.f;
   const int base = chunk * DG_CHUNK;
   const int end = min(base + DG_CHUNK, hw);
+  if (vec) {
+   for (int g0 = base; g0 < end; g0 += DG_THREADS * 4 * K5_VEC_PER_THREAD) {
+    float4 xv[K5_VEC_PER_THREAD], nv[K5_VEC_PER_THREAD], sv[K5_VEC_PER_THREAD], mt4[K5_VEC_PER_THREAD], mn4[K5_VEC_PER_THREAD],
+        sn4[K5_VEC_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < K5_VEC_PER_THREAD; ++u) {
+      const int i = g0 + (u * DG_THREADS + threadIdx.x) * 4;
+      if (i < end) {
+        xv[u] = *reinterpret_cast<const float4*>(x_t + po + i);
+        nv[u] = *reinterpret_cast<const float4*>(net + po + i);
+        sv[u] = shift.at4(b, c, i);
+        if (update) { mt4[u] = mask4(mask_t + mo, i); mn4[u] = mask4(mask_n + mo, i); }
+        if (x_in_next) sn4[u] = shift_next.at4(b, c, i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < K5_VEC_PER_THREAD; ++u) {
+      const int i = g0 + (u * DG_THREADS + threadIdx.x) * 4;
+      if (i >= end) break;
+      const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, ns[4] = {nv[u].x, nv[u].y, nv[u].z, nv[u].w};
+      const float ss[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
+      const float ts[4] = {mt4[u].x, mt4[u].y, mt4[u].z, mt4[u].w}, ms[4] = {mn4[u].x, mn4[u].y, mn4[u].z, mn4[u].w};
+      const float sn[4] = {sn4[u].x, sn4[u].y, sn4[u].z, sn4[u].w};
+      float v0[4], xn[4], xi[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v0[e] = x0_hat(xs[e], ns[e], ss[e]);
+        xn[e] = xs[e];
+        if (update) {
+          const float d_t = composite(ts[e], f_t, v0[e]);
+          const float d_n = composite(ms[e], f_n, v0[e]);
+          xn[e] = momentum ? __fadd_rn(xs[e], __fsub_rn(d_n, d_t)) : d_n;
+        }
+        xi[e] = x_in_next ? __fadd_rn(xn[e], sn[e]) : 0.f;
+      }
+      if (s0_out) *reinterpret_cast<float4*>(s0_out + po + i) = make_float4(v0[0], v0[1], v0[2], v0[3]);
+      if (x_next) *reinterpret_cast<float4*>(x_next + po + i) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+      if (x_in_next) *reinterpret_cast<float4*>(x_in_next + po + i) = make_float4(xi[0], xi[1], xi[2], xi[3]);
+    }
+   }
+    return;
+  }
   for (int i = base + threadIdx.x; i < end; i += DG_THREADS) {
     const float xt = x_t[po + i];
     const float v = x0_hat(xt, net[po + i], shift.at(b, c, i));
@@ -275,12 +411,16 @@ int mdm_sampler_step(const float* x_t, const float* net, const float* shift, int
   Shift s{shift, sb, sc, sp}, sn{shift_next, nb, nc_, np_};
   float* ws_t = ws;
   float* ws_n = ws ? ws + mdm_degrade_ws_floats(batch, channels, hw) : nullptr;
+  auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+  const int vec = (hw & 3) == 0 && al16(x_t) && al16(net) && al16(x_next) && al16(x_in_next) && al16(s0_out) &&
+                  (((uintptr_t)mask_t | (uintptr_t)mask_next) & 3) == 0 && shift_vec_ok(shift, sb, sc, sp) &&
+                  shift_vec_ok(shift_next, nb, nc_, np_);
   if (update && fill_mode != MDM_FILL_CONST) {
     MDM_CHECK_ARG(ws, "workspace is NULL");
-    launch_pdl(sampler_stats_kernel, dim3(grid), dim3(DG_THREADS), 0, st, x_t, net, s, mask_t, mask_next, mask_ch, ws_t, ws_n, channels, hw, nc);
+    launch_pdl(sampler_stats_kernel, dim3(grid), dim3(DG_THREADS), 0, st, x_t, net, s, mask_t, mask_next, mask_ch, ws_t, ws_n, channels, hw, nc, vec);
     MDM_LAUNCH_CHECK();
   }
-  launch_pdl(sampler_update_kernel, dim3(grid), dim3(DG_THREADS), 0, st, x_t, net, s, mask_t, mask_next, mask_ch, fill_mode, fill_const, mean_area, momentum, update, sn, ws_t, ws_n, x_next, x_in_next, s0_out, channels, hw, nc);
+  launch_pdl(sampler_update_kernel, dim3(grid), dim3(DG_THREADS), 0, st, x_t, net, s, mask_t, mask_next, mask_ch, fill_mode, fill_const, mean_area, momentum, update, sn, ws_t, ws_n, x_next, x_in_next, s0_out, channels, hw, nc, vec);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }

@@ -203,7 +203,9 @@ class Sampler:
                 check(lib().mdm_sampler_step(
                     ptr(x_t), ptr(net), ptr(shift_e), sb, sc, sp, ptr(m_t_bytes), ptr(cur_n), mask_ch,
                     mode, const, area, momentum, update, ptr(shift_ne), nb, nc, np_,
-                    ptr(x_next), ptr(x_in_next) if not last else None, ptr(sample_0), ptr(ws), N, C, hw,
+                    ptr(x_next), ptr(x_in_next) if not last else None,
+                    ptr(sample_0) if (last or history) else None,      # x0_hat is only read after the last iteration
+                    ptr(ws), N, C, hw,
                     stream_ptr(dev)))
                 if history:
                     difference_prev = self._record(hist, T - i, x_t, shift_e, x_in, net, sample_0, m_t_bytes, cur_n,

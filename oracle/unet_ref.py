@@ -6,7 +6,9 @@
 /root/reference nor installed (no requirements file pins a version; run dates suggest ~0.26).
 This module restates its published architecture with
 the diffusers state-dict key names so that a real checkpoint loads.
-Checkable anchors: parameter count 113,673,219 (C=3) / 113,668,609 (C=1) / 454,461,443
+The block algebra (ResnetBlock2D, Attention, the multi-head core) IS pinned against the reference's in-repo
+`unet6.ResidualBlock` / `unet6.AttentionBlock` / `unet4.QKVAttentionLegacy` (tests/golden/unet_blocks.npz,
+tests/test_oracle_blocks.py).  Further checkable anchors: parameter count 113,673,219 (C=3) / 113,668,609 (C=1) / 454,461,443
 (ch=256), equal to the in-repo `models/unet/unet6.py` configuration `[1,1,2,2,4,4]`.
 """
 from __future__ import annotations

@@ -38,7 +38,7 @@ for B, C, S, mode in ((128, 3, 32, "indexing"), (256, 3, 128, "thresholding"), (
     ws = torch.empty(max(1, 2 * lib().mdm_degrade_ws_floats(B, C, hw)), device="cuda")
     def k5():
         check(lib().mdm_sampler_step(ptr(x_t), ptr(net), ptr(shift), C * hw, hw, 1, ptr(mb), ptr(mb2), 1, 1, 0.0, 0, 1, 1,
-                                     ptr(shift), C * hw, hw, 1, ptr(x_next), ptr(x_in_next), ptr(s0), ptr(ws), B, C, hw, stream_ptr(x0.device)))
+                                     ptr(shift), C * hw, hw, 1, ptr(x_next), ptr(x_in_next), None, ptr(ws), B, C, hw, stream_ptr(x0.device)))   # (x0_hat is only materialised on the last iteration)
     t_k5 = timeit(k5)
     k5_bytes = B * C * hw * 4 * 5 + 2 * B * hw               # 5 fp32 image passes (+ the two byte masks)
     r = dict(shape=f"{B}x{C}x{S}x{S}", mask_mode=mode, mask_us=round(t_mask, 1), k1_us=round(t_k1, 1), k1_GBs=round(k1_bytes / t_k1 / 1e3, 1),
