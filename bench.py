@@ -220,7 +220,7 @@ def roofline_pass(tr, model, batch_dev, peaks):
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # a ~150 ms spin kernel first: the host enqueues the whole eager step behind it, so the stream never
         # starves and each event pair brackets its kernel only (not host launch latency)
-        torch.cuda._sleep(int(3e8))
+        torch.cuda._sleep(int(8e8))
         s0.record()
         tr._run_batch(0, (batch_dev,), 0, 1, 0, None, None)
         s1.record()

@@ -128,6 +128,15 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one lane of the (converged) warp.  With `elect.sync` -- instead of `lane == 0` -- and a warp index the compiler can
+// prove uniform, ptxas keeps the single-thread TMA / MMA issue loops in UNIFORM registers: the descriptor operands
+// of UTCHMMA / UTMALDG are uniform registers, and from a lane-divergent branch every issue paid a
+// vote + ELECT + 5x R2UR waterfall (~15 SASS instructions per MMA, more than the MMA's own 64 cycles)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -341,7 +350,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   uint64_t* c_full_bar = tmem_empty_bar + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_full_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < MAX_A_SLOTS; ++s) {
@@ -378,7 +388,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const int w_first = blockIdx.x, w_step = gridDim.x;
   pdl_wait();   // barrier init, TMEM allocation and descriptor prefetch above overlapped the previous kernel's tail
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
+   if (elect_one()) {
     // ============================== TMA producer: A operand ==================================
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
@@ -440,7 +451,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 6 && lane == 0) {
+   }
+  } else if (warp == 6) {
+   if (elect_one()) {
     // ============================== TMA producer: B operand ==================================
     int sb = 0;
     uint32_t pb = 0;
@@ -500,7 +513,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+   }
+  } else if (warp == 1) {
+   if (elect_one()) {
     // ============================== MMA issuer ================================================
     const int a_mn = kMode == 1 ? 1 : 0;
     const int b_mn = kMode == 1 ? 1 : args.b_mn_major;
@@ -581,6 +596,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       }
       umma_commit(&tmem_full_bar[acc]);
     }
+   }
   } else if (warp >= 2 && warp <= 5) {
     // ============================== epilogue ==================================================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
