@@ -1010,19 +1010,21 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
 
 // can this layer run in halo mode?  3x3, stride 1, bf16 output only.  returns 2: 16 x 16 patches (256-row work
 // items), 1: 8 x 16 patches, 0: plain stages.
-// MDM_IGEMM_HALO: 0 = never, 1 = 8 x 16 patches wherever possible, 2 (default) = 16 x 16 patches where they measured
-// faster than plain 256-row stages (bench_conv.py, B200): layers with >= 4 channel chunks and >= 2 cout tiles
-// (+14..23 %), and single-cout-tile layers with >= 1024 work items (+3..10 %); elsewhere the wait for a whole
-// 41 KB halo before the first MMA of an item costs more than the 2.3x cut in L2 -> SM operand traffic returns.
+// MDM_IGEMM_HALO: 0 = never, 1 = 8 x 16 patches wherever possible, 2 (default) = 16 x 16 patches wherever the map is a
+// multiple of 16 x 16 and at least 96 work items exist.  Measured (bench_conv.py, B200, after the issue loops moved
+// to uniform registers): 16 x 16 patches beat plain 256-row stages on every eligible shape by 0..19 % -- e.g.
+// 128x32x32 128->128 fprop 920 vs 824 TFLOP/s, 256->128 dgrad 1316 vs 1163; 64x128x128 128->128 1225 vs 1029 | 1334
+// vs 1157; 256->128 1357 vs 1161 | 1382 vs 1193 -- because they move 2.3x fewer operand bytes from L2 to the SMs.
 static int halo_ok(const mdm_conv_args* c, const void* out, int n_total, int k_chunks) {
+  (void)k_chunks;
   const int enabled = env_flag("MDM_IGEMM_HALO", 2);                   // read per call: the tests switch modes
-  const int force = env_flag("MDM_IGEMM_HALO_FORCE", 0);               // tests: every eligible layer
+  const int force = env_flag("MDM_IGEMM_HALO_FORCE", 0);               // tests: every eligible layer, however small
   if (!enabled || c->ksize != 3 || c->stride != 1 || out == nullptr || c->y_f32 != nullptr) return 0;
   if (enabled == 1) return (c->H % PATCH_H == 0 && c->W % PATCH_W == 0) ? 1 : 0;
   if (c->H % 16 == 0 && c->W % 16 == 0) {
     const int num_n = (n_total + TILE_N - 1) / TILE_N;
     const long long items = (long long)c->N * (c->H / 16) * (c->W / 16) * num_n;
-    if (force || (k_chunks >= 4 && num_n >= 2 && items >= 96) || (num_n == 1 && items >= 1024)) return 2;
+    if (force || items >= 96) return 2;
   }
   return 0;
 }
