@@ -324,7 +324,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
              const __grid_constant__ IgemmArgs args) {
   pdl_launch_dependents();   // the next kernel may be scheduled as SMs drain; it blocks in its own pdl_wait()
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET from the __shared__ array (not through an integer cast of the generic pointer): the
+  // compiler keeps the shared address space, so every epilogue access is LDS / STS instead of a generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int kASlots = kHalo ? 2 : 0;
   constexpr int kBSlots = kHalo ? (kMT == 2 ? 4 : 5) : (kMT == 2 ? 3 : 4);
   constexpr int kHaloW = kMT == 2 ? HALO2_W : HALO_W;             // halo row pitch (pixels)
