@@ -48,7 +48,8 @@ constexpr int HALO2_BYTES = HALO2_W * HALO2_H * 128;   // 41472
 constexpr int HALO2_SLOT = 41 * 1024;                   // slot pitch, 1024-aligned (swizzle atom)
 constexpr int MAX_A_SLOTS = 4, MAX_B_SLOTS = 6;
 constexpr int EPI_BYTES = 32768;               // one staging tile: 128 x 128 bf16, or 2 boxes of 128 x 32 fp32
-constexpr int IGEMM_THREADS = 224;
+constexpr int IGEMM_THREADS = 352;             // warps 0: TMA A, 1: MMA, 2-5 (+ 7-10): epilogue, 6: TMA B
+constexpr int IGEMM_THREADS_NARROW = 224;      // launch without warps 7-10: four epilogue warps (short grids)
 constexpr int RING_BYTES = 2 * HALO_BYTES + 5 * B_BYTES;    // halo: 2 A + 5 B slots (256-row: 2 x 41 KB + 4 B); plain: 4 A + 4 B slots (128 KB)
 static_assert(2 * HALO2_SLOT + 4 * B_BYTES <= RING_BYTES, "256-row halo ring must fit");
 constexpr int SMEM_EPI_OFF = RING_BYTES;
@@ -137,7 +138,7 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+__device__ __forceinline__ void epi_bar_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }   // the epilogue warps
 
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -366,7 +367,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[s], blockDim.x == IGEMM_THREADS ? 8 : 4);   // one arrival per epilogue warp
       mbar_init(&c_full_bar[s], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -599,11 +600,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       umma_commit(&tmem_full_bar[acc]);
     }
    }
-  } else if (warp >= 2 && warp <= 5) {
+  } else if ((warp >= 2 && warp <= 5) || warp >= 7) {
     // ============================== epilogue ==================================================
+    // FOUR or EIGHT warps (block size 224 / 352, chosen per launch).  With eight, two warps share a TMEM lane quarter
+    // (a warp may only touch lanes 32 * (warp % 4) ..): group 0 (warps 2-5) takes the 32-column chunks 0-1 of a tile,
+    // group 1 (warps 7-10) chunks 2-3 -- the store epilogue of a 256 x 128 item is as long as its main loop with four
+    // warps, which shows once a CTA runs >= 5 items (+10..19 % on those layers); short grids keep four (cheaper launch).
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const bool wide = blockDim.x == IGEMM_THREADS;
+    const int grp = warp >= 7 ? 1 : 0;
+    const int cc0 = wide ? grp * 2 : 0, cc1 = wide ? cc0 + 2 : TILE_N / 32;   // this warp's chunks
+    const int epi_threads = wide ? 256 : 128;
     const int row = q * 32 + lane;          // row of the 128 x 128 tile held by this thread
-    const int et = threadIdx.x - 64;        // 0..127
+    const int et = grp ? (int)threadIdx.x - 224 + 128 : (int)threadIdx.x - 64;   // 0..255
     const uint32_t sw = (uint32_t)(row & 7);
     uint8_t* stg_base = smem + SMEM_EPI_OFF;
     uint32_t v[32];
@@ -645,16 +654,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         else p = (long long)m128 * TILE_M + row;
         const bool valid = p < args.M_total;
         const bool col_ok = ncol0 + et < args.N_total;
-        bias_s[et] = ((args.bias && col_ok) ? __ldg(args.bias + ncol0 + et) : 0.f) + ((args.bias2 && col_ok) ? __ldg(args.bias2 + ncol0 + et) : 0.f);
+        if (et < TILE_N)
+          bias_s[et] = ((args.bias && col_ok) ? __ldg(args.bias + ncol0 + et) : 0.f) + ((args.bias2 && col_ok) ? __ldg(args.bias2 + ncol0 + et) : 0.f);
         const float* rv = (args.rowvec && valid) ? args.rowvec + (p / args.rows_per_vec) * args.ld_rowvec + ncol0 : nullptr;
         if (args.has_c) mbar_wait(&c_full_bar[buf], (hl >> 1) & 1);
-        epi_bar_sync();   // bias_s visible; staging[buf] is free (thread 0 waited for its last TMA store below)
+        epi_bar_sync(epi_threads);   // bias_s visible; staging[buf] is free (thread 0 waited for its last TMA store below)
         if (half == 0) mbar_wait(&tmem_full_bar[acc], acc_parity);
         tcgen05_fence_after();
 #pragma unroll 1
-        for (int cc = 0; cc < TILE_N / 32; ++cc) {
+        for (int cc = cc0; cc < cc1; ++cc) {
           tmem_ld32(tmem_acc + cc * 32, v);
-          if (cc == TILE_N / 32 - 1 && half == kMT - 1) {      // accumulator fully read: hand it back to the MMA warp
+          if (cc == cc1 - 1 && half == kMT - 1) {      // this warp has read its part of the accumulator: hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -735,7 +745,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           }
         }
         fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-        epi_bar_sync();
+        epi_bar_sync(epi_threads);
         if (kStats && et < 64) {
           const int quad = (ncol0 >> 2) + (et >> 1);
           if (quad < (args.N_total >> 2))
@@ -780,11 +790,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             y0 = k.m_tile * TILE_M;
           }
           if (et == 0) bulk_wait_read<0>();   // the previous reductions have read the staging tiles
-          epi_bar_sync();
+          epi_bar_sync(epi_threads);
           if (half == 0) {
             mbar_wait(&tmem_full_bar[acc], acc_parity);
             tcgen05_fence_after();
-            if (kMode == 1 && args.dbias != nullptr && k.y0 == 0) {
+            if (kMode == 1 && args.dbias != nullptr && k.y0 == 0 && grp == 0) {
               uint32_t b0, b1, b2, b3, b4, b5, b6, b7;
               asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                            : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3), "=r"(b4), "=r"(b5), "=r"(b6), "=r"(b7)
@@ -798,9 +808,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             }
           }
 #pragma unroll 1
-          for (int cc = 0; cc < TILE_N / 32; ++cc) {
+          for (int cc = cc0; cc < cc1; ++cc) {
             tmem_ld32(tmem_acc + cc * 32, v);
-            if (cc == TILE_N / 32 - 1 && half == nhalf - 1) {
+            if (cc == cc1 - 1 && half == nhalf - 1) {
               tcgen05_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -811,7 +821,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               *reinterpret_cast<uint4*>(rowp + (((uint32_t)j4 ^ sw) << 4)) = make_uint4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
           }
           fence_proxy_async();
-          epi_bar_sync();
+          epi_bar_sync(epi_threads);
           if (et == 0) {
 #pragma unroll
             for (int cc = 0; cc < TILE_N / 32; ++cc) tma_reduce_add_2d(&mapD, stg_base + cc * 16384, x0 + cc * 32, y0);
@@ -997,15 +1007,18 @@ static int env_flag(const char* name, int dflt) {
 static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CUtensorMap& mA1, const CUtensorMap& mB1,
                         const CUtensorMap& mC, const CUtensorMap& mD, IgemmArgs& a, void* stream) {
   const int grid = a.num_work < kNumSMs ? a.num_work : kNumSMs;
+  // eight epilogue warps once every CTA runs at least five work items (MDM_IGEMM_EPI8_MIN_ITEMS work items in total)
+  static const int epi8_min = env_flag("MDM_IGEMM_EPI8_MIN_ITEMS", 5 * kNumSMs);
+  const int IGEMM_BLOCK = a.num_work >= epi8_min ? IGEMM_THREADS : IGEMM_THREADS_NARROW;
   cudaStream_t st = as_stream(stream);
-  if (a.mode == 1) launch_pdl(igemm_kernel<1, false, 2>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.qsum && a.halo) launch_pdl(igemm_kernel<0, true, 2, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.qsum && a.mt == 2) launch_pdl(igemm_kernel<0, false, 2, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.qsum) launch_pdl(igemm_kernel<0, false, 1, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.halo && a.mt == 2) launch_pdl(igemm_kernel<0, true, 2>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.halo) launch_pdl(igemm_kernel<0, true, 1>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.mt == 2) launch_pdl(igemm_kernel<0, false, 2>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else launch_pdl(igemm_kernel<0, false, 1>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  if (a.mode == 1) launch_pdl(igemm_kernel<1, false, 2>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.qsum && a.halo) launch_pdl(igemm_kernel<0, true, 2, true>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.qsum && a.mt == 2) launch_pdl(igemm_kernel<0, false, 2, true>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.qsum) launch_pdl(igemm_kernel<0, false, 1, true>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.halo && a.mt == 2) launch_pdl(igemm_kernel<0, true, 2>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.halo) launch_pdl(igemm_kernel<0, true, 1>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.mt == 2) launch_pdl(igemm_kernel<0, false, 2>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else launch_pdl(igemm_kernel<0, false, 1>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
