@@ -67,7 +67,7 @@ class Sampler:
         if shape == "data":
             hist_shape, edges, cum = self.dataset_hist[0], self.dataset_hist[1], self.dataset_hist[2]
             u = torch.rand(a.sample_num)
-            idx = np.unravel_index(torch.searchsorted(cum, u), hist_shape)
+            idx = np.unravel_index(torch.searchsorted(cum, u).numpy(), hist_shape)
             cols = []
             for c in range(ch):
                 v = torch.rand(a.sample_num)

@@ -26,6 +26,7 @@ for N, H, C in SHAPES:
     nb = x.numel() * 2
     tf = timeit(lambda: ops.gn_silu_fwd(x, y, gamma, beta, stats, ws, N, H * H, C, 32, 1e-5, True))
     tb = timeit(lambda: ops.gn_silu_bwd(x, dy, dx, gamma, beta, stats, dg, db, ws, N, H * H, C, 32, True, add2=y))
+    tb0 = timeit(lambda: ops.gn_silu_bwd(x, dy, dx, gamma, beta, stats, dg, db, ws, N, H * H, C, 32, True))     # norm2 sites: no add / add2
     tc = timeit(lambda: ops.colsum(dy, dg, N * H * H, C))
     # algorithmic bytes: fwd = read x + write y; bwd = read x, dy, add2 + write dx
-    print(f"N={N} H={H} C={C} ({nb/1e6:.1f} MB): fwd {tf:6.1f} us = {2*nb/tf/1e6:5.2f} TB/s (2 passes) | bwd {tb:6.1f} us = {4*nb/tb/1e6:5.2f} TB/s (4 passes) | colsum {tc:6.1f} us = {nb/tc/1e6:5.2f} TB/s", flush=True)
+    print(f"N={N} H={H} C={C} ({nb/1e6:.1f} MB): fwd {tf:6.1f} us = {2*nb/tf/1e6:5.2f} TB/s (2 passes) | bwd {tb:6.1f} us = {4*nb/tb/1e6:5.2f} TB/s (4 passes) | bwd(no add) {tb0:6.1f} us = {3*nb/tb0/1e6:5.2f} TB/s (3 passes) | colsum {tc:6.1f} us = {nb/tc/1e6:5.2f} TB/s", flush=True)
