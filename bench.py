@@ -35,6 +35,12 @@ METRIC = "train_samples_per_sec"
 UNIT = "samples/s"
 
 
+def workload_name(C, S, method):
+    """the same string in both arms (the driver compares `config` of the two JSON lines)"""
+    return (f"masked U-Net {C}x{S}x{S} training step ({method} trainer, trainer_masked.py:95-183), "
+            f"113.67M-param UNet2DModel config")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -348,8 +354,8 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": a.gpus, "steps": done,
             "warmup": min(a.warmup, 2), "ms_per_step": round(1e3 * dt / done, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"masked U-Net {a.channels}x{a.size}x{a.size} training step ({a.method} trainer), "
-                                   f"batch {a.batch}/GPU", "reference_sample": sample},
+            "config": {"workload": workload_name(a.channels, a.size, a.method), "global_batch": a.gpus * a.batch,
+                       "per_gpu_batch": a.batch, "parallelism": f"dp{a.gpus}", "reference_sample": sample},
             "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -420,8 +426,8 @@ def run_b200(a):
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"masked U-Net {C}x{S}x{S} training step ({a.method} trainer, trainer_masked.py:95-183), "
-                               f"113.67M-param UNet2DModel config, bf16 activations / fp32 master weights + AdamW + EMA",
+        "config": {"workload": workload_name(C, S, a.method),
+                   "precision": "bf16 activations / fp32 master weights + AdamW + EMA",
                    "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "cuda_graph": not a.no_graph,
                    "l2": "per-step working set (weights 0.68 GB + activations > 2 GB) exceeds the 126 MB L2; "
