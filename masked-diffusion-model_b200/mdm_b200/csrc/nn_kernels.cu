@@ -254,7 +254,7 @@ __device__ __forceinline__ float dsilu_fast(float z) {
 
 // backward pass 1: per-channel dgamma / dbeta partials; per (n, chunk, group) sums of d*gamma and d*gamma*xhat
 template <int UNROLL>
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __restrict__ x, long long ld,
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_stats_kernel(const bf16* __restrict__ x, long long ld,
                                                                   const bf16* __restrict__ dy, long long lddy,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ stats, float* __restrict__ ws,
@@ -273,15 +273,17 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
   for (int j = 0; j < 8; ++j) dg[j] = db[j] = 0.f;
   if (w.count > 0) {
     const int c0 = w.lane * 8;
-    float rs[8], mb[8], ga[8], be[8];
+    // z = gamma * xhat + beta = x * za + zb.  The loop accumulates sum(d * x) and sum(d); sum(d * xhat) follows as
+    // rstd * sum(d * x) - mean * rstd * sum(d): two per-channel constants live in the loop instead of four
+    // (96 instead of 128 registers -> three CTAs per SM)
+    float za[8], zb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int grp = (c0 + j) / g.cpg;
       const float mean = stats[((long long)n * g.G + grp) * 2], rstd = stats[((long long)n * g.G + grp) * 2 + 1];
-      rs[j] = rstd;
-      mb[j] = -mean * rstd;
-      ga[j] = gamma[c0 + j];
-      be[j] = beta[c0 + j];
+      const float ga = gamma[c0 + j];
+      za[j] = rstd * ga;
+      zb[j] = fmaf(-mean * rstd, ga, beta[c0 + j]);
     }
     const bf16* px = x + w.off * ld + c0;
     const bf16* pd = dy + w.off * lddy + c0;
@@ -292,10 +294,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
       unpack8(vd, fd);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float xh = fmaf(fx[j], rs[j], mb[j]);
         float d = fd[j];
-        if (silu) d *= dsilu_fast(fmaf(xh, ga[j], be[j]));
-        dg[j] = fmaf(d, xh, dg[j]);
+        if (silu) d *= dsilu_fast(fmaf(fx[j], za[j], zb[j]));
+        dg[j] = fmaf(d, fx[j], dg[j]);      // sum d * x (converted to sum d * xhat below)
         db[j] += d;
       }
     };
@@ -310,6 +311,12 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
       for (int u = 0; u < UNROLL; ++u) body(vx[u], vd[u]);
     }
     for (; it < w.count; ++it, px += sx, pd += sd) body(ldg16(px), ldg16(pd));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int grp = (c0 + j) / g.cpg;
+      const float mean = stats[((long long)n * g.G + grp) * 2], rstd = stats[((long long)n * g.G + grp) * 2 + 1];
+      dg[j] = rstd * fmaf(-mean, db[j], dg[j]);
+    }
   }
   gn_reduce8(dg, sdg, w.lane, g.L, w.count > 0);
   gn_reduce8(db, sdb, w.lane, g.L, w.count > 0);
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
 // backward pass 2: dx = rstd * (d*gamma - mean(d*gamma) - xhat * mean(d*gamma*xhat)) (+ add + add2);
 // optionally colsum[n][c] += sum_pixels dx and dbias[c] += the same (conv bias / time-embedding gradients)
 template <int UNROLL, bool HAS_ADD, bool HAS_ADD2>
-__global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(
     const bf16* __restrict__ x, long long ld, const bf16* __restrict__ dy, long long lddy, const bf16* add /* may alias dx */,
     long long ldadd, const bf16* __restrict__ add2, long long ldadd2, bf16* dx, long long lddx,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
@@ -368,19 +375,17 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(
   if (w.count > 0) {
     const int c0 = w.lane * 8;
     // dx = d * A + x * B + Cc   with d already multiplied by silu'(z):  A = rstd*gamma, B = -rstd^2*m2, Cc = -rstd*(m1 - mean*rstd*m2)
-    float rs[8], mb[8], ga[8], be[8], A[8], Bc[8], Cc[8];
+    float zb[8], A[8], Bc[8], Cc[8];       // z = x * A + zb (A = rstd * gamma doubles as the z slope)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int grp = (c0 + j) / g.cpg;
       const float mean = stats[((long long)n * g.G + grp) * 2], rstd = stats[((long long)n * g.G + grp) * 2 + 1];
       const float m1 = m12[grp * 2], m2 = m12[grp * 2 + 1];
-      rs[j] = rstd;
-      mb[j] = -mean * rstd;
-      ga[j] = gamma[c0 + j];
-      be[j] = beta[c0 + j];
-      A[j] = rstd * ga[j];
+      const float mbj = -mean * rstd;
+      A[j] = rstd * gamma[c0 + j];
+      zb[j] = fmaf(mbj, gamma[c0 + j], beta[c0 + j]);
       Bc[j] = -rstd * rstd * m2;
-      Cc[j] = -rstd * (m1 + mb[j] * m2);
+      Cc[j] = -rstd * (m1 + mbj * m2);
     }
     const bf16* px = x + w.off * ld + c0;
     const bf16* pd = dy + w.off * lddy + c0;
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_apply_kernel(
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float d = fd[j];
-        if (silu) d *= dsilu_fast(fmaf(fmaf(fx[j], rs[j], mb[j]), ga[j], be[j]));
+        if (silu) d *= dsilu_fast(fmaf(fx[j], A[j], zb[j]));
         o[j] = fmaf(d, A[j], fmaf(fx[j], Bc[j], Cc[j]));
       }
       if (want_cs) {
@@ -1023,7 +1028,30 @@ static int gn_cluster_size(const GnGeom& g, int maxv) {
   return 0;
 }
 
-static int gn_geom(GnGeom& g, int HW, int C, int G, int* nchunk, int nbatch = 0) {
+// CTAs of the two-pass kernel family that are co-resident on the whole GPU (occupancy x SMs), queried once
+static int gn_slots(bool bwd) {
+  static int slots[2] = {0, 0};
+  if (slots[bwd] == 0) {
+    int a = 0, b = 0;
+    cudaError_t e1, e2;
+    if (!bwd) {
+      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, gn_stats_kernel<8>, GN_THREADS, 4096);
+      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, gn_apply_kernel<4>, GN_THREADS, 0);
+    } else {
+      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, gn_bwd_stats_kernel<4>, GN_THREADS, 4096);
+      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, gn_bwd_apply_kernel<2, true, true>, GN_THREADS, 2048);
+    }
+    if (e1 != cudaSuccess || e2 != cudaSuccess || a < 1 || b < 1) { cudaGetLastError(); a = b = bwd ? 3 : 5; }
+    slots[bwd] = (a < b ? a : b) * kNumSMs;
+  }
+  return slots[bwd];
+}
+
+// geometry of the two-pass kernels: a CTA owns `chunk_pix` pixels of one sample.  The chunk is chosen so that the
+// grid (nbatch x nchunk CTAs) is a whole number of WAVES of the co-resident CTAs with as little per-CTA overhead as
+// possible: cost(waves) = waves x (chunk elements + ~24K elements' worth of set-up / reduction / tail).  A grid one
+// CTA over a wave costs a whole extra wave (measured: 512 CTAs on 444 slots ran as long as 888).
+static int gn_geom(GnGeom& g, int HW, int C, int G, int* nchunk, int nbatch = 0, int slots = 0) {
   if (C % 8 != 0 || C % G != 0 || G > GN_MAX_GROUPS || C > GN_MAX_C) {
     set_error("GroupNorm: C=%d must be a multiple of 8 and of G=%d (G <= 32, C <= %d)", C, G, GN_MAX_C);
     return MDM_E_ARG;
@@ -1032,15 +1060,29 @@ static int gn_geom(GnGeom& g, int HW, int C, int G, int* nchunk, int nbatch = 0)
   g.L = C / 8;
   if (g.L > GN_THREADS) { set_error("GroupNorm: C=%d too wide", C); return MDM_E_ARG; }
   g.R = GN_THREADS / g.L;
-  // ~32K elements (64 KB of bf16) per CTA, a multiple of R pixels; big tensors get longer chunks (about 8 CTAs
-  // per SM in total) so the per-CTA set-up / reduction / tail is amortised over more streaming
-  long long per_cta = 32768;
-  if (nbatch > 0) {
-    const long long want = ((long long)nbatch * HW * C) / (kNumSMs * 8);
-    if (want > per_cta) per_cta = want;
+  int chunk;
+  if (nbatch > 0 && slots > 0) {
+    long long best = -1;
+    chunk = HW;
+    const int max_chunks = HW / g.R > 0 ? HW / g.R : 1;
+    for (int w = 1; w <= 8; ++w) {
+      int nch = (int)(((long long)slots * w) / nbatch);
+      if (nch < 1) nch = 1;
+      if (nch > max_chunks) nch = max_chunks;
+      int ck = (HW + nch - 1) / nch;
+      ck = ((ck + g.R - 1) / g.R) * g.R;
+      if (ck > HW) ck = HW;
+      if ((long long)ck * C < 8192 && ck < HW) continue;            // too little work per CTA
+      const int nch2 = (HW + ck - 1) / ck;
+      const long long waves = ((long long)nbatch * nch2 + slots - 1) / slots;
+      const long long cost = waves * ((long long)ck * C + 24576);
+      if (best < 0 || cost < best) { best = cost; chunk = ck; }
+    }
+  } else {
+    // no batch information: ~32K elements (64 KB of bf16) per CTA, a multiple of R pixels
+    chunk = (32768 + C - 1) / C;
+    chunk = ((chunk + g.R - 1) / g.R) * g.R;
   }
-  int chunk = (int)((per_cta + C - 1) / C);
-  chunk = ((chunk + g.R - 1) / g.R) * g.R;
   if (chunk > HW) chunk = HW;
   if (chunk < 1) chunk = 1;
   g.chunk_pix = chunk;
@@ -1578,7 +1620,10 @@ extern "C" {
 
 int64_t mdm_gn_ws_floats(int N, int HW, int C, int G) {
   GnGeom g; int nc;
-  if (gn_geom(g, HW, C, G, &nc, N)) return 0;
+  if (gn_geom(g, HW, C, G, &nc, N, gn_slots(false))) return 0;
+  int nc2 = nc;
+  if (gn_geom(g, HW, C, G, &nc2, N, gn_slots(true))) return 0;       // forward and backward families chunk differently
+  if (nc2 > nc) nc = nc2;
   return (int64_t)N * nc * GN_MAX_GROUPS * 2;
 }
 
@@ -1588,7 +1633,7 @@ int mdm_gn_silu_fwd(const void* x, long long ld_x, void* y, long long ld_y, cons
   MDM_CHECK_ARG(ld_x % 8 == 0 && ld_y % 8 == 0, "gn_silu_fwd: channel strides must be multiples of 8");
   MDM_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0), "gn_silu_fwd: pointers must be 16-byte aligned");
   GnGeom g; int nc;
-  int rc = gn_geom(g, HW, C, G, &nc, N);
+  int rc = gn_geom(g, HW, C, G, &nc, N, gn_slots(false));
   if (rc) return rc;
   if ((long long)HW * C <= 32768) {   // small map: one CTA per sample, single pass over registers
     const int per_thread = (HW + g.R - 1) / g.R;
@@ -1617,7 +1662,7 @@ int mdm_gn_silu_fwd_q(const void* x, long long ld_x, void* y, long long ld_y, co
   MDM_CHECK_ARG(x && y && gamma && beta && qa, "gn_silu_fwd_q: NULL pointer");
   MDM_CHECK_ARG(ld_x % 8 == 0 && ld_y % 8 == 0, "gn_silu_fwd_q: channel strides must be multiples of 8");
   GnGeom g; int nc;
-  int rc = gn_geom(g, HW, C, G, &nc, N);
+  int rc = gn_geom(g, HW, C, G, &nc, N, gn_slots(false));
   if (rc) return rc;
   MDM_CHECK_ARG(g.cpg % 4 == 0, "gn_silu_fwd_q: C/G = %d must be a multiple of 4 (quad sums)", g.cpg);
   MDM_CHECK_ARG(qa_quads > 0 && qa_quads <= C / 4 && (qa_quads == C / 4 || qb != nullptr), "gn_silu_fwd_q: bad quad split %d of %d", qa_quads, C / 4);
@@ -1630,7 +1675,7 @@ int mdm_gn_silu_fwd_q(const void* x, long long ld_x, void* y, long long ld_y, co
 
 int mdm_gn_fwd_kind(int N, int HW, int C, int G) {
   GnGeom g; int nc;
-  if (gn_geom(g, HW, C, G, &nc, N)) return -1;
+  if (gn_geom(g, HW, C, G, &nc, N, gn_slots(false))) return -1;
   if ((long long)HW * C <= 32768) return 0;
   return gn_cluster_size(g, GN_CL_FWD_V) ? 1 : 2;
 }
@@ -1643,7 +1688,7 @@ int mdm_gn_silu_bwd(const void* x, long long ld_x, const void* dy, long long ld_
   MDM_CHECK_ARG(ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0 && ld_add % 8 == 0 && ld_add2 % 8 == 0,
                 "gn_silu_bwd: channel strides must be multiples of 8");
   GnGeom g; int nc;
-  int rc = gn_geom(g, HW, C, G, &nc, N);
+  int rc = gn_geom(g, HW, C, G, &nc, N, gn_slots(true));
   if (rc) return rc;
   if ((long long)HW * C <= 16384) {   // small map: one CTA per sample, x and dy stay in registers across both phases
     const int per_thread = (HW + g.R - 1) / g.R;
