@@ -1,6 +1,6 @@
 """One small forward + backward of the B200 denoiser on cuda:0 checked against the fp32 oracle restatement
-(oracle/unet_ref.py).  Used by `__graft_entry__.smoke()`; the oracle import lives HERE only because this
-module is the smoke check, not part of the product path."""
+(oracle/unet_ref.py).  Used by `__graft_entry__.smoke()`; it lives under tests/ because it imports the oracle (the
+product package never does)."""
 from __future__ import annotations
 
 import torch
@@ -8,7 +8,7 @@ import torch
 
 def run(C=3, S=32, B=4):
     from oracle.unet_ref import UNet2DModelRef, unet_config   # test infrastructure (checker only)
-    from .denoiser import UNet2DModelB200, default_config
+    from mdm_b200.denoiser import UNet2DModelB200, default_config
     torch.manual_seed(0)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False

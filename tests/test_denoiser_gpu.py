@@ -122,3 +122,44 @@ def test_fused_groupnorm_statistics_match_unfused(monkeypatch):
         want = ref(x, t).sample
     assert rel_l2(outs["1"], outs["0"]) <= 1.5e-2       # two bf16 evaluations of the same network
     assert rel_l2(outs["1"], want) <= 2e-2
+
+
+def test_segmented_backward_equals_whole_backward():
+    """data-parallel overlap cuts the backward program into segments whose gradients are contiguous ranges of the flat
+    buffer (all-reduced while the next segment runs): running segment 0 through loss.backward() and the others through
+    backward_segment(k) must leave the same gradients as the unsegmented backward, and each range must be FINAL at the
+    end of its segment."""
+    _, mine = build_pair(3, 32, seed=4)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.rand(4, 3, 32, 32, device="cuda", generator=g) * 2 - 1
+    x0 = torch.rand(4, 3, 32, 32, device="cuda", generator=g) * 2 - 1
+    t = torch.tensor([5.0, 100.0, 500.0, 900.0], device="cuda")
+    mine.train()
+    mine.zero_grad()
+    torch.nn.functional.mse_loss(x + mine(x, t).sample, x0).backward()
+    whole = mine.flat_grad.clone()
+    ranges = mine.grad_segment_ranges()
+    n = mine.flat_grad.numel()
+    assert len(ranges) == 2 and all(0 <= lo < hi <= n for lo, hi in ranges)
+    assert ranges[1][1] == ranges[0][0]                         # down blocks 5..2 sit right below mid / up / head
+    plan = mine._last_plans[0]
+    assert len(plan.bwd_marks) == len(ranges)
+    mine.zero_grad()
+    mine.bwd_segmented = True
+    try:
+        torch.nn.functional.mse_loss(x + mine(x, t).sample, x0).backward()       # segment 0 only
+        torch.cuda.synchronize()
+        lo, hi = ranges[0]
+        # fp32 reduce-adds of the weight gradients are order-dependent: compare to run-to-run noise, not bitwise
+        tol = 1e-5 * whole.abs().max().item()
+        assert (mine.flat_grad[lo:hi] - whole[lo:hi]).abs().max().item() <= tol
+        assert mine.flat_grad[:ranges[1][0]].abs().max().item() == 0             # nothing below segment 1 touched yet
+        mine.backward_segment(1)
+        torch.cuda.synchronize()
+        lo, hi = ranges[1]
+        assert (mine.flat_grad[lo:hi] - whole[lo:hi]).abs().max().item() <= tol
+        mine.backward_segment(2)
+        torch.cuda.synchronize()
+    finally:
+        mine.bwd_segmented = False
+    assert (mine.flat_grad - whole).abs().max().item() <= tol

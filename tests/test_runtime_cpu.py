@@ -97,3 +97,12 @@ def test_no_cpu_fallback():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             S.degrade_training(torch.tensor([0.5]), torch.zeros(1, 3, 8, 8), 0, "image-wise")
+
+
+def test_complement_of_gradient_ranges():
+    """host logic of the segmented all-reduce: the last segment reduces everything the earlier ranges did not cover"""
+    from trainer_masked import _complement
+    assert _complement([(10, 20), (5, 10)], 30) == [(0, 5), (20, 30)]
+    assert _complement([(0, 30)], 30) == []
+    assert _complement([], 7) == [(0, 7)]
+    assert _complement([(3, 5), (8, 9)], 9) == [(0, 3), (5, 8)]
