@@ -138,6 +138,11 @@ def test_segmented_backward_equals_whole_backward():
     mine.zero_grad()
     torch.nn.functional.mse_loss(x + mine(x, t).sample, x0).backward()
     whole = mine.flat_grad.clone()
+    # run-to-run noise of the same unsegmented step (fp32 atomics in the GroupNorm / weight-gradient reductions change
+    # the summation order, bf16 roundings then differ): the yardstick for "same gradients"
+    mine.zero_grad()
+    torch.nn.functional.mse_loss(x + mine(x, t).sample, x0).backward()
+    noise = (mine.flat_grad - whole).abs().max().item()
     ranges = mine.grad_segment_ranges()
     n = mine.flat_grad.numel()
     assert len(ranges) == 2 and all(0 <= lo < hi <= n for lo, hi in ranges)
@@ -150,8 +155,7 @@ def test_segmented_backward_equals_whole_backward():
         torch.nn.functional.mse_loss(x + mine(x, t).sample, x0).backward()       # segment 0 only
         torch.cuda.synchronize()
         lo, hi = ranges[0]
-        # fp32 reduce-adds of the weight gradients are order-dependent: compare to run-to-run noise, not bitwise
-        tol = 1e-5 * whole.abs().max().item()
+        tol = max(4.0 * noise, 1e-5 * whole.abs().max().item())
         assert (mine.flat_grad[lo:hi] - whole[lo:hi]).abs().max().item() <= tol
         assert mine.flat_grad[:ranges[1][0]].abs().max().item() == 0             # nothing below segment 1 touched yet
         mine.backward_segment(1)
