@@ -1083,8 +1083,9 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
   int splits = 1;
   const long long ws_need = (long long)a.M_total * a.N_total;
   if (!a.halo && !a.qsum && c->splitk_ws && c->splitk_ws_floats >= ws_need && tiles * 2 <= kNumSMs && a.iters_total >= 8) {
+    static const int min_iters = env_flag("MDM_IGEMM_SPLITK_MIN_ITERS", 4);   // K iterations (64 channels x 1 tap) per split, at least
     splits = kNumSMs / tiles;
-    if (splits > a.iters_total / 4) splits = a.iters_total / 4;
+    if (splits > a.iters_total / min_iters) splits = a.iters_total / min_iters;
     if (splits < 1) splits = 1;
   }
   a.iters_per_split = (a.iters_total + splits - 1) / splits;
