@@ -16,13 +16,22 @@
 //   dgrad : D[pix][ci] = sum_tap sum_co dY[pix-tap][co] * W[co][tap][ci]     A K-major, B MN-major
 //   wgrad : D[co][ci]  = sum_pix dY[pix][co] * X[pix+tap][ci]   (per tap)   A,B MN-major, split-K
 //
-// PERSISTENT, warp-specialised kernel: one CTA per SM walks a static list of work items (output
-// tile x K split); 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM allocator),
-// warps 2-5 = epilogue.  Three pipelines: a 4-stage smem ring (TMA -> MMA), TWO TMEM accumulators
-// (MMA -> epilogue: the epilogue of tile i overlaps the main loop of tile i+1) and two 32 KB smem
-// staging tiles (epilogue -> TMA store / TMA reduce-add; the residual / accumulate operand is TMA-
-// loaded into the same staging tile while the main loop runs).  Epilogues:
-//   store : + bias (+ second bias) + per-sample time-embedding vector + residual -> bf16 NHWC TMA store
+// PERSISTENT, warp-specialised kernel: one CTA per SM walks a static list of work items (output tile x K split).
+// 224 or 352 threads: warp 0 = TMA producer of the A operand, warp 6 = TMA producer of B, warp 1 = MMA issuer
+// (+TMEM allocator), warps 2-5 (and 7-10 when a CTA runs >= 5 items) = epilogue.  The three single-thread roles are
+// entered through `elect.sync` with a warp index from `__shfl_sync`, so their loops live in uniform registers (the
+// operands of UTCHMMA / UTMALDG are uniform registers; see profiles/README.md section 8).  Three pipelines: a shared-
+// memory ring (TMA -> MMA), TWO TMEM accumulator stages (MMA -> epilogue: the epilogue of item i overlaps the main
+// loop of item i+1) and two 32 KB staging tiles (epilogue -> TMA store / TMA reduce-add; the residual / accumulate
+// operand is TMA-loaded into the same staging tile while the main loop runs).
+// Work items: 128 x 128 output tiles; 256 x 128 (two A sub-tiles share every B tile) when enough of them exist; for
+// 3x3 stride-1 layers on maps that are multiples of 16 x 16, HALO mode: the item is a 16 x 16 pixel patch whose
+// zero-padded 18 x 18 x 64-channel input halo is loaded ONCE per channel chunk and the nine taps are nine shifted
+// UMMA descriptors into it (2.3x fewer operand bytes from L2).  wgrad items: one dY tile against two (cin tile, tap)
+// entries; the first item of a cout tile carries entry 0 alone plus the bias gradient (one N=16 MMA against ones).
+// Epilogues:
+//   store : + bias (+ second bias) + per-sample time-embedding vector + residual -> bf16 NHWC TMA store; the kStats
+//           instantiations also accumulate GroupNorm quad sums (sum, sum of squares per 4 channels) of the output
 //   reduce: fp32 TMA reduce-add into global memory -- wgrad (split over pixels) and split-K partials of
 //           small-M fprop/dgrad layers (finished by splitk_finalize_kernel).
 #include <cuda.h>
@@ -1006,7 +1015,11 @@ static int env_flag(const char* name, int dflt) {
 
 static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CUtensorMap& mA1, const CUtensorMap& mB1,
                         const CUtensorMap& mC, const CUtensorMap& mD, IgemmArgs& a, void* stream) {
-  const int grid = a.num_work < kNumSMs ? a.num_work : kNumSMs;
+  // persistent grid: one CTA per SM -- minus the SMs reserved for a concurrently running collective (data-parallel
+  // overlap: NCCL's persistent CTAs would otherwise push a 148-CTA grid into a second wave); MDM_IGEMM_MAX_CTAS
+  static const int max_ctas = env_flag("MDM_IGEMM_MAX_CTAS", kNumSMs);
+  const int cap = max_ctas < kNumSMs && max_ctas > 0 ? max_ctas : kNumSMs;
+  const int grid = a.num_work < cap ? a.num_work : cap;
   // eight epilogue warps once every CTA runs at least five work items (MDM_IGEMM_EPI8_MIN_ITEMS work items in total)
   static const int epi8_min = env_flag("MDM_IGEMM_EPI8_MIN_ITEMS", 5 * kNumSMs);
   const int IGEMM_BLOCK = a.num_work >= epi8_min ? IGEMM_THREADS : IGEMM_THREADS_NARROW;
