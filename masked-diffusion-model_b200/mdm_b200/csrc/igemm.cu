@@ -215,6 +215,7 @@ struct IgemmArgs {
   int M_total, N_total;
   // persistent schedule: work item w -> (tile, K split)
   int num_work, num_n, splits;
+  int pair_work;        // halo mode with 256-row items: work items >= pair_work are TAIL items of one 128-row half each
   int iters_total, iters_per_split;   // mode 0: (tap, k-chunk) iterations; mode 1: 64-pixel chunks
   // epilogue 0
   const float* bias;
@@ -239,7 +240,9 @@ struct IgemmArgs {
 struct Work {
   int m_tile, n_tile;   // mode 0: pixel tile, cout tile;  mode 1: cout tile, -
   int y0;               // mode 1: first of the (up to two) consecutive (cin tile, tap) entries sharing this item's dY tiles
-  int nh;               // mode 1: entries of this item (item 0 of a cout tile: entry 0 alone + the bias gradient)
+  int nh;               // mode 1: entries of this item (item 0 of a cout tile: entry 0 alone + the bias gradient);
+                        // mode 0: 128-row sub-tiles of this item (a tail item of the halo kernel has one)
+  int half0;            // mode 0: first sub-tile of the item (tail items: 0 or 1)
   int it0, nit;         // iteration range
 };
 // wgrad entry y -> (cin tile, tap index)
@@ -252,11 +255,19 @@ __device__ __forceinline__ Work decode_work(const IgemmArgs& a, int w) {
   Work k;
   const int z = w % a.splits;
   const int t = w / a.splits;
+  k.half0 = 0;
   if (a.mode == 0) {
-    k.n_tile = t % a.num_n;
-    k.m_tile = t / a.num_n;
-    k.y0 = 0;
+    int tt = t;
     k.nh = a.mt;
+    if (a.pair_work > 0 && t >= a.pair_work) {      // tail wave: one half of a 16 x 16 patch per item
+      const int sidx = t - a.pair_work;
+      tt = a.pair_work + (sidx >> 1);
+      k.half0 = sidx & 1;
+      k.nh = 1;
+    }
+    k.n_tile = tt % a.num_n;
+    k.m_tile = tt / a.num_n;
+    k.y0 = 0;
   } else {
     // items of a cout tile: {entry 0 (+ bias gradient)}, {1, 2}, {3, 4}, ...
     k.m_tile = t % a.num_co;
@@ -424,9 +435,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               }
             } else {               // fused 1x1 shortcut segment: a plain patch in a halo slot
               mbar_wait(&a_empty[sa], pa ^ 1);
-              mbar_expect_tx(&a_full[sa], kMT * A_BYTES);
-              tma_load_4d(&mapA1, a_ring + sa * kHaloSlot, &a_full[sa], it.kc * TILE_K, w0, h0, n0);
-              if (kMT == 2) tma_load_4d(&mapA1, a_ring + sa * kHaloSlot + A_BYTES, &a_full[sa], it.kc * TILE_K, w1, h1, n1);
+              mbar_expect_tx(&a_full[sa], k.nh * A_BYTES);
+              if (k.nh == kMT) {
+                tma_load_4d(&mapA1, a_ring + sa * kHaloSlot, &a_full[sa], it.kc * TILE_K, w0, h0, n0);
+                if (kMT == 2) tma_load_4d(&mapA1, a_ring + sa * kHaloSlot + A_BYTES, &a_full[sa], it.kc * TILE_K, w1, h1, n1);
+              } else {             // tail item: its one patch goes to the front of the slot
+                tma_load_4d(&mapA1, a_ring + sa * kHaloSlot, &a_full[sa], it.kc * TILE_K, k.half0 ? w1 : w0, k.half0 ? h1 : h0,
+                            k.half0 ? n1 : n0);
+              }
               if (++sa == kASlots) { sa = 0; pa ^= 1; }
             }
           } else {
@@ -547,7 +563,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       mbar_wait(&tmem_empty_bar[acc], ((local / kAccStages) & 1) ^ 1);   // the epilogue has drained this accumulator
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * kAccCols;
-      const int nhalf = kMode == 1 ? k.nh : kMT;                // wgrad: the second entry of the pair may not exist
+      const int nhalf = k.nh;      // wgrad: the second entry of the pair may not exist; halo tail items: one sub-tile
+      const uint32_t half_shift = (kMode == 0 && kHalo) ? (uint32_t)k.half0 : 0u;   // tail item: which half of the patch
       uint32_t lo_a = 0;
       int sa_cur = 0, tap = 0;
       // wgrad work items (ci tile 0, first tap) also accumulate the bias gradient: A = dY tile, B = ones, N = 16
@@ -585,7 +602,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         for (int half = 0; half < kMT; ++half) {
           if (half < nhalf) {
             // mode 0: the halves are two A (pixel) sub-tiles against one B; mode 1: two B tiles against one A
-            const uint32_t la = lo_at + (kMode == 0 ? half * half_a : 0);
+            const uint32_t la = lo_at + (kMode == 0 ? (half + (halo_it ? half_shift : 0u)) * half_a : 0);
             const uint32_t lb = lo_b + (kMode == 1 ? half * (B_BYTES >> 4) : 0);
 #pragma unroll
             for (int kk = 0; kk < TILE_K / 16; ++kk) {
@@ -642,7 +659,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     };
     if (args.has_c && et == 0 && w_first < args.num_work) {
       const Work k0 = decode_work(args, w_first);
-      load_c(k0.m_tile * kMT, k0.n_tile, 0);
+      load_c(k0.m_tile * kMT + k0.half0, k0.n_tile, 0);
     }
     int hl = 0;   // 128 x 128 tiles finished by this CTA (staging buffer / C-tile barrier parity)
     for (int w = w_first; w < args.num_work; w += w_step, ++local) {
@@ -650,9 +667,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       const int acc = local % kAccStages;
       const uint32_t acc_parity = (local / kAccStages) & 1;
       if (args.epi == 0) {
-       for (int half = 0; half < kMT; ++half, ++hl) {
+       for (int half = 0; half < k.nh; ++half, ++hl) {
         const uint32_t tmem_acc = tmem_base + acc * kAccCols + half * TILE_N + ((uint32_t)(q * 32) << 16);
-        const int m128 = k.m_tile * kMT + half;
+        const int m128 = k.m_tile * kMT + k.half0 + half;
         const int buf = hl & 1;
         uint8_t* stg = stg_base + buf * EPI_BYTES;
         const int ncol0 = k.n_tile * TILE_N;
@@ -673,7 +690,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
 #pragma unroll 1
         for (int cc = cc0; cc < cc1; ++cc) {
           tmem_ld32(tmem_acc + cc * 32, v);
-          if (cc == cc1 - 1 && half == kMT - 1) {      // this warp has read its part of the accumulator: hand it back to the MMA warp
+          if (cc == cc1 - 1 && half == k.nh - 1) {      // this warp has read its part of the accumulator: hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -774,11 +791,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           bulk_commit();
           bulk_wait_read<1>();   // every store but the one just issued has read its smem: the OTHER tile is free
           if (args.has_c) {      // prefetch the C tile of the next 128 x 128 tile into the other staging buffer
-            if (half + 1 < kMT) {
+            if (half + 1 < k.nh) {
               load_c(m128 + 1, k.n_tile, buf ^ 1);
             } else if (w + w_step < args.num_work) {
               const Work kn = decode_work(args, w + w_step);
-              load_c(kn.m_tile * kMT, kn.n_tile, buf ^ 1);
+              load_c(kn.m_tile * kMT + kn.half0, kn.n_tile, buf ^ 1);
             }
           }
         }
@@ -1104,6 +1121,19 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
   a.iters_per_split = (a.iters_total + splits - 1) / splits;
   a.splits = (a.iters_total + a.iters_per_split - 1) / a.iters_per_split;
   a.num_work = tiles * a.splits;
+  a.pair_work = 0;
+  // halo mode with 256-row items: a last partial wave of at most half the SMs is re-cut into single 128-row items
+  // (two per patch), so it costs half a wave instead of a whole one (128x32x32: 512 items = 3.46 waves -> 3.46 + ...
+  // 444 pair items + 136 single items = 3.5 waves instead of 4)
+  static const int tail_split = env_flag("MDM_IGEMM_TAIL_SPLIT", 1);
+  if (tail_split && halo_kind == 2 && a.splits == 1) {
+    const int grid_cap = kNumSMs;
+    const int rem = tiles % grid_cap;
+    if (tiles > grid_cap && rem > 0 && 2 * rem <= grid_cap) {
+      a.pair_work = tiles - rem;
+      a.num_work = a.pair_work + 2 * rem;
+    }
+  }
   const void* c_ptr = c->accumulate ? out : c->resid;
   const long long c_ld = c->accumulate ? ld_out : c->ld_resid;
   const CUtensorMap& mB1r = mB1 ? *mB1 : mB0;

@@ -170,3 +170,28 @@ def test_halo_fused_shortcut_slices(halo_env):
     ref = F.conv2d(nchw(a), ops.unpack_conv_weight(wb.float(), 3), padding=1) + F.conv2d(nchw(x), ops.unpack_conv_weight(wsb.float(), 1))
     assert (nchw(y) - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
     assert ybuf[..., :256].abs().max().item() == 0
+
+
+def test_halo_tail_wave_single_items():
+    """the last partial wave of a 16x16-patch halo layer is re-cut into single 128-row items: 150 patches x 2 cout tiles
+    = 300 work items = 2 full waves of 148 + 4 pair items -> 8 single items; fprop with fused 1x1 shortcut and dgrad"""
+    from mdm_b200 import denoiser_ops as ops
+    N, H, cin, cout, cx = 150, 16, 128, 256, 64
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(N, cin, H, H, device="cuda", generator=g)
+    xs = torch.randn(N, cx, H, H, device="cuda", generator=g)
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (cin * 9) ** 0.5
+    ws = torch.randn(cout, cx, 1, 1, device="cuda", generator=g) / cx ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g)
+    xb, xsb = nhwc(x), nhwc(xs)
+    wb, wsb = ops.pack_conv_weight(w).to(torch.bfloat16), ops.pack_conv_weight(ws).to(torch.bfloat16)
+    y = torch.empty(N, H, H, cout, device="cuda", dtype=torch.bfloat16)
+    ops.conv_fprop(xb, wb, y, N, H, H, 3, 1, bias=b, x2=xsb, w2=wsb)
+    ref = F.conv2d(nchw(xb), ops.unpack_conv_weight(wb.float(), 3), b, padding=1) + F.conv2d(nchw(xsb), ops.unpack_conv_weight(wsb.float(), 1))
+    assert (nchw(y) - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    dyb = nhwc(torch.randn(N, cout, H, H, device="cuda", generator=g))
+    res = nhwc(torch.randn(N, cin, H, H, device="cuda", generator=g))
+    dx = torch.empty(N, H, H, cin, device="cuda", dtype=torch.bfloat16)
+    ops.conv_dgrad(dyb, wb, dx, N, H, H, 3, resid=res)
+    refd = torch.nn.grad.conv2d_input((N, cin, H, H), ops.unpack_conv_weight(wb.float(), 3), nchw(dyb), padding=1) + nchw(res)
+    assert (nchw(dx) - refd).abs().max().item() <= 1e-2 * refd.abs().max().item()
