@@ -217,6 +217,39 @@ def roofline_pass(tr, model, batch_dev, peaks):
     wrap("conv_fprop", fl_fprop)
     wrap("conv_dgrad", fl_dgrad)
     wrap("conv_wgrad", fl_wgrad)
+    # the HBM-bound kernels of the step, with their ALGORITHMIC bytes (bf16 activations: read x (+dy, +add, +add2),
+    # write y / dx); reported next to the dominant kernel as `roofline.hbm_kernels`
+    hbm = []
+
+    def wrap_bytes(name, bytes_fn):
+        f = getattr(ops, name)
+        orig[name] = f
+
+        def g(*args, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = f(*args, **kw)
+            e1.record()
+            hbm.append((name, bytes_fn(*args, **kw), e0, e1))
+            return r
+        setattr(ops, name, g)
+
+    from mdm_b200 import optim_ops as _oo
+    _adam = _oo.adam_ema_step_dev
+
+    def adam_timed(p, g, m, v, ema, p16, *a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = _adam(p, g, m, v, ema, p16, *a, **k)
+        e1.record()
+        # read p, g, m, v (+ema), write p, m, v (+ema) fp32 + the bf16 mirror
+        hbm.append(("adam_ema_step", float(p.numel()) * (4 * (7 + (2 if ema is not None else 0)) + 2), e0, e1))
+        return r
+    _oo.adam_ema_step_dev = adam_timed
+    wrap_bytes("gn_silu_fwd", lambda x, y, gamma, beta, stats, ws, N, HW, C, *a, **k: 2.0 * 2 * N * HW * C)
+    wrap_bytes("gn_silu_fwd_q", lambda x, y, gamma, beta, stats, qa, qb, N, HW, C, *a, **k: 2.0 * 2 * N * HW * C)
+    wrap_bytes("gn_silu_bwd", lambda x, dy, dx, gamma, beta, stats, dgamma, dbeta, ws, N, HW, C, *a, **k:
+               2.0 * N * HW * C * (3 + (k.get("add") is not None) + (k.get("add2") is not None)))
     saved = tr.args.cuda_graph
     tr.args.cuda_graph = False
     tr._graphs.clear()
@@ -234,9 +267,21 @@ def roofline_pass(tr, model, batch_dev, peaks):
     finally:
         for k, f in orig.items():
             setattr(ops, k, f)
+        _oo.adam_ema_step_dev = _adam
         model.wgrad_side_stream = True
         tr.args.cuda_graph = saved
         tr._graphs.clear()
+    hbm_peak = peaks.get("hbm_gbs", 6532.2)
+    hbm_by = {}
+    for name, nbytes, e0, e1 in hbm:
+        d = hbm_by.setdefault(name, [0, 0.0, 0.0])
+        d[0] += 1
+        d[1] += nbytes
+        d[2] += e0.elapsed_time(e1)
+    hbm_kernels = {k: {"launches": v[0], "algorithmic_GB": round(v[1] / 1e9, 3), "ms": round(v[2], 3),
+                       "GBps": round(v[1] / (v[2] * 1e-3) / 1e9, 1) if v[2] > 0 else None,
+                       "frac_of_hbm_peak": round(v[1] / (v[2] * 1e-3) / 1e9 / hbm_peak, 3) if v[2] > 0 else None}
+                   for k, v in hbm_by.items()}
     total_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in rec)
     total_fl = sum(f for _, f, _, _ in rec)
     by = {}
@@ -258,6 +303,9 @@ def roofline_pass(tr, model, batch_dev, peaks):
         "by_kind": {k: {"launches": v[0], "tflops": round(v[1] / (v[2] * 1e-3) / 1e12, 2) if v[2] > 0 else None,
                         "ms": round(v[2], 3)} for k, v in by.items()},
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback (B200_PROFILING.md)",
+        # GroupNorm(+SiLU) forward / backward call sites of the same step (1-2 kernels each, launch gaps of the eager
+        # pass included), achieved GB/s from ALGORITHMIC bytes against the measured HBM copy peak
+        "hbm_kernels": hbm_kernels,
     }
 
 
