@@ -330,7 +330,7 @@ def sampling_line(a, model, dev, world):
     ts = Sch.get_timesteps_epoch(0, 1)
     smp = sampler_mod.Sampler(None, sa, Sch, [None, None, None])
     torch.manual_seed(0)
-    smp.sample(m, ts[-2:])                        # warm-up (plans, workspaces)
+    smp.sample(m, ts[-4:])                        # warm-up (plans, workspaces; the denoiser captures its forward graph on call 3)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

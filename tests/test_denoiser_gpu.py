@@ -167,3 +167,36 @@ def test_segmented_backward_equals_whole_backward():
     finally:
         mine.bwd_segmented = False
     assert (mine.flat_grad - whole).abs().max().item() <= tol
+
+
+def test_inference_graph_replay_matches_eager(monkeypatch):
+    """eval-mode forwards replay one CUDA graph after two warm-up calls: same outputs as the eager program, for changing
+    inputs, timesteps and weights (the graph reads the static input buffers and the bf16 weight mirror)"""
+    _, mine = build_pair(3, 32, seed=5)
+    mine.eval()
+    g = torch.Generator(device="cuda").manual_seed(12)
+    xs = [torch.rand(4, 3, 32, 32, device="cuda", generator=g) * 2 - 1 for _ in range(5)]
+    ts = [torch.randint(1, 1000, (4,), device="cuda", generator=g).float() for _ in range(5)]
+    with torch.no_grad():
+        graphed = [mine(x, t).sample.clone() for x, t in zip(xs, ts)]        # calls 3.. replay the graph
+        plan = next(iter(mine._plans.values()))
+        assert plan._fwd_graph is not None
+        mine.flat_param.mul_(1.2)                                               # weights change between sampler calls (EMA copy_to)
+        mine._bf16_stale = True
+        graphed_w = mine(xs[0], ts[0]).sample.clone()
+        monkeypatch.setenv("MDM_INFER_GRAPH", "0")
+        mine._plans.clear()
+        eager_w = mine(xs[0], ts[0]).sample.clone()
+        mine.flat_param.div_(1.2)
+        mine._bf16_stale = True
+        eager = [mine(x, t).sample.clone() for x, t in zip(xs, ts)]
+        assert next(iter(mine._plans.values()))._fwd_graph is None
+        eager2 = [mine(x, t).sample.clone() for x, t in zip(xs, ts)]
+    # yardstick: two EAGER evaluations of the same inputs differ by the bf16 run-to-run noise (fp32 atomics in the
+    # GroupNorm statistics reorder sums, roundings then flip and propagate through ~60 layers)
+    noise = max(rel_l2(a, b) for a, b in zip(eager, eager2))
+    tol = max(3.0 * noise, 2e-3)
+    for a, b in zip(graphed, eager):
+        assert rel_l2(a, b) <= tol, (rel_l2(a, b), noise)
+    assert rel_l2(graphed_w, eager_w) <= tol
+    assert rel_l2(graphed_w, graphed[0]) > 2 * tol                               # the weight change was seen
