@@ -1,5 +1,6 @@
 """Per-op device-time breakdown of one denoiser forward (inference plan): python scripts/profile_infer.py [B] [S]"""
 import os, sys, collections
+os.environ["MDM_INFER_GRAPH"] = "0"      # per-op events need the eager program
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "masked-diffusion-model_b200"))
 import torch
