@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--sample-size", type=int, default=128)
     ap.add_argument("--sample-batch", type=int, default=256)
-    ap.add_argument("--sample-steps", type=int, default=12)
+    ap.add_argument("--sample-steps", type=int, default=24)
     ap.add_argument("--ref-batch", type=int, default=8, help="samples per reference-arm step (bounded sample of the workload)")
     return ap.parse_args()
 

@@ -180,6 +180,12 @@ typedef struct mdm_conv_args {
 int mdm_conv_fprop(const mdm_conv_args* a, void* stream);
 int mdm_conv_dgrad(const mdm_conv_args* a, void* stream);   /* stride-1 layers */
 int mdm_conv_wgrad(const mdm_conv_args* a, void* stream);
+/* The GEMM kernel is persistent (one CTA per SM, static work list): a caller that runs another long kernel
+ * concurrently on a second stream (sampler.py's restoration loop: the serial mt19937 mask / noise generator under
+ * the denoiser) reserves n SMs for it, later launches use 148 - n CTAs.  Returns the previous value (n < 0 only
+ * queries); process-wide,
+ * read at launch time (a captured CUDA graph keeps the grid it was captured with). */
+int mdm_reserve_sms(int n);
 
 /* K2: GroupNorm (+SiLU) forward / backward (csrc/nn_kernels.cu).  x, y, dy, dx: NHWC bf16 with
  * channel strides; stats: [N][G][2] = (mean, rstd) fp32 written by fwd, read by bwd;

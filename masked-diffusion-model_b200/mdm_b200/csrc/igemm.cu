@@ -37,6 +37,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace mdm {
@@ -1030,12 +1032,22 @@ static int env_flag(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+// persistent grid: one CTA per SM -- minus the SMs the caller reserved for kernels that run concurrently on another
+// stream (mdm_reserve_sms: the sampler's serial mt19937 mask / noise generator shares the GPU with the denoiser, and a
+// static work list makes the whole GEMM wait for the CTA that shares its SM: 45.3 -> 42.5 ms per denoising step at
+// 256x3x128x128 with one SM left free); MDM_IGEMM_MAX_CTAS caps it from the environment
+static std::atomic<int> g_reserved_sms{0};
+static int igemm_grid_cap() {
+  static const int max_ctas = env_flag("MDM_IGEMM_MAX_CTAS", kNumSMs);
+  int cap = max_ctas < kNumSMs && max_ctas > 0 ? max_ctas : kNumSMs;
+  const int r = g_reserved_sms.load(std::memory_order_relaxed);
+  if (r > 0 && kNumSMs - r < cap) cap = kNumSMs - r;
+  return cap < 1 ? 1 : cap;
+}
+
 static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CUtensorMap& mA1, const CUtensorMap& mB1,
                         const CUtensorMap& mC, const CUtensorMap& mD, IgemmArgs& a, void* stream) {
-  // persistent grid: one CTA per SM -- minus the SMs reserved for a concurrently running collective (data-parallel
-  // overlap: NCCL's persistent CTAs would otherwise push a 148-CTA grid into a second wave); MDM_IGEMM_MAX_CTAS
-  static const int max_ctas = env_flag("MDM_IGEMM_MAX_CTAS", kNumSMs);
-  const int cap = max_ctas < kNumSMs && max_ctas > 0 ? max_ctas : kNumSMs;
+  const int cap = igemm_grid_cap();
   const int grid = a.num_work < cap ? a.num_work : cap;
   // eight epilogue warps once every CTA runs at least five work items (MDM_IGEMM_EPI8_MIN_ITEMS work items in total)
   static const int epi8_min = env_flag("MDM_IGEMM_EPI8_MIN_ITEMS", 5 * kNumSMs);
@@ -1127,7 +1139,7 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
   // 444 pair items + 136 single items = 3.5 waves instead of 4)
   static const int tail_split = env_flag("MDM_IGEMM_TAIL_SPLIT", 1);
   if (tail_split && halo_kind == 2 && a.splits == 1) {
-    const int grid_cap = kNumSMs;
+    const int grid_cap = igemm_grid_cap();
     const int rem = tiles % grid_cap;
     if (tiles > grid_cap && rem > 0 && 2 * rem <= grid_cap) {
       a.pair_work = tiles - rem;
@@ -1177,6 +1189,12 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
 using namespace mdm;
 
 extern "C" {
+
+int mdm_reserve_sms(int n) {
+  if (n < 0) return g_reserved_sms.load(std::memory_order_relaxed);   // query
+  if (n > kNumSMs - 1) n = kNumSMs - 1;
+  return g_reserved_sms.exchange(n, std::memory_order_relaxed);
+}
 
 int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
   MDM_CHECK_ARG(c && c->x && c->w && (c->y || c->y_f32), "conv_fprop: NULL pointer");

@@ -562,7 +562,7 @@ class _Plan:
         self._cur_lane = None
         self._lane_side_used = [False] * max(1, self.lanes)
         self._qbufs = []
-        self._fwd_graph, self._fwd_calls = None, 0
+        self._fwd_graphs, self._fwd_calls = {}, 0       # inference graphs by SM reservation (grids are baked in)
         self._infer_graph_ok = bool(int(os.environ.get("MDM_INFER_GRAPH", "1"))) and bool(getattr(m, "graph_inference", True))
         self.fused_stats = bool(int(os.environ.get("MDM_GN_FUSED_STATS", "1")))
         self._build()
@@ -1188,16 +1188,16 @@ class _Plan:
         # small shapes are otherwise bound by the ~250 Python launches per denoising step (64x3x32x32: GPU busy 2.2 ms
         # of a 7.9 ms step).  Training forwards are captured by the trainer together with the backward.
         if (not self.need_grad and self._infer_graph_ok and not torch.cuda.is_current_stream_capturing()):
-            if self._fwd_graph is not None:
-                self._fwd_graph.replay()
-                return self.out if getattr(self, "static_output", False) else self.out.clone()
-            if self._fwd_calls >= 2:
+            key = ops.reserve_sms(-1)
+            g = self._fwd_graphs.get(key)
+            if g is None and self._fwd_calls >= 2:
                 torch.cuda.synchronize(self.dev)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     for op in self.fwd:
                         op()
-                self._fwd_graph = g
+                self._fwd_graphs[key] = g
+            if g is not None:
                 g.replay()
                 return self.out if getattr(self, "static_output", False) else self.out.clone()
             self._fwd_calls += 1

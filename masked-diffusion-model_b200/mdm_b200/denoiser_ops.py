@@ -38,6 +38,7 @@ _lib.register({
     "mdm_conv_fprop": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_conv_dgrad": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_conv_wgrad": (c_int, [POINTER(ConvArgs), _P]),
+    "mdm_reserve_sms": (c_int, [c_int]),
     "mdm_gn_ws_floats": (_I64, [c_int, c_int, c_int, c_int]),
     "mdm_gn_fwd_kind": (c_int, [c_int, c_int, c_int, c_int]),
     "mdm_gn_silu_fwd_q": (c_int, [_P, _LL, _P, _LL, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
@@ -118,6 +119,12 @@ def conv_fprop(x, w, y, N, H, W, ksize=3, stride=1, bias=None, rowvec=None, resi
     a.qsum = _dp(qsum)          # fused GroupNorm statistics of the output: qsum[N, cout/4, 2] += quad (sum, sumsq)
     _splitk(a, x.device)
     check(lib().mdm_conv_fprop(ctypes.byref(a), stream_ptr(x.device)))
+
+
+def reserve_sms(n):
+    """leave n SMs out of the persistent GEMM grids (a concurrent kernel on another stream owns them); returns the
+    previous reservation (n < 0: query only)"""
+    return int(lib().mdm_reserve_sms(int(n)))
 
 
 def conv_dgrad(dy, w, dx, N, H, W, ksize=3, resid=None, accumulate=False, dx_f32=None, cin=None):

@@ -16,6 +16,8 @@ them; otherwise `visual_list` keeps its 11 slots with `None`.
 Unsupported reference branches raise the same errors the reference raises (q11, q12)."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -160,59 +162,67 @@ class Sampler:
         x_in_next = torch.empty_like(x_t)
         difference_prev = None
 
-        with torch.no_grad():
-            for i in range(T - 1, -1, -1):
-                t = timesteps_used_epoch[i]
-                time = time_tensor(t)
-                next_t = time - 1 if i > 0 else time
-                # ---- side stream: masks of this iteration, shift of the next one ---------------
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    n_t = S.get_black_area_num_pixels_time(time)
-                    n_next = S.get_black_area_num_pixels_time(next_t)
-                    cur_n = mb_n[i & 1]
-                    prev_n = mb_n[(i + 1) & 1]
-                    if dep == "independent":
-                        S.make_mask_bytes(n_t, dev, out=mb_t)
-                        S.make_mask_bytes(n_next, dev, out=cur_n)
-                        m_t_bytes = mb_t
-                    elif dep == "dependent_prev":
-                        S.make_mask_bytes(n_next, dev, out=cur_n)
-                        m_t_bytes = prev_n                      # mask drawn for t in the previous iteration
-                    else:  # dependent_t: one uniform field, two thresholds
-                        if a.select_degrade_pixel != "thresholding":
-                            raise UnboundLocalError("masks_t")
-                        rng.threshold_mask(n_t.double(), N, mask_ch * hw, ratio2=n_next.double(), out=mb_t, out2=cur_n)
-                        m_t_bytes = mb_t
-                    if i > 0:
-                        time_n = time_tensor(timesteps_used_epoch[i - 1])
-                        shift_n = self._draw_shift(S, time_n, zeros_like)
-                        shift_ne, nb, nc, np_ = _strides_for(shift_n.float(), N, C, H, H)
-                    else:
-                        shift_ne, nb, nc, np_ = None, 0, 0, 0
-                # ---- main stream: denoiser ------------------------------------------------------
-                net = model(x_in, time).sample
-                if net.dtype != torch.float32 or not net.is_contiguous():
-                    net = net.float().contiguous()
-                main.wait_stream(side)
-                # ---- fused update (K5) ----------------------------------------------------------
-                last = (i == 0)
-                update = 0 if (last and momentum) else 1       # sampler.py:204-216
-                if last and not momentum:
-                    update = 0                                  # base_sampling breaks before the update
-                check(lib().mdm_sampler_step(
-                    ptr(x_t), ptr(net), ptr(shift_e), sb, sc, sp, ptr(m_t_bytes), ptr(cur_n), mask_ch,
-                    mode, const, area, momentum, update, ptr(shift_ne), nb, nc, np_,
-                    ptr(x_next), ptr(x_in_next) if not last else None,
-                    ptr(sample_0) if (last or history) else None,      # x0_hat is only read after the last iteration
-                    ptr(ws), N, C, hw,
-                    stream_ptr(dev)))
-                if history:
-                    difference_prev = self._record(hist, T - i, x_t, shift_e, x_in, net, sample_0, m_t_bytes, cur_n,
-                                                   mask_ch, mode, const, area, dep, last, momentum, difference_prev)
-                x_t, x_next = x_next, x_t
-                x_in, x_in_next = x_in_next, x_in
-                shift_e, sb, sc, sp = shift_ne, nb, nc, np_
+        # the mask / noise generator is a serial one-CTA kernel that runs on the side stream for about half of every
+        # denoising step: leave it an SM of its own, or every persistent GEMM launched meanwhile waits for the CTA that
+        # shares its SM (static work lists; measured 45.3 -> 42.5 ms per step at 256x3x128x128)
+        from mdm_b200 import denoiser_ops as _dops
+        reserved_before = _dops.reserve_sms(int(os.environ.get("MDM_SAMPLER_RESERVE_SMS", "1")))
+        try:
+            with torch.no_grad():
+                for i in range(T - 1, -1, -1):
+                    t = timesteps_used_epoch[i]
+                    time = time_tensor(t)
+                    next_t = time - 1 if i > 0 else time
+                    # ---- side stream: masks of this iteration, shift of the next one ---------------
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        n_t = S.get_black_area_num_pixels_time(time)
+                        n_next = S.get_black_area_num_pixels_time(next_t)
+                        cur_n = mb_n[i & 1]
+                        prev_n = mb_n[(i + 1) & 1]
+                        if dep == "independent":
+                            S.make_mask_bytes(n_t, dev, out=mb_t)
+                            S.make_mask_bytes(n_next, dev, out=cur_n)
+                            m_t_bytes = mb_t
+                        elif dep == "dependent_prev":
+                            S.make_mask_bytes(n_next, dev, out=cur_n)
+                            m_t_bytes = prev_n                      # mask drawn for t in the previous iteration
+                        else:  # dependent_t: one uniform field, two thresholds
+                            if a.select_degrade_pixel != "thresholding":
+                                raise UnboundLocalError("masks_t")
+                            rng.threshold_mask(n_t.double(), N, mask_ch * hw, ratio2=n_next.double(), out=mb_t, out2=cur_n)
+                            m_t_bytes = mb_t
+                        if i > 0:
+                            time_n = time_tensor(timesteps_used_epoch[i - 1])
+                            shift_n = self._draw_shift(S, time_n, zeros_like)
+                            shift_ne, nb, nc, np_ = _strides_for(shift_n.float(), N, C, H, H)
+                        else:
+                            shift_ne, nb, nc, np_ = None, 0, 0, 0
+                    # ---- main stream: denoiser ------------------------------------------------------
+                    net = model(x_in, time).sample
+                    if net.dtype != torch.float32 or not net.is_contiguous():
+                        net = net.float().contiguous()
+                    main.wait_stream(side)
+                    # ---- fused update (K5) ----------------------------------------------------------
+                    last = (i == 0)
+                    update = 0 if (last and momentum) else 1       # sampler.py:204-216
+                    if last and not momentum:
+                        update = 0                                  # base_sampling breaks before the update
+                    check(lib().mdm_sampler_step(
+                        ptr(x_t), ptr(net), ptr(shift_e), sb, sc, sp, ptr(m_t_bytes), ptr(cur_n), mask_ch,
+                        mode, const, area, momentum, update, ptr(shift_ne), nb, nc, np_,
+                        ptr(x_next), ptr(x_in_next) if not last else None,
+                        ptr(sample_0) if (last or history) else None,      # x0_hat is only read after the last iteration
+                        ptr(ws), N, C, hw,
+                        stream_ptr(dev)))
+                    if history:
+                        difference_prev = self._record(hist, T - i, x_t, shift_e, x_in, net, sample_0, m_t_bytes, cur_n,
+                                                       mask_ch, mode, const, area, dep, last, momentum, difference_prev)
+                    x_t, x_next = x_next, x_t
+                    x_in, x_in_next = x_in_next, x_in
+                    shift_e, sb, sc, sp = shift_ne, nb, nc, np_
+        finally:
+            _dops.reserve_sms(reserved_before)
         S.release_rng_to_torch()
         visual = hist if history else [None] * len(HISTORY_NAMES)
         return sample_0, visual

@@ -180,7 +180,14 @@ def test_inference_graph_replay_matches_eager(monkeypatch):
     with torch.no_grad():
         graphed = [mine(x, t).sample.clone() for x, t in zip(xs, ts)]        # calls 3.. replay the graph
         plan = next(iter(mine._plans.values()))
-        assert plan._fwd_graph is not None
+        assert len(plan._fwd_graphs) == 1
+        from mdm_b200 import denoiser_ops as dops
+        assert dops.reserve_sms(1) == 0                                           # the sampler's reservation: 147-CTA GEMM grids
+        try:
+            reserved = mine(xs[1], ts[1]).sample.clone()
+            assert len(plan._fwd_graphs) == 2 and dops.reserve_sms(-1) == 1
+        finally:
+            dops.reserve_sms(0)
         mine.flat_param.mul_(1.2)                                               # weights change between sampler calls (EMA copy_to)
         mine._bf16_stale = True
         graphed_w = mine(xs[0], ts[0]).sample.clone()
@@ -190,7 +197,7 @@ def test_inference_graph_replay_matches_eager(monkeypatch):
         mine.flat_param.div_(1.2)
         mine._bf16_stale = True
         eager = [mine(x, t).sample.clone() for x, t in zip(xs, ts)]
-        assert next(iter(mine._plans.values()))._fwd_graph is None
+        assert not next(iter(mine._plans.values()))._fwd_graphs
         eager2 = [mine(x, t).sample.clone() for x, t in zip(xs, ts)]
     # yardstick: two EAGER evaluations of the same inputs differ by the bf16 run-to-run noise (fp32 atomics in the
     # GroupNorm statistics reorder sums, roundings then flip and propagate through ~60 layers)
@@ -199,4 +206,5 @@ def test_inference_graph_replay_matches_eager(monkeypatch):
     for a, b in zip(graphed, eager):
         assert rel_l2(a, b) <= tol, (rel_l2(a, b), noise)
     assert rel_l2(graphed_w, eager_w) <= tol
+    assert rel_l2(reserved, eager[1]) <= tol
     assert rel_l2(graphed_w, graphed[0]) > 2 * tol                               # the weight change was seen
