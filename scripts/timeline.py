@@ -85,5 +85,15 @@ main = max(by_stream.values(), key=len)
 gaps = [main[i + 1]["ts"] - (main[i]["ts"] + main[i]["dur"]) for i in range(len(main) - 1)]
 gaps = [g for g in gaps if g < 1000]
 print(f"main stream: {len(main)/n:.0f} kernels/step, kernel time {sum(e['dur'] for e in main)/n:.0f} us, gaps total {sum(g for g in gaps if g > 0)/n:.0f} us, median gap {sorted(gaps)[len(gaps)//2]:.2f} us")
+# per-launch list of the LAST step (start relative to its first kernel, duration, stream, grid, block, name)
+if n >= 1:
+    per = len(ks) // n
+    last_step = ks[-per:]
+    base = last_step[0]["ts"]
+    with open("gpurun_out/timeline_launches.csv", "w") as f:
+        f.write("start_us,dur_us,stream,grid,block,kernel\n")
+        for e in last_step:
+            a = e.get("args", {})
+            f.write(f"{e['ts'] - base:.1f},{e['dur']:.1f},{a.get('stream', '')},{'x'.join(map(str, a.get('grid', [])))},{'x'.join(map(str, a.get('block', [])))},\"{short(e['name'])}\"\n")
 json.dump({"wall_us_per_step": wall / n, "busy_us": busy / n, "by_kernel": {k: v for k, v in agg.items()}}, open("gpurun_out/timeline.json", "w"))
 os.remove(path)
