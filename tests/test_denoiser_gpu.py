@@ -18,11 +18,11 @@ def rel_l2(a, b):
     return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-20)).item()
 
 
-def build_pair(C, S, seed=0, num_attention=1):
+def build_pair(C, S, seed=0, num_attention=1, base=128):
     from mdm_b200.denoiser import UNet2DModelB200, default_config
     torch.manual_seed(seed)
-    ref = UNet2DModelRef(**unet_config(C, S, num_attention)).cuda()
-    mine = UNet2DModelB200(device="cuda", **default_config(C, S, num_attention))
+    ref = UNet2DModelRef(**unet_config(C, S, num_attention, base=base)).cuda()
+    mine = UNet2DModelB200(device="cuda", **default_config(C, S, num_attention, base=base))
     mine.load_state_dict(ref.state_dict())
     return ref, mine
 
@@ -41,9 +41,15 @@ def test_param_count_and_state_dict_roundtrip():
     assert UNet2DModelB200(device="cuda", **default_config(1, 32)).num_parameters() == 113_668_609
 
 
-@pytest.mark.parametrize("C,S,B", [(3, 32, 4), (1, 32, 3), (3, 64, 2)])
-def test_forward_matches_fp32_oracle(C, S, B):
-    ref, mine = build_pair(C, S)
+# BASELINE configs: c2 / c1 / c3 shapes, the c4 sampling shape (3x128x128: attention over 64 tokens), 3x256x256
+# (attention over 16x16 = 256 tokens, the kernel's maximum), and the c5 architecture (ch=256: 454.46 M parameters) at
+# a reduced and at its full 3x256x256 resolution
+@pytest.mark.parametrize("C,S,B,base", [(3, 32, 4, 128), (1, 32, 3, 128), (3, 64, 2, 128), (3, 128, 2, 128),
+                                        (3, 256, 1, 128), (3, 64, 2, 256), (3, 256, 1, 256)])
+def test_forward_matches_fp32_oracle(C, S, B, base):
+    ref, mine = build_pair(C, S, base=base)
+    if base == 256:
+        assert mine.num_parameters() == 454_461_443                          # SURVEY.md 8c anchor
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.rand(B, C, S, S, device="cuda", generator=g) * 2 - 1
     t = torch.tensor([1.0, 250.0, 999.0, 37.0][:B], device="cuda")
@@ -61,9 +67,9 @@ def test_forward_matches_fp32_oracle(C, S, B):
     assert err <= 2e-2 and err <= 1.5 * autocast_err + 2e-3, (err, autocast_err)
 
 
-def test_backward_matches_fp32_oracle():
-    C, S, B = 3, 32, 4
-    ref, mine = build_pair(C, S, seed=3)
+@pytest.mark.parametrize("C,S,B,base", [(3, 32, 4, 128), (3, 64, 4, 128), (3, 32, 4, 256)])
+def test_backward_matches_fp32_oracle(C, S, B, base):
+    ref, mine = build_pair(C, S, seed=3, base=base)
     g = torch.Generator(device="cuda").manual_seed(2)
     x = torch.rand(B, C, S, S, device="cuda", generator=g) * 2 - 1
     x0 = torch.rand(B, C, S, S, device="cuda", generator=g) * 2 - 1
