@@ -127,7 +127,11 @@ class Sampler:
         history = bool(getattr(a, "sample_history", False))
         hist = None
         if history:
-            hist = [torch.zeros(T + 1, N, C, H, H) for _ in HISTORY_NAMES]
+            # the eleven history tensors of sampler.py:116-126: recorded on the device (no per-step synchronising
+            # device-to-host copies) when they fit the budget, handed back as CPU tensors like the reference's
+            hist_bytes = len(HISTORY_NAMES) * (T + 1) * N * C * H * H * 4
+            hist_dev = dev if hist_bytes <= int(os.environ.get("MDM_HISTORY_DEVICE_BYTES", str(8 << 30))) else "cpu"
+            hist = [torch.zeros(T + 1, N, C, H, H, device=hist_dev) for _ in HISTORY_NAMES]
 
         mask_ch = S._mask_channels()
         mode, const, area = S._fill_mode(a.mean_option, a.mean_area)
@@ -224,7 +228,7 @@ class Sampler:
         finally:
             _dops.reserve_sms(reserved_before)
         S.release_rng_to_torch()
-        visual = hist if history else [None] * len(HISTORY_NAMES)
+        visual = [h.cpu() for h in hist] if history else [None] * len(HISTORY_NAMES)
         return sample_0, visual
 
     # -- opt-in history (visualisation; not on the timed path) ----------------------------------
@@ -237,22 +241,22 @@ class Sampler:
         m_n = mb_n.view(N, mask_ch, H, H).float()
         d_t = S.degrade_with_mask(s0, m_t, self.args.mean_option, self.args.mean_area)
         d_n = S.degrade_with_mask(s0, m_n, self.args.mean_option, self.args.mean_area)
-        hist[0][k] = x_t.cpu()
-        hist[1][k] = full(shift).cpu()
-        hist[2][k] = x_in.cpu()
-        hist[3][k] = net.cpu()
-        hist[4][k] = (x_in + net).cpu()
-        hist[5][k] = s0.cpu()
+        hist[0][k] = x_t
+        hist[1][k] = full(shift)
+        hist[2][k] = x_in
+        hist[3][k] = net
+        hist[4][k] = (x_in + net)
+        hist[5][k] = s0
         if dep == "dependent_prev":
-            hist[6][k] = full(m_n).cpu()
+            hist[6][k] = full(m_n)
         else:
-            hist[6][k] = full(m_t).cpu()
-            hist[7][k] = full(m_n).cpu()
+            hist[6][k] = full(m_t)
+            hist[7][k] = full(m_n)
         if last and not momentum:
             return difference_prev                      # base_sampling breaks before recording
-        hist[8][k] = d_t.cpu()
-        hist[10][k] = d_n.cpu()
+        hist[8][k] = d_t
+        hist[10][k] = d_n
         difference = (d_n - d_t) if not (last and momentum) else difference_prev   # quirk q21
         if difference is not None:
-            hist[9][k] = difference.cpu()
+            hist[9][k] = difference
         return difference

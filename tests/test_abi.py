@@ -53,3 +53,17 @@ def test_no_cpu_fallback():
         with pytest.raises(RuntimeError):
             S.degrade_training(torch.tensor([0.5, 0.5], dtype=torch.float64), x, "degraded_area", "image-wise")
     assert _lib.lib().mdm_version() >= 100
+
+
+def test_reserve_sms_is_host_state():
+    """mdm_reserve_sms only records how many SMs later persistent GEMM launches leave free (host side, no GPU needed):
+    set / query / clamp / restore"""
+    l = _lib.lib()
+    before = l.mdm_reserve_sms(3)
+    try:
+        assert l.mdm_reserve_sms(-1) == 3            # query
+        assert l.mdm_reserve_sms(10_000) == 3        # clamped to 147 of the 148 SMs
+        assert l.mdm_reserve_sms(-1) == 147
+    finally:
+        l.mdm_reserve_sms(before)
+    assert l.mdm_reserve_sms(-1) == before

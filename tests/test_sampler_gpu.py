@@ -20,11 +20,13 @@ def tol_for(a):
 
 
 @pytest.mark.parametrize("name", list(SAMPLER_CASES))
-@pytest.mark.parametrize("history", [False, True])
-def test_sampler_against_reference_golden(golden, name, history):
+@pytest.mark.parametrize("history", [False, True, "host"])
+def test_sampler_against_reference_golden(golden, name, history, monkeypatch):
     g = golden("sampler")
     a = mk_args(data_size=16, ddpm_num_steps=10, sample_num=4, **SAMPLER_CASES[name])
-    a.sample_history = history
+    if history == "host":            # history tensors too large for the device budget: recorded straight into CPU tensors
+        monkeypatch.setenv("MDM_HISTORY_DEVICE_BYTES", "0")
+    a.sample_history = bool(history)
     S = scheduler.Scheduler(a)
     Tp = S.update_ddpm_num_steps(10)
     ts = S.get_timesteps_epoch(0, 1)
@@ -36,6 +38,7 @@ def test_sampler_against_reference_golden(golden, name, history):
     key, pos = torch_state_words(torch.get_rng_state().numpy())     # released back to torch's CPU generator
     assert pos == gp and np.array_equal(key, gk)
     if history:
+        assert all(not v.is_cuda for v in vis)                     # handed back as CPU tensors, like the reference's
         np.testing.assert_allclose(vis[0].numpy(), g[f"{name}/sample_t_list"], atol=tol_for(a), rtol=0)
         np.testing.assert_allclose(vis[5].numpy(), g[f"{name}/sample_0_list"], atol=tol_for(a), rtol=0)
         np.testing.assert_allclose(vis[8].numpy(), g[f"{name}/degraded_t_list"], atol=tol_for(a), rtol=0)
