@@ -296,8 +296,8 @@ def roofline_pass(tr, model, batch_dev, peaks):
         "bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv/linear: fprop+dgrad+wgrad)",
         "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
         # dram__bytes_read.sum + dram__bytes_write.sum per igemm launch, averaged over the 441 igemm launches of the ncu
-        # launch list of this command (profiles/launches_r01d.csv: 7.33 GB read + 0.15 GB written, cold cache)
-        "traffic": 16.96e6, "traffic_source": "profiles/launches_r01d.csv (ncu, per launch, average over the step's igemm launches)",
+        # launch list of this command (profiles/launches_r01f.csv: 7.45 GB read + 0.13 GB written, cold cache)
+        "traffic": 17.20e6, "traffic_source": "profiles/launches_r01f.csv (ncu, per launch, average over the step's igemm launches)",
         "launches_per_step": len(rec), "avg_launch_us": round(1e3 * total_ms / max(1, len(rec)), 2),
         "kernel_ms_per_step": round(total_ms, 3),
         "by_kind": {k: {"launches": v[0], "tflops": round(v[1] / (v[2] * 1e-3) / 1e12, 2) if v[2] > 0 else None,
