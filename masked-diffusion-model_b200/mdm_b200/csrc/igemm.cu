@@ -68,7 +68,10 @@ constexpr int SMEM_BIAS_OFF = SMEM_EPI_OFF + 2 * EPI_BYTES;   // 128 floats
 constexpr int SMEM_QACC_OFF = SMEM_BIAS_OFF + 512;            // [4 epilogue warps][64] floats: per-tile quad (sum, sumsq) partials
 constexpr int SMEM_BAR_OFF = SMEM_QACC_OFF + 1024;
 constexpr int SMEM_ONES_OFF = 3 * (A_BYTES + 2 * B_BYTES);   // mode 1 only (ring = 3 x 48 KB): the unused ring tail
-constexpr int IGEMM_SMEM = SMEM_BAR_OFF + 256 + 1024 /*alignment slack*/;
+// dynamic work distribution (kDyn): a ring of (this item, next item) pairs published by the A producer
+constexpr int WQ_SLOTS = 4;
+constexpr int SMEM_WQ_OFF = SMEM_BAR_OFF + 256;   // wq_full[4], wq_empty[4] (mbarriers), wq[4] (int2)
+constexpr int IGEMM_SMEM = SMEM_BAR_OFF + 512 + 1024 /*alignment slack*/;
 constexpr int TMEM_COLS = 512;                 // two accumulator stages of 256 fp32 columns
 // wgrad bias gradient: D2[co][0..15] = sum_pix dY[pix][co] * 1 lives in the (unused) second half of the stage of a
 // single-entry work item (the first item of every cout tile), so both stages stay 256 columns wide
@@ -232,6 +235,9 @@ struct IgemmArgs {
   // squares) of every 4-channel quad of sample n (fp32 atomics; the consumer combines cpg/4 quads per group).
   // Needs H*W % 128 == 0: the 128 rows of a tile belong to one sample.
   float* qsum;
+  // dynamic work distribution (kDyn instantiations): sched[0] = items handed out beyond the first one of every CTA,
+  // sched[1] = CTAs that have finished; the last CTA zeroes both for the next launch that gets this pair
+  int* sched;
   // wgrad
   int taps;             // valid taps
   int ci_total;
@@ -329,6 +335,96 @@ constexpr uint32_t DESC_LO_KMAJOR = (16u >> 4) << 16;     // LBO (unused for swi
 constexpr uint32_t DESC_LO_MNMAJOR = (8192u >> 4) << 16;  // LBO = distance between the two 64-wide MN atoms
 __device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
+// ---- work distribution --------------------------------------------------------------------------------------------
+// static (kDyn = false): CTA b runs items b, b + grid, b + 2 grid, ... -- every role computes the sequence itself.
+// dynamic (kDyn = true): item b first, then whatever an atomic counter hands out.  A persistent CTA that shares its SM
+// with a kernel of another stream (the sampler's mt19937 generator, NCCL's channels) then simply takes fewer items,
+// instead of making the whole grid wait for it.  The A producer owns the sequence: it fetches two items ahead (the
+// atomic's latency hides behind an item's loads) and publishes (item, next item) pairs through a shared-memory ring
+// to the B producer, the MMA issuer and the epilogue warps; -1 ends the sequence.
+template <bool kDyn>
+struct WorkPub;
+template <>
+struct WorkPub<false> {
+  int w, step, n;
+  __device__ __forceinline__ WorkPub(const IgemmArgs& a, int first, int step_, uint64_t*, uint64_t*, volatile int2*)
+      : w(first - step_), step(step_), n(a.num_work) {}
+  __device__ __forceinline__ int next() {
+    w += step;
+    return w < n ? w : -1;
+  }
+};
+template <>
+struct WorkPub<true> {
+  int first, w1, w2, step, n, slot;
+  uint32_t ph;
+  bool started;
+  int* ctr;
+  uint64_t *full, *empty;
+  volatile int2* q;
+  __device__ __forceinline__ WorkPub(const IgemmArgs& a, int first_, int step_, uint64_t* full_, uint64_t* empty_, volatile int2* q_)
+      : first(first_), w1(-1), w2(-1), step(step_), n(a.num_work), slot(0), ph(0), started(false), ctr(a.sched), full(full_),
+        empty(empty_), q(q_) {}
+  __device__ __forceinline__ int fetch() {
+    const int t = atomicAdd(ctr, 1) + step;
+    return t < n ? t : -1;
+  }
+  __device__ __forceinline__ int next() {
+    int w;
+    if (!started) {
+      started = true;
+      w = first < n ? first : -1;
+      w1 = w >= 0 ? fetch() : -1;
+    } else {
+      w = w1;
+      w1 = w2;
+    }
+    w2 = w1 >= 0 ? fetch() : -1;     // needed at the call after this one
+    mbar_wait(&empty[slot], ph ^ 1);
+    q[slot].x = w;
+    q[slot].y = w1;
+    mbar_arrive(&full[slot]);        // release: the pair is visible to whoever acquires this phase
+    if (++slot == WQ_SLOTS) { slot = 0; ph ^= 1; }
+    return w;
+  }
+};
+template <bool kDyn>
+struct WorkSub;
+template <>
+struct WorkSub<false> {
+  int w, step, n;
+  __device__ __forceinline__ WorkSub(const IgemmArgs& a, int first, int step_, uint64_t*, uint64_t*, volatile int2*, bool)
+      : w(first - step_), step(step_), n(a.num_work) {}
+  __device__ __forceinline__ int next(int& wn) {
+    w += step;
+    wn = w + step < n ? w + step : -1;
+    return w < n ? w : -1;
+  }
+};
+template <>
+struct WorkSub<true> {
+  int slot;
+  uint32_t ph;
+  bool whole_warp;   // all 32 lanes run the loop (epilogue warps): one arrival per warp, after every lane has read
+  uint64_t *full, *empty;
+  volatile int2* q;
+  __device__ __forceinline__ WorkSub(const IgemmArgs&, int, int, uint64_t* full_, uint64_t* empty_, volatile int2* q_, bool whole_warp_)
+      : slot(0), ph(0), whole_warp(whole_warp_), full(full_), empty(empty_), q(q_) {}
+  __device__ __forceinline__ int next(int& wn) {
+    mbar_wait(&full[slot], ph);
+    const int w = q[slot].x;
+    wn = q[slot].y;
+    if (whole_warp) {
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot]);
+    } else {
+      mbar_arrive(&empty[slot]);
+    }
+    if (++slot == WQ_SLOTS) { slot = 0; ph ^= 1; }
+    return w;
+  }
+};
+
 // kMode 0: activation GEMM (fprop / dgrad), 1: wgrad.  kHalo: see HALO_* above.  Template parameters keep the
 // single-thread producer / MMA-issue loops minimal: those loops pace the tensor pipe (4 MMAs = 256 cycles per
 // iteration), every extra instruction in them showed up 1:1 in the measured throughput.
@@ -339,7 +435,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return
 // kStats: the store epilogue also accumulates GroupNorm quad sums of the output (IgemmArgs::qsum); a template
 // parameter so that the plain instantiations carry none of that code (measured: +4 % on the level-0 convolutions when
 // it was a run-time branch -- the store epilogue of a 256 x 128 item is as long as its main loop).
-template <int kMode, bool kHalo, int kMT, bool kStats = false>
+template <int kMode, bool kHalo, int kMT, bool kStats = false, bool kDyn = false>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
              const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
@@ -374,6 +470,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
   uint64_t* c_full_bar = tmem_empty_bar + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_full_bar + 2);
+  uint64_t* wq_full = reinterpret_cast<uint64_t*>(smem + SMEM_WQ_OFF);   // [WQ_SLOTS] (kDyn)
+  uint64_t* wq_empty = wq_full + WQ_SLOTS;
+  volatile int2* wq = reinterpret_cast<volatile int2*>(wq_empty + WQ_SLOTS);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -391,6 +490,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], blockDim.x == IGEMM_THREADS ? 8 : 4);   // one arrival per epilogue warp
       mbar_init(&c_full_bar[s], 1);
+    }
+    if (kDyn) {
+      for (int s = 0; s < WQ_SLOTS; ++s) {
+        mbar_init(&wq_full[s], 1);
+        mbar_init(&wq_empty[s], 2 + (blockDim.x == IGEMM_THREADS ? 8 : 4));   // B producer, MMA issuer, one per epilogue warp
+      }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapA0) : "memory");
@@ -418,7 +523,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     // ============================== TMA producer: A operand ==================================
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    for (int w = w_first; w < args.num_work; w += w_step) {
+    WorkPub<kDyn> feed(args, w_first, w_step, wq_full, wq_empty, wq);
+    for (int w = feed.next(); w >= 0; w = feed.next()) {
       const Work k = decode_work(args, w);
       if (kMode == 0) {
         int w0, h0, n0, w1 = 0, h1 = 0, n1 = 0;
@@ -485,9 +591,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   } else if (warp == 6) {
    if (elect_one()) {
     // ============================== TMA producer: B operand ==================================
-    int sb = 0;
+    int sb = 0, wn_unused;
     uint32_t pb = 0;
-    for (int w = w_first; w < args.num_work; w += w_step) {
+    WorkSub<kDyn> feed(args, w_first, w_step, wq_full, wq_empty, wq, false);
+    for (int w = feed.next(wn_unused); w >= 0; w = feed.next(wn_unused)) {
       const Work k = decode_work(args, w);
       if (kMode == 0) {
         const int ncol0 = k.n_tile * TILE_N;
@@ -557,9 +664,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     const uint32_t kstep_a = a_mn ? (2048u >> 4) : (32u >> 4);
     const uint32_t kstep_b = b_mn ? (2048u >> 4) : (32u >> 4);
     const uint32_t lo_halo0 = ((smem_u32(a_ring) >> 4) & 0x3FFF) | DESC_LO_KMAJOR;
-    int sa = 0, sb = 0, local = 0;
+    int sa = 0, sb = 0, local = 0, wn_unused;
     uint32_t pa = 0, pb = 0;
-    for (int w = w_first; w < args.num_work; w += w_step, ++local) {
+    WorkSub<kDyn> feed(args, w_first, w_step, wq_full, wq_empty, wq, false);
+    for (int w = feed.next(wn_unused); w >= 0; w = feed.next(wn_unused), ++local) {
       const Work k = decode_work(args, w);
       const int acc = local % kAccStages;
       mbar_wait(&tmem_empty_bar[acc], ((local / kAccStages) & 1) ^ 1);   // the epilogue has drained this accumulator
@@ -664,7 +772,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       load_c(k0.m_tile * kMT + k0.half0, k0.n_tile, 0);
     }
     int hl = 0;   // 128 x 128 tiles finished by this CTA (staging buffer / C-tile barrier parity)
-    for (int w = w_first; w < args.num_work; w += w_step, ++local) {
+    int wn;       // the item after this one (-1: none): its C tile is prefetched below
+    WorkSub<kDyn> feed(args, w_first, w_step, wq_full, wq_empty, wq, true);
+    for (int w = feed.next(wn); w >= 0; w = feed.next(wn), ++local) {
       const Work k = decode_work(args, w);
       const int acc = local % kAccStages;
       const uint32_t acc_parity = (local / kAccStages) & 1;
@@ -795,8 +905,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           if (args.has_c) {      // prefetch the C tile of the next 128 x 128 tile into the other staging buffer
             if (half + 1 < k.nh) {
               load_c(m128 + 1, k.n_tile, buf ^ 1);
-            } else if (w + w_step < args.num_work) {
-              const Work kn = decode_work(args, w + w_step);
+            } else if (wn >= 0) {
+              const Work kn = decode_work(args, wn);
               load_c(kn.m_tile * kMT + kn.half0, kn.n_tile, buf ^ 1);
             }
           }
@@ -868,6 +978,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+  if (kDyn && threadIdx.x == 0) {   // this CTA has fetched its last item: the last CTA to get here re-arms the counters
+    __threadfence();
+    if (atomicAdd(args.sched + 1, 1) == (int)gridDim.x - 1) {
+      args.sched[0] = 0;
+      args.sched[1] = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -990,17 +1108,23 @@ static void pixel_box(int count, int H, int W, int* bw, int* bh, int* bn) {
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
+template <int kMode, bool kHalo, int kMT, bool kStats>
+static cudaError_t set_smem_attr() {
+  cudaError_t e = cudaFuncSetAttribute(igemm_kernel<kMode, kHalo, kMT, kStats, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(igemm_kernel<kMode, kHalo, kMT, kStats, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM);
+}
 static int ensure_smem_attr() {
   static bool done = false;
   if (!done) {
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
-    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA((set_smem_attr<0, false, 1, false>()));
+    MDM_CUDA((set_smem_attr<0, false, 2, false>()));
+    MDM_CUDA((set_smem_attr<0, true, 1, false>()));
+    MDM_CUDA((set_smem_attr<0, true, 2, false>()));
+    MDM_CUDA((set_smem_attr<1, false, 2, false>()));
+    MDM_CUDA((set_smem_attr<0, true, 2, true>()));
+    MDM_CUDA((set_smem_attr<0, false, 2, true>()));
+    MDM_CUDA((set_smem_attr<0, false, 1, true>()));
     done = true;
   }
   return MDM_OK;
@@ -1045,6 +1169,24 @@ static int igemm_grid_cap() {
   return cap < 1 ? 1 : cap;
 }
 
+// dynamic work distribution: pairs of ints from a caller-allocated, zeroed device buffer (mdm_set_sched_workspace),
+// handed out round-robin so that GEMMs in flight on different streams never share a pair; every launch leaves its pair
+// zeroed again.  MDM_IGEMM_DYNAMIC: 0 = static lists, 1 (default) = dynamic wherever a CTA runs >= 2 items, 2 = every
+// launch (tests).  Measured (B200, one gpurun call): training step 3x32x32 b128 8.12 ms dynamic vs 8.10 static (noise);
+// sampling 256x3x128x128 with the mt19937 generator co-running and NO reserved SM 42.5 ms per step dynamic vs 44.5
+// static (43.2 static with one SM reserved).
+static int* g_sched_base = nullptr;
+static int g_sched_pairs = 0, g_sched_dev = -1;
+static std::atomic<unsigned> g_sched_seq{0};
+
+template <int kMode, bool kHalo, int kMT, bool kStats>
+static void launch_variant(bool dyn, int grid, int block, cudaStream_t st, const CUtensorMap& mA0, const CUtensorMap& mB0,
+                           const CUtensorMap& mA1, const CUtensorMap& mB1, const CUtensorMap& mC, const CUtensorMap& mD,
+                           const IgemmArgs& a) {
+  if (dyn) launch_pdl(igemm_kernel<kMode, kHalo, kMT, kStats, true>, dim3(grid), dim3(block), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else launch_pdl(igemm_kernel<kMode, kHalo, kMT, kStats, false>, dim3(grid), dim3(block), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+}
+
 static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CUtensorMap& mA1, const CUtensorMap& mB1,
                         const CUtensorMap& mC, const CUtensorMap& mD, IgemmArgs& a, void* stream) {
   const int cap = igemm_grid_cap();
@@ -1053,14 +1195,22 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
   static const int epi8_min = env_flag("MDM_IGEMM_EPI8_MIN_ITEMS", 5 * kNumSMs);
   const int IGEMM_BLOCK = a.num_work >= epi8_min ? IGEMM_THREADS : IGEMM_THREADS_NARROW;
   cudaStream_t st = as_stream(stream);
-  if (a.mode == 1) launch_pdl(igemm_kernel<1, false, 2>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.qsum && a.halo) launch_pdl(igemm_kernel<0, true, 2, true>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.qsum && a.mt == 2) launch_pdl(igemm_kernel<0, false, 2, true>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.qsum) launch_pdl(igemm_kernel<0, false, 1, true>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.halo && a.mt == 2) launch_pdl(igemm_kernel<0, true, 2>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.halo) launch_pdl(igemm_kernel<0, true, 1>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else if (a.mt == 2) launch_pdl(igemm_kernel<0, false, 2>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-  else launch_pdl(igemm_kernel<0, false, 1>, dim3(grid), dim3(IGEMM_BLOCK), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  static const int dyn_enabled = env_flag("MDM_IGEMM_DYNAMIC", 1);
+  a.sched = nullptr;
+  if (dyn_enabled && g_sched_base != nullptr && (dyn_enabled >= 2 || a.num_work >= 2 * grid)) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev == g_sched_dev)
+      a.sched = g_sched_base + 2 * (g_sched_seq.fetch_add(1, std::memory_order_relaxed) % (unsigned)g_sched_pairs);
+  }
+  const bool dyn = a.sched != nullptr;
+  if (a.mode == 1) launch_variant<1, false, 2, false>(dyn, grid, IGEMM_BLOCK, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.qsum && a.halo) launch_variant<0, true, 2, true>(dyn, grid, IGEMM_BLOCK, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.qsum && a.mt == 2) launch_variant<0, false, 2, true>(dyn, grid, IGEMM_BLOCK, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.qsum) launch_variant<0, false, 1, true>(dyn, grid, IGEMM_BLOCK, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.halo && a.mt == 2) launch_variant<0, true, 2, false>(dyn, grid, IGEMM_BLOCK, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.halo) launch_variant<0, true, 1, false>(dyn, grid, IGEMM_BLOCK, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else if (a.mt == 2) launch_variant<0, false, 2, false>(dyn, grid, IGEMM_BLOCK, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  else launch_variant<0, false, 1, false>(dyn, grid, IGEMM_BLOCK, st, mA0, mB0, mA1, mB1, mC, mD, a);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
@@ -1189,6 +1339,21 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
 using namespace mdm;
 
 extern "C" {
+
+int mdm_set_sched_workspace(void* zeroed_ints, int n_ints) {
+  if (zeroed_ints == nullptr || n_ints < 2) {   // unregister: static work lists everywhere
+    g_sched_base = nullptr;
+    g_sched_pairs = 0;
+    g_sched_dev = -1;
+    return MDM_OK;
+  }
+  int dev = -1;
+  MDM_CUDA(cudaGetDevice(&dev));
+  g_sched_base = static_cast<int*>(zeroed_ints);
+  g_sched_pairs = n_ints / 2;
+  g_sched_dev = dev;
+  return MDM_OK;
+}
 
 int mdm_reserve_sms(int n) {
   if (n < 0) return g_reserved_sms.load(std::memory_order_relaxed);   // query

@@ -39,6 +39,7 @@ _lib.register({
     "mdm_conv_dgrad": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_conv_wgrad": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_reserve_sms": (c_int, [c_int]),
+    "mdm_set_sched_workspace": (c_int, [_P, c_int]),
     "mdm_gn_ws_floats": (_I64, [c_int, c_int, c_int, c_int]),
     "mdm_gn_fwd_kind": (c_int, [c_int, c_int, c_int, c_int]),
     "mdm_gn_silu_fwd_q": (c_int, [_P, _LL, _P, _LL, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
@@ -76,7 +77,19 @@ SPLITK_WS_FLOATS = 1 << 20
 _splitk_ws = {}
 
 
+_sched_ws = {}
+
+
+def _ensure_sched_ws(device):
+    """zeroed counters for the GEMM kernel's optional dynamic work distribution (MDM_IGEMM_DYNAMIC=1), lent once per
+    process (one process per GPU)"""
+    if not _sched_ws:
+        ws = _sched_ws[device] = torch.zeros(512, dtype=torch.int32, device=device)
+        check(lib().mdm_set_sched_workspace(ws.data_ptr(), ws.numel()))
+
+
 def _splitk(a, device):
+    _ensure_sched_ws(device)
     # one workspace per (device, stream): GEMMs on different streams may run concurrently
     key = (device, torch.cuda.current_stream(device).cuda_stream)
     ws = _splitk_ws.get(key)
@@ -156,6 +169,7 @@ def conv_wgrad(x, dy, dw, N, H, W, ksize=3, stride=1, dbias=None, dbias2=None):
     a.dw = _dp(dw)
     a.dbias, a.dbias2 = _dp(dbias), _dp(dbias2)
     a.w_cols = dw.shape[-1]
+    _ensure_sched_ws(dw.device)
     check(lib().mdm_conv_wgrad(ctypes.byref(a), stream_ptr(dw.device)))
 
 

@@ -167,10 +167,13 @@ class Sampler:
         difference_prev = None
 
         # the mask / noise generator is a serial one-CTA kernel that runs on the side stream for about half of every
-        # denoising step: leave it an SM of its own, or every persistent GEMM launched meanwhile waits for the CTA that
-        # shares its SM (static work lists; measured 45.3 -> 42.5 ms per step at 256x3x128x128)
+        # denoising step.  With STATIC work lists (MDM_IGEMM_DYNAMIC=0) every persistent GEMM launched meanwhile waits
+        # for the CTA that shares its SM, so the generator gets an SM of its own (44.5 -> 41.2 ms per step at
+        # 256x3x128x128); with the dynamic work distribution (the default) that CTA just takes fewer items and no SM
+        # has to stay idle.
         from mdm_b200 import denoiser_ops as _dops
-        reserved_before = _dops.reserve_sms(int(os.environ.get("MDM_SAMPLER_RESERVE_SMS", "1")))
+        static_lists = os.environ.get("MDM_IGEMM_DYNAMIC", "1") == "0"
+        reserved_before = _dops.reserve_sms(int(os.environ.get("MDM_SAMPLER_RESERVE_SMS", "1" if static_lists else "0")))
         try:
             with torch.no_grad():
                 for i in range(T - 1, -1, -1):
