@@ -1195,7 +1195,7 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
   static const int epi8_min = env_flag("MDM_IGEMM_EPI8_MIN_ITEMS", 5 * kNumSMs);
   const int IGEMM_BLOCK = a.num_work >= epi8_min ? IGEMM_THREADS : IGEMM_THREADS_NARROW;
   cudaStream_t st = as_stream(stream);
-  static const int dyn_enabled = env_flag("MDM_IGEMM_DYNAMIC", 1);
+  const int dyn_enabled = env_flag("MDM_IGEMM_DYNAMIC", 1);   // read per call: the tests switch modes
   a.sched = nullptr;
   if (dyn_enabled && g_sched_base != nullptr && (dyn_enabled >= 2 || a.num_work >= 2 * grid)) {
     int dev = -1;

@@ -195,3 +195,38 @@ def test_halo_tail_wave_single_items():
     ops.conv_dgrad(dyb, wb, dx, N, H, H, 3, resid=res)
     refd = torch.nn.grad.conv2d_input((N, cin, H, H), ops.unpack_conv_weight(wb.float(), 3), nchw(dyb), padding=1) + nchw(res)
     assert (nchw(dx) - refd).abs().max().item() <= 1e-2 * refd.abs().max().item()
+
+
+@pytest.mark.parametrize("halo", ["0", "2"])
+def test_dynamic_work_distribution_matches_static(monkeypatch, halo):
+    """work items drawn from the atomic counter (every launch forced dynamic) vs the static lists: every output tile is
+    computed by the same arithmetic whichever CTA gets it, so fprop (bias + residual + fused GroupNorm quad sums'
+    output) and dgrad are BIT-identical; wgrad's fp32 reduce-adds only change order.  300+ items: several per CTA."""
+    from mdm_b200 import denoiser_ops as ops
+    monkeypatch.setenv("MDM_IGEMM_HALO", halo)
+    N, H, cin, cout = 150, 16, 128, 256
+    g = torch.Generator(device="cuda").manual_seed(33)
+    xb = nhwc(torch.randn(N, cin, H, H, device="cuda", generator=g))
+    dyb = nhwc(torch.randn(N, cout, H, H, device="cuda", generator=g))
+    res = nhwc(torch.randn(N, cout, H, H, device="cuda", generator=g))
+    wb = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (cin * 9) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(cout, device="cuda", generator=g)
+    out = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("MDM_IGEMM_DYNAMIC", mode)
+        y = torch.empty(N, H, H, cout, device="cuda", dtype=torch.bfloat16)
+        q = torch.zeros(N, cout // 4, 2, device="cuda")
+        ops.conv_fprop(xb, wb, y, N, H, H, 3, 1, bias=b, resid=res, qsum=q)
+        dx = torch.empty(N, H, H, cin, device="cuda", dtype=torch.bfloat16)
+        ops.conv_dgrad(dyb, wb, dx, N, H, H, 3)
+        dw = torch.zeros(cout, 9, cin, device="cuda")
+        db = torch.zeros(cout, device="cuda")
+        ops.conv_wgrad(xb, dyb, dw, N, H, H, 3, 1, dbias=db)
+        torch.cuda.synchronize()
+        out[mode] = (y, dx, dw, db, q)
+    assert torch.equal(out["0"][0], out["2"][0]) and torch.equal(out["0"][1], out["2"][1])
+    for i in (2, 3, 4):
+        a, c = out["0"][i], out["2"][i]
+        assert (a - c).abs().max().item() <= 1e-4 * a.abs().max().item()
+    ref = F.conv2d(nchw(xb), ops.unpack_conv_weight(wb.float(), 3), b, padding=1) + nchw(res)
+    assert (nchw(out["2"][0]) - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
