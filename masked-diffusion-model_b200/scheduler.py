@@ -322,7 +322,16 @@ class Scheduler:
         elif kind == "non_shift":
             shift = torch.zeros(B, 3, H, W, device=dev)
         elif kind == "noise_std_reduction":
-            raise NotImplementedError("shift_type='noise_std_reduction' (per-sample normal_ with std=ratio[i]) is not on the B200 path yet")
+            # scheduler.py:686-694: one FloatTensor(1,3,H,W).normal_(mean, std = ratio[i]) per sample.  3*H*W is a
+            # multiple of 16, so the B calls consume the stream exactly like ONE 16-wide Box-Muller pass over
+            # B*3*H*W uniforms; normal_ computes (radius * cos) * float(std) + mean in fp32: take the unit normals
+            # from the device generator (x * 1 + 0 is exact) and apply the per-sample std and the mean as two
+            # separately rounded fp32 operations.
+            if (3 * H * W) % 16 != 0:
+                raise NotImplementedError("noise_std_reduction: 3*H*W must be a multiple of 16 on the B200 path")
+            z = rng.normal(B, 3 * H * W, 0.0, 1.0).view(B, 3, H, W)
+            shift = z * ratio.to(torch.float32)[:, None, None, None]
+            shift = shift + float(a.noise_mean)
         else:
             raise UnboundLocalError("shift_time")
         return shift.to(a.weight_dtype).expand_as(binarymasks)

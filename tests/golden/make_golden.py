@@ -35,7 +35,7 @@ DEGRADE_CASES = {
     "idx_log_deg_img_c1": dict(select_degrade_pixel="indexing", ddpm_schedule="log", mean_option="degraded_area", mean_area="image-wise", in_channel=1, out_channel=1),
     "idx_log_deg_img_bf16": dict(select_degrade_pixel="indexing", ddpm_schedule="log", mean_option="degraded_area", mean_area="image-wise", weight_dtype="bf16"),
 }
-SHIFT_TYPES = ["1-d_constant", "3-d_constant", "noise_reduction", "noise_with_perturbation", "non_shift"]
+SHIFT_TYPES = ["1-d_constant", "3-d_constant", "noise_reduction", "noise_std_reduction", "noise_with_perturbation", "non_shift"]
 
 SAMPLER_CASES = {
     "indep_mom_noise": dict(select_degrade_pixel="indexing", ddpm_schedule="log", sampling_mask_dependency="independent", momentum_adaptive="base_momentum", shift_type="noise_with_perturbation", sample_latent_shape="uniform"),
