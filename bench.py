@@ -478,6 +478,7 @@ def run_b200(a):
                    "precision": "bf16 activations / fp32 master weights + AdamW + EMA",
                    "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "cuda_graph": not a.no_graph,
+                   "igemm_work_distribution": "static" if os.environ.get("MDM_IGEMM_DYNAMIC", "1") == "0" else "dynamic",
                    "l2": "per-step working set (weights 0.68 GB + activations > 2 GB) exceeds the 126 MB L2; "
                          "8 distinct input batches rotate"},
         "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": B * C * S * S * 4, "d2h_bytes_per_step": 12,
