@@ -187,9 +187,11 @@ int mdm_conv_wgrad(const mdm_conv_args* a, void* stream);
  * read at launch time (a captured CUDA graph keeps the grid it was captured with). */
 int mdm_reserve_sms(int n);
 /* Optional dynamic work distribution of the same kernel (MDM_IGEMM_DYNAMIC=1): the caller lends a ZEROED device
- * buffer of n_ints ints (>= 64 recommended; the current device's); launches whose CTAs run >= 2 items then draw their
- * items from an atomic counter in it instead of a static list, so a CTA that shares its SM with another stream's
- * kernel just takes fewer items.  Every launch leaves its counters zeroed.  NULL / 0 unregisters. */
+ * buffer of n_ints ints (the current device's; counter pairs are partitioned into 32 per-stream classes so that GEMMs
+ * in flight on different streams never share a pair: n_ints >= 128, 4096 recommended); launches whose CTAs run >= 2
+ * items then draw their items from an atomic counter in it instead of a static list, so a CTA that shares its SM with
+ * another stream's kernel just takes fewer items.  Every launch leaves its counters zeroed.  A 33rd distinct stream
+ * falls back to static lists.  NULL / 0 unregisters. */
 int mdm_set_sched_workspace(void* zeroed_ints, int n_ints);
 
 /* K2: GroupNorm (+SiLU) forward / backward (csrc/nn_kernels.cu).  x, y, dy, dx: NHWC bf16 with

@@ -38,6 +38,7 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -1177,7 +1178,31 @@ static int igemm_grid_cap() {
 // static (43.2 static with one SM reserved).
 static int* g_sched_base = nullptr;
 static int g_sched_pairs = 0, g_sched_dev = -1;
-static std::atomic<unsigned> g_sched_seq{0};
+// Pairs are partitioned by STREAM: launches of one stream are ordered (the last CTA re-arms the pair before the next
+// kernel of that stream can draw from it), launches of different streams -- the wgrad side stream, the sampler's
+// generator stream, graph branches captured from them -- may run concurrently and must never share a pair.  Every
+// stream seen gets its own class of pairs (round robin inside the class); when the classes run out the launch falls
+// back to its static work list.
+constexpr int SCHED_CLASSES = 32;
+static std::mutex g_sched_mu;
+static void* g_sched_streams[SCHED_CLASSES];
+static unsigned g_sched_seq[SCHED_CLASSES];
+static int g_sched_nstreams = 0;
+static int* sched_pair_for(void* stream) {
+  std::lock_guard<std::mutex> lk(g_sched_mu);
+  const int per = g_sched_pairs / SCHED_CLASSES;
+  if (per < 1) return nullptr;
+  int cls = -1;
+  for (int i = 0; i < g_sched_nstreams; ++i)
+    if (g_sched_streams[i] == stream) { cls = i; break; }
+  if (cls < 0) {
+    if (g_sched_nstreams == SCHED_CLASSES) return nullptr;
+    cls = g_sched_nstreams++;
+    g_sched_streams[cls] = stream;
+    g_sched_seq[cls] = 0;
+  }
+  return g_sched_base + 2 * (cls * per + (int)(g_sched_seq[cls]++ % (unsigned)per));
+}
 
 template <int kMode, bool kHalo, int kMT, bool kStats>
 static void launch_variant(bool dyn, int grid, int block, cudaStream_t st, const CUtensorMap& mA0, const CUtensorMap& mB0,
@@ -1199,8 +1224,7 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
   a.sched = nullptr;
   if (dyn_enabled && g_sched_base != nullptr && (dyn_enabled >= 2 || a.num_work >= 2 * grid)) {
     int dev = -1;
-    if (cudaGetDevice(&dev) == cudaSuccess && dev == g_sched_dev)
-      a.sched = g_sched_base + 2 * (g_sched_seq.fetch_add(1, std::memory_order_relaxed) % (unsigned)g_sched_pairs);
+    if (cudaGetDevice(&dev) == cudaSuccess && dev == g_sched_dev) a.sched = sched_pair_for(stream);
   }
   const bool dyn = a.sched != nullptr;
   if (a.mode == 1) launch_variant<1, false, 2, false>(dyn, grid, IGEMM_BLOCK, st, mA0, mB0, mA1, mB1, mC, mD, a);
@@ -1342,13 +1366,17 @@ extern "C" {
 
 int mdm_set_sched_workspace(void* zeroed_ints, int n_ints) {
   if (zeroed_ints == nullptr || n_ints < 2) {   // unregister: static work lists everywhere
+    std::lock_guard<std::mutex> lk(g_sched_mu);
     g_sched_base = nullptr;
     g_sched_pairs = 0;
     g_sched_dev = -1;
+    g_sched_nstreams = 0;
     return MDM_OK;
   }
   int dev = -1;
   MDM_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_sched_mu);
+  g_sched_nstreams = 0;
   g_sched_base = static_cast<int*>(zeroed_ints);
   g_sched_pairs = n_ints / 2;
   g_sched_dev = dev;

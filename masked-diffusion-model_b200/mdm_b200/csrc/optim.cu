@@ -58,7 +58,7 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
     coef *= fminf(1.0f, a.max_norm / (total + 1e-6f));
   }
   const float step = a.lr / a.bias_c1;
-  const float inv_sqrt_c2 = rsqrtf(a.bias_c2);
+  const float sqrt_c2 = sqrtf(a.bias_c2);   // torch: denom = sqrt(v) / sqrt(bias_correction2) + eps
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
     float4 P = *reinterpret_cast<const float4*>(p + i);
     const float4 Gr = *reinterpret_cast<const float4*>(g + i);
@@ -72,7 +72,7 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
       else gk += a.weight_decay * pp[k];
       mm[k] = a.beta1 * mm[k] + (1.0f - a.beta1) * gk;
       vv[k] = a.beta2 * vv[k] + (1.0f - a.beta2) * gk * gk;
-      const float denom = sqrtf(vv[k]) * inv_sqrt_c2 + a.eps;
+      const float denom = sqrtf(vv[k]) / sqrt_c2 + a.eps;
       pp[k] -= step * (mm[k] / denom);
     }
     *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);

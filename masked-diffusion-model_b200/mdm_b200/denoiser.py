@@ -292,9 +292,18 @@ class UNet2DModelB200:
         self.flat_grad.zero_()
 
     def mark_params_updated(self):
-        """call after the fp32 master was changed by a kernel torch cannot see (fused optimizer);
-        in-place torch ops on the parameters are detected through the tensor version counter."""
+        """call after the fp32 master was changed outside the fused optimiser kernel (load_state_dict, EMA
+        copy_to / restore, broadcast, a kernel torch cannot see).  The bf16 mirror the GEMMs read is re-cast
+        IMMEDIATELY: a captured step graph contains no fp32 -> bf16 cast (the optimiser kernel writes the mirror),
+        so a lazily refreshed mirror would be read stale by the next replay.  In-place torch ops on the parameters
+        are detected through the tensor version counter (`params_dirty`)."""
         self._bf16_stale = True
+        if not torch.cuda.is_current_stream_capturing():
+            self._refresh_bf16()
+
+    def params_dirty(self):
+        """the bf16 mirror does not reflect the fp32 master (checked by the trainer before every graph replay)"""
+        return self._bf16_stale or self.flat_param._version != getattr(self, "_bf16_version", None)
 
     def _refresh_bf16(self):
         v = self.flat_param._version

@@ -84,7 +84,7 @@ def _ensure_sched_ws(device):
     """zeroed counters for the GEMM kernel's optional dynamic work distribution (MDM_IGEMM_DYNAMIC=1), lent once per
     process (one process per GPU)"""
     if not _sched_ws:
-        ws = _sched_ws[device] = torch.zeros(512, dtype=torch.int32, device=device)
+        ws = _sched_ws[device] = torch.zeros(4096, dtype=torch.int32, device=device)
         check(lib().mdm_set_sched_workspace(ws.data_ptr(), ws.numel()))
 
 

@@ -277,6 +277,13 @@ class FusedOptimizer:
                 "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
 
     def load_state_dict(self, sd):
+        if "step" not in sd or ("state" in sd and "m" not in sd):
+            # torch.optim layout ({"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups"}) as written by the
+            # reference's accelerate run: the per-parameter moments follow diffusers' module order, which this
+            # framework cannot verify offline -- refuse loudly instead of loading moments into the wrong slots.
+            raise RuntimeError("FusedOptimizer.load_state_dict: expected this framework's flat layout "
+                               "{'step', 'm', 'v', 'param_groups'}; a torch.optim state dict (reference-produced "
+                               "optimizer.bin) is not interchangeable -- only unet/ and unet_ema/ are (INTEGRATION.md)")
         self.step_count = sd["step"]
         if self.m is not None:
             self.m.copy_(sd["m"]); self.v.copy_(sd["v"])
@@ -485,8 +492,8 @@ class Accelerator:
                   "torch_manual_seed": torch.get_rng_state()}
         if torch.cuda.is_available():
             states["torch_cuda_manual_seed"] = torch.cuda.get_rng_state_all()
-        with open(os.path.join(output_dir, f"random_states_{self.rank}.pkl"), "wb") as f:
-            pickle.dump(states, f)
+        # accelerate writes this file with torch.save (checkpointing.py: save_accelerator_state)
+        torch.save(states, os.path.join(output_dir, f"random_states_{self.rank}.pkl"))
         return output_dir
 
     def load_state(self, input_dir):
@@ -507,8 +514,11 @@ class Accelerator:
                 s.load_state_dict(torch.load(p, weights_only=False))
         p = os.path.join(input_dir, f"random_states_{self.rank}.pkl")
         if os.path.exists(p):
-            with open(p, "rb") as f:
-                st = pickle.load(f)
+            try:
+                st = torch.load(p, weights_only=False)
+            except Exception:                        # round-1 checkpoints of this framework: plain pickle
+                with open(p, "rb") as f:
+                    st = pickle.load(f)
             random.setstate(st["random_state"])
             np.random.set_state(st["numpy_random_seed"])
             torch.set_rng_state(st["torch_manual_seed"])

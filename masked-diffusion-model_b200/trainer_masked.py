@@ -178,6 +178,10 @@ class Trainer:
                      train_ops.GraphedCallable(self._optimizer_tail_device, enabled=use_graph), segs)
             self._graphs[key] = g
         self.optimizer.upload_hyper()
+        if self.model.params_dirty():
+            # the captured step holds no fp32 -> bf16 cast (the optimiser kernel refreshes the mirror): anything that
+            # rewrote the master weights since the last step (EMA copy_to / restore, load_state_dict) re-casts here
+            self.model._refresh_bf16()
         if g[1] is None:
             acc._defer_all_reduce = False
             stats = g[0]()
@@ -216,9 +220,10 @@ class Trainer:
         stats = self._forward_backward()
         if self.accelerator.sync_gradients:
             self.accelerator.clip_grad_norm_(self.model.parameters(), 1.0)
-        self.optimizer.step()
-        self.lr_scheduler.step()
-        self.optimizer.zero_grad()
+            # accelerate wraps optimiser and scheduler: both skip the micro-batches that only accumulate
+            self.optimizer.step()
+            self.lr_scheduler.step()
+            self.optimizer.zero_grad()
         return stats
 
     # ------------------------------------------------------------------------------------------
@@ -239,7 +244,8 @@ class Trainer:
         self._set_input(self._extract_input(input))
         if self._fused():
             stats = self._step_fused()
-            self.lr_scheduler.step()
+            if self.accelerator.sync_gradients:      # accelerate's AcceleratedScheduler skips non-sync micro-batches
+                self.lr_scheduler.step()
         else:
             stats = self._step_generic()
         if self.accelerator.sync_gradients:

@@ -218,6 +218,34 @@ def gen_sampler(ref_sched, ref_samp):
     np.savez_compressed(os.path.join(OUT, "sampler.npz"), **out)
 
 
+HISTORY_EXTRA = {1: "shift_list", 2: "shifted_list", 3: "mask_list", 4: "shifted_result_list", 6: "degraded_mask_list",
+                 7: "degraded_mask_next_list", 9: "difference_list"}
+
+
+def gen_sampler_history(ref_sched, ref_samp):
+    """the seven history tensors of sampler.py:116-126 that sampler.npz does not hold (same cases, same seed);
+    a separate file so that the round-1 fixtures stay byte-identical"""
+    out = {}
+    S, N, T = 16, 4, 10
+    for name, cfg in SAMPLER_CASES.items():
+        a = mk_args(data_size=S, ddpm_num_steps=T, sample_num=N, **cfg)
+        torch.manual_seed(21)
+        R = ref_sched.Scheduler(a)
+        Tp = R.update_ddpm_num_steps(T)
+        a.updated_ddpm_num_steps = Tp
+        ts = R.get_timesteps_epoch(0, 1)
+        s0, vis = ref_samp.Sampler(None, a, R, [None, None, None]).sample(ToyModel(Tp), ts)
+        for k, nm in HISTORY_EXTRA.items():
+            v = vis[k]
+            if nm.startswith("degraded_mask"):
+                assert set(np.unique(v.numpy())) <= {0.0, 1.0}
+                out[f"{name}/{nm}"] = pack_mask(v)
+                out[f"{name}/{nm}_shape"] = np.array(v.shape)
+            else:
+                out[f"{name}/{nm}"] = v.numpy().astype(np.float16 if nm == "never" else np.float32)
+    np.savez_compressed(os.path.join(OUT, "sampler_hist.npz"), **out)
+
+
 def gen_train(ref_base, ref_ms):
     out = {}
     S, B, T = 16, 6, 100
@@ -258,6 +286,7 @@ if __name__ == "__main__":
     gen_degrade(ref_sched)
     gen_shift(ref_sched)
     gen_sampler(ref_sched, ref_samp)
+    gen_sampler_history(ref_sched, ref_samp)
     gen_train(ref_base, ref_ms)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):

@@ -1,0 +1,127 @@
+"""GPU: the drop-in Sampler and both trainers' `_run_batch` driving the REAL B200 denoiser (tcgen05 convs, fused
+GroupNorm, attention), against the oracle restatement of the same loops (oracle/mdm_oracle.py, pinned to the
+reference's sampler.py / trainer_masked*.py by tests/test_oracle_golden.py) driving the fp32 restatement of the
+network (oracle/unet_ref.py) with the SAME weights, the SAME CPU-generator stream (hence identical masks, timestep
+indices and shift noise) and the same inputs.  SURVEY.md section 8d tolerances: 10-step restoration x0_hat relative
+L2 <= 2e-2 (bf16 denoiser), loss relative <= 5e-3 through `_run_batch`."""
+import numpy as np
+import pytest
+import torch
+
+import sampler
+import scheduler
+from oracle.mdm_oracle import OracleRNG, OracleSampler, OracleScheduler, oracle_train_step
+from oracle.unet_ref import UNet2DModelRef, unet_config
+from tests.golden.make_golden import mk_args
+from tests.helpers import torch_state_words
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-20)).item()
+
+
+class RefOnGpu:
+    """the fp32 oracle network evaluated on the GPU (TF32 off) behind the CPU tensors the oracle loops use"""
+    device = torch.device("cpu")
+
+    def __init__(self, ref):
+        self.ref = ref
+
+    def __call__(self, x, t):
+        from types import SimpleNamespace
+        return SimpleNamespace(sample=self.ref(x.float().cuda(), t.float().cuda()).sample.cpu())
+
+
+def _pair(C, S, seed):
+    from mdm_b200.denoiser import UNet2DModelB200, default_config
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(seed)
+    ref = UNet2DModelRef(**unet_config(C, S)).cuda()
+    mine = UNet2DModelB200(device="cuda", **default_config(C, S))
+    mine.load_state_dict(ref.state_dict())
+    return ref, mine
+
+
+@pytest.mark.parametrize("case", [
+    dict(select_degrade_pixel="indexing", ddpm_schedule="log", sampling_mask_dependency="independent",
+         momentum_adaptive="base_momentum", shift_type="noise_with_perturbation", sample_latent_shape="uniform",
+         mean_option="degraded_area", mean_area="image-wise"),
+    dict(select_degrade_pixel="thresholding", ddpm_schedule="linear", degrade_channel="1-channel", mean_option="0",
+         sampling_mask_dependency="dependent_t", momentum_adaptive="base_sampling", shift_type="3-d_constant",
+         sample_latent_shape="normal"),
+])
+def test_ten_step_restoration_with_the_real_denoiser(case):
+    C, S, N, T = 3, 32, 4, 10
+    ref, mine = _pair(C, S, seed=0)
+    a = mk_args(data_size=S, ddpm_num_steps=T, sample_num=N, **case)
+    Sch = scheduler.Scheduler(a)
+    Tp = Sch.update_ddpm_num_steps(T)
+    ts = Sch.get_timesteps_epoch(0, 1)
+    torch.manual_seed(33)
+    s0, _ = sampler.Sampler(None, a, Sch, None).sample(mine.eval(), ts)
+    state_mine = torch.get_rng_state().numpy()
+    O = OracleScheduler(a, OracleRNG(33))
+    O.update_ddpm_num_steps()
+    with torch.no_grad():
+        r0, _ = OracleSampler(a, O, None).sample(RefOnGpu(ref), ts)
+    err = rel_l2(s0.cpu(), r0)
+    print(f"10-step restoration, real denoiser: x0_hat rel L2 = {err:.3e}")
+    assert torch.isfinite(s0).all() and err <= 2e-2, err
+    # identical stream consumption: masks / noise came from the same words
+    key, pos = torch_state_words(state_mine)
+    okey, opos = O.rng.state_words()
+    assert pos == opos and np.array_equal(key, okey)
+
+
+@pytest.mark.parametrize("method", ["base", "mean_shift"])
+def test_run_batch_with_the_real_denoiser(method):
+    import trainer_masked
+    import trainer_masked_mean_shift
+    from mdm_b200.runtime import Accelerator, FusedOptimizer, get_scheduler
+    C, S, B, T = 3, 32, 6, 100
+    ref, mine = _pair(C, S, seed=2)
+    a = mk_args(data_size=S, ddpm_num_steps=T, select_degrade_pixel="indexing", ddpm_schedule="log",
+                mean_option="degraded_area", mean_area="image-wise", shift_type="noise_with_perturbation", method=method)
+    a.use_ema, a.cuda_graph, a.timeindex_rng = False, False, "cpu_stream"
+    opt = FusedOptimizer(mine, "sgd", lr=0.0)
+    opt.zero_grad = lambda *args, **kw: None                      # keep the gradients for the comparison
+    sched = get_scheduler("constant", opt, num_warmup_steps=0)
+    acc = Accelerator()
+    mine, opt, sched = acc.prepare(mine, opt, sched)
+    if method == "base":
+        tr = trainer_masked.Trainer(a, None, None, mine, None, opt, sched, acc)
+    else:
+        tr = trainer_masked_mean_shift.Trainer(a, None, None, [None, None, None], mine, None, opt, sched, acc)
+    tr.prepare_schedule()
+    tr.timesteps_used_epoch = tr.Scheduler.get_timesteps_epoch(0, 1)
+    g = torch.Generator().manual_seed(31)
+    x0 = torch.rand(B, C, S, S, generator=g) * 2 - 1
+    mine.train()
+    mine.zero_grad()
+    torch.manual_seed(41)
+    tr.Scheduler.adopt_torch_rng("cuda")
+    r = tr._run_batch(0, (x0.cuda(),), 0, 1, 0, None, None)
+    tr.Scheduler.release_rng_to_torch()
+    loss = r[0] if isinstance(r, tuple) else r
+    # oracle: same stream, fp32 network
+    O = OracleScheduler(a, OracleRNG(41))
+    O.update_ddpm_num_steps()
+    ref.zero_grad()
+    loss_ref, aux = oracle_train_step(a, O, RefOnGpu(ref), x0, tr.timesteps_used_epoch, method=method)
+    assert torch.equal(tr.timesteps.float().cpu(), aux["timesteps"].float())                 # same timestep draw
+    kept_ref = aux["degraded"].float() == x0
+    kept_mine = tr.degraded_img.float().cpu() == x0
+    assert torch.equal(kept_ref, kept_mine)                                                   # identical masks
+    np.testing.assert_allclose(tr.degraded_img.float().cpu().numpy(), aux["degraded"].float().numpy(), atol=2e-6, rtol=0)
+    print(f"{method} _run_batch, real denoiser: loss {loss:.6f} vs oracle {loss_ref.item():.6f}")
+    assert abs(loss - loss_ref.item()) <= 5e-3 * abs(loss_ref.item()), (loss, loss_ref.item())
+    got = mine.state_dict_grads()
+    num = sum(((got[n].float() - p.grad.float()) ** 2).sum().item() for n, p in ref.named_parameters())
+    den = sum((p.grad.float() ** 2).sum().item() for _, p in ref.named_parameters())
+    assert (num / den) ** 0.5 <= 3e-2, (num / den) ** 0.5
+    key, pos = torch_state_words(torch.get_rng_state().numpy())
+    okey, opos = O.rng.state_words()
+    assert pos == opos and np.array_equal(key, okey)

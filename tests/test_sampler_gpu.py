@@ -8,7 +8,7 @@ import sampler
 import scheduler
 from oracle.mdm_oracle import OracleRNG, OracleSampler, OracleScheduler
 from tests.golden.make_golden import SAMPLER_CASES, ToyModel, mk_args
-from tests.helpers import torch_state_words
+from tests.helpers import torch_state_words, unpack_mask
 
 pytestmark = pytest.mark.gpu
 
@@ -43,6 +43,14 @@ def test_sampler_against_reference_golden(golden, name, history, monkeypatch):
         np.testing.assert_allclose(vis[5].numpy(), g[f"{name}/sample_0_list"], atol=tol_for(a), rtol=0)
         np.testing.assert_allclose(vis[8].numpy(), g[f"{name}/degraded_t_list"], atol=tol_for(a), rtol=0)
         np.testing.assert_allclose(vis[10].numpy(), g[f"{name}/degraded_next_t_list"], atol=tol_for(a), rtol=0)
+        # the other seven history tensors (sampler.py:116-126; fixture sampler_hist.npz): shift, shifted input, network
+        # output, shifted result, both mask histories (bit-exact) and the difference incl. its stale last slot (q21)
+        gh = golden("sampler_hist")
+        for k, nm in ((1, "shift_list"), (2, "shifted_list"), (3, "mask_list"), (4, "shifted_result_list"), (9, "difference_list")):
+            np.testing.assert_allclose(vis[k].numpy(), gh[f"{name}/{nm}"], atol=tol_for(a), rtol=0, err_msg=nm)
+        for k, nm in ((6, "degraded_mask_list"), (7, "degraded_mask_next_list")):
+            want = unpack_mask(gh[f"{name}/{nm}"], gh[f"{name}/{nm}_shape"])
+            assert torch.equal(vis[k], want), nm
     else:
         assert all(v is None for v in vis)
 

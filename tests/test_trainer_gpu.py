@@ -129,3 +129,73 @@ def test_training_reduces_loss_c1_shape():
     assert all(np.isfinite(ls)), ls
     # the timestep (hence the loss scale) is redrawn every step: compare averages
     assert np.mean(ls[-6:]) < 0.8 * np.mean(ls[:6]), ls
+
+
+def test_ema_sample_then_graph_replay_uses_training_weights():
+    """`_ema_sample()` = store, copy_to (EMA weights), Sampler.sample, restore.  The captured step
+    graph contains no fp32 -> bf16 cast, so the restore must re-cast the mirror itself: the step after an EMA sample
+    has to equal the same step of a run that never sampled."""
+    g = torch.Generator().manual_seed(5)
+    x0 = (torch.rand(8, 3, 32, 32, generator=g) * 2 - 1).cuda()
+    out = {}
+    for do_sample in (False, True):
+        a, model, ema, opt, sched, tr = _b200_setup("base", graph=True, optim="sgd", lr=1e-2, T=20)
+        a.sample_num, a.sample_latent_shape = 2, "uniform"
+        torch.manual_seed(11)
+        tr.Scheduler.adopt_torch_rng("cuda")
+        for i in range(4):
+            tr._run_batch(i, (x0,), 0, 1, 0, None, None)
+        tr.Scheduler.release_rng_to_torch()
+        state = torch.get_rng_state()
+        if do_sample:
+            ema.flat.mul_(0.0)                                   # make the EMA weights unmistakably different
+            tr._ema_sample()
+            assert torch.equal(model.flat_bf16, model.flat_param.to(torch.bfloat16))
+        torch.set_rng_state(state)                               # the sampler consumed the CPU stream
+        tr.Scheduler.adopt_torch_rng("cuda")
+        out[do_sample] = tr._run_batch(4, (x0,), 0, 1, 0, None, None)[0]
+        tr.Scheduler.release_rng_to_torch()
+    assert abs(out[True] - out[False]) <= 2e-3 * abs(out[False]), out
+
+
+def test_gradient_accumulation_follows_accelerate():
+    """with gradient_accumulation_steps = 2 the optimiser, the LR schedule and zero_grad act on
+    every second micro-batch only (accelerate's AcceleratedOptimizer / AcceleratedScheduler), both on the generic
+    path (torch optimiser) and on the fused path."""
+    from mdm_b200.runtime import Accelerator
+    g = torch.Generator().manual_seed(5)
+    x0 = (torch.rand(4, 3, 16, 16, generator=g) * 2 - 1).cuda()
+    # generic path
+    a = mk_args(data_size=16, ddpm_num_steps=100, select_degrade_pixel="indexing", ddpm_schedule="log",
+                mean_option="degraded_area", mean_area="image-wise", method="base")
+    a.use_ema, a.timeindex_rng = False, "cpu_stream"
+    net = TinyNet(3).cuda()
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0 / (1 + s))
+    acc = Accelerator(gradient_accumulation_steps=2)
+    tr = _trainer("base", a, net, opt, sched, acc)
+    tr.prepare_schedule()
+    tr.timesteps_used_epoch = tr.Scheduler.get_timesteps_epoch(0, 1)
+    torch.manual_seed(3)
+    tr.Scheduler.adopt_torch_rng("cuda")
+    w0 = net.conv.weight.detach().clone()
+    tr._run_batch(0, (x0,), 0, 1, 0, None, None)
+    assert torch.equal(net.conv.weight, w0) and net.conv.weight.grad.abs().sum() > 0        # accumulated, not applied
+    assert sched.last_epoch == 0 and tr.global_step == 0
+    g1 = net.conv.weight.grad.clone()
+    tr._run_batch(1, (x0,), 0, 1, 0, None, None)
+    assert not torch.equal(net.conv.weight, w0) and sched.last_epoch == 1 and tr.global_step == 1
+    assert net.conv.weight.grad is None or float(net.conv.weight.grad.abs().sum()) == 0.0
+    assert float(g1.abs().sum()) > 0
+    # fused path
+    a2, model, ema, opt2, sched2, tr2 = _b200_setup("base", graph=True, optim="sgd", lr=1e-2, T=20)
+    tr2.accelerator.gradient_accumulation_steps = 2
+    p0 = model.flat_param.clone()
+    x1 = (torch.rand(8, 3, 32, 32, generator=g) * 2 - 1).cuda()
+    tr2.Scheduler.adopt_torch_rng("cuda")
+    tr2._run_batch(0, (x1,), 0, 1, 0, None, None)
+    assert torch.equal(model.flat_param, p0) and sched2.last_epoch == 0 and opt2.step_count == 0
+    assert float(model.flat_grad.abs().sum()) > 0 and ema.optimization_step == 0
+    tr2._run_batch(1, (x1,), 0, 1, 0, None, None)
+    assert not torch.equal(model.flat_param, p0) and sched2.last_epoch == 1 and opt2.step_count == 1
+    assert float(model.flat_grad.abs().sum()) == 0.0 and ema.optimization_step == 1 and tr2.global_step == 1
