@@ -117,6 +117,15 @@ class UNet2DModelB200:
         cfg.update(config)
         self.config = SimpleNamespace(**cfg)
         self._cfg = cfg
+        # the kernels implement the configuration `utils/model.py:3-33` builds; other values of these diffusers fields
+        # would silently compute a different network, so they are refused (the fp32 oracle honours them: that is how
+        # it is pinned to the reference's in-repo unet6, tests/test_oracle_unet6.py)
+        fixed = dict(attention_head_dim=8, norm_num_groups=32, flip_sin_to_cos=True, freq_shift=0, downsample_padding=1,
+                     act_fn="silu", time_embedding_type="positional", resnet_time_scale_shift="default",
+                     downsample_type="conv", upsample_type="conv", add_attention=True, center_input_sample=False)
+        for k, v in fixed.items():
+            if cfg.get(k, v) != v:
+                raise NotImplementedError(f"UNet2DModelB200: config field {k}={cfg[k]!r} is not implemented (only {v!r})")
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("UNet2DModelB200 runs on a CUDA device only (no CPU fallback)")

@@ -2,10 +2,22 @@
 `utils/model.py:3-33` (`diffusers.UNet2DModel`, block_out_channels (128,128,256,256,512,512),
 2 layers per block, attention in the blocks `num_attention` selects and in the mid block).
 
-**Parity unpinned**: `diffusers` is a third-party dependency that is neither vendored under
-/root/reference nor installed (no requirements file pins a version; run dates suggest ~0.26).
-This module restates its published architecture with
-the diffusers state-dict key names so that a real checkpoint loads.
+`diffusers` is a third-party dependency that is neither vendored under /root/reference nor installed (no
+requirements file pins a version; run dates suggest ~0.26).  This module restates its published architecture
+ with the diffusers state-dict key names so that a
+real checkpoint loads.
+
+**Pinned as a whole network to reference-held code**: the reference ships a runnable U-Net of the same topology,
+`models/unet/unet6.py:365-506` instantiated as `UNet(C, 128, C, [1,1,2,2,4,4], 2, [F,F,F,F,T,F])`
+(`models_Unet.py:153-159`).  It differs from the diffusers network in four places, each of which IS a diffusers
+config field that this restatement honours the way diffusers does -- `unet6_compat()` below: GroupNorm eps 1e-6
+(`norm_eps`), timestep embedding `[sin, cos]` with `half - 1` in the exponent (`flip_sin_to_cos=False`,
+`freq_shift=1`), one attention head scaled 1/sqrt(C) (`attention_head_dim = C`), stride-2 convolutions padded
+right / bottom only (`downsample_padding=0`).  `tests/golden/make_golden_unet6.py` runs the REFERENCE network with
+seeded weights (mapped key by key from the diffusers names, `unet6_key_map`) and `tests/test_oracle_unet6.py` checks
+this module under `unet6_compat()` against its output to 1e-5 relative L2: skip wiring, channel plan, up / down
+ordering, where the time embedding and the attention enter are pinned.  What stays UNPINNED is only the default
+value of those four fields (diffusers' own defaults: 1e-5, `[cos, sin]` / `half`, head_dim 8, symmetric padding).
 The block algebra (ResnetBlock2D, Attention, the multi-head core) IS pinned against the reference's in-repo
 `unet6.ResidualBlock` / `unet6.AttentionBlock` / `unet4.QKVAttentionLegacy` (tests/golden/unet_blocks.npz,
 tests/test_oracle_blocks.py).  Further checkable anchors: parameter count 113,673,219 (C=3) / 113,668,609 (C=1) / 454,461,443
@@ -53,12 +65,22 @@ def unet_config(dim_channel=3, dim_height=32, num_attention=1, base=128, layers_
     )
 
 
-def timestep_embedding(t: torch.Tensor, dim: int = 128) -> torch.Tensor:
-    """diffusers `Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0)` [upstream]."""
+def timestep_embedding(t: torch.Tensor, dim: int = 128, flip_sin_to_cos: bool = True, freq_shift: float = 0) -> torch.Tensor:
+    """diffusers `Timesteps(dim, flip_sin_to_cos, downscale_freq_shift)` [upstream]: exponent denominator
+    `half - freq_shift`, `[sin, cos]` order unless flipped.  (flip=False, shift=1) is the embedding of the
+    reference's in-repo models/unet/unet6.py:18-35."""
     half = dim // 2
-    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half
+    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / (half - freq_shift)
     emb = t[:, None].float() * torch.exp(exponent)[None, :]
-    return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
+    if flip_sin_to_cos:
+        return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
+    return torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+
+
+# the four places where the reference's in-repo unet6 differs from the diffusers defaults, as diffusers config fields
+def unet6_compat(channels_at_attention: int = 512) -> dict:
+    return dict(norm_eps=1e-6, flip_sin_to_cos=False, freq_shift=1, attention_head_dim=channels_at_attention,
+                downsample_padding=0)
 
 
 class TimestepEmbedding(nn.Module):
@@ -113,11 +135,17 @@ class Attention(nn.Module):
 
 
 class Downsample2D(nn.Module):
-    def __init__(self, c):
+    """diffusers Downsample2D(use_conv=True, padding=downsample_padding): padding 0 pads right / bottom by one
+    instead (`F.pad(x, (0, 1, 0, 1))` [upstream]) -- the `SamePad2d(3, 2)` of unet6.py:258-275 on even maps"""
+
+    def __init__(self, c, padding=1):
         super().__init__()
-        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=1)
+        self.padding = padding
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=padding)
 
     def forward(self, x):
+        if self.padding == 0:
+            x = F.pad(x, (0, 1, 0, 1), mode="constant", value=0.0)
         return self.conv(x)
 
 
@@ -131,14 +159,14 @@ class Upsample2D(nn.Module):
 
 
 class DownBlock(nn.Module):
-    def __init__(self, cin, cout, temb, n, attn, down, hd, groups, eps):
+    def __init__(self, cin, cout, temb, n, attn, down, hd, groups, eps, down_pad=1):
         super().__init__()
         self.resnets = nn.ModuleList([ResnetBlock2D(cin if j == 0 else cout, cout, temb, groups, eps) for j in range(n)])
         if attn:
             self.attentions = nn.ModuleList([Attention(cout, hd, groups, eps) for _ in range(n)])
         self.has_attn = attn
         if down:
-            self.downsamplers = nn.ModuleList([Downsample2D(cout)])
+            self.downsamplers = nn.ModuleList([Downsample2D(cout, down_pad)])
         self.has_down = down
 
     def forward(self, h, temb):
@@ -209,7 +237,8 @@ class UNet2DModelRef(nn.Module):
         c = boc[0]
         for i, ty in enumerate(cfg["down_block_types"]):
             cin, c = c, boc[i]
-            self.down_blocks.append(DownBlock(cin, c, temb, n, ty.startswith("Attn"), i != len(boc) - 1, hd, g, eps))
+            self.down_blocks.append(DownBlock(cin, c, temb, n, ty.startswith("Attn"), i != len(boc) - 1, hd, g, eps,
+                                              cfg["downsample_padding"]))
         self.mid_block = MidBlock(boc[-1], temb, hd, g, eps)
         rev = list(reversed(boc))
         self.up_blocks = nn.ModuleList()
@@ -232,7 +261,8 @@ class UNet2DModelRef(nn.Module):
         if t.dim() == 0:
             t = t[None]
         t = t.to(sample.device).expand(sample.shape[0])
-        temb = self.time_embedding(timestep_embedding(t, self.config.block_out_channels[0]).to(sample.dtype))
+        temb = self.time_embedding(timestep_embedding(t, self.config.block_out_channels[0], self.config.flip_sin_to_cos,
+                                                      self.config.freq_shift).to(sample.dtype))
         h = self.conv_in(sample)
         skips = [h]
         for blk in self.down_blocks:
@@ -243,6 +273,82 @@ class UNet2DModelRef(nn.Module):
             h = blk(h, skips, temb)
         h = self.conv_out(F.silu(self.conv_norm_out(h)))
         return SimpleNamespace(sample=h)
+
+
+def seeded_state_dict(model: nn.Module, seed: int) -> dict:
+    """deterministic weights for every parameter of `model` in state-dict order (CPU mt19937 generator): N(0, 1)
+    scaled by 1/sqrt(fan_in) for matrices / filters, 1 + 0.1 N(0,1) for norm scales, 0.1 N(0,1) for biases -- nothing
+    is left at the zero initialisation the reference gives its last convolutions, so every path contributes.
+    The golden generator feeds the SAME tensors to the reference network (447 MB of weights never enter the repo)."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, v in model.state_dict().items():
+        r = torch.randn(v.shape, generator=g)
+        if v.dim() >= 2:
+            out[k] = r / math.sqrt(v[0].numel())
+        elif "norm" in k and k.endswith("weight"):
+            out[k] = 1.0 + 0.1 * r
+        else:
+            out[k] = 0.1 * r
+    return out
+
+
+def unet6_key_map(cfg: dict) -> dict:
+    """diffusers state-dict key (without .weight/.bias) -> module path inside the reference's `unet6.UNet`
+    (models/unet/unet6.py:365-506).  Attention q/k/v map to slices of `project_in` (handled by the caller)."""
+    n = cfg["layers_per_block"]
+    L = len(cfg["block_out_channels"])
+    m = {"conv_in": "in_conv", "time_embedding.linear_1": "embed.0", "time_embedding.linear_2": "embed.2",
+         "conv_norm_out": "out_conv.0", "conv_out": "out_conv.2"}
+    res = {"norm1": "norm1", "conv1": "conv1", "time_emb_proj": "fc", "norm2": "norm2", "conv2": "conv2", "conv_shortcut": "skip"}
+    att = {"group_norm": "norm", "to_out.0": "project_out"}
+
+    def block(dprefix, uprefix, attn):
+        for a, b in res.items():
+            m[f"{dprefix[0]}.{a}"] = f"{uprefix}.0.{b}" if attn else f"{uprefix}.{b}"
+        if attn:
+            for a, b in att.items():
+                m[f"{dprefix[1]}.{a}"] = f"{uprefix}.1.{b}"
+            m[f"{dprefix[1]}.qkv"] = f"{uprefix}.1.project_in"
+
+    for i, ty in enumerate(cfg["down_block_types"]):
+        for j in range(n):
+            block((f"down_blocks.{i}.resnets.{j}", f"down_blocks.{i}.attentions.{j}"), f"downsamples.level_{i}.{j}", ty.startswith("Attn"))
+        if i != L - 1:
+            m[f"down_blocks.{i}.downsamplers.0.conv"] = f"downsamples.level_{i}.{n}.1"
+    block(("mid_block.resnets.0", None), "middle.0", False)
+    for a, b in att.items():
+        m[f"mid_block.attentions.0.{a}"] = f"middle.1.{b}"
+    m["mid_block.attentions.0.qkv"] = "middle.1.project_in"
+    block(("mid_block.resnets.1", None), "middle.2", False)
+    for i, ty in enumerate(cfg["up_block_types"]):
+        lvl = L - 1 - i
+        for j in range(n + 1):
+            block((f"up_blocks.{i}.resnets.{j}", f"up_blocks.{i}.attentions.{j}"), f"upsamples.level_{lvl}.{j}", ty.startswith("Attn"))
+        if i != L - 1:
+            m[f"up_blocks.{i}.upsamplers.0.conv"] = f"upsamples.level_{lvl}.{n + 1}.1"
+    return m
+
+
+def to_unet6_state_dict(sd: dict, cfg: dict) -> dict:
+    """re-key a diffusers-named state dict for `unet6.UNet`: Linear q/k/v -> one 1x1 `project_in` filter (q, k, v
+    stacked: unet6.py:327 chunks in that order), Linear `to_out.0` -> a 1x1 filter"""
+    km = unet6_key_map(cfg)
+    out = {}
+    for k, v in sd.items():
+        stem, leaf = k.rsplit(".", 1)
+        if stem.rsplit(".", 1)[-1] in ("to_q", "to_k", "to_v"):
+            continue
+        tgt = km[stem]
+        if tgt.endswith("project_out"):
+            v = v[:, :, None, None] if v.dim() == 2 else v
+        out[f"{tgt}.{leaf}"] = v
+    for stem, tgt in km.items():
+        if stem.endswith(".qkv"):
+            base = stem[:-4]
+            out[f"{tgt}.weight"] = torch.cat([sd[f"{base}.to_{c}.weight"] for c in "qkv"], 0)[:, :, None, None]
+            out[f"{tgt}.bias"] = torch.cat([sd[f"{base}.to_{c}.bias"] for c in "qkv"], 0)
+    return out
 
 
 def fwd_flops_per_image(cfg: dict) -> float:
