@@ -67,6 +67,22 @@ long long mdm_launch_count(void);
 /* host helper: init_genrand(seed) == torch.manual_seed(seed) (left_=1 -> position 624) */
 int mdm_rng_seed_host(uint32_t* state_host /*[625]*/, uint32_t seed);
 
+/* Parallel stream generation (csrc/mt_jump.cu + csrc/rng.cu).  mt19937 is linear over GF(2): the state J words ahead
+ * is g_J(T) s with g_J = x^J mod the characteristic polynomial, so CTA c of a draw can start c * W words into the
+ * stream from a precomputed polynomial and the words of one torch-exact stream are produced by many CTAs.
+ *   mdm_rng_jump_table_host: host-side precomputation (Berlekamp-Massey for the characteristic polynomial, then
+ *     x^{(c * blocks_per_cta - 1) * 624} mod phi for c = 1 .. n_polys; 624 uint32 per polynomial).
+ *   mdm_rng_enable_parallel: lends the table (copied to the DEVICE by the caller) to the library.  From then on every
+ *     draw of at least MDM_RNG_PAR_MIN_WORDS words is split over ceil(n / (blocks_per_cta * 624)) CTAs and every `rng`
+ *     buffer passed to the draw functions must be MDM_RNG_PAR_WORDS uint32 long: words 640 .. 1264 stage the advanced
+ *     state (all CTAs read the old state; one tiny follow-up kernel commits the new one).  NULL / 0 disables.
+ *   mdm_rng_advance_host: host utility, the state after n more draws (same polynomial arithmetic; CPU tests). */
+#define MDM_RNG_PAR_WORDS 1280
+#define MDM_RNG_PAR_MIN_WORDS 262144
+int mdm_rng_jump_table_host(uint32_t* polys_host, int n_polys, int blocks_per_cta);
+int mdm_rng_enable_parallel(const uint32_t* polys_dev, int n_polys, int blocks_per_cta);
+int mdm_rng_advance_host(const uint32_t* state_in_host /*[625]*/, int64_t n, uint32_t* state_out_host /*[625]*/);
+
 /* n raw 32-bit outputs (untransformed) */
 int mdm_rng_raw(uint32_t* rng, uint32_t* out, int64_t n, void* stream);
 /* advance the stream by n words, nothing written (scheduler.py:703-705: a uniform draw whose

@@ -18,6 +18,7 @@ MDM_F32, MDM_BF16 = 0, 1
 FILL_CONST, FILL_DEGRADED_AREA, FILL_NON_DEGRADED = 0, 1, 2
 AREA_IMAGE, AREA_CHANNEL = 0, 1
 RNG_WORDS = 625
+RNG_PAR_WORDS = 1280          # state buffers are allocated this long: words 640.. stage the advanced state
 
 _P = c_void_p
 _SIGS = {
@@ -26,6 +27,9 @@ _SIGS = {
     "mdm_device_available": (c_int, []),
     "mdm_launch_count": (ctypes.c_longlong, []),
     "mdm_rng_seed_host": (c_int, [_P, c_uint32]),
+    "mdm_rng_jump_table_host": (c_int, [_P, c_int, c_int]),
+    "mdm_rng_enable_parallel": (c_int, [_P, c_int, c_int]),
+    "mdm_rng_advance_host": (c_int, [_P, c_int64, _P]),
     "mdm_rng_raw": (c_int, [_P, _P, c_int64, _P]),
     "mdm_rng_skip": (c_int, [_P, c_int64, _P]),
     "mdm_rng_uniform": (c_int, [_P, _P, c_int64, c_float, c_float, _P]),

@@ -4,12 +4,20 @@
 // 658,675,703-707): `torch.FloatTensor(..).uniform_/normal_`, `torch.randperm`.  The word ->
 // value transforms are those of ATen's CPU kernels.
 //
-// mt19937 is one serial recurrence, x[k+624] = x[k+397] ^ twist(x[k], x[k+1]), so the stream is
-// produced by ONE CTA that keeps the 624-word block in shared memory.  The usual in-place update
-// needs three dependent phases per block (words 0-226, 227-453, 454-623).  Here every new word
-// is written as a function of the OLD block only (substituting the recurrence into itself up to
-// three times), so a block costs one barrier: 624 threads each evaluate <= 4 twists, write the
-// new word to the other half of a double buffer, temper it and emit it.
+// mt19937 is one serial recurrence, x[k+624] = x[k+397] ^ twist(x[k], x[k+1]).  Inside a CTA the 624-word block
+// lives in shared memory; the usual in-place update needs three dependent phases per block (words 0-226, 227-453,
+// 454-623) -- here every new word is written as a function of the OLD block only (substituting the recurrence into
+// itself up to three times), so a block costs one barrier: 624 threads each evaluate <= 4 twists, write the new word
+// to the other half of a double buffer, temper it and emit it (1.3 words/ns per CTA).
+//
+// ACROSS CTAs the stream is cut into pieces of W = blocks_per_cta * 624 words: the recurrence is linear over GF(2),
+// so CTA c obtains the block that starts (c * W - 624) words ahead as a fixed GF(2) polynomial of the transition
+// applied to the current state (csrc/mt_jump.cu: y[J + m] = XOR_{i : g_i = 1} y[i + m]): it generates 33 blocks
+// (20592 words) of the sequence into shared memory, XORs the ~10000 shifted copies its polynomial selects (LDS.128
+// over a sliding register window, 4 output words per thread), and streams its W words from there.  All CTAs read the
+// OLD state; the CTA that owns the last word stages the advanced state behind it and a one-CTA follow-up kernel
+// commits it, so consecutive calls on one stream continue the sequence with no host round trip.  Draws below
+// MDM_RNG_PAR_MIN_WORDS use one CTA (a jump costs ~0.1 ms).  A 256x1x128x128 threshold mask: 3.3 ms -> ~0.15 ms.
 //
 // The stream is data independent: the host side launches these kernels on a side stream so they
 // overlap the denoiser of the previous step; the data-dependent work (fill + composite, K1/K5)
@@ -44,37 +52,112 @@ __device__ __forceinline__ uint32_t mt_next_word(const uint32_t* s, int k) {
          mt_twist(s[k], hi);
 }
 
+constexpr int MT_DEG = 19937;
+constexpr int MT_SEQ_BLOCKS = 33;                 // 33 * 624 = 20592 >= 19968 + 623 words of sequence for the jump
+constexpr int MT_STAGE_OFF = 640;                 // rng[640 .. 1264]: staged advanced state (parallel draws)
+constexpr int MT_JUMP_GROUPS = 4, MT_JUMP_Q = 156;   // 4 groups x 156 threads x 4 output words = 624 words
+constexpr size_t MT_SMEM_SERIAL = 2 * MT_N * sizeof(uint32_t);
+constexpr size_t MT_SMEM_PAR = (MT_SEQ_BLOCKS * MT_N + MT_N + MT_JUMP_GROUPS * MT_N) * sizeof(uint32_t);
+
+// One stream, many CTAs.  Window k of the untempered sequence = y[624 k + 1 .. 624 k + 624] (one word past torch's
+// block boundaries: y[0] of a freshly seeded state is not a sequence word, every later one is).  CTA c emits the words
+// y[pos + c W .. pos + (c + 1) W) of the draw; it starts at window c W / 624 - 1 (c >= 1: from its jump polynomial;
+// c = 0: window 0 straight from the state).
 template <class Emit>
-__global__ void __launch_bounds__(MT_THREADS, 1) mt_stream_kernel(uint32_t* rng, int64_t n, Emit emit) {
+__global__ void __launch_bounds__(MT_THREADS, 1)
+mt_stream_kernel(uint32_t* rng, const uint32_t* __restrict__ polys, int blocks_per_cta, int64_t n, Emit emit) {
   MDM_PDL_ENTER();
-  __shared__ uint32_t st[2][MT_N];
+  extern __shared__ __align__(16) uint32_t mt_sm[];
+  uint32_t* seq = mt_sm;                           // [33][624] during the jump; windows 0 / 1 afterwards
   const int k = threadIdx.x;
-  int cur = 0;
-  if (k < MT_N) st[0][k] = rng[k];
-  int pos = (int)rng[MT_N];
+  const int c = blockIdx.x;
+  const int64_t W = (int64_t)blocks_per_cta * MT_N;
+  const int64_t pos = (int64_t)rng[MT_N];
+  const int64_t P = pos + n;                       // stream position after this draw
+  const uint32_t y0 = rng[0];
+  // window 0: y[1 .. 624] = state words 1 .. 623 and the first word of the next block
+  if (k < MT_N) seq[k] = (k < MT_N - 1) ? rng[k + 1] : (rng[397] ^ mt_twist(rng[0], rng[1]));
   __syncthreads();
-  int64_t done = 0;
-  if (pos < MT_N && n > 0) {  // words left in the current block
-    const int take = (int)min((int64_t)(MT_N - pos), n);
-    if (k >= pos && k < pos + take) emit(done + (k - pos), mt_temper(st[0][k]));
-    done += take;
-    pos += take;
-  }
-  while (done < n) {
-    uint32_t w = 0;
-    if (k < MT_N) {
-      w = mt_next_word(st[cur], k);
-      st[cur ^ 1][k] = w;
+  int64_t win = 0;                                 // index of the window in st[cur]
+  uint32_t* st[2] = {seq, seq + MT_N};
+  int cur = 0;
+  if (c > 0) {
+    uint32_t* poly = mt_sm + MT_SEQ_BLOCKS * MT_N;
+    uint32_t* part = poly + MT_N;
+    const uint32_t* g = polys + (size_t)(c - 1) * MT_N;
+    if (k < MT_N) poly[k] = g[k];
+    for (int t = 1; t < MT_SEQ_BLOCKS; ++t) {
+      if (k < MT_N) seq[t * MT_N + k] = mt_next_word(seq + (t - 1) * MT_N, k);
+      __syncthreads();
+    }
+    // out[m] = XOR_{i : g_i} seq[i + m]: thread (grp, q) covers polynomial words [grp * 156, grp * 156 + 156) for the
+    // four outputs m = 4 q .. 4 q + 3; per polynomial word one 36-word register window (nine LDS.128)
+    if (k < MT_JUMP_GROUPS * MT_JUMP_Q) {
+      const int grp = k / MT_JUMP_Q, q = k - grp * MT_JUMP_Q;
+      uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      for (int wi = grp * MT_JUMP_Q; wi < (grp + 1) * MT_JUMP_Q; ++wi) {
+        const uint32_t pw = poly[wi];
+        if (pw == 0) continue;
+        const uint4* src = reinterpret_cast<const uint4*>(seq + wi * 32 + 4 * q);
+        uint32_t r[36];
+#pragma unroll
+        for (int v = 0; v < 9; ++v) {
+          const uint4 u = src[v];
+          r[4 * v] = u.x; r[4 * v + 1] = u.y; r[4 * v + 2] = u.z; r[4 * v + 3] = u.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t msk = 0u - ((pw >> j) & 1u);
+          a0 ^= r[j] & msk; a1 ^= r[j + 1] & msk; a2 ^= r[j + 2] & msk; a3 ^= r[j + 3] & msk;
+        }
+      }
+      *reinterpret_cast<uint4*>(part + grp * MT_N + 4 * q) = make_uint4(a0, a1, a2, a3);
     }
     __syncthreads();
-    cur ^= 1;
-    const int take = (int)min((int64_t)MT_N, n - done);
-    if (k < take) emit(done + k, mt_temper(w));
-    done += take;
-    pos = take;
+    uint32_t w = 0;
+    if (k < MT_N) w = part[k] ^ part[MT_N + k] ^ part[2 * MT_N + k] ^ part[3 * MT_N + k];
+    __syncthreads();
+    if (k < MT_N) seq[k] = w;
+    __syncthreads();
+    win = (int64_t)c * blocks_per_cta - 1;
   }
-  if (k < MT_N) rng[k] = st[cur][k];
-  if (k == 0) rng[MT_N] = (uint32_t)pos;
+  const int64_t lo = pos + (int64_t)c * W;                       // y-index range [lo, hi) of this CTA
+  const int64_t hi = min(lo + W, P);
+  const bool last_cta = hi == P;
+  if (c == 0 && pos == 0 && k == 0 && n > 0) emit(0, mt_temper(y0));      // y[0] itself (never inside a window)
+  // torch block holding the final position: the last CTA runs on until it holds window b_final and its predecessor
+  const int64_t b_final = P == 0 ? 0 : (P + MT_N - 1) / MT_N - 1;
+  while (true) {
+    if (k < MT_N) {
+      const int64_t idx = win * MT_N + 1 + k;
+      if (idx >= lo && idx < hi) emit(idx - pos, mt_temper(st[cur][k]));
+    }
+    const bool more_out = (win + 1) * MT_N + 1 < hi;
+    const bool more_state = last_cta && win < b_final;
+    if (!more_out && !more_state) break;
+    if (k < MT_N) st[cur ^ 1][k] = mt_next_word(st[cur], k);
+    __syncthreads();
+    cur ^= 1;
+    ++win;
+  }
+  if (last_cta) {
+    // advanced torch state: key[0] = y[624 b], key[j] = y[624 b + j] = window_b[j - 1]; position P - 624 b.
+    // Single-CTA draws write it in place; multi-CTA draws stage it (the other CTAs may not have read rng yet).
+    uint32_t* dst = gridDim.x == 1 ? rng : rng + MT_STAGE_OFF;
+    __syncthreads();
+    if (k < MT_N) {
+      uint32_t v;
+      if (k == 0) v = b_final == 0 ? y0 : st[cur ^ 1][MT_N - 1];
+      else v = st[cur][k - 1];
+      dst[k] = v;
+    }
+    if (k == 0) dst[MT_N] = (uint32_t)(P - b_final * MT_N);
+  }
+}
+
+__global__ void __launch_bounds__(MT_THREADS, 1) mt_commit_kernel(uint32_t* rng) {
+  MDM_PDL_ENTER();
+  if (threadIdx.x <= MT_N) rng[threadIdx.x] = rng[MT_STAGE_OFF + threadIdx.x];
 }
 
 struct EmitNone {
@@ -113,13 +196,52 @@ struct EmitThreshold {
   }
 };
 
+// parallel generation: table lent by the caller (mdm_rng_enable_parallel)
+static const uint32_t* g_polys = nullptr;
+static int g_npolys = 0, g_blocks_per_cta = 0, g_polys_dev = -1;
+
+template <class Emit>
+struct EmitShifted {   // a later launch of a draw that exceeds the table: indices continue where the previous one stopped
+  Emit e;
+  int64_t off;
+  __device__ void operator()(int64_t i, uint32_t w) const { e(i + off, w); }
+};
+
 template <class Emit>
 static int launch_stream(uint32_t* rng, int64_t n, Emit e, void* stream) {
   MDM_CHECK_ARG(rng != nullptr, "rng state is NULL");
   MDM_CHECK_ARG(n >= 0, "negative draw count");
   if (n == 0) return MDM_OK;
-  launch_pdl(mt_stream_kernel<Emit>, dim3(1), dim3(MT_THREADS), 0, as_stream(stream), rng, n, e);
-  MDM_LAUNCH_CHECK();
+  int dev = -1;
+  const bool par = g_polys != nullptr && n >= MDM_RNG_PAR_MIN_WORDS && cudaGetDevice(&dev) == cudaSuccess && dev == g_polys_dev;
+  if (!par) {
+    launch_pdl(mt_stream_kernel<Emit>, dim3(1), dim3(MT_THREADS), MT_SMEM_SERIAL, as_stream(stream), rng,
+               (const uint32_t*)nullptr, 1 << 24, n, e);
+    MDM_LAUNCH_CHECK();
+    return MDM_OK;
+  }
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    MDM_CUDA(cudaFuncSetAttribute(mt_stream_kernel<Emit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM_PAR));
+    MDM_CUDA(cudaFuncSetAttribute(mt_stream_kernel<EmitShifted<Emit>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM_PAR));
+    attr_set = true;
+  }
+  const int64_t W = (int64_t)g_blocks_per_cta * MT_N;
+  const int64_t per_launch = W * (g_npolys + 1);       // CTA 0 needs no polynomial
+  for (int64_t done = 0; done < n; done += per_launch) {
+    const int64_t m = n - done < per_launch ? n - done : per_launch;
+    const int ctas = (int)((m + W - 1) / W);
+    if (done == 0)
+      launch_pdl(mt_stream_kernel<Emit>, dim3(ctas), dim3(MT_THREADS), MT_SMEM_PAR, as_stream(stream), rng, g_polys, g_blocks_per_cta, m, e);
+    else
+      launch_pdl(mt_stream_kernel<EmitShifted<Emit>>, dim3(ctas), dim3(MT_THREADS), MT_SMEM_PAR, as_stream(stream), rng, g_polys,
+                 g_blocks_per_cta, m, EmitShifted<Emit>{e, done});
+    MDM_LAUNCH_CHECK();
+    if (ctas > 1) {
+      launch_pdl(mt_commit_kernel, dim3(1), dim3(MT_THREADS), 0, as_stream(stream), rng);
+      MDM_LAUNCH_CHECK();
+    }
+  }
   return MDM_OK;
 }
 
@@ -197,6 +319,23 @@ int mdm_rng_seed_host(uint32_t* s, uint32_t seed) {
   s[0] = seed;
   for (int j = 1; j < MT_N; ++j) s[j] = 1812433253u * (s[j - 1] ^ (s[j - 1] >> 30)) + (uint32_t)j;
   s[MT_N] = MT_N;
+  return MDM_OK;
+}
+
+int mdm_rng_enable_parallel(const uint32_t* polys_dev, int n_polys, int blocks_per_cta) {
+  if (polys_dev == nullptr || n_polys <= 0) {
+    g_polys = nullptr;
+    g_npolys = g_blocks_per_cta = 0;
+    g_polys_dev = -1;
+    return MDM_OK;
+  }
+  MDM_CHECK_ARG(blocks_per_cta >= 2 && blocks_per_cta <= (1 << 16), "enable_parallel: blocks_per_cta out of range");
+  int dev = -1;
+  MDM_CUDA(cudaGetDevice(&dev));
+  g_polys = polys_dev;
+  g_npolys = n_polys;
+  g_blocks_per_cta = blocks_per_cta;
+  g_polys_dev = dev;
   return MDM_OK;
 }
 

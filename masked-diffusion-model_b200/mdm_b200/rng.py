@@ -34,6 +34,30 @@ def pack_torch_state(seed: int, key: np.ndarray, pos: int, template: torch.Tenso
     return torch.frombuffer(buf, dtype=torch.uint8).clone()
 
 
+# parallel stream generation (csrc/mt_jump.cu): one jump-polynomial table per process and device
+JUMP_POLYS = 512            # CTAs per launch beyond the first: 513 x 64 blocks x 624 words = 20.5 M words per launch
+JUMP_BLOCKS_PER_CTA = 64    # 39936 words per CTA (~30 us of generation behind a ~0.1 ms jump)
+_jump_tables = {}
+
+
+def ensure_parallel(device):
+    """compute the jump polynomials on the host (Berlekamp-Massey + 512 modular products, ~0.5 s, once per process),
+    copy them to `device` and lend them to the library; MDM_RNG_PARALLEL=0 keeps every draw on one CTA"""
+    import os
+    if os.environ.get("MDM_RNG_PARALLEL", "1") == "0":
+        return False
+    key = (device.type, device.index)
+    if key not in _jump_tables:
+        host = np.empty(JUMP_POLYS * MT_N, dtype=np.uint32)
+        check(lib().mdm_rng_jump_table_host(host.ctypes.data, JUMP_POLYS, JUMP_BLOCKS_PER_CTA))
+        t = torch.from_numpy(host.view(np.int32)).to(device)
+        with torch.cuda.device(device):
+            check(lib().mdm_rng_enable_parallel(t.data_ptr(), JUMP_POLYS, JUMP_BLOCKS_PER_CTA))
+        _jump_tables.clear()            # the library holds ONE table (one process per GPU)
+        _jump_tables[key] = t
+    return True
+
+
 class DeviceMT19937:
     def __init__(self, device):
         self.device = torch.device(device)
@@ -41,7 +65,9 @@ class DeviceMT19937:
             raise RuntimeError("DeviceMT19937 needs a CUDA device (no CPU fallback)")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self.state = torch.empty(_lib.RNG_WORDS, dtype=torch.int32, device=self.device)
+        # 1280 words: [0..624] key + position, [640..1264] staging of the advanced state (multi-CTA draws)
+        self.state = torch.zeros(_lib.RNG_PAR_WORDS, dtype=torch.int32, device=self.device)
+        ensure_parallel(self.device)
         self.seed = 0
         self._template = None
         self.words_drawn = 0
@@ -51,13 +77,13 @@ class DeviceMT19937:
         host = np.empty(_lib.RNG_WORDS, dtype=np.uint32)
         host[:MT_N] = key
         host[MT_N] = pos
-        self.state.copy_(torch.from_numpy(host.view(np.int32)))
+        self.state[:_lib.RNG_WORDS].copy_(torch.from_numpy(host.view(np.int32)))
 
     def manual_seed(self, seed: int):
         host = np.empty(_lib.RNG_WORDS, dtype=np.uint32)
         check(lib().mdm_rng_seed_host(host.ctypes.data, int(seed) & 0xFFFFFFFF))
         self.seed = int(seed)
-        self.state.copy_(torch.from_numpy(host.view(np.int32)))
+        self.state[:_lib.RNG_WORDS].copy_(torch.from_numpy(host.view(np.int32)))
         return self
 
     def adopt_torch(self, generator: torch.Generator | None = None):
@@ -68,7 +94,7 @@ class DeviceMT19937:
         return self
 
     def export(self):
-        host = self.state.cpu().numpy().view(np.uint32)
+        host = self.state[:_lib.RNG_WORDS].cpu().numpy().view(np.uint32)
         return host[:MT_N].copy(), int(host[MT_N])
 
     def release_to_torch(self, generator: torch.Generator | None = None):

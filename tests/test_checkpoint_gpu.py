@@ -31,6 +31,7 @@ def _build(seed):
     a = mk_args(data_size=16, ddpm_num_steps=50, select_degrade_pixel="indexing", ddpm_schedule="log",
                 mean_option="degraded_area", mean_area="image-wise", method="base", mixed_precision="bf16")
     a.use_ema, a.cuda_graph, a.timeindex_rng = True, True, "cpu_stream"
+    a.ema_max_decay, a.ema_inv_gamma, a.ema_power = 0.9999, 1.0, 0.75          # main_train_masked.py:372-374 defaults
     model = UNet2DModelB200(device="cuda", **SMALL)
     model.reset_parameters(seed=seed)
     ema = M.get_ema(a, model)

@@ -94,3 +94,74 @@ def test_large_stream_matches_oracle():
     n = 3_000_000
     a = dev_rng(2).raw(n).cpu().numpy().view(np.uint32)
     assert np.array_equal(a, OracleRNG(2).raw(n))
+
+
+# ---- multi-CTA generation (GF(2) jump-ahead, csrc/mt_jump.cu + the kernel in csrc/rng.cu) -------------------------------
+W = 64 * 624          # words per CTA (mdm_b200.rng.JUMP_BLOCKS_PER_CTA)
+
+
+@pytest.mark.parametrize("pre,n", [(0, 262144), (1, 262144 + 13), (623, 7 * W), (624, 7 * W + 1), (300, 7 * W - 1),
+                                   (17, 12_582_912), (5, 20 * W + 623), (5, 20 * W + 624), (5, 20 * W + 625)])
+def test_parallel_stream_is_the_serial_stream(pre, n):
+    """draws above MDM_RNG_PAR_MIN_WORDS are cut over ceil(n / W) CTAs: same words, same advanced state, and the next
+    (serial) draw continues the sequence"""
+    r = dev_rng(31)
+    o = OracleRNG(31)
+    if pre:
+        assert np.array_equal(r.raw(pre).cpu().numpy().view(np.uint32), o.raw(pre))
+    got = r.raw(n).cpu().numpy().view(np.uint32)
+    want = o.raw(n)
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, (bad[:5], bad.size)
+    key, pos = r.export()
+    okey, opos = o.state_words()
+    assert pos == opos and np.array_equal(key, okey)
+    assert np.array_equal(r.raw(1000).cpu().numpy().view(np.uint32), o.raw(1000))
+    assert np.array_equal(r.raw(n).cpu().numpy().view(np.uint32), o.raw(n))      # a second parallel draw from a mid-block position
+
+
+def test_parallel_draw_longer_than_the_table(monkeypatch):
+    """a draw that needs more CTAs than there are polynomials runs as several launches, each committing its state"""
+    from mdm_b200 import rng as rng_mod
+    from mdm_b200._lib import check, lib
+    r = dev_rng(9)
+    table = next(iter(rng_mod._jump_tables.values()))
+    check(lib().mdm_rng_enable_parallel(table.data_ptr(), 4, rng_mod.JUMP_BLOCKS_PER_CTA))     # 5 CTAs per launch
+    try:
+        n = 12 * W + 5
+        got = r.raw(n).cpu().numpy().view(np.uint32)
+        o = OracleRNG(9)
+        assert np.array_equal(got, o.raw(n))
+        key, pos = r.export()
+        okey, opos = o.state_words()
+        assert pos == opos and np.array_equal(key, okey)
+    finally:
+        check(lib().mdm_rng_enable_parallel(table.data_ptr(), rng_mod.JUMP_POLYS, rng_mod.JUMP_BLOCKS_PER_CTA))
+
+
+def test_parallel_masks_and_noise_equal_serial():
+    """the consumers of the stream at the configs[3] sizes: threshold masks, uniforms and Box-Muller noise are identical
+    with the table lent and with it withdrawn (one CTA), and so is the state left behind"""
+    from mdm_b200 import rng as rng_mod
+    from mdm_b200._lib import check, lib
+    B, hw = 32, 128 * 128
+    ratio = torch.linspace(0.01, 0.99, B, dtype=torch.float64).cuda()
+    outs = {}
+    table = next(iter(rng_mod._jump_tables.values())) if rng_mod._jump_tables else None
+    for par in (True, False):
+        r = dev_rng(4)
+        if not par:
+            check(lib().mdm_rng_enable_parallel(None, 0, 0))
+        try:
+            r.raw(5)
+            m = r.threshold_mask(ratio, B, hw)
+            m1, m2 = r.threshold_mask(ratio, B, hw, ratio2=ratio * 0.5)
+            u = r.uniform(B * hw, -1.0, 1.0)
+            nz = r.normal(B, 3 * hw, 0.25, 1.0, ratio=ratio)
+            outs[par] = (m.clone(), m1.clone(), m2.clone(), u.clone(), nz.clone(), r.export())
+        finally:
+            if not par and table is not None:
+                check(lib().mdm_rng_enable_parallel(table.data_ptr(), rng_mod.JUMP_POLYS, rng_mod.JUMP_BLOCKS_PER_CTA))
+    for a, b in zip(outs[True][:5], outs[False][:5]):
+        assert torch.equal(a, b)
+    assert outs[True][5][1] == outs[False][5][1] and np.array_equal(outs[True][5][0], outs[False][5][0])
