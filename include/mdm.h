@@ -285,15 +285,44 @@ int mdm_cast_f32_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
  * coef = min(1, max_norm / (norm + 1e-6)); grad_scale multiplies g first (1/world for a summed
  * all-reduce); ema / p_bf16 may be NULL. */
 int mdm_grad_sumsq(const float* g, int64_t n, float* ws, float* out, void* stream);
+/* beta1 / beta2 / bias corrections are DOUBLES: torch derives 1 - beta, lr / bias_c1 and sqrt(bias_c2) from python
+ * doubles and rounds once (1.0f - 0.999f is 4.7e-5 away from 0.001f); the kernel uses the same fp32 scalars. */
 int mdm_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, int64_t n,
-                      const float* gnorm_sq, float lr, float beta1, float beta2, float eps,
-                      float weight_decay, float bias_c1, float bias_c2, float max_norm, float ema_decay,
+                      const float* gnorm_sq, float lr, double beta1, double beta2, float eps,
+                      float weight_decay, double bias_c1, double bias_c2, float max_norm, float ema_decay,
                       float grad_scale, int mode, void* stream);
-/* same, with the per-step scalars read from DEVICE memory: hyper[4] = {lr, bias_c1, bias_c2,
- * ema_decay}, so the launch can sit inside a replayed CUDA graph while the LR schedule advances. */
+/* same, with the per-step scalars read from DEVICE memory: hyper[4] = {lr, lr / bias_c1, sqrt(bias_c2),
+ * ema_decay} (computed in double on the host, stored as fp32), so the launch can sit inside a replayed CUDA graph
+ * while the LR schedule advances. */
 int mdm_adam_ema_step_dev(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, int64_t n,
-                          const float* gnorm_sq, const float* hyper, float beta1, float beta2, float eps,
+                          const float* gnorm_sq, const float* hyper, double beta1, double beta2, float eps,
                           float weight_decay, float max_norm, float grad_scale, int mode, void* stream);
+/* Step statistics without a device synchronisation (replaces the blocking `loss.item()` of trainer_masked.py:160 /
+ * trainer_masked_mean_shift.py:172): copies src[0..n) to dst_host_mapped[0..n) -- PINNED HOST memory, device-mapped
+ * (cudaHostAlloc under UVA) -- then increments *counter and stores the new count, as int bits, to
+ * dst_host_mapped[n].  The host polls that word: the statistics of a step are readable as soon as the forward part of
+ * the (captured) step has run, while its backward and optimiser are still in flight.  n <= 31. */
+int mdm_publish_stats(const float* src, int n, int* counter, float* dst_host_mapped, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel gradient all-reduce over NVLink peer memory (csrc/allreduce.cu).  Replaces the NCCL all-reduce that
+ * accelerate / DDP run behind `accelerator.backward` (trainer_masked.py:142): ONE kernel per
+ * gradient range, capturable inside the training-step graph on a forked stream, 256-thread blocks that co-reside with
+ * the persistent GEMM CTAs.  One process per GPU: every rank exports its flat gradient buffer and a zeroed flag array
+ * (mdm_p2p_flag_words() uint32) with mdm_ipc_export, exchanges the 64-byte handles + offsets through its process
+ * group, and maps the peers' with mdm_ipc_open.  mdm_p2p_allreduce sums buf[offset .. offset + count) over the ranks
+ * in rank order (bit-identical on every rank) in place; every rank must issue the same sequence of calls, each rank's
+ * calls stream-ordered.  The caller divides by world.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  void* buf[8];    /* flat fp32 gradient buffer of rank p (own or IPC-mapped), p < world */
+  void* flag[8];   /* flag array of rank p */
+  int rank, world;
+} mdm_p2p_comm;
+int mdm_p2p_flag_words(void);
+int mdm_ipc_export(const void* ptr, void* handle_out /*64 bytes, host*/, int64_t* offset_out /*host*/);
+int mdm_ipc_open(const void* handle /*64 bytes, host*/, int64_t offset, void** ptr_out /*host*/);
+int mdm_p2p_allreduce(const mdm_p2p_comm* comm /*host*/, int64_t offset, int64_t count, int blocks, void* stream);
 
 #ifdef __cplusplus
 }

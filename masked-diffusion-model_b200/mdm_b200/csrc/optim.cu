@@ -39,8 +39,26 @@ __global__ void sumsq_final_kernel(const float* __restrict__ partial, int n, flo
   }
 }
 
+// step statistics -> host-mapped pinned memory, straight from the device: the trainer reads the loss of a step as soon
+// as the FORWARD part of the captured step has run (the backward and the optimiser are still in flight), so the host
+// prepares and enqueues the next step while the GPU finishes this one instead of idling through a full
+// device synchronisation per batch (the reference's `loss.item()`, trainer_masked.py:160).
+__global__ void publish_stats_kernel(const float* __restrict__ src, int n, int* __restrict__ counter, volatile float* dst_host) {
+  MDM_PDL_ENTER();
+  if (threadIdx.x < n) dst_host[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(counter, 1) + 1;
+    dst_host[n] = __int_as_float(t);        // the tick the host polls for: written after the values are visible
+    __threadfence_system();
+  }
+}
+
+// scalars exactly as torch.optim derives them (python doubles rounded to fp32 once): 1 - beta from the DOUBLE beta
+// (1.0f - 0.999f is 4.7e-5 off 0.001f), step_size = lr / bias_correction1, sqrt(bias_correction2)
 struct AdamArgs {
-  float lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2, max_norm, ema_decay, grad_scale;
+  float lr, beta1, beta2, omb1, omb2, eps, weight_decay, step_size, sqrt_c2, max_norm, ema_decay, grad_scale;
   int decoupled;   // 1 = AdamW, 0 = Adam (L2 added to the gradient)
 };
 
@@ -49,7 +67,7 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
                                 long long n, const float* __restrict__ gnorm_sq, const float* __restrict__ hyper, AdamArgs a) {
   MDM_PDL_ENTER();
   if (hyper) {  // per-step scalars read from device memory so that a captured CUDA graph can be replayed
-    a.lr = hyper[0]; a.bias_c1 = hyper[1]; a.bias_c2 = hyper[2]; a.ema_decay = hyper[3];
+    a.lr = hyper[0]; a.step_size = hyper[1]; a.sqrt_c2 = hyper[2]; a.ema_decay = hyper[3];
   }
   float coef = a.grad_scale;
   if (gnorm_sq && a.max_norm > 0.f) {
@@ -57,8 +75,8 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
     const float total = sqrtf(*gnorm_sq) * a.grad_scale;
     coef *= fminf(1.0f, a.max_norm / (total + 1e-6f));
   }
-  const float step = a.lr / a.bias_c1;
-  const float sqrt_c2 = sqrtf(a.bias_c2);   // torch: denom = sqrt(v) / sqrt(bias_correction2) + eps
+  const float step = a.step_size;
+  const float sqrt_c2 = a.sqrt_c2;          // torch: denom = sqrt(v) / sqrt(bias_correction2) + eps
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
     float4 P = *reinterpret_cast<const float4*>(p + i);
     const float4 Gr = *reinterpret_cast<const float4*>(g + i);
@@ -70,8 +88,8 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
       float gk = gg[k] * coef;
       if (a.decoupled) pp[k] *= (1.0f - a.lr * a.weight_decay);
       else gk += a.weight_decay * pp[k];
-      mm[k] = a.beta1 * mm[k] + (1.0f - a.beta1) * gk;
-      vv[k] = a.beta2 * vv[k] + (1.0f - a.beta2) * gk * gk;
+      mm[k] = a.beta1 * mm[k] + a.omb1 * gk;
+      vv[k] = a.beta2 * vv[k] + a.omb2 * gk * gk;
       const float denom = sqrtf(vv[k]) / sqrt_c2 + a.eps;
       pp[k] -= step * (mm[k] / denom);
     }
@@ -125,13 +143,21 @@ int mdm_grad_sumsq(const float* g, int64_t n, float* ws, float* out, void* strea
   return MDM_OK;
 }
 
+int mdm_publish_stats(const float* src, int n, int* counter, float* dst_host_mapped, void* stream) {
+  MDM_CHECK_ARG(src && counter && dst_host_mapped && n >= 1 && n <= 31, "publish_stats: bad arguments");
+  launch_pdl(publish_stats_kernel, dim3(1), dim3(32), 0, as_stream(stream), src, n, counter, (volatile float*)dst_host_mapped);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
 static int adam_launch(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, int64_t n,
-                       const float* gnorm_sq, const float* hyper, float lr, float beta1, float beta2, float eps,
-                       float weight_decay, float bias_c1, float bias_c2, float max_norm, float ema_decay,
+                       const float* gnorm_sq, const float* hyper, float lr, double beta1, double beta2, float eps,
+                       float weight_decay, double bias_c1, double bias_c2, float max_norm, float ema_decay,
                        float grad_scale, int mode, void* stream) {
   MDM_CHECK_ARG(p && g && n > 0 && n % 4 == 0, "adam_ema_step: n must be a positive multiple of 4");
   MDM_CHECK_ARG(mode >= 0 && mode <= 2, "adam_ema_step: mode 0 = Adam, 1 = AdamW, 2 = SGD");
-  AdamArgs a{lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2, max_norm, ema_decay, grad_scale, mode == 1};
+  AdamArgs a{lr, (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), eps, weight_decay,
+             (float)((double)lr / bias_c1), (float)sqrt(bias_c2), max_norm, ema_decay, grad_scale, mode == 1};
   const int blocks = kNumSMs * 8;
   if (mode == 2) {
     launch_pdl(sgd_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), p, g, ema, (__nv_bfloat16*)p_bf16, n, gnorm_sq, hyper, a);
@@ -144,18 +170,18 @@ static int adam_launch(float* p, const float* g, float* m, float* v, float* ema,
 }
 
 int mdm_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, int64_t n,
-                      const float* gnorm_sq, float lr, float beta1, float beta2, float eps, float weight_decay,
-                      float bias_c1, float bias_c2, float max_norm, float ema_decay, float grad_scale, int mode,
+                      const float* gnorm_sq, float lr, double beta1, double beta2, float eps, float weight_decay,
+                      double bias_c1, double bias_c2, float max_norm, float ema_decay, float grad_scale, int mode,
                       void* stream) {
   return adam_launch(p, g, m, v, ema, p_bf16, n, gnorm_sq, nullptr, lr, beta1, beta2, eps, weight_decay, bias_c1,
                      bias_c2, max_norm, ema_decay, grad_scale, mode, stream);
 }
 
 int mdm_adam_ema_step_dev(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, int64_t n,
-                          const float* gnorm_sq, const float* hyper, float beta1, float beta2, float eps,
+                          const float* gnorm_sq, const float* hyper, double beta1, double beta2, float eps,
                           float weight_decay, float max_norm, float grad_scale, int mode, void* stream) {
   MDM_CHECK_ARG(hyper, "adam_ema_step_dev: hyper is NULL");
-  return adam_launch(p, g, m, v, ema, p_bf16, n, gnorm_sq, hyper, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f,
+  return adam_launch(p, g, m, v, ema, p_bf16, n, gnorm_sq, hyper, 0.f, beta1, beta2, eps, weight_decay, 1.0, 1.0,
                      max_norm, 0.f, grad_scale, mode, stream);
 }
 

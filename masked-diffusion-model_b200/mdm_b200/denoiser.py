@@ -250,6 +250,16 @@ class UNet2DModelB200:
             self._params[s.name] = p
         self._bf16_stale = True
 
+    def rehome_grad(self, buf):
+        """move the flat gradient into `buf` (a dedicated, IPC-exportable allocation: data-parallel peer-memory all-reduce);
+        every p.grad becomes a view of it, plans built against the old buffer are dropped"""
+        assert buf.numel() == self.numel_flat and buf.dtype == torch.float32 and buf.device == self.flat_grad.device
+        buf.copy_(self.flat_grad)
+        self.flat_grad = buf
+        for s in self._specs:
+            self._params[s.name].grad = buf[s.offset:s.offset + s.numel].view(s.shape)
+        self._plans = {}
+
     def num_parameters(self):
         return sum(s.numel for s in self._specs)
 
@@ -512,14 +522,26 @@ class UNet2DModelB200:
         """segment k >= 1 of the last backward (after `bwd_segmented = True` made loss.backward() stop at segment 0)"""
         self._last_plans[0].run_backward(None, k)
 
+    def dp_cut_prefixes(self):
+        """resnet prefixes at which the backward program is cut for data-parallel overlap, in backward order (the first
+        is always the mid block: everything from there to the head lies contiguously at the end of the flat buffer).
+        MDM_DP_CUTS overrides (comma-separated `down_blocks.<i>` indices, descending), e.g. "4,2,1"."""
+        n = len(self._cfg["block_out_channels"])
+        spec = os.environ.get("MDM_DP_CUTS", getattr(self, "dp_cuts", "4,2,1"))
+        cuts = [int(c) for c in str(spec).split(",") if c.strip() != ""]
+        cuts = [c for c in sorted(set(cuts), reverse=True) if 0 < c < n]
+        return ["mid_block.resnets.0"] + [f"down_blocks.{c}.resnets.0" for c in cuts]
+
     def grad_segment_ranges(self):
         """[(lo, hi)] of the flat gradient finished by backward segment 0, 1, ...; the last segment finishes the
         complement.  Matches `_Plan.bwd_marks`."""
         lo0, hi0 = self.late_grad_range()
         out = [(lo0, hi0)]
-        d2 = self._by_name.get("down_blocks.2.resnets.0.norm1.weight")
-        if d2 is not None and len(self._cfg["block_out_channels"]) > 3:
-            out.append((d2.offset, lo0))
+        prev = lo0
+        for pre in self.dp_cut_prefixes()[1:]:
+            off = self._by_name[f"{pre}.norm1.weight"].offset
+            out.append((off, prev))
+            prev = off
         return out
 
     def backward(self, d_out: torch.Tensor):
@@ -794,12 +816,11 @@ class _Plan:
         emit = dict(conv_in=self._emit_conv_in, resnet=self._emit_resnet, attn=self._emit_attn, down=self._emit_down,
                     up=self._emit_up, head=self._emit_head)
         entries = []
-        first_mid = first_d2 = None
+        cut_at = {}                     # op index -> position in dp_cut_prefixes() (segment boundary BEFORE this op in forward order)
+        cut_names = m.dp_cut_prefixes()
         for i, (kind, d) in enumerate(self._ops):
-            if first_mid is None and kind == "resnet" and d["r"].prefix == "mid_block.resnets.0":
-                first_mid = i
-            if first_d2 is None and kind == "resnet" and d["r"].prefix == "down_blocks.2.resnets.0":
-                first_d2 = i
+            if kind == "resnet" and d["r"].prefix in cut_names:
+                cut_at[i] = cut_names.index(d["r"].prefix)
             rows = None
             if self.lanes > 1 and kind in ("resnet", "attn", "down", "up"):
                 hh = 2 * d["H"] if kind == "up" else d["H"]          # resolution the op's GEMMs run at
@@ -827,7 +848,8 @@ class _Plan:
         self._alloc_q()
         # backward segments for data-parallel overlap: the gradients of a contiguous range of the flat buffer are
         # final at the end of each segment (UNet2DModelB200.grad_segment_ranges), so their all-reduce runs while
-        # the next segment computes.  segment 0: head, up path, mid block; 1: down blocks 5..2; 2: the rest.
+        # the next segment computes.  segment 0: head, up path, mid block; then one segment per cut of dp_cut_prefixes()
+        # (default: down blocks 5..4, 3..2, 1); the last one: the rest.
         self.bwd_marks = []
         if ng:
             region = None
@@ -842,20 +864,19 @@ class _Plan:
                 else:
                     region = None
                     self.bwd += bw
-                if i == first_mid:
+                if i in cut_at:
                     region = None            # a segment boundary closes the region: its lanes have joined
-                    self.bwd.append(self._grads_ready_mid)
-                    self.bwd_marks.append(len(self.bwd))
-                elif i == first_d2 and first_mid is not None and len(self.m._cfg["block_out_channels"]) > 3:
-                    region = None
+                    self.bwd.append(lambda k=cut_at[i]: self._grads_ready(k))
                     self.bwd_marks.append(len(self.bwd))
             self.bwd.append(self._temb_bwd)
 
-    def _grads_ready_mid(self):
+    def _grads_ready(self, k):
+        """end of backward segment k: the gradients of grad_segment_ranges()[k] are final.  `model.grad_ready_hook(lo, hi)`
+        (the trainer's in-graph peer-memory all-reduce) is called with the main stream ordered after the side streams."""
         hook = getattr(self.m, "grad_ready_hook", None)
         if hook is not None:
             self.join_side()                     # the weight gradients of that range ran on the side stream
-            lo, hi = self.m.late_grad_range()
+            lo, hi = self.m.grad_segment_ranges()[k]
             hook(lo, hi)
 
     def _sym_resnet(self, r, x, res):

@@ -248,8 +248,10 @@ class FusedOptimizer:
         if self.ema is not None:
             ema_decay = self.ema.get_decay(self.ema.optimization_step + 1)
             self.ema._fused_done = True
-        self._hyper.copy_(torch.tensor([g["lr"], 1.0 - b1 ** self.step_count, 1.0 - b2 ** self.step_count, ema_decay],
-                                       dtype=torch.float32), non_blocking=True)
+        # the scalars torch.optim.Adam derives per step, in double, rounded to fp32 once: step_size, sqrt(bias_correction2)
+        bc1, bc2 = 1.0 - b1 ** self.step_count, 1.0 - b2 ** self.step_count
+        self._hyper.copy_(torch.tensor([g["lr"], g["lr"] / bc1, math.sqrt(bc2), ema_decay], dtype=torch.float32),
+                          non_blocking=True)
 
     def launch(self, clip=None):
         """device part of a step (one kernel): clip + Adam/AdamW/SGD + EMA + bf16 mirror"""
@@ -289,6 +291,47 @@ class FusedOptimizer:
             self.m.copy_(sd["m"]); self.v.copy_(sd["v"])
         for g, n in zip(self.param_groups, sd["param_groups"]):
             g.update(n)
+
+
+# ---------------------------------------------------------------------------------------------
+# gradient all-reduce over NVLink peer memory (csrc/allreduce.cu)
+# ---------------------------------------------------------------------------------------------
+class P2PAllReduce:
+    """Maps every rank's flat gradient buffer into every process (CUDA IPC; handles exchanged through the process
+    group) and reduces ranges of it with ONE hand-written kernel per range -- capturable inside the training-step
+    graph, small blocks that co-reside with the persistent GEMM CTAs (NCCL's channels wait for free SMs: the
+    round-1 all-reduce stayed exposed).  SUM semantics, like the NCCL path: the fused optimiser folds in 1/world."""
+
+    def __init__(self, model, rank, world, device):
+        from . import comm_ops
+        self._ops = comm_ops
+        if world > comm_ops.MAX_RANKS:
+            raise RuntimeError(f"P2PAllReduce: at most {comm_ops.MAX_RANKS} ranks (one NVSwitch domain)")
+        self.rank, self.world, self.device = rank, world, device
+        self.blocks = int(os.environ.get("MDM_P2P_BLOCKS", "48"))
+        n = model.numel_flat
+        # a dedicated allocation for the gradients (the IPC handle covers a whole cudaMalloc segment)
+        self.buf = torch.zeros(n, dtype=torch.float32, device=device)
+        self.flags = torch.zeros(comm_ops.flag_words(), dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        mine = (comm_ops.ipc_export(self.buf), comm_ops.ipc_export(self.flags))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        self.comm = comm_ops.P2PCommStruct()
+        self.comm.rank, self.comm.world = rank, world
+        for p in range(world):
+            if p == rank:
+                self.comm.buf[p], self.comm.flag[p] = self.buf.data_ptr(), self.flags.data_ptr()
+            else:
+                (hb, ob), (hf, of) = everyone[p]
+                self.comm.buf[p] = comm_ops.ipc_open(hb, ob)
+                self.comm.flag[p] = comm_ops.ipc_open(hf, of)
+        model.rehome_grad(self.buf)
+        dist.barrier()
+
+    def all_reduce(self, lo, hi):
+        """enqueue the SUM all-reduce of flat_grad[lo:hi] on the current stream"""
+        self._ops.p2p_allreduce(self.comm, lo, hi - lo, self.blocks, self.device)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -349,6 +392,7 @@ class Accelerator:
         self._accum = 0
         self._models, self._optimizers, self._schedulers = [], [], []
         self._save_hooks, self._load_hooks = [], []
+        self.p2p = None                   # P2PAllReduce of the (single) B200 denoiser, data parallel on CUDA
 
     # -- properties ----------------------------------------------------------------------------
     @property
@@ -384,6 +428,7 @@ class Accelerator:
                 if isinstance(o, torch.nn.Module):
                     o.to(self.device)
                 self._broadcast_params(o)
+                self._setup_p2p(o)
                 out.append(o)
             elif isinstance(o, (FusedOptimizer, torch.optim.Optimizer)):
                 self._optimizers.append(o)
@@ -400,6 +445,22 @@ class Accelerator:
             else:
                 out.append(o)
         return out[0] if len(out) == 1 else tuple(out)
+
+    def _setup_p2p(self, model):
+        """data parallel on CUDA with the B200 denoiser: gradients are reduced by the peer-memory kernel
+        (MDM_DP_ALLREDUCE=nccl keeps the NCCL all-reduce; a failed IPC set-up falls back to it on every rank)"""
+        if (self.num_processes <= 1 or self.device.type != "cuda" or not hasattr(model, "rehome_grad") or self.p2p is not None
+                or os.environ.get("MDM_DP_ALLREDUCE", "p2p").lower() != "p2p"):
+            return
+        ok = torch.ones(1, device=self.device)
+        p2p = None
+        try:
+            p2p = P2PAllReduce(model, self.rank, self.num_processes, self.device)
+        except Exception as e:                                   # e.g. IPC not permitted in this container
+            print(f"[mdm_b200] rank {self.rank}: peer-memory all-reduce unavailable ({e!r}); using NCCL", flush=True)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)                # all ranks or none
+        self.p2p = p2p if ok.item() > 0 else None
 
     def _broadcast_params(self, model):
         if self.num_processes <= 1:
@@ -431,7 +492,10 @@ class Accelerator:
         fused = any(isinstance(o, FusedOptimizer) for o in self._optimizers)
         for m in self._models:
             if hasattr(m, "flat_grad"):
-                dist.all_reduce(m.flat_grad, op=dist.ReduceOp.SUM)
+                if self.p2p is not None and m.flat_grad.data_ptr() == self.p2p.buf.data_ptr():
+                    self.p2p.all_reduce(0, m.flat_grad.numel())
+                else:
+                    dist.all_reduce(m.flat_grad, op=dist.ReduceOp.SUM)
                 if not fused:                       # the fused optimiser folds 1/world into its kernel
                     m.flat_grad.mul_(1.0 / self.num_processes)
             else:

@@ -66,6 +66,7 @@ class Trainer:
         self._graphs = {}
         self._ts_dev = {}
         self.degradation_mask = None
+        self._pin, self._ticks_expected, self._stats_published = None, 0, False
         if self._fused() and getattr(args, "use_ema", False) and ema_model is not None:
             self.optimizer.attach_ema(ema_model)      # EMA update rides in the optimiser kernel
 
@@ -125,14 +126,45 @@ class Trainer:
             # recon = degraded + net ; loss = mean(w (recon - x0)^2)   (one fused kernel, fwd + grad)
             self.reconstruct_loss, self.reconstructed_img = train_ops.residual_mse(self.mask, self.degraded_img, x0,
                                                                                    shift=None, weight=weight)
+            stats = self._publish(self._stats())      # forward-only statistics: readable before the backward has run
             self.accelerator.backward(self.reconstruct_loss)
-        return self._stats()
+        return stats
 
     def _stats(self):
         self.reconstruct_train_mean = self.reconstructed_img.mean()
         self.degraded_train_mean = self.degraded_img.mean()
         return torch.stack([self.reconstruct_loss.detach().float(), self.reconstruct_train_mean.float(),
                             self.degraded_train_mean.float()])
+
+    # ------------------------------------------------------------------------------------------
+    # step statistics without a full device synchronisation
+    # ------------------------------------------------------------------------------------------
+    def _publish(self, stats):
+        """fused path: a kernel stores the statistics and a tick into pinned host memory right after the forward part
+        of the step; `_return_values` polls the tick instead of synchronising with the whole step, so the host enqueues
+        step i + 1 while the GPU still runs the backward / optimiser of step i."""
+        if not self._fused() or not bool(getattr(self.args, "async_stats", True)):
+            return stats
+        from mdm_b200 import optim_ops
+        if getattr(self, "_pin", None) is None:
+            self._pin = torch.zeros(32, dtype=torch.float32).pin_memory()
+            self._pin_f = self._pin.numpy()
+            self._pin_i = self._pin_f.view("int32")
+            self._tick_dev = torch.zeros(1, dtype=torch.int32, device=stats.device)
+        self._n_stats = stats.numel()
+        optim_ops.publish_stats(stats.float().contiguous(), self._tick_dev, self._pin)
+        return stats
+
+    def _await_stats(self):
+        """the statistics of the step just enqueued (None when nothing was published: generic path)"""
+        if getattr(self, "_pin", None) is None or not self._stats_published:
+            return None
+        n, want = self._n_stats, self._ticks_expected
+        t0 = timer()
+        while int(self._pin_i[n]) != want:
+            if timer() - t0 > 120.0:
+                raise RuntimeError(f"step statistics never arrived (tick {int(self._pin_i[n])}, expected {want})")
+        return [float(v) for v in self._pin_f[:n]]
 
     def _optimizer_tail_device(self):
         """clip + optimiser + EMA + zero_grad for the fused optimiser (device part)"""
@@ -155,22 +187,29 @@ class Trainer:
         g = self._graphs.get(key)
         if g is None:
             self._graphs.clear()
-            if single:
+            p2p = getattr(acc, "p2p", None)
+            if single or p2p is not None:
+                # single GPU, or data parallel with the peer-memory all-reduce: the WHOLE step is one graph.  Under DP
+                # the backward program calls `_dp_range_ready` at every cut (denoiser.py: dp_cut_prefixes): the range
+                # that just became final is all-reduced by one kernel on a forked stream while the next segment
+                # computes; the remaining ranges and the join come right before the optimiser.
                 def body():
                     stats = self._forward_backward()
+                    if not single:
+                        self._dp_finish()
                     self._optimizer_tail_device()
                     return stats
                 g = (train_ops.GraphedCallable(body, enabled=use_graph), None)
             else:
-                # data parallel: graph(fwd+bwd) -> NCCL all-reduce of the flat gradient -> graph(optimiser tail).
-                # (Capturing the all-reduce inside one graph, started mid-backward through
-                # `model.grad_ready_hook` / `Accelerator.start_late_all_reduce`, hung on 2 GPUs in round 1: the
-                # plumbing stays, the trainer uses the validated three-piece sequence.)
+                # data parallel over NCCL (MDM_DP_ALLREDUCE=nccl): graph(fwd+bwd) -> NCCL all-reduce of the flat
+                # gradient -> graph(optimiser tail).  (Capturing the NCCL all-reduce inside one graph hung on 2 GPUs
+                # in round 1.)
                 # With `dp_overlap` (default) the backward is cut into segments, each its own graph: the flat-gradient
                 # range a segment finishes is all-reduced asynchronously (NCCL stream) under the next segment.
                 segs = []
                 m = self.model
-                if bool(getattr(self.args, "dp_overlap", True)) and hasattr(m, "grad_segment_ranges"):
+                if (bool(getattr(self.args, "dp_overlap", True)) and os.environ.get("MDM_DP_OVERLAP", "1") != "0"
+                        and hasattr(m, "grad_segment_ranges")):
                     ranges = m.grad_segment_ranges()
                     segs = [train_ops.GraphedCallable((lambda k=k: m.backward_segment(k)), enabled=use_graph)
                             for k in range(1, len(ranges) + 1)]
@@ -183,8 +222,16 @@ class Trainer:
             # rewrote the master weights since the last step (EMA copy_to / restore, load_state_dict) re-casts here
             self.model._refresh_bf16()
         if g[1] is None:
-            acc._defer_all_reduce = False
-            stats = g[0]()
+            dp = not single
+            acc._defer_all_reduce = dp          # (DP: the ranges are reduced by the in-graph peer-memory kernels)
+            if dp:
+                self.model.grad_ready_hook = self._dp_range_ready
+            try:
+                stats = g[0]()
+            finally:
+                acc._defer_all_reduce = False
+                if dp:
+                    self.model.grad_ready_hook = None
         elif not g[2]:
             acc._defer_all_reduce = True        # the all-reduce runs between the two graphs
             try:
@@ -215,6 +262,35 @@ class Trainer:
             g[1]()
         return stats
 
+    # -- data parallel, peer-memory all-reduce inside the step graph ---------------------------------------
+    def _comm(self):
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream(device=self.accelerator.device)
+            self._comm_used = False
+        return self._comm_stream
+
+    def _dp_range_ready(self, lo, hi):
+        """called by the backward program when flat_grad[lo:hi] is final (main stream already ordered after the
+        weight-gradient side streams): fork the communication stream and reduce the range there"""
+        cs = self._comm()
+        cs.wait_stream(torch.cuda.current_stream(self.accelerator.device))
+        with torch.cuda.stream(cs):
+            self.accelerator.p2p.all_reduce(lo, hi)
+        self._comm_used = True
+
+    def _dp_finish(self):
+        """after the backward: reduce whatever the cuts did not cover, then join the communication stream"""
+        m, acc = self.model, self.accelerator
+        main = torch.cuda.current_stream(acc.device)
+        cs = self._comm()
+        done = m.grad_segment_ranges() if self._comm_used else []
+        cs.wait_stream(main)
+        with torch.cuda.stream(cs):
+            for lo, hi in _complement(done, m.flat_grad.numel()):
+                acc.p2p.all_reduce(lo, hi)
+        main.wait_stream(cs)
+        self._comm_used = False
+
     def _step_generic(self):
         """any nn.Module + torch optimiser: the reference's sequence, op by op"""
         stats = self._forward_backward()
@@ -242,7 +318,11 @@ class Trainer:
 
     def _run_batch(self, batch: int, input, epoch: int, epoch_length: int, resume_step: int, dirs: dict, visualizer):
         self._set_input(self._extract_input(input))
+        self._stats_published = False
         if self._fused():
+            if bool(getattr(self.args, "async_stats", True)):
+                self._ticks_expected += 1            # exactly one publish kernel executes per step (eager, capture + replay, or replay)
+                self._stats_published = True
             stats = self._step_fused()
             if self.accelerator.sync_gradients:      # accelerate's AcceleratedScheduler skips non-sync micro-batches
                 self.lr_scheduler.step()
@@ -258,7 +338,10 @@ class Trainer:
         return self._return_values(stats)
 
     def _return_values(self, stats):
-        loss, rmean, dmean = stats.tolist()          # the single device->host sync of the step
+        vals = self._await_stats()
+        if vals is None:
+            vals = stats.tolist()                    # generic path: the single device->host sync of the step
+        loss, rmean, dmean = vals
         return loss, rmean, dmean
 
     def _run_epoch(self, epoch: int, epoch_length: int, resume_step: int, dirs: dict, visualizer):

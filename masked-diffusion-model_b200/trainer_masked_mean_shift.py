@@ -60,8 +60,9 @@ class Trainer(_base.Trainer):
             # inverse = (x_in + net) - shift ; loss = mean(w (inverse - x0)^2) in fp32
             self.reconstruct_loss, self.inverse_shift_reconstructed_img = train_ops.residual_mse(
                 self.mask, self.shifted_degrade_img, x0, shift=self.shift, weight=weight)
+            stats = self._publish(self._stats())      # forward-only statistics: readable before the backward has run
             self.accelerator.backward(self.reconstruct_loss)
-        return self._stats()
+        return stats
 
     def _stats(self):
         self.train_loss = self.reconstruct_loss.detach()
@@ -75,7 +76,8 @@ class Trainer(_base.Trainer):
                             self.shifted_degrade_img_mean.float(), self.degraded_train_mean.float()])
 
     def _return_values(self, stats):
-        return stats[0].item()
+        vals = self._await_stats()
+        return float(vals[0]) if vals is not None else stats[0].item()
 
     def _run_epoch(self, epoch: int, epoch_length: int, resume_step: int, dirs: dict, visualizer):
         loss_batch = []

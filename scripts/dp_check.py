@@ -1,9 +1,11 @@
 """Data-parallel consistency check (run under torchrun, >= 2 GPUs):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/dp_check.py
-Trains a few steps twice from the same seed -- once with the gradient all-reduce between the graphs (3-piece step) and
-once with the segmented backward whose all-reduces overlap the following segments -- and compares losses and
-parameters (tolerances 1e-4 / 5e-5: the fp32 reduce-add order of the weight gradients differs run to run); also
-checks that every rank holds bit-identical parameters afterwards."""
+Stage 1: the peer-memory all-reduce kernel alone (csrc/allreduce.cu) on random buffers and ranges against
+torch.distributed's all-reduce (tolerance: fp32 summation order) -- and bit-identical results on every rank.
+Stage 2: trains a few steps three times from the same seed -- NCCL all-reduce between the graphs (3-piece step), NCCL
+with the segmented backward whose all-reduces overlap the following segments, and the peer-memory all-reduce inside
+ONE step graph -- and compares losses and parameters (tolerances 1e-4 / 5e-5: the fp32 reduce-add order of the weight
+gradients differs run to run); also checks that every rank holds bit-identical parameters afterwards."""
 import argparse, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "masked-diffusion-model_b200"))
@@ -17,7 +19,56 @@ dev = torch.device("cuda", local)
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 
 
-def run(overlap):
+def stage1():
+    from mdm_b200.runtime import P2PAllReduce
+
+    class FakeModel:                      # the part of the denoiser the communicator touches
+        numel_flat = 6_000_000
+        flat_grad = torch.zeros(numel_flat, device=dev)
+
+        def rehome_grad(self, buf):
+            self.flat_grad = buf
+    if not dist.is_initialized():
+        dist.init_process_group(backend="nccl")
+    m = FakeModel()
+    comm = P2PAllReduce(m, rank, world, dev)
+    ok = True
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    for it, (lo, hi) in enumerate([(0, 6_000_000), (64, 4096 + 64), (1_000_000, 1_000_004), (12, 5_999_996), (0, 6_000_000)]):
+        m.flat_grad.copy_(torch.randn(m.numel_flat, device=dev, generator=g))
+        want = m.flat_grad.clone()
+        dist.all_reduce(want[lo:hi])
+        torch.cuda.synchronize()
+        dist.barrier()
+        comm.all_reduce(lo, hi)
+        torch.cuda.synchronize()
+        got = m.flat_grad
+        err = (got[lo:hi] - want[lo:hi]).abs().max().item()
+        untouched = bool(torch.equal(got[:lo], want[:lo]) and torch.equal(got[hi:], want[hi:]))
+        ref = got.clone()
+        dist.broadcast(ref, src=0)
+        same = bool(torch.equal(ref[lo:hi], got[lo:hi]))
+        if rank == 0:
+            print(f"stage1 range [{lo}, {hi}): max |p2p - nccl| = {err:.2e}, outside untouched {untouched}, identical on all ranks {same}")
+        ok = ok and err <= 1e-5 * world and untouched and same
+        dist.barrier()
+    # bandwidth of the kernel alone
+    n = m.numel_flat
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        comm.all_reduce(0, n)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    if rank == 0:
+        print(f"stage1 p2p all-reduce of {n * 4 / 1e6:.0f} MB: {ms * 1e3:.0f} us = {2 * (world - 1) / world * n * 4 / ms / 1e6:.0f} GB/s per GPU over NVLink")
+    return ok
+
+
+def run(mode):
+    os.environ["MDM_DP_ALLREDUCE"] = "p2p" if mode == "p2p" else "nccl"
+    overlap = mode != "nccl_3piece"
     a = argparse.Namespace(batch=32, size=32, channels=3, method="base", no_graph=False)
     wa = bench.workload_args(a)
     wa.dp_overlap = overlap
@@ -35,17 +86,23 @@ def run(overlap):
     return losses, p
 
 
-l0, p0 = run(False)
-l1, p1 = run(True)
-ref = p1.clone()
-dist.broadcast(ref, src=0)
-same_ranks = bool((ref == p1).all().item())
-diff = (p0 - p1).abs().max().item()
+ok1 = stage1()
+l0, p0 = run("nccl_3piece")
+l1, p1 = run("nccl_overlap")
+l2, p2 = run("p2p")
+same_ranks = True
+for p in (p1, p2):
+    ref = p.clone()
+    dist.broadcast(ref, src=0)
+    same_ranks = same_ranks and bool((ref == p).all().item())
+diff = max((p0 - p1).abs().max().item(), (p0 - p2).abs().max().item())
 if rank == 0:
-    print("losses 3-piece :", [round(v, 6) for v in l0])
-    print("losses overlap :", [round(v, 6) for v in l1])
-    print(f"max |param diff| between the two schedules: {diff:.3e}; identical parameters on every rank: {same_ranks}")
-ok = torch.tensor([1.0 if (same_ranks and diff <= 5e-5 and all(abs(a - b) <= 1e-4 for a, b in zip(l0, l1))) else 0.0], device=dev)
+    print("losses nccl 3-piece      :", [round(v, 6) for v in l0])
+    print("losses nccl overlap      :", [round(v, 6) for v in l1])
+    print("losses p2p in-graph      :", [round(v, 6) for v in l2])
+    print(f"max |param diff| between the schedules: {diff:.3e}; identical parameters on every rank: {same_ranks}")
+good = ok1 and same_ranks and diff <= 5e-5 and all(abs(a - b) <= 1e-4 and abs(a - c) <= 1e-4 for a, b, c in zip(l0, l1, l2))
+ok = torch.tensor([1.0 if good else 0.0], device=dev)
 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("DP_CHECK", "OK" if ok.item() == 1.0 else "FAILED")

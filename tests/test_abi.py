@@ -26,7 +26,7 @@ def test_header_symbols_exported():
 
 def test_ctypes_table_matches_header():
     import importlib
-    for mod in ("mdm_b200.denoiser_ops", "mdm_b200.optim_ops"):   # register their entry points
+    for mod in ("mdm_b200.denoiser_ops", "mdm_b200.optim_ops", "mdm_b200.comm_ops"):   # register their entry points
         try:
             importlib.import_module(mod)
         except ModuleNotFoundError:

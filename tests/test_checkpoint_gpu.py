@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.golden.make_golden import mk_args
+from mdm_b200.config import default_args
 
 pytestmark = pytest.mark.gpu
 
@@ -28,10 +28,9 @@ def _build(seed):
     import trainer_masked
     from mdm_b200.denoiser import UNet2DModelB200
     from mdm_b200.runtime import get_scheduler
-    a = mk_args(data_size=16, ddpm_num_steps=50, select_degrade_pixel="indexing", ddpm_schedule="log",
-                mean_option="degraded_area", mean_area="image-wise", method="base", mixed_precision="bf16")
+    a = default_args(data_size=16, ddpm_num_steps=50, select_degrade_pixel="indexing", ddpm_schedule="log",   # the reference's
+                     mean_option="degraded_area", mean_area="image-wise", method="base", mixed_precision="bf16")  # flag namespace
     a.use_ema, a.cuda_graph, a.timeindex_rng = True, True, "cpu_stream"
-    a.ema_max_decay, a.ema_inv_gamma, a.ema_power = 0.9999, 1.0, 0.75          # main_train_masked.py:372-374 defaults
     model = UNet2DModelB200(device="cuda", **SMALL)
     model.reset_parameters(seed=seed)
     ema = M.get_ema(a, model)

@@ -66,7 +66,7 @@ def test_fused_step_matches_torch(mode, clip, use_ema, entry):
             optim_ops.adam_ema_step(p, grad, m, v, ema, p16, gsq if clip > 0 else None, lr, b1, b2, eps, wd, bc1, bc2,
                                     clip, decay, 1.0, optim_ops.MODE[mode])
         else:
-            hyper.copy_(torch.tensor([lr, bc1, bc2, decay]))
+            hyper.copy_(torch.tensor([lr, lr / bc1, bc2 ** 0.5, decay]))
             optim_ops.adam_ema_step_dev(p, grad, m, v, ema, p16, gsq if clip > 0 else None, hyper, b1, b2, eps, wd,
                                         clip, 1.0, optim_ops.MODE[mode])
         torch.testing.assert_close(p, pr.detach(), rtol=2e-6, atol=1e-7)
@@ -75,8 +75,10 @@ def test_fused_step_matches_torch(mode, clip, use_ema, entry):
             torch.testing.assert_close(ema, ema_r, rtol=2e-6, atol=1e-7)
     if mode != "sgd":
         st = opt.state[pr]
-        torch.testing.assert_close(m, st["exp_avg"], rtol=2e-6, atol=1e-9)
-        torch.testing.assert_close(v, st["exp_avg_sq"], rtol=2e-6, atol=1e-12)
+        # |m| ~ 5e-3, v ~ 2.5e-6 after three steps; elements where beta * m and (1 - beta) * g cancel differ by one rounding
+        # of the LARGER term (torch: lerp, here: the textbook form) -> absolute floors at 4e-6 of the typical magnitude
+        torch.testing.assert_close(m, st["exp_avg"], rtol=2e-6, atol=2e-8)
+        torch.testing.assert_close(v, st["exp_avg_sq"], rtol=2e-6, atol=1e-11)
 
 
 def test_grad_scale_is_the_data_parallel_mean():

@@ -197,5 +197,8 @@ def test_gradient_accumulation_follows_accelerate():
     assert torch.equal(model.flat_param, p0) and sched2.last_epoch == 0 and opt2.step_count == 0
     assert float(model.flat_grad.abs().sum()) > 0 and ema.optimization_step == 0
     tr2._run_batch(1, (x1,), 0, 1, 0, None, None)
-    assert not torch.equal(model.flat_param, p0) and sched2.last_epoch == 1 and opt2.step_count == 1
+    assert sched2.last_epoch == 1 and opt2.step_count == 1          # (lr is still 0 at warm-up step 0: parameters unchanged)
     assert float(model.flat_grad.abs().sum()) == 0.0 and ema.optimization_step == 1 and tr2.global_step == 1
+    tr2._run_batch(2, (x1,), 0, 1, 0, None, None)
+    tr2._run_batch(3, (x1,), 0, 1, 0, None, None)
+    assert not torch.equal(model.flat_param, p0) and sched2.last_epoch == 2 and opt2.step_count == 2
