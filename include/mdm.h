@@ -35,6 +35,7 @@ extern "C" {
 /* element types of image/activation buffers */
 #define MDM_F32 0
 #define MDM_BF16 1
+#define MDM_U8 2      /* raw image bytes: normalised on load, (u / 255 - 0.5) / 0.5 (utils/mydataset.py:81) */
 
 /* fill value for degraded pixels: scheduler.py:298-317 (`mean_option`) */
 #define MDM_FILL_CONST 0            /* float(mean_option)                         */
@@ -125,6 +126,14 @@ int mdm_degrade(const void* img, int img_dtype, const uint8_t* mask, int mask_ch
                 float fill_const, int mean_area, float* x_t, float* mask_f32,
                 float* degrade_mask, float* fill_out, float* ws, int batch, int channels, int hw,
                 void* stream);
+/* GPU data-feeding path: the same operator on RAW uint8 images [batch, C, HW].  The normalisation
+ * the reference's CPU data pipeline applies -- torchvision ToTensor (u / 255) + Normalize(0.5, 0.5), utils/mydataset.py:81
+ * -- is fused into K1's read, op for op in fp32, so x_t is bit-identical to feeding the normalised fp32 image; the
+ * normalised image itself is written to x0_out (optional; the loss of the training step reads it).  Host -> device
+ * traffic per batch drops 4x. */
+int mdm_degrade_u8(const uint8_t* img_u8, const uint8_t* mask, int mask_ch, int fill_mode, float fill_const,
+                   int mean_area, float* x_t, float* x0_out, float* mask_f32, float* degrade_mask, float* fill_out,
+                   float* ws, int batch, int channels, int hw, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5: one restoration-loop update.  Replaces sampler.py:143-152 and :167-216:
@@ -305,9 +314,18 @@ int mdm_adam_ema_step_dev(float* p, const float* g, float* m, float* v, float* e
 int mdm_publish_stats(const float* src, int n, int* counter, float* dst_host_mapped, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Visual side on the device (csrc/grid.cu): `normalize01` / `normalize01_global`
+ * (utils/datautils.py:211-229) + torchvision `make_grid(nrow, padding)` as sampler.py:369-417 composes them.
+ * imgs: [batch, C, H, W] fp32; normalization 0 none / 1 per image (NaN -> 0) / 2 global; out: [C' , (H + pad) * rows + pad,
+ * (W + pad) * min(nrow, batch) + pad] fp32 with C' = 3 when C == 1 (torchvision replicates grey images).
+ * ------------------------------------------------------------------------------------------- */
+int mdm_image_grid(const float* imgs, int batch, int channels, int H, int W, int nrow, int pad, float pad_value,
+                   int normalization, float* minmax_ws /*2 * batch floats*/, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Data-parallel gradient all-reduce over NVLink peer memory (csrc/allreduce.cu).  Replaces the NCCL all-reduce that
  * accelerate / DDP run behind `accelerator.backward` (trainer_masked.py:142): ONE kernel per
- * gradient range, capturable inside the training-step graph on a forked stream, 256-thread blocks that co-reside with
+ * gradient range, capturable inside the training-step graph on a forked stream, 128-thread blocks that co-reside with
  * the persistent GEMM CTAs.  One process per GPU: every rank exports its flat gradient buffer and a zeroed flag array
  * (mdm_p2p_flag_words() uint32) with mdm_ipc_export, exchanges the 64-byte handles + offsets through its process
  * group, and maps the peers' with mdm_ipc_open.  mdm_p2p_allreduce sums buf[offset .. offset + count) over the ranks

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MDM_LIB_PATH") or os.path.join(_HERE, "libmdm_sm100.so")   # override: A/B builds of the kernels
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "mdm.h"))
 
-MDM_F32, MDM_BF16 = 0, 1
+MDM_F32, MDM_BF16, MDM_U8 = 0, 1, 2
 FILL_CONST, FILL_DEGRADED_AREA, FILL_NON_DEGRADED = 0, 1, 2
 AREA_IMAGE, AREA_CHANNEL = 0, 1
 RNG_WORDS = 625
@@ -40,9 +40,11 @@ _SIGS = {
     "mdm_degrade_ws_floats": (c_int64, [c_int, c_int, c_int]),
     "mdm_degrade": (c_int, [_P, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P,
                             c_int, c_int, c_int, _P]),
+    "mdm_degrade_u8": (c_int, [_P, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "mdm_sampler_step": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, c_int, c_int,
                                  c_float, c_int, c_int, c_int, _P, c_int64, c_int64, c_int64,
                                  _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "mdm_image_grid": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P]),
     "mdm_add_shift": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, _P]),
 }
 

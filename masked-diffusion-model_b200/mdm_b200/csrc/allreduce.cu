@@ -5,18 +5,18 @@
 // One kernel, launched on a forked stream INSIDE the captured training step: every rank maps every peer's flat fp32
 // gradient buffer (CUDA IPC, one process per GPU) and
 //   1. waits until the peers' gradients of the range are final            (flag exchange, system-scope release/acquire)
-//   2. reduce-scatter: sums ITS 1/world slice over all ranks with peer loads in rank order (so every rank would compute
-//      the same bits) and stores the sum into its own buffer
-//   3. all-gather: pulls the other ranks' reduced slices
-//   4. tells the peers it has stopped reading their buffer (they may overwrite it after the kernel).
+//   2. sums ITS 1/world slice over all ranks with peer loads in rank order (so every rank would compute the same bits)
+//      and PUSHES the sum into every rank's buffer (posted peer stores: the all-gather costs no round trips)
+//   3. waits until every peer has pushed its slice: the buffer is complete, and nobody reads it any more (the peers
+//      may overwrite theirs after the kernel).
 // Synchronisation is PER BLOCK: block b of every rank works on the same chunk of every slice, so block b only ever
 // waits for block b of its peers -- no grid-wide barrier, no requirement that all blocks be resident, no dead-lock
-// with the compute kernels that share the SMs.  Blocks are small (256 threads, no shared memory) and fit next to a
+// with the compute kernels that share the SMs.  Blocks are small (128 threads, ~100 registers, no shared memory) and fit next to a
 // resident implicit-GEMM CTA (which owns the SM's shared memory and TMEM but only 45 K registers), unlike NCCL's
 // channels, which wait for whole SMs: measured in round 1, the NCCL all-reduce stayed fully exposed (+0.9 ms per step at
 // 8 GPUs).  The range finished by each backward segment is reduced while the next segment computes.
-// Traffic per GPU: 2 (world - 1) / world x bytes over NVLink, all of it pulled (peer loads, 16 bytes per thread,
-// up to `world` loads in flight per thread).
+// Traffic per GPU: (world - 1) / world x bytes pulled + the same pushed over NVLink, 16 bytes per thread and access,
+// 16 peer loads in flight per thread.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -25,8 +25,8 @@ namespace mdm {
 
 constexpr int AR_MAX_RANKS = 8;
 constexpr int AR_MAX_BLOCKS = 128;
-constexpr int AR_THREADS = 256;
-constexpr int AR_PHASES = 3;
+constexpr int AR_THREADS = 128;
+constexpr int AR_PHASES = 2;
 // flag words per rank: [AR_PHASES][AR_MAX_BLOCKS][AR_MAX_RANKS] uint32, then per-block epochs [AR_MAX_BLOCKS]
 constexpr int AR_FLAG_WORDS = AR_PHASES * AR_MAX_BLOCKS * AR_MAX_RANKS + AR_MAX_BLOCKS;
 
@@ -67,6 +67,13 @@ __device__ __forceinline__ void block_exchange(const P2PComm& c, int phase, uint
   __syncthreads();
 }
 
+__device__ __forceinline__ void st_peer(float4* p, const float4& v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// W ranks, U elements (float4) per thread in flight: W * U peer loads are issued before the first add -- a peer load
+// takes microseconds, the kernel lives on bytes in flight (measured with one element per thread: 90 GB/s on 2 GPUs).
+template <int W, int U>
 __global__ void __launch_bounds__(AR_THREADS) p2p_allreduce_kernel(const P2PComm c, long long offset, long long count) {
   MDM_PDL_ENTER();
   __shared__ uint32_t s_epoch;
@@ -74,47 +81,46 @@ __global__ void __launch_bounds__(AR_THREADS) p2p_allreduce_kernel(const P2PComm
   if (threadIdx.x == 0) s_epoch = ++epochs[blockIdx.x];
   __syncthreads();
   const uint32_t epoch = s_epoch;
-  const int W = c.world, r = c.rank;
+  const int r = c.rank;
   const long long n4 = count >> 2;                               // float4 elements of the range (count % 4 == 0)
   const long long slice = (n4 + W - 1) / W;                      // per rank
   const long long chunk = (slice + gridDim.x - 1) / gridDim.x;   // per block inside a slice
-  const long long c0 = (long long)blockIdx.x * chunk;
-  const long long c1 = min(c0 + chunk, slice);
-  const float4* src[AR_MAX_RANKS];
+  const long long s0 = (long long)r * slice;                     // this rank reduces slice r
+  const long long e0 = s0 + (long long)blockIdx.x * chunk;
+  const long long e1 = min(min(e0 + chunk, s0 + slice), n4);
+  float4* bufs[W];
 #pragma unroll
-  for (int p = 0; p < AR_MAX_RANKS; ++p) src[p] = reinterpret_cast<const float4*>(c.buf[p < W ? p : 0] + offset);
-  float4* mine = reinterpret_cast<float4*>(c.buf[r] + offset);
+  for (int p = 0; p < W; ++p) bufs[p] = reinterpret_cast<float4*>(c.buf[p] + offset);
 
   block_exchange(c, 0, epoch);     // the peers' gradients of this range are final
-  // ---- reduce-scatter: slice r, summed in rank order ------------------------------------------------------------
-  {
-    const long long s0 = (long long)r * slice;
-    for (long long i = c0 + threadIdx.x; i < c1; i += AR_THREADS) {
-      const long long e = s0 + i;
-      if (e >= n4) break;
-      float4 v[AR_MAX_RANKS];
+  // ---- reduce slice r in rank order (every rank would compute the same bits), push the sums to every rank -----------
+  for (long long i = e0 + threadIdx.x; i < e1; i += (long long)AR_THREADS * U) {
+    float4 v[U][W];
 #pragma unroll
-      for (int p = 0; p < AR_MAX_RANKS; ++p)
-        if (p < W) v[p] = (p == r) ? mine[e] : ld_peer(src[p] + e);
-      float4 acc = v[0];
+    for (int u = 0; u < U; ++u) {
+      const long long e = i + (long long)u * AR_THREADS;
+      if (e < e1) {
 #pragma unroll
-      for (int p = 1; p < AR_MAX_RANKS; ++p)
-        if (p < W) { acc.x += v[p].x; acc.y += v[p].y; acc.z += v[p].z; acc.w += v[p].w; }
-      mine[e] = acc;
+        for (int p = 0; p < W; ++p) v[u][p] = ld_peer(bufs[p] + e);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long e = i + (long long)u * AR_THREADS;
+      if (e < e1) {
+        float4 acc = v[u][0];
+#pragma unroll
+        for (int p = 1; p < W; ++p) { acc.x += v[u][p].x; acc.y += v[u][p].y; acc.z += v[u][p].z; acc.w += v[u][p].w; }
+#pragma unroll
+        for (int d = 0; d < W; ++d) {       // own copy first, then the peers, nearest neighbour first
+          int p = r + d;
+          if (p >= W) p -= W;
+          st_peer(bufs[p] + e, acc);
+        }
+      }
     }
   }
-  block_exchange(c, 1, epoch);     // every rank's slice is reduced
-  // ---- all-gather: the other ranks' slices, nearest neighbour first (spreads the load over the links) ---------------
-  for (int d = 1; d < W; ++d) {
-    const int p = (r + d) % W;
-    const long long s0 = (long long)p * slice;
-    for (long long i = c0 + threadIdx.x; i < c1; i += AR_THREADS) {
-      const long long e = s0 + i;
-      if (e >= n4) break;
-      mine[e] = ld_peer(src[p] + e);
-    }
-  }
-  block_exchange(c, 2, epoch);     // nobody reads this rank's buffer any more
+  block_exchange(c, 1, epoch);     // every rank has pushed its slice: this buffer is complete, and nobody reads it any more
 }
 
 typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
@@ -178,7 +184,17 @@ int mdm_p2p_allreduce(const mdm_p2p_comm* comm, int64_t offset, int64_t count, i
   }
   c.rank = comm->rank;
   c.world = comm->world;
-  launch_pdl(p2p_allreduce_kernel, dim3(blocks), dim3(AR_THREADS), 0, as_stream(stream), c, (long long)offset, (long long)count);
+  cudaStream_t st = as_stream(stream);
+  const long long off = offset, cnt = count;
+  switch (c.world) {
+    case 2: launch_pdl(p2p_allreduce_kernel<2, 8>, dim3(blocks), dim3(AR_THREADS), 0, st, c, off, cnt); break;
+    case 3: launch_pdl(p2p_allreduce_kernel<3, 5>, dim3(blocks), dim3(AR_THREADS), 0, st, c, off, cnt); break;
+    case 4: launch_pdl(p2p_allreduce_kernel<4, 4>, dim3(blocks), dim3(AR_THREADS), 0, st, c, off, cnt); break;
+    case 5: launch_pdl(p2p_allreduce_kernel<5, 3>, dim3(blocks), dim3(AR_THREADS), 0, st, c, off, cnt); break;
+    case 6: launch_pdl(p2p_allreduce_kernel<6, 3>, dim3(blocks), dim3(AR_THREADS), 0, st, c, off, cnt); break;
+    case 7: launch_pdl(p2p_allreduce_kernel<7, 2>, dim3(blocks), dim3(AR_THREADS), 0, st, c, off, cnt); break;
+    default: launch_pdl(p2p_allreduce_kernel<8, 2>, dim3(blocks), dim3(AR_THREADS), 0, st, c, off, cnt); break;
+  }
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }

@@ -56,6 +56,36 @@ struct Shift {
 static bool shift_vec_ok(const float* p, int64_t sb, int64_t sc, int64_t sp) {
   return p == nullptr || sp == 0 || (sp == 1 && (sb & 3) == 0 && (sc & 3) == 0 && ((uintptr_t)p & 15) == 0);
 }
+// uint8 images (the GPU data-feeding path): the reference's `ToTensor()` + `Normalize(0.5, 0.5)` (utils/mydataset.py:81)
+// op for op -- u / 255, then (x - 0.5) / 0.5 -- so a uint8 batch gives the bits the CPU transforms give
+__device__ __forceinline__ float u8_normalise(uint8_t u) {
+  return __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.0f), 0.5f), 0.5f);
+}
+__device__ __forceinline__ float ld_as_float(const uint8_t* p, int64_t i) { return u8_normalise(p[i]); }
+
+// four consecutive pixels of a plane as floats
+template <typename T> struct Ld4;
+template <> struct Ld4<float> {
+  static constexpr int kAlign = 16;
+  static __device__ __forceinline__ float4 at(const float* x, int i) { return *reinterpret_cast<const float4*>(x + i); }
+};
+template <> struct Ld4<__nv_bfloat16> {
+  static constexpr int kAlign = 8;
+  static __device__ __forceinline__ float4 at(const __nv_bfloat16* x, int i) {
+    const uint2 u = *reinterpret_cast<const uint2*>(x + i);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+template <> struct Ld4<uint8_t> {
+  static constexpr int kAlign = 4;
+  static __device__ __forceinline__ float4 at(const uint8_t* x, int i) {
+    const uchar4 k = *reinterpret_cast<const uchar4*>(x + i);
+    return make_float4(u8_normalise(k.x), u8_normalise(k.y), u8_normalise(k.z), u8_normalise(k.w));
+  }
+};
+
 __device__ __forceinline__ float4 mask4(const uint8_t* m, int64_t i) {
   const uchar4 k = *reinterpret_cast<const uchar4*>(m + i);
   return make_float4((float)k.x, (float)k.y, (float)k.z, (float)k.w);
@@ -105,7 +135,7 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_stats_kernel(const T* __re
   float s0 = 0.f, s1 = 0.f, n0 = 0.f;
   const int base = chunk * DG_CHUNK;
   const int end = min(base + DG_CHUNK, hw);
-  if (sizeof(T) == 4 && (hw & 3) == 0 && ((uintptr_t)img & 15) == 0 && ((uintptr_t)mask & 3) == 0) {
+  if ((hw & 3) == 0 && ((uintptr_t)img & (Ld4<T>::kAlign - 1)) == 0 && ((uintptr_t)mask & 3) == 0) {
     // all of this thread's 16-byte loads are issued before the first use (4 image + 4 mask vectors in flight)
     for (int g0 = base; g0 < end; g0 += DG_THREADS * 4 * DG_VEC_PER_THREAD) {
       float4 v[DG_VEC_PER_THREAD], k[DG_VEC_PER_THREAD];
@@ -113,7 +143,7 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_stats_kernel(const T* __re
       for (int u = 0; u < DG_VEC_PER_THREAD; ++u) {
         const int i = g0 + (u * DG_THREADS + threadIdx.x) * 4;
         const bool ok = i < end;
-        v[u] = ok ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u] = ok ? Ld4<T>::at(x, i) : make_float4(0.f, 0.f, 0.f, 0.f);
         k[u] = ok ? mask4(m, i) : make_float4(1.f, 1.f, 1.f, 1.f);      // mask 1, value 0: contributes nothing
       }
 #pragma unroll
@@ -149,11 +179,12 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_apply_kernel(
     const T* __restrict__ img, const uint8_t* __restrict__ mask, int mask_ch, int fill_mode,
     float fill_const, int mean_area, const float* __restrict__ ws, float* __restrict__ x_t,
     float* __restrict__ mask_f32, float* __restrict__ degrade_mask, float* __restrict__ fill_out,
-    int C, int hw, int nchunk) {
+    float* __restrict__ x0_out, int C, int hw, int nchunk) {
   MDM_PDL_ENTER();
   const int chunk = blockIdx.x, plane = blockIdx.y;
   const int b = plane / C, c = plane % C;
   const float fill = fill_value(ws + (int64_t)b * C * nchunk * 3, c, C, nchunk, fill_mode, fill_const, mean_area);
+  float* x0o = x0_out ? x0_out + (int64_t)plane * hw : nullptr;     // the image as fp32 (uint8 feed: the loss reads it)
   if (fill_out && chunk == 0 && threadIdx.x == 0) fill_out[plane] = fill;
   const T* x = img + (int64_t)plane * hw;
   const uint8_t* m = mask + ((int64_t)b * mask_ch + (mask_ch == 1 ? 0 : c)) * hw;
@@ -162,14 +193,14 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_apply_kernel(
   float* mf = (mask_f32 && (mask_ch != 1 || c == 0)) ? mask_f32 + ((int64_t)b * mask_ch + (mask_ch == 1 ? 0 : c)) * hw : nullptr;
   const int base = chunk * DG_CHUNK;
   const int end = min(base + DG_CHUNK, hw);
-  if ((hw & 3) == 0 && sizeof(T) == 4) {
+  if ((hw & 3) == 0 && ((uintptr_t)img & (Ld4<T>::kAlign - 1)) == 0 && ((uintptr_t)mask & 3) == 0) {
    for (int g0 = base; g0 < end; g0 += DG_THREADS * 4 * DG_VEC_PER_THREAD) {
     float4 vv[DG_VEC_PER_THREAD], kk[DG_VEC_PER_THREAD];
 #pragma unroll
     for (int u = 0; u < DG_VEC_PER_THREAD; ++u) {
       const int i = g0 + (u * DG_THREADS + threadIdx.x) * 4;
       if (i < end) {
-        vv[u] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i);
+        vv[u] = Ld4<T>::at(x, i);
         kk[u] = mask4(m, i);
       }
     }
@@ -183,6 +214,7 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_apply_kernel(
       r.x = composite(m0, fill, v.x); r.y = composite(m1, fill, v.y);
       r.z = composite(m2, fill, v.z); r.w = composite(m3, fill, v.w);
       *reinterpret_cast<float4*>(o + i) = r;
+      if (x0o) *reinterpret_cast<float4*>(x0o + i) = v;
       if (dm) {
         float4 d;
         d.x = composite(m0, fill, 1.0f); d.y = composite(m1, fill, 1.0f);
@@ -197,6 +229,7 @@ __global__ void __launch_bounds__(DG_THREADS) degrade_apply_kernel(
       const float v = ld_as_float(x, i);
       const float mk = (float)m[i];
       o[i] = composite(mk, fill, v);
+      if (x0o) x0o[i] = v;
       if (dm) dm[i] = composite(mk, fill, 1.0f);
       if (mf) mf[i] = mk;
     }
@@ -365,13 +398,13 @@ int64_t mdm_degrade_ws_floats(int batch, int channels, int hw) {
   return (int64_t)batch * channels * nchunks(hw) * 3;
 }
 
-int mdm_degrade(const void* img, int img_dtype, const uint8_t* mask, int mask_ch, int fill_mode,
-                float fill_const, int mean_area, float* x_t, float* mask_f32, float* degrade_mask,
-                float* fill_out, float* ws, int batch, int channels, int hw, void* stream) {
+static int degrade_launch(const void* img, int img_dtype, const uint8_t* mask, int mask_ch, int fill_mode,
+                          float fill_const, int mean_area, float* x_t, float* mask_f32, float* degrade_mask,
+                          float* fill_out, float* x0_out, float* ws, int batch, int channels, int hw, void* stream) {
   MDM_CHECK_ARG(img && mask && x_t, "img/mask/x_t is NULL");
   MDM_CHECK_ARG(batch > 0 && channels > 0 && hw > 0, "empty image batch");
   MDM_CHECK_ARG(mask_ch == 1 || mask_ch == channels, "mask_ch must be 1 or C");
-  MDM_CHECK_ARG(img_dtype == MDM_F32 || img_dtype == MDM_BF16, "img dtype");
+  MDM_CHECK_ARG(img_dtype == MDM_F32 || img_dtype == MDM_BF16 || img_dtype == MDM_U8, "img dtype");
   MDM_CHECK_ARG(fill_mode >= 0 && fill_mode <= 2, "fill_mode");
   MDM_CHECK_ARG(fill_mode == MDM_FILL_CONST || ws, "workspace is NULL");
   MDM_CHECK_ARG((int64_t)batch * channels <= 65535, "batch*channels exceeds grid.y");
@@ -381,16 +414,35 @@ int mdm_degrade(const void* img, int img_dtype, const uint8_t* mask, int mask_ch
   if (fill_mode != MDM_FILL_CONST) {
     if (img_dtype == MDM_F32)
       launch_pdl(degrade_stats_kernel<float>, dim3(grid), dim3(DG_THREADS), 0, st, (const float*)img, mask, mask_ch, ws, channels, hw, nc);
-    else
+    else if (img_dtype == MDM_BF16)
       launch_pdl(degrade_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(DG_THREADS), 0, st, (const __nv_bfloat16*)img, mask, mask_ch, ws, channels, hw, nc);
+    else
+      launch_pdl(degrade_stats_kernel<uint8_t>, dim3(grid), dim3(DG_THREADS), 0, st, (const uint8_t*)img, mask, mask_ch, ws, channels, hw, nc);
     MDM_LAUNCH_CHECK();
   }
   if (img_dtype == MDM_F32)
-    launch_pdl(degrade_apply_kernel<float>, dim3(grid), dim3(DG_THREADS), 0, st, (const float*)img, mask, mask_ch, fill_mode, fill_const, mean_area, ws, x_t, mask_f32, degrade_mask, fill_out, channels, hw, nc);
+    launch_pdl(degrade_apply_kernel<float>, dim3(grid), dim3(DG_THREADS), 0, st, (const float*)img, mask, mask_ch, fill_mode, fill_const, mean_area, ws, x_t, mask_f32, degrade_mask, fill_out, x0_out, channels, hw, nc);
+  else if (img_dtype == MDM_BF16)
+    launch_pdl(degrade_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(DG_THREADS), 0, st, (const __nv_bfloat16*)img, mask, mask_ch, fill_mode, fill_const, mean_area, ws, x_t, mask_f32, degrade_mask, fill_out, x0_out, channels, hw, nc);
   else
-    launch_pdl(degrade_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(DG_THREADS), 0, st, (const __nv_bfloat16*)img, mask, mask_ch, fill_mode, fill_const, mean_area, ws, x_t, mask_f32, degrade_mask, fill_out, channels, hw, nc);
+    launch_pdl(degrade_apply_kernel<uint8_t>, dim3(grid), dim3(DG_THREADS), 0, st, (const uint8_t*)img, mask, mask_ch, fill_mode, fill_const, mean_area, ws, x_t, mask_f32, degrade_mask, fill_out, x0_out, channels, hw, nc);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
+}
+
+int mdm_degrade(const void* img, int img_dtype, const uint8_t* mask, int mask_ch, int fill_mode,
+                float fill_const, int mean_area, float* x_t, float* mask_f32, float* degrade_mask,
+                float* fill_out, float* ws, int batch, int channels, int hw, void* stream) {
+  MDM_CHECK_ARG(img_dtype == MDM_F32 || img_dtype == MDM_BF16, "img dtype (uint8 images go through mdm_degrade_u8)");
+  return degrade_launch(img, img_dtype, mask, mask_ch, fill_mode, fill_const, mean_area, x_t, mask_f32, degrade_mask, fill_out,
+                        nullptr, ws, batch, channels, hw, stream);
+}
+
+int mdm_degrade_u8(const uint8_t* img_u8, const uint8_t* mask, int mask_ch, int fill_mode, float fill_const, int mean_area,
+                   float* x_t, float* x0_out, float* mask_f32, float* degrade_mask, float* fill_out, float* ws,
+                   int batch, int channels, int hw, void* stream) {
+  return degrade_launch(img_u8, MDM_U8, mask, mask_ch, fill_mode, fill_const, mean_area, x_t, mask_f32, degrade_mask, fill_out,
+                        x0_out, ws, batch, channels, hw, stream);
 }
 
 int mdm_sampler_step(const float* x_t, const float* net, const float* shift, int64_t sb, int64_t sc,

@@ -875,9 +875,10 @@ class _Plan:
         (the trainer's in-graph peer-memory all-reduce) is called with the main stream ordered after the side streams."""
         hook = getattr(self.m, "grad_ready_hook", None)
         if hook is not None:
-            self.join_side()                     # the weight gradients of that range ran on the side stream
+            # the weight gradients of that range ran on the side stream(s): the hook orders ITS stream after them (and
+            # after the main stream) -- the main stream itself does not wait, the dgrad / GroupNorm chain goes on
             lo, hi = self.m.grad_segment_ranges()[k]
-            hook(lo, hi)
+            hook(lo, hi, [s for s in self.sides if s in self._sides_used])
 
     def _sym_resnet(self, r, x, res):
         out = self.act(res, r.cout, r.prefix)

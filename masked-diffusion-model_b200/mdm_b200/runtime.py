@@ -308,7 +308,7 @@ class P2PAllReduce:
         if world > comm_ops.MAX_RANKS:
             raise RuntimeError(f"P2PAllReduce: at most {comm_ops.MAX_RANKS} ranks (one NVSwitch domain)")
         self.rank, self.world, self.device = rank, world, device
-        self.blocks = int(os.environ.get("MDM_P2P_BLOCKS", "48"))
+        self.blocks = int(os.environ.get("MDM_P2P_BLOCKS", "96"))
         n = model.numel_flat
         # a dedicated allocation for the gradients (the IPC handle covers a whole cudaMalloc segment)
         self.buf = torch.zeros(n, dtype=torch.float32, device=device)

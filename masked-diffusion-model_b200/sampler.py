@@ -234,6 +234,47 @@ class Sampler:
         visual = [h.cpu() for h in hist] if history else [None] * len(HISTORY_NAMES)
         return sample_0, visual
 
+    # -- image grids on the device (sampler.py:369-417) ------------------------------------------------------
+    @staticmethod
+    def _grid(sample: torch.Tensor, nrow: int, normalization) -> torch.Tensor:
+        """`make_grid(normalize01[_global](sample), nrow)` in one pass on the device (csrc/grid.cu)"""
+        if not sample.is_cuda:
+            raise RuntimeError("image grids are built on the device (no CPU fallback)")
+        x = sample.float().contiguous()
+        B, C, H, W = x.shape
+        mode = {None: 0, "image": 1, "global": 2}[normalization]
+        xm = min(nrow, B)
+        ym = (B + xm - 1) // xm
+        pad = 2
+        out = torch.empty(3 if C == 1 else C, (H + pad) * ym + pad, (W + pad) * xm + pad, device=x.device)
+        ws = torch.empty(2 * B, device=x.device)
+        check(lib().mdm_image_grid(ptr(x), B, C, H, W, nrow, pad, 0.0, mode, ptr(ws), ptr(out), stream_ptr(x.device)))
+        return out
+
+    def _save_image_grid(self, sample: torch.Tensor, normalization='global', dir_save=None, file_sample=None):
+        """sampler.py:369-388: square grid of a batch; written as an image file when a path is given"""
+        batch_size = sample.shape[0]
+        nrow = int(np.ceil(np.sqrt(batch_size)))
+        if nrow == 0:
+            return None                                  # the reference's ZeroDivisionError branch
+        grid_sample = self._grid(sample, nrow, normalization if normalization in ("global", "image") else None)
+        if dir_save is not None and file_sample is not None:
+            from torchvision.utils import save_image      # host-side PNG encoding only
+            save_image(grid_sample, os.path.join(dir_save, file_sample))
+        return grid_sample
+
+    def _save_multi_index_image_grid(self, sample: torch.Tensor, nrow=None, normalization='global', option=None):
+        """sampler.py:391-417: one grid per batch element over its timesteps; sample: (batch, timesteps, C, H, W)"""
+        num_timesteps = sample.shape[1]
+        if nrow is None:
+            nrow = int(np.ceil(np.sqrt(num_timesteps)))
+        grids = []
+        for i in range(sample.shape[0]):
+            s_i = sample[i][1:] if option == 'skip_first' else sample[i]
+            grids.append(self._grid(s_i.to("cuda") if not s_i.is_cuda else s_i, nrow,
+                                    normalization if normalization in ("global", "image") else None))
+        return grids
+
     # -- opt-in history (visualisation; not on the timed path) ----------------------------------
     def _record(self, hist, k, x_t, shift, x_in, net, s0, mb_t, mb_n, mask_ch, mode, const, area, dep, last,
                 momentum, difference_prev):

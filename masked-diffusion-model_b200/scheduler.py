@@ -222,8 +222,10 @@ class Scheduler:
             dt = _lib.MDM_F32
         elif img.dtype == torch.bfloat16:
             dt = _lib.MDM_BF16
+        elif img.dtype == torch.uint8:
+            dt = _lib.MDM_U8           # raw image bytes: ToTensor + Normalize(0.5, 0.5) fused into the read (utils/mydataset.py:81)
         else:
-            raise TypeError(f"img dtype {img.dtype} not supported (float32 / bfloat16)")
+            raise TypeError(f"img dtype {img.dtype} not supported (float32 / bfloat16 / uint8)")
         if mask_ch not in (1, C):
             raise RuntimeError(f"mask with {mask_ch} channels cannot broadcast over {C} image channels")
         mode, const, area = self._fill_mode(mean_option, mean_area)
@@ -233,6 +235,12 @@ class Scheduler:
         dmask = torch.empty_like(x_t) if want_degrade_mask else None
         fill = torch.empty(B, C, 1, 1, dtype=torch.float32, device=dev)
         ws = self._buf("degrade_ws", (max(1, lib().mdm_degrade_ws_floats(B, C, hw)),), torch.float32, dev)
+        if dt == _lib.MDM_U8:
+            # the normalised fp32 image is a by-product (the trainers' loss reads it): `self.x0_normalised`
+            self.x0_normalised = torch.empty_like(x_t)
+            check(lib().mdm_degrade_u8(ptr(img), ptr(mask_bytes), mask_ch, mode, const, area, ptr(x_t), ptr(self.x0_normalised),
+                                       ptr(mask_f), ptr(dmask), ptr(fill), ptr(ws), B, C, hw, stream_ptr(dev)))
+            return x_t, mask_f, dmask, fill
         check(lib().mdm_degrade(ptr(img), dt, ptr(mask_bytes), mask_ch, mode, const, area, ptr(x_t), ptr(mask_f),
                                 ptr(dmask), ptr(fill), ptr(ws), B, C, hw, stream_ptr(dev)))
         return x_t, mask_f, dmask, fill

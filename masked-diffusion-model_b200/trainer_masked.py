@@ -124,6 +124,8 @@ class Trainer:
             if a.loss_weight_use:
                 weight = self.Scheduler.get_weight_timesteps(timeindex, a.loss_weight_power_base)
             # recon = degraded + net ; loss = mean(w (recon - x0)^2)   (one fused kernel, fwd + grad)
+            if x0.dtype == torch.uint8:
+                x0 = self.Scheduler.x0_normalised         # written by K1 next to x_t
             self.reconstruct_loss, self.reconstructed_img = train_ops.residual_mse(self.mask, self.degraded_img, x0,
                                                                                    shift=None, weight=weight)
             stats = self._publish(self._stats())      # forward-only statistics: readable before the backward has run
@@ -265,15 +267,19 @@ class Trainer:
     # -- data parallel, peer-memory all-reduce inside the step graph ---------------------------------------
     def _comm(self):
         if getattr(self, "_comm_stream", None) is None:
-            self._comm_stream = torch.cuda.Stream(device=self.accelerator.device)
+            # high priority: the few small communication blocks should be placed as soon as their range is ready
+            self._comm_stream = torch.cuda.Stream(device=self.accelerator.device, priority=-1)
             self._comm_used = False
         return self._comm_stream
 
-    def _dp_range_ready(self, lo, hi):
-        """called by the backward program when flat_grad[lo:hi] is final (main stream already ordered after the
-        weight-gradient side streams): fork the communication stream and reduce the range there"""
+    def _dp_range_ready(self, lo, hi, side_streams=()):
+        """called by the backward program when the kernels that finish flat_grad[lo:hi] have been enqueued (dgrad chain on
+        the current stream, weight gradients on `side_streams`): the communication stream waits for both and reduces
+        the range there; the main stream does not wait"""
         cs = self._comm()
         cs.wait_stream(torch.cuda.current_stream(self.accelerator.device))
+        for s_ in side_streams:
+            cs.wait_stream(s_)
         with torch.cuda.stream(cs):
             self.accelerator.p2p.all_reduce(lo, hi)
         self._comm_used = True
@@ -306,7 +312,9 @@ class Trainer:
     # trainer_masked.py:95-183
     # ------------------------------------------------------------------------------------------
     def _set_input(self, x):
-        x = x.to(self.args.weight_dtype)
+        # uint8 batches stay raw: K1 normalises them on load (the GPU data-feeding path)
+        if x.dtype != torch.uint8:
+            x = x.to(self.args.weight_dtype)
         if not x.is_cuda:
             raise RuntimeError("Trainer: the batch must be on a CUDA device (no CPU fallback)")
         buf = getattr(self, "_input_buf", None)

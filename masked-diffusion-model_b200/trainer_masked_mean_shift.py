@@ -58,6 +58,8 @@ class Trainer(_base.Trainer):
             if a.loss_weight_use:
                 weight = self.Scheduler.get_weight_timesteps(timeindex, a.loss_weight_power_base)
             # inverse = (x_in + net) - shift ; loss = mean(w (inverse - x0)^2) in fp32
+            if x0.dtype == torch.uint8:
+                x0 = self.Scheduler.x0_normalised         # written by K1 next to x_t
             self.reconstruct_loss, self.inverse_shift_reconstructed_img = train_ops.residual_mse(
                 self.mask, self.shifted_degrade_img, x0, shift=self.shift, weight=weight)
             stats = self._publish(self._stats())      # forward-only statistics: readable before the backward has run

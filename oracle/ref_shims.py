@@ -46,6 +46,10 @@ def install_stubs():
     mpl = _stub("matplotlib")
     mpl.pyplot = _stub("matplotlib.pyplot")
     mpl.ticker = _stub("matplotlib.ticker", MaxNLocator=_Dummy)
+    try:
+        import cv2  # noqa: F401   (tester.py:15 imports it; only its plotting paths use it)
+    except Exception:
+        _stub("cv2")
     tm = _stub("torchmetrics")
     tm.image = _stub("torchmetrics.image")
     tm.image.fid = _stub("torchmetrics.image.fid", FrechetInceptionDistance=_Dummy)
@@ -60,7 +64,7 @@ def import_reference(*names):
     out = []
     saved_path = list(sys.path)
     saved = {k: sys.modules.get(k) for k in ("scheduler", "sampler", "trainer_masked",
-                                             "trainer_masked_mean_shift", "utils",
+                                             "trainer_masked_mean_shift", "tester", "utils",
                                              "utils.datautils", "utils.util")}
     try:
         sys.path.insert(0, REFERENCE_CODE)

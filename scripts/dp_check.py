@@ -23,7 +23,7 @@ def stage1():
     from mdm_b200.runtime import P2PAllReduce
 
     class FakeModel:                      # the part of the denoiser the communicator touches
-        numel_flat = 6_000_000
+        numel_flat = 32_000_000
         flat_grad = torch.zeros(numel_flat, device=dev)
 
         def rehome_grad(self, buf):
@@ -61,8 +61,16 @@ def stage1():
         comm.all_reduce(0, n)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
+    dist.barrier()
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0.record()
+    for _ in range(10):
+        dist.all_reduce(m.flat_grad)
+    n1.record(); torch.cuda.synchronize()
     if rank == 0:
-        print(f"stage1 p2p all-reduce of {n * 4 / 1e6:.0f} MB: {ms * 1e3:.0f} us = {2 * (world - 1) / world * n * 4 / ms / 1e6:.0f} GB/s per GPU over NVLink")
+        print(f"stage1 NCCL all-reduce of the same buffer: {n0.elapsed_time(n1) / 10 * 1e3:.0f} us")
+    if rank == 0:
+        print(f"stage1 p2p all-reduce ({comm.blocks} blocks) of {n * 4 / 1e6:.0f} MB: {ms * 1e3:.0f} us = {2 * (world - 1) / world * n * 4 / ms / 1e6:.0f} GB/s per GPU over NVLink")
     return ok
 
 

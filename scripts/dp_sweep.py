@@ -4,18 +4,21 @@ Every configuration runs `bench.py --gpus N` (headline only) under torchrun; N =
 import json, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+NCCL = {"MDM_DP_ALLREDUCE": "nccl"}
 CONFIGS = {
-    "default":        {},
-    "static_lists":   {"MDM_IGEMM_DYNAMIC": "0"},
-    "cuts_2":         {"MDM_DP_CUTS": "2"},                         # round-1 segmentation (3 segments)
-    "cuts_54321":     {"MDM_DP_CUTS": "5,4,3,2,1"},
-    "nch8":           {"NCCL_MAX_NCHANNELS": "8"},
-    "nch4":           {"NCCL_MAX_NCHANNELS": "4"},
-    "nthreads256":    {"NCCL_NTHREADS": "256", "NCCL_MAX_NCHANNELS": "16"},
-    "reserve16":      {"MDM_IGEMM_MAX_CTAS": "132"},
-    "reserve16_nch16": {"MDM_IGEMM_MAX_CTAS": "132", "NCCL_MAX_NCHANNELS": "16"},
-    "no_overlap":     {"MDM_DP_OVERLAP": "0"},
-    "p2p":            {"MDM_DP_ALLREDUCE": "p2p"},
+    "p2p":            {},                                            # default: peer-memory all-reduce inside the step graph
+    "p2p_cuts_2":     {"MDM_DP_CUTS": "2"},
+    "p2p_cuts_54321": {"MDM_DP_CUTS": "5,4,3,2,1"},
+    "p2p_blocks48":   {"MDM_P2P_BLOCKS": "48"},
+    "p2p_blocks128":  {"MDM_P2P_BLOCKS": "128"},
+    "p2p_static":     {"MDM_IGEMM_DYNAMIC": "0"},
+    "nccl":           dict(NCCL),                                    # round-1 path: segmented graphs + async NCCL
+    "nccl_cuts_2":    dict(NCCL, MDM_DP_CUTS="2"),
+    "nccl_static":    dict(NCCL, MDM_IGEMM_DYNAMIC="0"),
+    "nccl_nch8":      dict(NCCL, NCCL_MAX_NCHANNELS="8"),
+    "nccl_nthreads256": dict(NCCL, NCCL_NTHREADS="256", NCCL_MAX_NCHANNELS="16"),
+    "nccl_reserve16": dict(NCCL, MDM_IGEMM_MAX_CTAS="132"),
+    "nccl_no_overlap": dict(NCCL, MDM_DP_OVERLAP="0"),
 }
 want = sys.argv[2:] or list(CONFIGS)
 flags = ["--steps", "30", "--warmup", "8", "--no-sampling", "--no-extra", "--no-cpu-baseline", "--no-roofline"]

@@ -159,3 +159,52 @@ def test_full_size_properties():
     assert torch.allclose(again, d, atol=FILL_TOL, rtol=0)
     # words consumed: B*HW
     assert S.rng.words_drawn == B * S_ * S_
+
+
+def test_uint8_feed_equals_the_cpu_transforms():
+    """raw uint8 batches are normalised inside K1's read exactly like the reference's CPU pipeline
+    (torchvision ToTensor: u / 255, then Normalize(0.5, 0.5): (x - 0.5) / 0.5, utils/mydataset.py:81) -- x_t, masks and the
+    fp32 image handed to the loss are bit-identical to feeding the CPU-normalised fp32 batch."""
+    from tests.golden.make_golden import mk_args
+    g = torch.Generator().manual_seed(2)
+    for shape in ((5, 3, 16, 16), (3, 1, 32, 32), (2, 3, 6, 6)):             # the last one takes the scalar (unaligned) path
+        u8 = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g)
+        x_ref = u8.to(torch.float32).div(255).sub_(0.5).div_(0.5)           # ToTensor + Normalize(0.5, 0.5)
+        for opt, area in (("degraded_area", "image-wise"), ("non_degraded_area", "channel-wise"), (0, "image-wise")):
+            a = mk_args(data_size=shape[2], in_channel=shape[1], out_channel=shape[1], ddpm_num_steps=50,
+                        select_degrade_pixel="indexing", ddpm_schedule="log", mean_option=opt, mean_area=area)
+            outs = []
+            for x in (x_ref, u8):
+                S = scheduler.Scheduler(a)
+                Tp = S.update_ddpm_num_steps(50)
+                ts = torch.tensor([1, Tp // 2, Tp][: shape[0]] + [3] * max(0, shape[0] - 3), device="cuda")
+                torch.manual_seed(7)
+                S.adopt_torch_rng("cuda")
+                outs.append((S.degrade_training(S.get_black_area_num_pixels_time(ts), x.cuda(), opt, area), S))
+            (f32, _), (raw, S_u8) = outs
+            assert torch.equal(raw[0], f32[0]) and torch.equal(raw[1], f32[1]) and torch.equal(raw[3], f32[3])
+            assert raw[0].dtype == torch.float32 and torch.equal(S_u8.x0_normalised.cpu(), x_ref)
+
+
+def test_uint8_batches_through_run_batch():
+    """the trainer keeps a uint8 batch raw (4x fewer host -> device bytes), K1 normalises it and hands the fp32 image to the
+    loss: same loss and gradients as the CPU-normalised batch"""
+    import trainer_masked
+    from tests.golden.make_golden import FakeAccelerator, TinyNet, mk_args
+    a = mk_args(data_size=16, ddpm_num_steps=100, select_degrade_pixel="indexing", ddpm_schedule="log",
+                mean_option="degraded_area", mean_area="image-wise", method="base")
+    a.use_ema, a.timeindex_rng = False, "cpu_stream"
+    u8 = torch.randint(0, 256, (6, 3, 16, 16), dtype=torch.uint8, generator=torch.Generator().manual_seed(4))
+    res = []
+    for x in (u8.to(torch.float32).div(255).sub_(0.5).div_(0.5), u8):
+        net = TinyNet(3).cuda()
+        opt = torch.optim.SGD(net.parameters(), lr=0.0)
+        opt.zero_grad = lambda *args, **kw: None
+        tr = trainer_masked.Trainer(a, None, None, net, None, opt, torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0), FakeAccelerator())
+        tr.prepare_schedule()
+        tr.timesteps_used_epoch = tr.Scheduler.get_timesteps_epoch(0, 1)
+        torch.manual_seed(41)
+        tr.Scheduler.adopt_torch_rng("cuda")
+        loss = tr._run_batch(0, (x.cuda(),), 0, 1, 0, None, None)[0]
+        res.append((loss, net.conv.weight.grad.clone()))
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
