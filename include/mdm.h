@@ -199,8 +199,19 @@ typedef struct mdm_conv_args {
                          * qsum[n][cout/4][2] += (sum, sum of squares) over the pixels of sample n of every 4-channel
                          * quad (fp32 atomics into a buffer the caller zeroed); needs H*W % 128 == 0.  Consumed by
                          * mdm_gn_silu_fwd_q, which then reads the activation once instead of twice. */
+  int up2x;             /* fprop only: nearest-neighbour 2x upsample FUSED into a 3x3 convolution (diffusers Upsample2D:
+                         * F.interpolate(scale 2, nearest) + conv; reference equivalent unet6.py:468-470).  The upsampled
+                         * image is never built: output pixels of parity (up_a, up_b) = (row % 2, col % 2) see a 2x2
+                         * neighbourhood of the LOW-resolution input with pre-summed weights, 4/9 of the FLOPs.
+                         * x: [N][H][W][cin] low-resolution input, y: the FULL [N][2H][2W][cout] output (this call writes
+                         * one parity class), w: [cout][4][cin] from mdm_up2x_weights for that parity; H, W multiples of 16. */
+  int up_a, up_b;
 } mdm_conv_args;
 
+/* parity weights of the fused upsample convolution: w32 fp32 [cout][9][cin] (packed layout) -> out bf16
+ * [4 = 2 a + b][cout][4 = 2 u + v][cin], W_ab[u][v] = sum of the 3x3 taps that land on low-resolution offset
+ * (a - 1 + u, b - 1 + v): rows {0} | {1, 2} for a = 0, {0, 1} | {2} for a = 1, columns alike. */
+int mdm_up2x_weights(const float* w32, void* out_bf16, int cout, int cin, void* stream);
 /* tcgen05/TMEM implicit GEMM fed by TMA (csrc/igemm.cu) */
 int mdm_conv_fprop(const mdm_conv_args* a, void* stream);
 int mdm_conv_dgrad(const mdm_conv_args* a, void* stream);   /* stride-1 layers */

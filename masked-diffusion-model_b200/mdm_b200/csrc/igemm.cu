@@ -1061,6 +1061,26 @@ static int make_act_map(CUtensorMap* m, const void* ptr, long long ld, int C, in
   return MDM_OK;
 }
 
+// parity view of a full-resolution NHWC tensor [N][2H][2W][C]: the pixels (2h + a, 2w + b), addressed as (c, w, h, n)
+// with doubled pixel / row strides -- the store target of the fused upsample convolution
+static int make_parity_map(CUtensorMap* m, const void* ptr, long long ld, int C, int W, int H, int N, int a, int b, int bw, int bh) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return MDM_E_CUDA; }
+  const char* base = (const char*)ptr + ((long long)a * 2 * W + b) * ld * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)2 * ld * 2, (cuuint64_t)2 * (2 * W) * ld * 2, (cuuint64_t)(2 * H) * (2 * W) * ld * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(parity) failed: %d (ptr=%p ld=%lld C=%d W=%d H=%d N=%d)", (int)r, ptr, ld, C, W, H, N);
+    return MDM_E_CUDA;
+  }
+  return MDM_OK;
+}
+
 // weight map: bf16 [rows][taps][cols]; box {64 cols, 1 tap, box_rows}
 static int make_w_map(CUtensorMap* m, const void* ptr, int cols, int taps, int rows, int box_rows) {
   EncodeTiledFn enc = get_encode();
@@ -1250,6 +1270,7 @@ static int halo_ok(const mdm_conv_args* c, const void* out, int n_total, int k_c
   (void)k_chunks;
   const int enabled = env_flag("MDM_IGEMM_HALO", 2);                   // read per call: the tests switch modes
   const int force = env_flag("MDM_IGEMM_HALO_FORCE", 0);               // tests: every eligible layer, however small
+  if (c->up2x) return 2;                                               // (checked by the caller: H, W multiples of 16)
   if (!enabled || c->ksize != 3 || c->stride != 1 || out == nullptr || c->y_f32 != nullptr) return 0;
   if (enabled == 1) return (c->H % PATCH_H == 0 && c->W % PATCH_W == 0) ? 1 : 0;
   if (c->H % 16 == 0 && c->W % 16 == 0) {
@@ -1329,7 +1350,8 @@ static int run_activation_gemm(IgemmArgs& a, const mdm_conv_args* c, const void*
     a.has_c = (c_ptr != nullptr && out != nullptr) ? 1 : 0;
     mD = mA0;   // placeholder when nothing is TMA-stored (fp32-only output of the tiny Linear layers)
     if (out) {
-      if (a.halo) rc = make_act_map(&mD, out, ld_out, a.N_total, c->W, c->H, c->N, PATCH_W, PATCH_H, 1, 1);
+      if (c->up2x) rc = make_parity_map(&mD, out, ld_out, a.N_total, c->W, c->H, c->N, c->up_a, c->up_b, PATCH_W, PATCH_H);
+      else if (a.halo) rc = make_act_map(&mD, out, ld_out, a.N_total, c->W, c->H, c->N, PATCH_W, PATCH_H, 1, 1);
       else rc = make_tile_map(&mD, out, false, a.N_total, a.M_total, ld_out);
       if (rc) return rc;
     }
@@ -1402,7 +1424,24 @@ int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
   memset(&a, 0, sizeof(a));
   a.mode = 0;
   a.nseg = 1;
-  fill_taps(a, 0, c->ksize, false, c->H, c->W, c->stride);
+  if (c->up2x) {
+    // fused nearest-2x upsample: parity (up_a, up_b) of the output = a 2x2 convolution of the low-resolution input with
+    // offsets {up_a - 1, up_a} x {up_b - 1, up_b} (always inside the 18 x 18 halo) and pre-summed weights [cout][4][cin]
+    MDM_CHECK_ARG(c->ksize == 3 && c->stride == 1 && c->y && !c->y_f32 && !c->x2 && !c->resid && !c->accumulate && !c->rowvec,
+                  "conv_fprop(up2x): plain 3x3 stride-1 layer with a bf16 output only");
+    MDM_CHECK_ARG(c->H % 16 == 0 && c->W % 16 == 0 && (c->up_a | c->up_b) >= 0 && c->up_a <= 1 && c->up_b <= 1,
+                  "conv_fprop(up2x): low-resolution H, W must be multiples of 16 (got %d x %d), parity in {0,1}^2", c->H, c->W);
+    int n = 0;
+    for (int u = 0; u < 2; ++u)
+      for (int v = 0; v < 2; ++v, ++n) {
+        a.tap_dh[0][n] = (signed char)(c->up_a - 1 + u);
+        a.tap_dw[0][n] = (signed char)(c->up_b - 1 + v);
+        a.tap_b[0][n] = (signed char)(u * 2 + v);
+      }
+    a.seg_taps[0] = 4;
+  } else {
+    fill_taps(a, 0, c->ksize, false, c->H, c->W, c->stride);
+  }
   a.seg_kc[0] = c->cin / 64;
   a.a_stride[0] = c->stride;
   a.H = c->H; a.W = c->W;
@@ -1416,7 +1455,7 @@ int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
     a.qsum = c->qsum;
   }
   CUtensorMap mB0, mB1;
-  rc = make_w_map(&mB0, c->w, c->cin, c->ksize * c->ksize, c->cout, 128);
+  rc = make_w_map(&mB0, c->w, c->cin, c->up2x ? 4 : c->ksize * c->ksize, c->cout, 128);
   if (rc) return rc;
   if (c->x2) {  // fused 1x1 shortcut: extra K segment on a second activation / weight pair
     MDM_CHECK_ARG(c->w2 && c->cin2 % 64 == 0 && c->ld_x2 % 8 == 0, "conv_fprop: bad shortcut segment");

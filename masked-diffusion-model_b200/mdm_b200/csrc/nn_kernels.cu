@@ -1374,43 +1374,126 @@ __global__ void zero_insert2x_kernel(const bf16* __restrict__ x, long long ldx, 
   *reinterpret_cast<uint4*>(y + ((n * 2 * H + ho) * 2 * W + wo) * ldy + cv * 8) = v;
 }
 
+// parity weights of the fused nearest-2x upsample + 3x3 convolution (igemm.cu: up2x): out[2a+b][co][2u+v][ci] = sum of the
+// 3x3 taps (r, s) of w[co][3r+s][ci] whose upsampled position lands on low-resolution offset (a-1+u, b-1+v)
+__global__ void up2x_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cout, int cin) {
+  MDM_PDL_ENTER();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (co, ci)
+  if (i >= (long long)cout * cin) return;
+  const int co = (int)(i / cin), ci = (int)(i % cin);
+  float t[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) t[k] = w[((long long)co * 9 + k) * cin + ci];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          // rows: a = 0 -> u = 0: {0}, u = 1: {1, 2};  a = 1 -> u = 0: {0, 1}, u = 1: {2}   (columns alike)
+          const int r0 = a == 0 ? (u == 0 ? 0 : 1) : (u == 0 ? 0 : 2), r1 = a == 0 ? (u == 0 ? 0 : 2) : (u == 0 ? 1 : 2);
+          const int s0 = b == 0 ? (v == 0 ? 0 : 1) : (v == 0 ? 0 : 2), s1 = b == 0 ? (v == 0 ? 0 : 2) : (v == 0 ? 1 : 2);
+          float acc = 0.f;
+          for (int r = r0; r <= r1; ++r)
+            for (int s_ = s0; s_ <= s1; ++s_) acc += t[r * 3 + s_];
+          out[(((long long)(2 * a + b) * cout + co) * 4 + (2 * u + v)) * cin + ci] = __float2bfloat16(acc);
+        }
+}
+
 // =============================================================================================
-// K4: attention core for L <= 256 tokens, head_dim 8 (heads = C/8).  qkv: [N*L][3C] bf16.
-// One CTA per (head, n); K and V of the head live in shared memory; one thread per query.
+// K4: attention core for L <= 1024 tokens, head_dim 8 (heads = C/8).  qkv: [N*L][3C] bf16.
 // (The q/k/v/out projections, >99% of the attention FLOPs, are tcgen05 GEMMs in igemm.cu; the
 // L x L x 8 core is far too small for a tensor-core tile.)
 // =============================================================================================
 constexpr int ATT_D = 8;
-__global__ void attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int C, float scale) {
+// Forward: one CTA = HPC adjacent heads of one sample (their q / k / v slices are contiguous: HPC x 16 bytes per token, so
+// every global access is a full 16-byte vector of a >= 64-byte segment); K and V of those heads live in shared memory as
+// fp32 [token][head][8] (a warp reads one 128-byte line per key, broadcast inside a head); one thread per (query, head)
+// row holds KC scores in registers, so the soft-max costs ONE exp2 per key (scale * log2 e folded into q) and one
+// rescale per KC keys instead of two exps and a rescale per key.  fp32 FMA bound: 32 L^2 flops per (sample, head).
+template <int KC>
+__global__ void __launch_bounds__(256) attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int C, int HPC,
+                                                            float scale_log2e) {
   MDM_PDL_ENTER();
-  extern __shared__ float att_sm[];  // K[L][8], V[L][8]
+  extern __shared__ __align__(16) float att_sm[];  // K[L][HPC][8], V[L][HPC][8]
   float* Ks = att_sm;
-  float* Vs = att_sm + L * ATT_D;
-  const int head = blockIdx.x, n = blockIdx.y;
-  const bf16* base = qkv + (long long)n * L * 3 * C + head * ATT_D;
-  for (int i = threadIdx.x; i < L * ATT_D; i += blockDim.x) {
-    const int j = i / ATT_D, d = i % ATT_D;
-    Ks[i] = __bfloat162float(base[(long long)j * 3 * C + C + d]);
-    Vs[i] = __bfloat162float(base[(long long)j * 3 * C + 2 * C + d]);
+  float* Vs = att_sm + (size_t)L * HPC * ATT_D;
+  const int h0 = blockIdx.x * HPC, n = blockIdx.y;
+  const bf16* base = qkv + (long long)n * L * 3 * C + h0 * ATT_D;
+  for (int i = threadIdx.x; i < L * HPC; i += blockDim.x) {        // i = token * HPC + head: 16-byte pieces, coalesced
+    const int j = i / HPC, h = i - j * HPC;
+    const bf16* row = base + (long long)j * 3 * C + h * ATT_D;
+    const uint4 kq = *reinterpret_cast<const uint4*>(row + C);
+    const uint4 vq = *reinterpret_cast<const uint4*>(row + 2 * C);
+    const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kq);
+    const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vq);
+    float4 a, b;
+    float2 t0 = __bfloat1622float2(k2[0]), t1 = __bfloat1622float2(k2[1]), t2 = __bfloat1622float2(k2[2]), t3 = __bfloat1622float2(k2[3]);
+    a = make_float4(t0.x, t0.y, t1.x, t1.y); b = make_float4(t2.x, t2.y, t3.x, t3.y);
+    *reinterpret_cast<float4*>(Ks + (size_t)i * ATT_D) = a;
+    *reinterpret_cast<float4*>(Ks + (size_t)i * ATT_D + 4) = b;
+    t0 = __bfloat1622float2(v2[0]); t1 = __bfloat1622float2(v2[1]); t2 = __bfloat1622float2(v2[2]); t3 = __bfloat1622float2(v2[3]);
+    a = make_float4(t0.x, t0.y, t1.x, t1.y); b = make_float4(t2.x, t2.y, t3.x, t3.y);
+    *reinterpret_cast<float4*>(Vs + (size_t)i * ATT_D) = a;
+    *reinterpret_cast<float4*>(Vs + (size_t)i * ATT_D + 4) = b;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+  for (int r = threadIdx.x; r < L * HPC; r += blockDim.x) {        // r = query * HPC + head
+    const int i = r / HPC, h = r - i * HPC;
     float q[ATT_D];
-    for (int d = 0; d < ATT_D; ++d) q[d] = __bfloat162float(base[(long long)i * 3 * C + d]) * scale;
+    {
+      const uint4 qq = *reinterpret_cast<const uint4*>(base + (long long)i * 3 * C + h * ATT_D);
+      const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qq);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const float2 t = __bfloat1622float2(q2[d]);
+        q[2 * d] = t.x * scale_log2e;
+        q[2 * d + 1] = t.y * scale_log2e;
+      }
+    }
     float m = -INFINITY, l = 0.f, acc[ATT_D];
+#pragma unroll
     for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
-    for (int j = 0; j < L; ++j) {
-      float s = 0.f;
-      for (int d = 0; d < ATT_D; ++d) s += q[d] * Ks[j * ATT_D + d];
-      const float mn = fmaxf(m, s);
-      const float corr = __expf(m - mn), p = __expf(s - mn);
-      l = l * corr + p;
-      for (int d = 0; d < ATT_D; ++d) acc[d] = acc[d] * corr + p * Vs[j * ATT_D + d];
+    const float* Kh = Ks + h * ATT_D;
+    const float* Vh = Vs + h * ATT_D;
+    const int pitch = HPC * ATT_D;
+    for (int j0 = 0; j0 < L; j0 += KC) {
+      float s[KC];
+      float cm = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < KC; ++jj) {
+        const float4 ka = *reinterpret_cast<const float4*>(Kh + (size_t)(j0 + jj) * pitch);
+        const float4 kb = *reinterpret_cast<const float4*>(Kh + (size_t)(j0 + jj) * pitch + 4);
+        float v = q[0] * ka.x;
+        v = fmaf(q[1], ka.y, v); v = fmaf(q[2], ka.z, v); v = fmaf(q[3], ka.w, v);
+        v = fmaf(q[4], kb.x, v); v = fmaf(q[5], kb.y, v); v = fmaf(q[6], kb.z, v); v = fmaf(q[7], kb.w, v);
+        s[jj] = v;
+        cm = fmaxf(cm, v);
+      }
+      const float mn = fmaxf(m, cm);
+      const float corr = exp2f(m - mn);       // first chunk: exp2(-inf) = 0
+      l *= corr;
+#pragma unroll
+      for (int d = 0; d < ATT_D; ++d) acc[d] *= corr;
+#pragma unroll
+      for (int jj = 0; jj < KC; ++jj) {
+        const float p = exp2f(s[jj] - mn);
+        const float4 va = *reinterpret_cast<const float4*>(Vh + (size_t)(j0 + jj) * pitch);
+        const float4 vb = *reinterpret_cast<const float4*>(Vh + (size_t)(j0 + jj) * pitch + 4);
+        l += p;
+        acc[0] = fmaf(p, va.x, acc[0]); acc[1] = fmaf(p, va.y, acc[1]); acc[2] = fmaf(p, va.z, acc[2]); acc[3] = fmaf(p, va.w, acc[3]);
+        acc[4] = fmaf(p, vb.x, acc[4]); acc[5] = fmaf(p, vb.y, acc[5]); acc[6] = fmaf(p, vb.z, acc[6]); acc[7] = fmaf(p, vb.w, acc[7]);
+      }
       m = mn;
     }
     const float inv = 1.0f / l;
-    bf16* o = out + ((long long)n * L + i) * C + head * ATT_D;
-    for (int d = 0; d < ATT_D; ++d) o[d] = __float2bfloat16(acc[d] * inv);
+    uint4 o;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int d = 0; d < 4; ++d) o2[d] = __floats2bfloat162_rn(acc[2 * d] * inv, acc[2 * d + 1] * inv);
+    *reinterpret_cast<uint4*>(out + ((long long)n * L + i) * C + (h0 + h) * ATT_D) = o;
   }
 }
 
@@ -1838,12 +1921,43 @@ int mdm_zero_insert2x(const void* x, long long ld_x, void* y, long long ld_y, in
   return MDM_OK;
 }
 
+int mdm_up2x_weights(const float* w32, void* out_bf16, int cout, int cin, void* stream) {
+  MDM_CHECK_ARG(w32 && out_bf16 && cout > 0 && cin > 0, "up2x_weights: bad arguments");
+  const long long total = (long long)cout * cin;
+  launch_pdl(up2x_weights_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, as_stream(stream), w32, (bf16*)out_bf16, cout, cin);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
 int mdm_attention_fwd(const void* qkv, void* out, int N, int L, int C, void* stream) {
   MDM_CHECK_ARG(qkv && out && C % ATT_D == 0 && L >= 1 && L <= 1024, "attention_fwd: bad arguments (L=%d C=%d)", L, C);
-  const int th = L < 32 ? 32 : (L > 256 ? 256 : ((L + 31) / 32) * 32);
-  const size_t smem = (size_t)2 * L * ATT_D * sizeof(float);
-  dim3 grid(C / ATT_D, N);
-  launch_pdl(attention_fwd_kernel, dim3(grid), dim3(th), smem, as_stream(stream), (const bf16*)qkv, (bf16*)out, L, C, 1.0f / sqrtf((float)ATT_D));
+  MDM_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, "attention_fwd: pointers must be 16-byte aligned");
+  const int heads = C / ATT_D;
+  // heads per CTA: 256 (query, head) rows per CTA when the sample has that many, at least 4 heads (64-byte segments),
+  // a divisor of the head count, K + V within 96 KB of shared memory
+  int hpc = 256 / L;
+  if (hpc < 4) hpc = 4;
+  while (hpc > 1 && (heads % hpc != 0 || (size_t)2 * L * hpc * ATT_D * sizeof(float) > 96 * 1024)) hpc >>= 1;
+  if (heads % hpc != 0) hpc = 1;
+  const size_t smem = (size_t)2 * L * hpc * ATT_D * sizeof(float);
+  const int kc = (L % 64 == 0) ? 64 : (L % 16 == 0 ? 16 : (L % 4 == 0 ? 4 : 1));
+  static bool attr_set = false;
+  if (!attr_set) {
+    MDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  int th = L * hpc;
+  th = th < 32 ? 32 : (th > 256 ? 256 : ((th + 31) / 32) * 32);
+  dim3 grid(heads / hpc, N);
+  const float sl2 = 1.4426950408889634f / sqrtf((float)ATT_D);
+  cudaStream_t st = as_stream(stream);
+  if (kc == 64) launch_pdl(attention_fwd_kernel<64>, dim3(grid), dim3(th), smem, st, (const bf16*)qkv, (bf16*)out, L, C, hpc, sl2);
+  else if (kc == 16) launch_pdl(attention_fwd_kernel<16>, dim3(grid), dim3(th), smem, st, (const bf16*)qkv, (bf16*)out, L, C, hpc, sl2);
+  else if (kc == 4) launch_pdl(attention_fwd_kernel<4>, dim3(grid), dim3(th), smem, st, (const bf16*)qkv, (bf16*)out, L, C, hpc, sl2);
+  else launch_pdl(attention_fwd_kernel<1>, dim3(grid), dim3(th), smem, st, (const bf16*)qkv, (bf16*)out, L, C, hpc, sl2);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }

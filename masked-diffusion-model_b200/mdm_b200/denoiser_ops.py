@@ -28,6 +28,7 @@ class ConvArgs(Structure):
         ("dbias", c_void_p), ("dbias2", c_void_p),
         ("splitk_ws", c_void_p), ("splitk_ws_floats", c_longlong),
         ("qsum", c_void_p),
+        ("up2x", c_int), ("up_a", c_int), ("up_b", c_int),
     ]
 
 
@@ -38,6 +39,7 @@ _lib.register({
     "mdm_conv_fprop": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_conv_dgrad": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_conv_wgrad": (c_int, [POINTER(ConvArgs), _P]),
+    "mdm_up2x_weights": (c_int, [_P, _P, c_int, c_int, _P]),
     "mdm_reserve_sms": (c_int, [c_int]),
     "mdm_set_sched_workspace": (c_int, [_P, c_int]),
     "mdm_gn_ws_floats": (_I64, [c_int, c_int, c_int, c_int]),
@@ -132,6 +134,28 @@ def conv_fprop(x, w, y, N, H, W, ksize=3, stride=1, bias=None, rowvec=None, resi
     a.qsum = _dp(qsum)          # fused GroupNorm statistics of the output: qsum[N, cout/4, 2] += quad (sum, sumsq)
     _splitk(a, x.device)
     check(lib().mdm_conv_fprop(ctypes.byref(a), stream_ptr(x.device)))
+
+
+def up2x_weights(w32, out_bf16, cout, cin):
+    """parity weights of the fused upsample convolution: w32 [cout, 9, cin] fp32 -> out [4, cout, 4, cin] bf16"""
+    check(lib().mdm_up2x_weights(ptr(w32), ptr(out_bf16), cout, cin, stream_ptr(w32.device)))
+
+
+def conv_up2x_fprop(x, w4, y, N, H, W, bias=None, qsum=None):
+    """y[N, 2H, 2W, cout] = conv3x3(nearest_upsample_2x(x[N, H, W, cin])) + bias without building the upsampled image:
+    four launches, one per output parity, each a 2x2 convolution of x with the pre-summed weights w4[2a+b] (up2x_weights)"""
+    for pa in range(2):
+        for pb in range(2):
+            a = ConvArgs()
+            a.x, a.ld_x, a.cin = _dp(x), pix_ld(x), x.shape[-1]
+            a.w = _dp(w4[2 * pa + pb])
+            a.y, a.ld_y, a.cout = _dp(y), pix_ld(y), y.shape[-1]
+            a.N, a.H, a.W, a.ksize, a.stride = N, H, W, 3, 1
+            a.bias = _dp(bias)
+            a.qsum = _dp(qsum)
+            a.up2x, a.up_a, a.up_b = 1, pa, pb
+            _ensure_sched_ws(x.device)
+            check(lib().mdm_conv_fprop(ctypes.byref(a), stream_ptr(x.device)))
 
 
 def reserve_sms(n):

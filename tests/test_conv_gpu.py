@@ -230,3 +230,41 @@ def test_dynamic_work_distribution_matches_static(monkeypatch, halo):
         assert (a - c).abs().max().item() <= 1e-4 * a.abs().max().item()
     ref = F.conv2d(nchw(xb), ops.unpack_conv_weight(wb.float(), 3), b, padding=1) + nchw(res)
     assert (nchw(out["2"][0]) - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("N,H,cin", [(2, 16, 128), (3, 32, 256), (1, 64, 128)])
+def test_fused_upsample_conv(N, H, cin):
+    """diffusers Upsample2D = conv3x3(interpolate(x, 2, 'nearest')): four parity launches over the low-resolution input
+    with pre-summed 2x2 weights (4/9 of the FLOPs, no upsampled tensor), output incl. bias and the fused GroupNorm
+    quad sums equals the explicit upsample + convolution"""
+    from mdm_b200 import denoiser_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    cout = cin
+    x = torch.randn(N, cin, H, H, device="cuda", generator=g)
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (9 * cin) ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g)
+    xb = nhwc(x)
+    wp = ops.pack_conv_weight(w).contiguous()                       # fp32 [cout, 9, cin]: the master-weight layout
+    w4 = torch.empty(4, cout, 4, cin, device="cuda", dtype=torch.bfloat16)
+    ops.up2x_weights(wp, w4, cout, cin)
+    # the parity weights are exact sums of the fp32 taps, rounded once
+    wr = wp.view(cout, 3, 3, cin)
+    rows = {0: [wr[:, 0:1].sum(1), wr[:, 1:3].sum(1)], 1: [wr[:, 0:2].sum(1), wr[:, 2:3].sum(1)]}
+    for a in range(2):
+        for bb in range(2):
+            for u in range(2):
+                r = rows[a][u]                                      # [cout, 3 (s), cin]
+                cols = [r[:, 0:1].sum(1), r[:, 1:3].sum(1)] if bb == 0 else [r[:, 0:2].sum(1), r[:, 2:3].sum(1)]
+                for v in range(2):
+                    torch.testing.assert_close(w4[2 * a + bb, :, 2 * u + v].float(), cols[v].to(torch.bfloat16).float(), rtol=1e-2, atol=1e-3)
+    y = torch.zeros(N, 2 * H, 2 * H, cout, device="cuda", dtype=torch.bfloat16)
+    q = torch.zeros(N, cout // 4, 2, device="cuda")
+    ops.conv_up2x_fprop(xb, w4, y, N, H, H, bias=b, qsum=q)
+    up = F.interpolate(nchw(xb), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w, b, padding=1)                             # fp32 weights: the fused path rounds the SUMS, not the taps
+    err = (nchw(y) - ref).abs().max().item()
+    assert err <= 1.5e-2 * ref.abs().max().item(), err
+    yq = nchw(y).view(N, cout // 4, 4, -1)
+    want = torch.stack([yq.sum(dim=(2, 3)), (yq * yq).sum(dim=(2, 3))], dim=-1)
+    # the statistics are taken from the fp32 accumulators before the bf16 rounding of y
+    assert (q - want).abs().max().item() <= 2e-2 * want.abs().max().item()
