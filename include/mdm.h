@@ -352,6 +352,15 @@ int mdm_p2p_flag_words(void);
 int mdm_ipc_export(const void* ptr, void* handle_out /*64 bytes, host*/, int64_t* offset_out /*host*/);
 int mdm_ipc_open(const void* handle /*64 bytes, host*/, int64_t offset, void** ptr_out /*host*/);
 int mdm_p2p_allreduce(const mdm_p2p_comm* comm /*host*/, int64_t offset, int64_t count, int blocks, void* stream);
+/* Copy-engine variant of the same all-reduce, as pieces the caller strings together on its communication stream
+ * (mdm_b200/runtime.py: P2PAllReduce.all_reduce_ce): mdm_p2p_barrier(0) -- the peers' gradients are final;
+ * (world - 1) x mdm_memcpy_async pulls of this rank's slice from the peers into a local staging area (copy engines, no
+ * SM); mdm_reduce_slices sums them in rank order into the local slice; (world - 1) x mdm_memcpy_async pushes of the
+ * reduced slice; mdm_p2p_barrier(1) -- every push has landed and nobody reads this rank's buffer any more.  The SMs run
+ * two one-warp kernels and one local HBM-rate reduction per range. */
+int mdm_p2p_barrier(const mdm_p2p_comm* comm /*host*/, int which, void* stream);
+int mdm_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
+int mdm_reduce_slices(float* slice, const float* staging, int64_t stride, int64_t count, int rank, int world, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,9 @@ _lib.register({
     "mdm_ipc_export": (c_int, [_P, _P, ctypes.POINTER(c_int64)]),
     "mdm_ipc_open": (c_int, [_P, c_int64, ctypes.POINTER(c_void_p)]),
     "mdm_p2p_allreduce": (c_int, [ctypes.POINTER(P2PCommStruct), c_int64, c_int64, c_int, _P]),
+    "mdm_p2p_barrier": (c_int, [ctypes.POINTER(P2PCommStruct), c_int, _P]),
+    "mdm_memcpy_async": (c_int, [_P, _P, c_int64, _P]),
+    "mdm_reduce_slices": (c_int, [_P, _P, c_int64, c_int64, c_int, c_int, _P]),
 })
 
 
@@ -45,3 +48,15 @@ def ipc_open(handle: bytes, offset: int) -> int:
 
 def p2p_allreduce(comm: P2PCommStruct, offset: int, count: int, blocks: int, device):
     check(lib().mdm_p2p_allreduce(ctypes.byref(comm), offset, count, blocks, stream_ptr(device)))
+
+
+def p2p_barrier(comm: P2PCommStruct, which: int, device):
+    check(lib().mdm_p2p_barrier(ctypes.byref(comm), which, stream_ptr(device)))
+
+
+def memcpy_async(dst_ptr: int, src_ptr: int, nbytes: int, device):
+    check(lib().mdm_memcpy_async(c_void_p(dst_ptr), c_void_p(src_ptr), nbytes, stream_ptr(device)))
+
+
+def reduce_slices(slice_ptr: int, staging_ptr: int, stride: int, count: int, rank: int, world: int, device):
+    check(lib().mdm_reduce_slices(c_void_p(slice_ptr), c_void_p(staging_ptr), stride, count, rank, world, stream_ptr(device)))

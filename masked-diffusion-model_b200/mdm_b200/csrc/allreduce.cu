@@ -27,8 +27,11 @@ constexpr int AR_MAX_RANKS = 8;
 constexpr int AR_MAX_BLOCKS = 128;
 constexpr int AR_THREADS = 128;
 constexpr int AR_PHASES = 2;
-// flag words per rank: [AR_PHASES][AR_MAX_BLOCKS][AR_MAX_RANKS] uint32, then per-block epochs [AR_MAX_BLOCKS]
-constexpr int AR_FLAG_WORDS = AR_PHASES * AR_MAX_BLOCKS * AR_MAX_RANKS + AR_MAX_BLOCKS;
+// flag words per rank: [AR_PHASES][AR_MAX_BLOCKS][AR_MAX_RANKS] uint32, then per-block epochs [AR_MAX_BLOCKS], then the
+// stand-alone barriers of the copy-engine variant: [AR_BARRIERS][AR_MAX_RANKS] flags + [AR_BARRIERS] epochs
+constexpr int AR_BARRIERS = 4;
+constexpr int AR_BAR_OFF = AR_PHASES * AR_MAX_BLOCKS * AR_MAX_RANKS + AR_MAX_BLOCKS;
+constexpr int AR_FLAG_WORDS = AR_BAR_OFF + AR_BARRIERS * AR_MAX_RANKS + AR_BARRIERS;
 
 struct P2PComm {
   float* buf[AR_MAX_RANKS];       // every rank's flat gradient buffer, mapped into this process
@@ -123,6 +126,51 @@ __global__ void __launch_bounds__(AR_THREADS) p2p_allreduce_kernel(const P2PComm
   block_exchange(c, 1, epoch);     // every rank has pushed its slice: this buffer is complete, and nobody reads it any more
 }
 
+// ---- copy-engine variant -------------------------------------------------------------------------------------------
+// The bulk of the bytes moves through the COPY ENGINES (cudaMemcpyAsync nodes between IPC-mapped buffers, no SM
+// involved): pull the peers' copies of this rank's slice into a local staging area, reduce locally (HBM-rate, ~70 us for
+// the largest range), push the reduced slice to every peer.  The SMs only run two one-warp barriers and the local
+// reduction -- measured: the SM-driven kernel above slows the co-running backward in proportion to its block count.
+__global__ void __launch_bounds__(32) p2p_barrier_kernel(const P2PComm c, int which) {
+  MDM_PDL_ENTER();
+  uint32_t* epochs = c.flag[c.rank] + AR_BAR_OFF + AR_BARRIERS * AR_MAX_RANKS;
+  uint32_t epoch = 0;
+  if (threadIdx.x == 0) epoch = ++epochs[which];
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
+  const int slot = AR_BAR_OFF + which * AR_MAX_RANKS;
+  if (threadIdx.x < c.world) {
+    __threadfence_system();
+    st_release_sys(c.flag[threadIdx.x] + slot + c.rank, epoch);
+    const uint32_t* mine = c.flag[c.rank] + slot + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+      if (clock64() - t0 > 40000000000LL) __trap();
+    }
+  }
+}
+
+// slice[e] = sum over ranks in rank order of (p == rank ? slice[e] : staging[k(p)][e]); staging holds the peers' copies
+// in the order p = rank + 1, rank + 2, ... (mod world), `stride` floats apart
+template <int W>
+__global__ void __launch_bounds__(256) reduce_slices_kernel(float* __restrict__ slice, const float* __restrict__ staging,
+                                                            long long stride, long long n4, int rank) {
+  MDM_PDL_ENTER();
+  float4* mine = reinterpret_cast<float4*>(slice);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    float4 v[W];
+#pragma unroll
+    for (int p = 0; p < W; ++p) {
+      int k = p - rank - 1;
+      if (k < 0) k += W;                 // position of rank p's copy in the staging area (p != rank)
+      v[p] = (p == rank) ? mine[e] : *reinterpret_cast<const float4*>(staging + (long long)k * stride + 4 * e);
+    }
+    float4 acc = v[0];
+#pragma unroll
+    for (int p = 1; p < W; ++p) { acc.x += v[p].x; acc.y += v[p].y; acc.z += v[p].z; acc.w += v[p].w; }
+    mine[e] = acc;
+  }
+}
+
 typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
 
 }  // namespace mdm
@@ -168,22 +216,66 @@ int mdm_ipc_open(const void* handle /*64 bytes*/, int64_t offset, void** ptr_out
   return MDM_OK;
 }
 
+static int fill_comm(P2PComm& c, const mdm_p2p_comm* comm) {
+  MDM_CHECK_ARG(comm && comm->world >= 2 && comm->world <= AR_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world,
+                "p2p: bad communicator");
+  for (int p = 0; p < AR_MAX_RANKS; ++p) {
+    c.buf[p] = (float*)comm->buf[p < comm->world ? p : 0];
+    c.flag[p] = (uint32_t*)comm->flag[p < comm->world ? p : 0];
+    MDM_CHECK_ARG(c.buf[p] && c.flag[p], "p2p: NULL peer pointer");
+  }
+  c.rank = comm->rank;
+  c.world = comm->world;
+  return MDM_OK;
+}
+
+// copy-engine variant, pieces (the caller strings them together on its communication stream, see runtime.P2PAllReduce):
+int mdm_p2p_barrier(const mdm_p2p_comm* comm, int which, void* stream) {
+  P2PComm c;
+  int rc = fill_comm(c, comm);
+  if (rc) return rc;
+  MDM_CHECK_ARG(which >= 0 && which < AR_BARRIERS, "p2p_barrier: 0 <= which < %d", AR_BARRIERS);
+  launch_pdl(p2p_barrier_kernel, dim3(1), dim3(32), 0, as_stream(stream), c, which);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream) {
+  MDM_CHECK_ARG(dst && src && bytes > 0, "memcpy_async: bad arguments");
+  MDM_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, as_stream(stream)));
+  return MDM_OK;
+}
+
+int mdm_reduce_slices(float* slice, const float* staging, int64_t stride, int64_t count, int rank, int world, void* stream) {
+  MDM_CHECK_ARG(slice && staging && count > 0 && count % 4 == 0 && stride % 4 == 0 && world >= 2 && world <= AR_MAX_RANKS && rank >= 0 && rank < world,
+                "reduce_slices: bad arguments");
+  const long long n4 = count / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  cudaStream_t st = as_stream(stream);
+  const long long str = stride;
+  switch (world) {
+    case 2: launch_pdl(reduce_slices_kernel<2>, dim3(blocks), dim3(256), 0, st, slice, staging, str, n4, rank); break;
+    case 3: launch_pdl(reduce_slices_kernel<3>, dim3(blocks), dim3(256), 0, st, slice, staging, str, n4, rank); break;
+    case 4: launch_pdl(reduce_slices_kernel<4>, dim3(blocks), dim3(256), 0, st, slice, staging, str, n4, rank); break;
+    case 5: launch_pdl(reduce_slices_kernel<5>, dim3(blocks), dim3(256), 0, st, slice, staging, str, n4, rank); break;
+    case 6: launch_pdl(reduce_slices_kernel<6>, dim3(blocks), dim3(256), 0, st, slice, staging, str, n4, rank); break;
+    case 7: launch_pdl(reduce_slices_kernel<7>, dim3(blocks), dim3(256), 0, st, slice, staging, str, n4, rank); break;
+    default: launch_pdl(reduce_slices_kernel<8>, dim3(blocks), dim3(256), 0, st, slice, staging, str, n4, rank); break;
+  }
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
 // SUM all-reduce of buf[offset .. offset + count) (floats; offset and count multiples of 4) across `world` ranks.
 // Every rank must launch the same sequence of calls with the same (offset, count, blocks); calls on one rank must be
 // stream-ordered (one communication stream).  The caller divides by world (the fused optimiser folds it in).
 int mdm_p2p_allreduce(const mdm_p2p_comm* comm, int64_t offset, int64_t count, int blocks, void* stream) {
-  MDM_CHECK_ARG(comm && comm->world >= 2 && comm->world <= AR_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world,
-                "p2p_allreduce: bad communicator");
   MDM_CHECK_ARG(offset >= 0 && count > 0 && offset % 4 == 0 && count % 4 == 0, "p2p_allreduce: offset / count must be multiples of 4 floats");
   MDM_CHECK_ARG(blocks >= 1 && blocks <= AR_MAX_BLOCKS, "p2p_allreduce: 1 <= blocks <= %d", AR_MAX_BLOCKS);
   P2PComm c;
-  for (int p = 0; p < AR_MAX_RANKS; ++p) {
-    c.buf[p] = (float*)comm->buf[p < comm->world ? p : 0];
-    c.flag[p] = (uint32_t*)comm->flag[p < comm->world ? p : 0];
-    MDM_CHECK_ARG(c.buf[p] && c.flag[p], "p2p_allreduce: NULL peer pointer");
-  }
-  c.rank = comm->rank;
-  c.world = comm->world;
+  int rc = fill_comm(c, comm);
+  if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   const long long off = offset, cnt = count;
   switch (c.world) {

@@ -229,6 +229,13 @@ class UNet2DModelB200:
         for r in L.resnets:
             self._p(f"{r.prefix}.time_emb_proj.bias", (r.cout,))
         L.tproj_total = off
+        # flat layout: the projections sit right behind the time-embedding MLP, i.e. in FRONT of the down path.  Their
+        # gradient is the last one the backward finishes (it sums over every resnet), like that of conv_in and of
+        # down_blocks.0: with all of them at the front the data-parallel all-reduce has ONE final range.
+        tp = [s for s in self._specs if ".time_emb_proj." in s.name]
+        rest = [s for s in self._specs if ".time_emb_proj." not in s.name]
+        at = next(i for i, s in enumerate(rest) if s.name == "time_embedding.linear_2.bias") + 1
+        self._specs = rest[:at] + tp + rest[at:]
         self.layers = L
 
     def _alloc_params(self):

@@ -308,7 +308,14 @@ class P2PAllReduce:
         if world > comm_ops.MAX_RANKS:
             raise RuntimeError(f"P2PAllReduce: at most {comm_ops.MAX_RANKS} ranks (one NVSwitch domain)")
         self.rank, self.world, self.device = rank, world, device
-        self.blocks = int(os.environ.get("MDM_P2P_BLOCKS", "96"))
+        self.blocks = int(os.environ.get("MDM_P2P_BLOCKS", "48"))
+        # "sm": one kernel per range moves everything with peer loads / stores; "ce": the copy engines move the bytes,
+        # the SMs only synchronise and reduce locally (csrc/allreduce.cu)
+        self.mode = os.environ.get("MDM_P2P_MODE", "ce").lower()
+        self.n_sub = max(1, int(os.environ.get("MDM_P2P_COPY_STREAMS", "3")))
+        self.ce_min_bytes = int(os.environ.get("MDM_P2P_CE_MIN_BYTES", str(32 << 20)))
+        self._subs = None
+        self.staging = None
         n = model.numel_flat
         # a dedicated allocation for the gradients (the IPC handle covers a whole cudaMalloc segment)
         self.buf = torch.zeros(n, dtype=torch.float32, device=device)
@@ -331,7 +338,41 @@ class P2PAllReduce:
 
     def all_reduce(self, lo, hi):
         """enqueue the SUM all-reduce of flat_grad[lo:hi] on the current stream"""
+        # big ranges: copy engines (no SM interference with the co-running backward); small ranges: the one-kernel
+        # variant (two in-kernel flag exchanges instead of 2 (world - 1) copy nodes: lower latency, and the final
+        # range of a step is exposed)
+        if self.mode == "ce" and 4 * (hi - lo) >= self.ce_min_bytes:
+            return self._all_reduce_ce(lo, hi)
         self._ops.p2p_allreduce(self.comm, lo, hi - lo, self.blocks, self.device)
+
+    def _all_reduce_ce(self, lo, hi):
+        ops, W, r, dev = self._ops, self.world, self.rank, self.device
+        if self.staging is None:
+            self._stride = ((self.buf.numel() + W - 1) // W + 3) // 4 * 4           # floats per peer copy (largest slice)
+            self.staging = torch.empty((W - 1) * self._stride, dtype=torch.float32, device=dev)
+            self._subs = [torch.cuda.Stream(device=dev) for _ in range(min(self.n_sub, W - 1))]
+        n4 = (hi - lo) // 4
+        slice_ = (n4 + W - 1) // W * 4                                              # floats per rank
+        s0 = lo + r * slice_
+        my_n = max(0, min(s0 + slice_, hi) - s0)
+        cs = torch.cuda.current_stream(dev)
+        ops.p2p_barrier(self.comm, 0, dev)                                          # every rank's gradients of the range are final
+        if my_n > 0:
+            mine = self.buf.data_ptr() + 4 * s0
+
+            def copies(make):
+                for sub in self._subs:
+                    sub.wait_stream(cs)
+                for k in range(W - 1):
+                    with torch.cuda.stream(self._subs[k % len(self._subs)]):
+                        make(k, (r + 1 + k) % W)
+                for sub in self._subs:
+                    cs.wait_stream(sub)
+            # pull the peers' copies of this rank's slice (copy engines), reduce locally in rank order, push the result
+            copies(lambda k, p: ops.memcpy_async(self.staging.data_ptr() + 4 * k * self._stride, self.comm.buf[p] + 4 * s0, 4 * my_n, dev))
+            ops.reduce_slices(mine, self.staging.data_ptr(), self._stride, my_n, r, W, dev)
+            copies(lambda k, p: ops.memcpy_async(self.comm.buf[p] + 4 * s0, mine, 4 * my_n, dev))
+        ops.p2p_barrier(self.comm, 1, dev)                                          # all pushes landed; nobody reads this buffer any more
 
 
 # ---------------------------------------------------------------------------------------------

@@ -33,6 +33,14 @@ def stage1():
     m = FakeModel()
     comm = P2PAllReduce(m, rank, world, dev)
     ok = True
+    for mode in ("sm", "ce"):
+        comm.mode = mode
+        ok = stage1_mode(m, comm, mode) and ok
+    return ok
+
+
+def stage1_mode(m, comm, mode):
+    ok = True
     g = torch.Generator(device=dev).manual_seed(77 + rank)
     for it, (lo, hi) in enumerate([(0, 6_000_000), (64, 4096 + 64), (1_000_000, 1_000_004), (12, 5_999_996), (0, 6_000_000)]):
         m.flat_grad.copy_(torch.randn(m.numel_flat, device=dev, generator=g))
@@ -49,7 +57,7 @@ def stage1():
         dist.broadcast(ref, src=0)
         same = bool(torch.equal(ref[lo:hi], got[lo:hi]))
         if rank == 0:
-            print(f"stage1 range [{lo}, {hi}): max |p2p - nccl| = {err:.2e}, outside untouched {untouched}, identical on all ranks {same}")
+            print(f"stage1 {mode} range [{lo}, {hi}): max |p2p - nccl| = {err:.2e}, outside untouched {untouched}, identical on all ranks {same}")
         ok = ok and err <= 1e-5 * world and untouched and same
         dist.barrier()
     # bandwidth of the kernel alone
@@ -70,12 +78,13 @@ def stage1():
     if rank == 0:
         print(f"stage1 NCCL all-reduce of the same buffer: {n0.elapsed_time(n1) / 10 * 1e3:.0f} us")
     if rank == 0:
-        print(f"stage1 p2p all-reduce ({comm.blocks} blocks) of {n * 4 / 1e6:.0f} MB: {ms * 1e3:.0f} us = {2 * (world - 1) / world * n * 4 / ms / 1e6:.0f} GB/s per GPU over NVLink")
+        print(f"stage1 {mode} all-reduce ({comm.blocks} blocks) of {n * 4 / 1e6:.0f} MB: {ms * 1e3:.0f} us = {2 * (world - 1) / world * n * 4 / ms / 1e6:.0f} GB/s per GPU over NVLink")
     return ok
 
 
 def run(mode):
-    os.environ["MDM_DP_ALLREDUCE"] = "p2p" if mode == "p2p" else "nccl"
+    os.environ["MDM_DP_ALLREDUCE"] = "p2p" if mode in ("p2p", "ce") else "nccl"
+    os.environ["MDM_P2P_MODE"] = "ce" if mode == "ce" else "sm"
     overlap = mode != "nccl_3piece"
     a = argparse.Namespace(batch=32, size=32, channels=3, method="base", no_graph=False)
     wa = bench.workload_args(a)
@@ -98,18 +107,20 @@ ok1 = stage1()
 l0, p0 = run("nccl_3piece")
 l1, p1 = run("nccl_overlap")
 l2, p2 = run("p2p")
+l3, p3 = run("ce")
 same_ranks = True
-for p in (p1, p2):
+for p in (p1, p2, p3):
     ref = p.clone()
     dist.broadcast(ref, src=0)
     same_ranks = same_ranks and bool((ref == p).all().item())
-diff = max((p0 - p1).abs().max().item(), (p0 - p2).abs().max().item())
+diff = max((p0 - p1).abs().max().item(), (p0 - p2).abs().max().item(), (p0 - p3).abs().max().item())
 if rank == 0:
     print("losses nccl 3-piece      :", [round(v, 6) for v in l0])
     print("losses nccl overlap      :", [round(v, 6) for v in l1])
     print("losses p2p in-graph      :", [round(v, 6) for v in l2])
+    print("losses copy-engine graph :", [round(v, 6) for v in l3])
     print(f"max |param diff| between the schedules: {diff:.3e}; identical parameters on every rank: {same_ranks}")
-good = ok1 and same_ranks and diff <= 5e-5 and all(abs(a - b) <= 1e-4 and abs(a - c) <= 1e-4 for a, b, c in zip(l0, l1, l2))
+good = ok1 and same_ranks and diff <= 5e-5 and all(abs(a - b) <= 1e-4 and abs(a - c) <= 1e-4 and abs(a - d) <= 1e-4 for a, b, c, d in zip(l0, l1, l2, l3))
 ok = torch.tensor([1.0 if good else 0.0], device=dev)
 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
 if rank == 0:

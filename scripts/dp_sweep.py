@@ -6,7 +6,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 NCCL = {"MDM_DP_ALLREDUCE": "nccl"}
 CONFIGS = {
-    "p2p":            {},                                            # default: peer-memory all-reduce inside the step graph
+    "ce":             {"MDM_P2P_MODE": "ce"},                        # default: copy-engine all-reduce inside the step graph
+    "ce_1stream":     {"MDM_P2P_MODE": "ce", "MDM_P2P_COPY_STREAMS": "1"},
+    "ce_7streams":    {"MDM_P2P_MODE": "ce", "MDM_P2P_COPY_STREAMS": "7"},
+    "sm48":           {"MDM_P2P_MODE": "sm", "MDM_P2P_BLOCKS": "48"},
+    "sm32":           {"MDM_P2P_MODE": "sm", "MDM_P2P_BLOCKS": "32"},
+    "sm24":           {"MDM_P2P_MODE": "sm", "MDM_P2P_BLOCKS": "24"},
+    "sm16":           {"MDM_P2P_MODE": "sm", "MDM_P2P_BLOCKS": "16"},
+    "p2p":            {"MDM_P2P_MODE": "sm"},
     "p2p_cuts_2":     {"MDM_DP_CUTS": "2"},
     "p2p_cuts_54321": {"MDM_DP_CUTS": "5,4,3,2,1"},
     "p2p_blocks48":   {"MDM_P2P_BLOCKS": "48"},
