@@ -444,6 +444,7 @@ def train_section(a, dev, world, rank, C, S, B, method, base, steps, warmup, lab
            "config": {"workload": f"{label}: {workload_name(C, S, method)}" if base == 128 else
                       f"{label}: large-channel masked U-Net (ch={base}, {model.num_parameters() / 1e6:.2f}M parameters) {C}x{S}x{S} training step ({method} trainer)",
                       "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graph": bool(wa.cuda_graph)}}
+    acc.close()                    # (data parallel: unmap the peers' gradient buffers before this model is freed)
     del tr, model, acc, devb
     torch.cuda.empty_cache()
     return out
@@ -688,6 +689,7 @@ def run_b200(a):
         if rank == 0:
             line["roofline"] = rl
     tr.Scheduler.release_rng_to_torch()
+    acc.close()                    # (data parallel: unmap the peers' gradient buffers before this model is freed)
     del tr, model, acc, devb
     torch.cuda.empty_cache()
     if world > 1:

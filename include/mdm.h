@@ -351,6 +351,7 @@ typedef struct {
 int mdm_p2p_flag_words(void);
 int mdm_ipc_export(const void* ptr, void* handle_out /*64 bytes, host*/, int64_t* offset_out /*host*/);
 int mdm_ipc_open(const void* handle /*64 bytes, host*/, int64_t offset, void** ptr_out /*host*/);
+int mdm_ipc_close(void* ptr /*as returned by mdm_ipc_open*/, int64_t offset /*as passed to it*/);
 int mdm_p2p_allreduce(const mdm_p2p_comm* comm /*host*/, int64_t offset, int64_t count, int blocks, void* stream);
 /* Copy-engine variant of the same all-reduce, as pieces the caller strings together on its communication stream
  * (mdm_b200/runtime.py: P2PAllReduce.all_reduce_ce): mdm_p2p_barrier(0) -- the peers' gradients are final;

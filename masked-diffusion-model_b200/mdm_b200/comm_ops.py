@@ -21,6 +21,7 @@ _lib.register({
     "mdm_p2p_flag_words": (c_int, []),
     "mdm_ipc_export": (c_int, [_P, _P, ctypes.POINTER(c_int64)]),
     "mdm_ipc_open": (c_int, [_P, c_int64, ctypes.POINTER(c_void_p)]),
+    "mdm_ipc_close": (c_int, [_P, c_int64]),
     "mdm_p2p_allreduce": (c_int, [ctypes.POINTER(P2PCommStruct), c_int64, c_int64, c_int, _P]),
     "mdm_p2p_barrier": (c_int, [ctypes.POINTER(P2PCommStruct), c_int, _P]),
     "mdm_memcpy_async": (c_int, [_P, _P, c_int64, _P]),
@@ -60,3 +61,7 @@ def memcpy_async(dst_ptr: int, src_ptr: int, nbytes: int, device):
 
 def reduce_slices(slice_ptr: int, staging_ptr: int, stride: int, count: int, rank: int, world: int, device):
     check(lib().mdm_reduce_slices(c_void_p(slice_ptr), c_void_p(staging_ptr), stride, count, rank, world, stream_ptr(device)))
+
+
+def ipc_close(ptr: int, offset: int):
+    check(lib().mdm_ipc_close(c_void_p(ptr), offset))

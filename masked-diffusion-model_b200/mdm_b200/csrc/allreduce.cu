@@ -267,6 +267,12 @@ int mdm_reduce_slices(float* slice, const float* staging, int64_t stride, int64_
   return MDM_OK;
 }
 
+int mdm_ipc_close(void* ptr, int64_t offset) {
+  MDM_CHECK_ARG(ptr, "ipc_close: NULL pointer");
+  MDM_CUDA(cudaIpcCloseMemHandle((char*)ptr - offset));
+  return MDM_OK;
+}
+
 // SUM all-reduce of buf[offset .. offset + count) (floats; offset and count multiples of 4) across `world` ranks.
 // Every rank must launch the same sequence of calls with the same (offset, count, blocks); calls on one rank must be
 // stream-ordered (one communication stream).  The caller divides by world (the fused optimiser folds it in).

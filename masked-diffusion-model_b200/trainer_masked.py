@@ -293,7 +293,7 @@ class Trainer:
         cs.wait_stream(main)
         with torch.cuda.stream(cs):
             for lo, hi in _complement(done, m.flat_grad.numel()):
-                acc.p2p.all_reduce(lo, hi)
+                acc.p2p.all_reduce(lo, hi, exposed=True)      # the backward is over: nothing left to disturb
         main.wait_stream(cs)
         self._comm_used = False
 

@@ -36,6 +36,7 @@ def stage1():
     for mode in ("sm", "ce"):
         comm.mode = mode
         ok = stage1_mode(m, comm, mode) and ok
+    comm.close()
     return ok
 
 
@@ -100,6 +101,7 @@ def run(mode):
         losses.append(float(out[0] if isinstance(out, tuple) else out))
     torch.cuda.synchronize()
     p = model.flat_param.clone()
+    acc.close()
     return losses, p
 
 
