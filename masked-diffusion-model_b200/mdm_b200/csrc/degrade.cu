@@ -385,6 +385,242 @@ __global__ void __launch_bounds__(DG_THREADS) add_shift_kernel(const float* __re
   for (int i = base + threadIdx.x; i < end; i += DG_THREADS) out[po + i] = __fadd_rn(x[po + i], shift.at(b, c, i));
 }
 
+// =================================================================================================================
+// Single-pass forms of K1 and K5 (round 2): the per-sample masked mean is a reduction over the sample that must finish
+// before the composite can start -- the two-pass kernels above re-read the image for it (K1 49 %, K5 35 % of the HBM
+// peak at 256x3x128x128, where the tensors exceed L2).  Here a thread-block CLUSTER owns one sample: CTA (c, j) of the
+// cluster holds part j of channel plane c IN REGISTERS (VPT 16-byte vectors per thread and tensor), reduces its sums,
+// publishes them in its shared memory, and after one cluster barrier every CTA gathers the C x parts partials through
+// distributed shared memory in a fixed order (same fill value everywhere, deterministic), then composites from
+// registers.  Every tensor crosses HBM exactly once.  Samples that do not fit a cluster of <= 8 CTAs (3x256x256) keep
+// the two-pass kernels.  MDM_DEGRADE_FUSED=0 switches back.
+// =================================================================================================================
+constexpr int K1_VPT = 12, K5_VPT = 8, FUSED_MAX_CLUSTER = 8, FUSED_MAXC = 4;
+
+__device__ __forceinline__ uint32_t dg_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void dg_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float dg_ld_remote(const float* local_ptr, uint32_t rank) {
+  uint32_t remote;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(local_ptr)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+// fill value of channel c from per-channel totals tot[c][3] = {sum img*(1-m), sum img*m, sum (1-m)}
+__device__ __forceinline__ float fill_from_totals(const float (*tot)[3], int c, int C, int fill_mode, float fill_const, int mean_area) {
+  if (fill_mode == MDM_FILL_CONST) return fill_const;
+  if (fill_mode == MDM_FILL_DEGRADED_AREA) {
+    float s = 0.f, n = 0.f;
+    if (mean_area == MDM_AREA_IMAGE) { for (int cc = 0; cc < C; ++cc) { s += tot[cc][0]; n += tot[cc][2]; } }
+    else { s = tot[c][0]; n = tot[c][2]; }
+    return __fdiv_rn(s, n);
+  }
+  const float v = __fmul_rn(__fdiv_rn(tot[c][1], tot[c][2]), -1.0f);
+  return isnan(v) ? 0.0f : v;
+}
+// gathers the NS sums of every CTA of the cluster: all[q * NS + k] (q = channel * parts + part), then per-channel totals
+template <int NS>
+__device__ __forceinline__ void gather_cluster_sums(const float* my_part /*shared*/, float* all /*shared*/, int CS) {
+  dg_cluster_sync();                                            // every CTA's partial sums are published
+  if ((int)threadIdx.x < CS * NS) all[threadIdx.x] = dg_ld_remote(my_part + threadIdx.x % NS, threadIdx.x / NS);
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(DG_THREADS) degrade_fused_kernel(
+    const T* __restrict__ img, const uint8_t* __restrict__ mask, int mask_ch, int fill_mode, float fill_const, int mean_area,
+    float* __restrict__ x_t, float* __restrict__ mask_f32, float* __restrict__ degrade_mask, float* __restrict__ fill_out,
+    float* __restrict__ x0_out, int C, int hw, int parts) {
+  MDM_PDL_ENTER();
+  __shared__ float red[3 * 32];
+  __shared__ float part[3];
+  __shared__ float all[FUSED_MAX_CLUSTER * 3];
+  const int CS = C * parts;
+  const int q = (int)dg_cluster_ctarank(), c = q / parts, j = q - c * parts;
+  const int b = blockIdx.x / CS;
+  const int plane = b * C + c;
+  const T* x = img + (int64_t)plane * hw;
+  const uint8_t* m = mask + ((int64_t)b * mask_ch + (mask_ch == 1 ? 0 : c)) * hw;
+  const int cap = DG_THREADS * 4 * K1_VPT;
+  const int base = j * cap, end = min(base + cap, hw);
+  float4 v[K1_VPT], k[K1_VPT];
+#pragma unroll
+  for (int u = 0; u < K1_VPT; ++u) {
+    const int i = base + (u * DG_THREADS + threadIdx.x) * 4;
+    const bool ok = i < end;
+    v[u] = ok ? Ld4<T>::at(x, i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    k[u] = ok ? mask4(m, i) : make_float4(1.f, 1.f, 1.f, 1.f);      // mask 1, value 0: contributes nothing
+  }
+  float r3[3] = {0.f, 0.f, 0.f};
+  if (fill_mode != MDM_FILL_CONST) {
+#pragma unroll
+    for (int u = 0; u < K1_VPT; ++u) {
+      const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, kk[4] = {k[u].x, k[u].y, k[u].z, k[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        r3[0] += __fmul_rn(vv[e], __fsub_rn(1.0f, kk[e]));
+        r3[1] += __fmul_rn(vv[e], kk[e]);
+        r3[2] += __fsub_rn(1.0f, kk[e]);
+      }
+    }
+    block_sum_n(r3, red);
+  }
+  if (threadIdx.x < 3) part[threadIdx.x] = r3[threadIdx.x];
+  gather_cluster_sums<3>(part, all, CS);
+  float tot[FUSED_MAXC][3];
+#pragma unroll
+  for (int cc = 0; cc < FUSED_MAXC; ++cc) {
+    tot[cc][0] = tot[cc][1] = tot[cc][2] = 0.f;
+    if (cc < C)
+      for (int jj = 0; jj < parts; ++jj) {
+        tot[cc][0] += all[(cc * parts + jj) * 3];
+        tot[cc][1] += all[(cc * parts + jj) * 3 + 1];
+        tot[cc][2] += all[(cc * parts + jj) * 3 + 2];
+      }
+  }
+  const float fill = fill_from_totals(tot, c, C, fill_mode, fill_const, mean_area);
+  if (fill_out && j == 0 && threadIdx.x == 0) fill_out[plane] = fill;
+  float* o = x_t + (int64_t)plane * hw;
+  float* x0o = x0_out ? x0_out + (int64_t)plane * hw : nullptr;
+  float* dm = degrade_mask ? degrade_mask + (int64_t)plane * hw : nullptr;
+  float* mf = (mask_f32 && (mask_ch != 1 || c == 0)) ? mask_f32 + ((int64_t)b * mask_ch + (mask_ch == 1 ? 0 : c)) * hw : nullptr;
+#pragma unroll
+  for (int u = 0; u < K1_VPT; ++u) {
+    const int i = base + (u * DG_THREADS + threadIdx.x) * 4;
+    if (i < end) {
+      const float4 vv = v[u], kk = k[u];
+      *reinterpret_cast<float4*>(o + i) = make_float4(composite(kk.x, fill, vv.x), composite(kk.y, fill, vv.y),
+                                                      composite(kk.z, fill, vv.z), composite(kk.w, fill, vv.w));
+      if (x0o) *reinterpret_cast<float4*>(x0o + i) = vv;
+      if (dm) *reinterpret_cast<float4*>(dm + i) = make_float4(composite(kk.x, fill, 1.0f), composite(kk.y, fill, 1.0f),
+                                                                composite(kk.z, fill, 1.0f), composite(kk.w, fill, 1.0f));
+      if (mf) *reinterpret_cast<float4*>(mf + i) = kk;
+    }
+  }
+  dg_cluster_sync();      // nobody leaves while a peer may still read its partial sums
+}
+
+__global__ void __launch_bounds__(DG_THREADS) sampler_fused_kernel(
+    const float* __restrict__ x_t, const float* __restrict__ net, Shift shift, const uint8_t* __restrict__ mask_t,
+    const uint8_t* __restrict__ mask_n, int mask_ch, int fill_mode, float fill_const, int mean_area, int momentum, int update,
+    Shift shift_next, float* __restrict__ x_next, float* __restrict__ x_in_next, float* __restrict__ s0_out, int C, int hw, int parts) {
+  MDM_PDL_ENTER();
+  __shared__ float red[6 * 32];
+  __shared__ float part[6];
+  __shared__ float all[FUSED_MAX_CLUSTER * 6];
+  const int CS = C * parts;
+  const int q = (int)dg_cluster_ctarank(), c = q / parts, j = q - c * parts;
+  const int b = blockIdx.x / CS;
+  const int64_t po = (int64_t)(b * C + c) * hw;
+  const int64_t mo = ((int64_t)b * mask_ch + (mask_ch == 1 ? 0 : c)) * hw;
+  const int cap = DG_THREADS * 4 * K5_VPT;
+  const int base = j * cap, end = min(base + cap, hw);
+  float4 xv[K5_VPT], v0[K5_VPT], mt4[K5_VPT], mn4[K5_VPT];
+#pragma unroll
+  for (int u = 0; u < K5_VPT; ++u) {
+    const int i = base + (u * DG_THREADS + threadIdx.x) * 4;
+    if (i < end) {
+      xv[u] = *reinterpret_cast<const float4*>(x_t + po + i);
+      const float4 nv = *reinterpret_cast<const float4*>(net + po + i);
+      const float4 sv = shift.at4(b, c, i);
+      v0[u] = make_float4(x0_hat(xv[u].x, nv.x, sv.x), x0_hat(xv[u].y, nv.y, sv.y), x0_hat(xv[u].z, nv.z, sv.z), x0_hat(xv[u].w, nv.w, sv.w));
+      if (update) { mt4[u] = mask4(mask_t + mo, i); mn4[u] = mask4(mask_n + mo, i); }
+      else { mt4[u] = mn4[u] = make_float4(1.f, 1.f, 1.f, 1.f); }
+    } else {
+      xv[u] = v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mt4[u] = mn4[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+  }
+  float f_t = 0.f, f_n = 0.f;
+  if (update) {
+    float r6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (fill_mode != MDM_FILL_CONST) {
+#pragma unroll
+      for (int u = 0; u < K5_VPT; ++u) {
+        const float vs[4] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w};
+        const float ts[4] = {mt4[u].x, mt4[u].y, mt4[u].z, mt4[u].w}, ms[4] = {mn4[u].x, mn4[u].y, mn4[u].z, mn4[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          r6[0] += __fmul_rn(vs[e], __fsub_rn(1.0f, ts[e])); r6[1] += __fmul_rn(vs[e], ts[e]); r6[2] += __fsub_rn(1.0f, ts[e]);
+          r6[3] += __fmul_rn(vs[e], __fsub_rn(1.0f, ms[e])); r6[4] += __fmul_rn(vs[e], ms[e]); r6[5] += __fsub_rn(1.0f, ms[e]);
+        }
+      }
+      block_sum_n(r6, red);
+    }
+    if (threadIdx.x < 6) part[threadIdx.x] = r6[threadIdx.x];
+    gather_cluster_sums<6>(part, all, CS);
+    float tt[FUSED_MAXC][3], tn[FUSED_MAXC][3];
+#pragma unroll
+    for (int cc = 0; cc < FUSED_MAXC; ++cc) {
+      tt[cc][0] = tt[cc][1] = tt[cc][2] = tn[cc][0] = tn[cc][1] = tn[cc][2] = 0.f;
+      if (cc < C)
+        for (int jj = 0; jj < parts; ++jj) {
+          const float* a = all + (cc * parts + jj) * 6;
+          tt[cc][0] += a[0]; tt[cc][1] += a[1]; tt[cc][2] += a[2];
+          tn[cc][0] += a[3]; tn[cc][1] += a[4]; tn[cc][2] += a[5];
+        }
+    }
+    f_t = fill_from_totals(tt, c, C, fill_mode, fill_const, mean_area);
+    f_n = fill_from_totals(tn, c, C, fill_mode, fill_const, mean_area);
+  }
+#pragma unroll
+  for (int u = 0; u < K5_VPT; ++u) {
+    const int i = base + (u * DG_THREADS + threadIdx.x) * 4;
+    if (i < end) {
+      const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, vs[4] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w};
+      const float ts[4] = {mt4[u].x, mt4[u].y, mt4[u].z, mt4[u].w}, ms[4] = {mn4[u].x, mn4[u].y, mn4[u].z, mn4[u].w};
+      float sn[4] = {0.f, 0.f, 0.f, 0.f};
+      if (x_in_next) { const float4 s4 = shift_next.at4(b, c, i); sn[0] = s4.x; sn[1] = s4.y; sn[2] = s4.z; sn[3] = s4.w; }
+      float xn[4], xi[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        xn[e] = xs[e];
+        if (update) {
+          const float d_t = composite(ts[e], f_t, vs[e]);
+          const float d_n = composite(ms[e], f_n, vs[e]);
+          xn[e] = momentum ? __fadd_rn(xs[e], __fsub_rn(d_n, d_t)) : d_n;
+        }
+        xi[e] = x_in_next ? __fadd_rn(xn[e], sn[e]) : 0.f;
+      }
+      if (s0_out) *reinterpret_cast<float4*>(s0_out + po + i) = v0[u];
+      if (x_next) *reinterpret_cast<float4*>(x_next + po + i) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+      if (x_in_next) *reinterpret_cast<float4*>(x_in_next + po + i) = make_float4(xi[0], xi[1], xi[2], xi[3]);
+    }
+  }
+  if (update) dg_cluster_sync();
+}
+
+template <typename... KArgs, typename... Args>
+static inline void launch_fused_cluster(void (*kernel)(KArgs...), int grid, int cluster, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(DG_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+// parts per channel plane for the fused form, 0 when the sample does not fit a cluster (or the fused form is disabled)
+static int fused_parts(int channels, int hw, int vpt) {
+  static const int enabled = [] { const char* v = getenv("MDM_DEGRADE_FUSED"); return v ? atoi(v) : 1; }();
+  if (!enabled || (hw & 3) != 0 || channels > FUSED_MAXC) return 0;
+  const int cap = DG_THREADS * 4 * vpt;
+  const int parts = (hw + cap - 1) / cap;
+  return channels * parts <= FUSED_MAX_CLUSTER ? parts : 0;
+}
+
 static inline int nchunks(int hw) { return (hw + DG_CHUNK - 1) / DG_CHUNK; }
 
 }  // namespace mdm
@@ -408,9 +644,22 @@ static int degrade_launch(const void* img, int img_dtype, const uint8_t* mask, i
   MDM_CHECK_ARG(fill_mode >= 0 && fill_mode <= 2, "fill_mode");
   MDM_CHECK_ARG(fill_mode == MDM_FILL_CONST || ws, "workspace is NULL");
   MDM_CHECK_ARG((int64_t)batch * channels <= 65535, "batch*channels exceeds grid.y");
+  cudaStream_t st = as_stream(stream);
+  const int esz = img_dtype == MDM_F32 ? 4 : (img_dtype == MDM_BF16 ? 2 : 1);
+  if (const int parts = fused_parts(channels, hw, K1_VPT); parts > 0 && ((uintptr_t)img & (4 * esz - 1)) == 0 && ((uintptr_t)mask & 3) == 0 &&
+      ((uintptr_t)x_t & 15) == 0 && ((uintptr_t)mask_f32 & 15) == 0 && ((uintptr_t)degrade_mask & 15) == 0 && ((uintptr_t)x0_out & 15) == 0) {
+    const int CS = channels * parts;
+    if (img_dtype == MDM_F32)
+      launch_fused_cluster(degrade_fused_kernel<float>, batch * CS, CS, st, (const float*)img, mask, mask_ch, fill_mode, fill_const, mean_area, x_t, mask_f32, degrade_mask, fill_out, x0_out, channels, hw, parts);
+    else if (img_dtype == MDM_BF16)
+      launch_fused_cluster(degrade_fused_kernel<__nv_bfloat16>, batch * CS, CS, st, (const __nv_bfloat16*)img, mask, mask_ch, fill_mode, fill_const, mean_area, x_t, mask_f32, degrade_mask, fill_out, x0_out, channels, hw, parts);
+    else
+      launch_fused_cluster(degrade_fused_kernel<uint8_t>, batch * CS, CS, st, (const uint8_t*)img, mask, mask_ch, fill_mode, fill_const, mean_area, x_t, mask_f32, degrade_mask, fill_out, x0_out, channels, hw, parts);
+    MDM_LAUNCH_CHECK();
+    return MDM_OK;
+  }
   const int nc = nchunks(hw);
   dim3 grid(nc, batch * channels);
-  cudaStream_t st = as_stream(stream);
   if (fill_mode != MDM_FILL_CONST) {
     if (img_dtype == MDM_F32)
       launch_pdl(degrade_stats_kernel<float>, dim3(grid), dim3(DG_THREADS), 0, st, (const float*)img, mask, mask_ch, ws, channels, hw, nc);
@@ -467,6 +716,13 @@ int mdm_sampler_step(const float* x_t, const float* net, const float* shift, int
   const int vec = (hw & 3) == 0 && al16(x_t) && al16(net) && al16(x_next) && al16(x_in_next) && al16(s0_out) &&
                   (((uintptr_t)mask_t | (uintptr_t)mask_next) & 3) == 0 && shift_vec_ok(shift, sb, sc, sp) &&
                   shift_vec_ok(shift_next, nb, nc_, np_);
+  if (const int parts = fused_parts(channels, hw, K5_VPT); parts > 0 && vec) {
+    const int CS = channels * parts;
+    launch_fused_cluster(sampler_fused_kernel, batch * CS, CS, st, x_t, net, s, mask_t, mask_next, mask_ch, fill_mode, fill_const, mean_area,
+                         momentum, update, sn, x_next, x_in_next, s0_out, channels, hw, parts);
+    MDM_LAUNCH_CHECK();
+    return MDM_OK;
+  }
   if (update && fill_mode != MDM_FILL_CONST) {
     MDM_CHECK_ARG(ws, "workspace is NULL");
     launch_pdl(sampler_stats_kernel, dim3(grid), dim3(DG_THREADS), 0, st, x_t, net, s, mask_t, mask_next, mask_ch, ws_t, ws_n, channels, hw, nc, vec);
