@@ -1410,11 +1410,13 @@ __global__ void up2x_weights_kernel(const float* __restrict__ w, bf16* __restric
 constexpr int ATT_D = 8;
 // Forward: one CTA = HPC adjacent heads of one sample (their q / k / v slices are contiguous: HPC x 16 bytes per token, so
 // every global access is a full 16-byte vector of a >= 64-byte segment); K and V of those heads live in shared memory as
-// fp32 [token][head][8] (a warp reads one 128-byte line per key, broadcast inside a head); one thread per (query, head)
-// row holds KC scores in registers, so the soft-max costs ONE exp2 per key (scale * log2 e folded into q) and one
-// rescale per KC keys instead of two exps and a rescale per key.  fp32 FMA bound: 32 L^2 flops per (sample, head).
-template <int KC>
-__global__ void __launch_bounds__(256) attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int C, int HPC,
+// fp32 [token][head][8] (a warp reads one 128-byte line per key, broadcast inside a head).  One thread owns QPT
+// consecutive queries of one head: every K / V vector it reads from shared memory feeds QPT queries (the first version,
+// one query per thread, was bound by shared-memory reads: ncu short-scoreboard / MIO stalls, 31 % FMA pipe), KC scores
+// per query in registers, so the soft-max costs ONE exp2 per key (scale * log2 e folded into q) and one rescale per KC
+// keys.  fp32 FMA bound: 32 L^2 flops per (sample, head).
+template <int KC, int QPT>
+__global__ void __launch_bounds__(256, 2) attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int C, int HPC,
                                                             float scale_log2e) {
   MDM_PDL_ENTER();
   extern __shared__ __align__(16) float att_sm[];  // K[L][HPC][8], V[L][HPC][8]
@@ -1440,60 +1442,78 @@ __global__ void __launch_bounds__(256) attention_fwd_kernel(const bf16* __restri
     *reinterpret_cast<float4*>(Vs + (size_t)i * ATT_D + 4) = b;
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < L * HPC; r += blockDim.x) {        // r = query * HPC + head
-    const int i = r / HPC, h = r - i * HPC;
-    float q[ATT_D];
-    {
-      const uint4 qq = *reinterpret_cast<const uint4*>(base + (long long)i * 3 * C + h * ATT_D);
+  const int groups = L / QPT;                                        // L % QPT == 0 (checked by the host)
+  for (int r = threadIdx.x; r < groups * HPC; r += blockDim.x) {     // r = query group * HPC + head
+    const int g = r / HPC, h = r - g * HPC;
+    const int i0 = g * QPT;
+    float q[QPT][ATT_D], acc[QPT][ATT_D], m[QPT], l[QPT];
+#pragma unroll
+    for (int a = 0; a < QPT; ++a) {
+      const uint4 qq = *reinterpret_cast<const uint4*>(base + (long long)(i0 + a) * 3 * C + h * ATT_D);
       const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qq);
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         const float2 t = __bfloat1622float2(q2[d]);
-        q[2 * d] = t.x * scale_log2e;
-        q[2 * d + 1] = t.y * scale_log2e;
+        q[a][2 * d] = t.x * scale_log2e;
+        q[a][2 * d + 1] = t.y * scale_log2e;
       }
-    }
-    float m = -INFINITY, l = 0.f, acc[ATT_D];
+      m[a] = -INFINITY;
+      l[a] = 0.f;
 #pragma unroll
-    for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
+      for (int d = 0; d < ATT_D; ++d) acc[a][d] = 0.f;
+    }
     const float* Kh = Ks + h * ATT_D;
     const float* Vh = Vs + h * ATT_D;
     const int pitch = HPC * ATT_D;
     for (int j0 = 0; j0 < L; j0 += KC) {
-      float s[KC];
-      float cm = -INFINITY;
+      float s[QPT][KC], cm[QPT];
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) cm[a] = -INFINITY;
 #pragma unroll
       for (int jj = 0; jj < KC; ++jj) {
         const float4 ka = *reinterpret_cast<const float4*>(Kh + (size_t)(j0 + jj) * pitch);
         const float4 kb = *reinterpret_cast<const float4*>(Kh + (size_t)(j0 + jj) * pitch + 4);
-        float v = q[0] * ka.x;
-        v = fmaf(q[1], ka.y, v); v = fmaf(q[2], ka.z, v); v = fmaf(q[3], ka.w, v);
-        v = fmaf(q[4], kb.x, v); v = fmaf(q[5], kb.y, v); v = fmaf(q[6], kb.z, v); v = fmaf(q[7], kb.w, v);
-        s[jj] = v;
-        cm = fmaxf(cm, v);
-      }
-      const float mn = fmaxf(m, cm);
-      const float corr = exp2f(m - mn);       // first chunk: exp2(-inf) = 0
-      l *= corr;
 #pragma unroll
-      for (int d = 0; d < ATT_D; ++d) acc[d] *= corr;
+        for (int a = 0; a < QPT; ++a) {
+          float v = q[a][0] * ka.x;
+          v = fmaf(q[a][1], ka.y, v); v = fmaf(q[a][2], ka.z, v); v = fmaf(q[a][3], ka.w, v);
+          v = fmaf(q[a][4], kb.x, v); v = fmaf(q[a][5], kb.y, v); v = fmaf(q[a][6], kb.z, v); v = fmaf(q[a][7], kb.w, v);
+          s[a][jj] = v;
+          cm[a] = fmaxf(cm[a], v);
+        }
+      }
+      float mn[QPT];
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) {
+        mn[a] = fmaxf(m[a], cm[a]);
+        const float corr = exp2f(m[a] - mn[a]);       // first chunk: exp2(-inf) = 0
+        l[a] *= corr;
+#pragma unroll
+        for (int d = 0; d < ATT_D; ++d) acc[a][d] *= corr;
+        m[a] = mn[a];
+      }
 #pragma unroll
       for (int jj = 0; jj < KC; ++jj) {
-        const float p = exp2f(s[jj] - mn);
         const float4 va = *reinterpret_cast<const float4*>(Vh + (size_t)(j0 + jj) * pitch);
         const float4 vb = *reinterpret_cast<const float4*>(Vh + (size_t)(j0 + jj) * pitch + 4);
-        l += p;
-        acc[0] = fmaf(p, va.x, acc[0]); acc[1] = fmaf(p, va.y, acc[1]); acc[2] = fmaf(p, va.z, acc[2]); acc[3] = fmaf(p, va.w, acc[3]);
-        acc[4] = fmaf(p, vb.x, acc[4]); acc[5] = fmaf(p, vb.y, acc[5]); acc[6] = fmaf(p, vb.z, acc[6]); acc[7] = fmaf(p, vb.w, acc[7]);
-      }
-      m = mn;
-    }
-    const float inv = 1.0f / l;
-    uint4 o;
-    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-    for (int d = 0; d < 4; ++d) o2[d] = __floats2bfloat162_rn(acc[2 * d] * inv, acc[2 * d + 1] * inv);
-    *reinterpret_cast<uint4*>(out + ((long long)n * L + i) * C + (h0 + h) * ATT_D) = o;
+        for (int a = 0; a < QPT; ++a) {
+          const float p = exp2f(s[a][jj] - mn[a]);
+          l[a] += p;
+          acc[a][0] = fmaf(p, va.x, acc[a][0]); acc[a][1] = fmaf(p, va.y, acc[a][1]); acc[a][2] = fmaf(p, va.z, acc[a][2]); acc[a][3] = fmaf(p, va.w, acc[a][3]);
+          acc[a][4] = fmaf(p, vb.x, acc[a][4]); acc[a][5] = fmaf(p, vb.y, acc[a][5]); acc[a][6] = fmaf(p, vb.z, acc[a][6]); acc[a][7] = fmaf(p, vb.w, acc[a][7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < QPT; ++a) {
+      const float inv = 1.0f / l[a];
+      uint4 o;
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) o2[d] = __floats2bfloat162_rn(acc[a][2 * d] * inv, acc[a][2 * d + 1] * inv);
+      *reinterpret_cast<uint4*>(out + ((long long)n * L + i0 + a) * C + (h0 + h) * ATT_D) = o;
+    }
   }
 }
 
@@ -1933,31 +1953,31 @@ int mdm_attention_fwd(const void* qkv, void* out, int N, int L, int C, void* str
   MDM_CHECK_ARG(qkv && out && C % ATT_D == 0 && L >= 1 && L <= 1024, "attention_fwd: bad arguments (L=%d C=%d)", L, C);
   MDM_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, "attention_fwd: pointers must be 16-byte aligned");
   const int heads = C / ATT_D;
-  // heads per CTA: 256 (query, head) rows per CTA when the sample has that many, at least 4 heads (64-byte segments),
-  // a divisor of the head count, K + V within 96 KB of shared memory
-  int hpc = 256 / L;
+  // queries per thread: 4 when L allows; heads per CTA: 256 (query group, head) rows per CTA when the sample has that
+  // many, at least 4 heads (64-byte segments), a divisor of the head count, K + V within 64 KB of shared memory
+  const int qpt = (L % 4 == 0) ? 4 : 1;
+  int hpc = 256 * qpt / L;
   if (hpc < 4) hpc = 4;
-  while (hpc > 1 && (heads % hpc != 0 || (size_t)2 * L * hpc * ATT_D * sizeof(float) > 96 * 1024)) hpc >>= 1;
+  if (hpc > heads) hpc = heads;
+  while (hpc > 1 && (heads % hpc != 0 || (size_t)2 * L * hpc * ATT_D * sizeof(float) > 64 * 1024)) hpc >>= 1;
   if (heads % hpc != 0) hpc = 1;
   const size_t smem = (size_t)2 * L * hpc * ATT_D * sizeof(float);
-  const int kc = (L % 64 == 0) ? 64 : (L % 16 == 0 ? 16 : (L % 4 == 0 ? 4 : 1));
+  MDM_CHECK_ARG(smem <= 96 * 1024, "attention_fwd: K + V of one head do not fit shared memory (L=%d)", L);
   static bool attr_set = false;
   if (!attr_set) {
-    MDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    MDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    MDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    MDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
-  int th = L * hpc;
+  int th = (L / qpt) * hpc;
   th = th < 32 ? 32 : (th > 256 ? 256 : ((th + 31) / 32) * 32);
   dim3 grid(heads / hpc, N);
   const float sl2 = 1.4426950408889634f / sqrtf((float)ATT_D);
   cudaStream_t st = as_stream(stream);
-  if (kc == 64) launch_pdl(attention_fwd_kernel<64>, dim3(grid), dim3(th), smem, st, (const bf16*)qkv, (bf16*)out, L, C, hpc, sl2);
-  else if (kc == 16) launch_pdl(attention_fwd_kernel<16>, dim3(grid), dim3(th), smem, st, (const bf16*)qkv, (bf16*)out, L, C, hpc, sl2);
-  else if (kc == 4) launch_pdl(attention_fwd_kernel<4>, dim3(grid), dim3(th), smem, st, (const bf16*)qkv, (bf16*)out, L, C, hpc, sl2);
-  else launch_pdl(attention_fwd_kernel<1>, dim3(grid), dim3(th), smem, st, (const bf16*)qkv, (bf16*)out, L, C, hpc, sl2);
+  if (qpt == 4 && L % 8 == 0) launch_pdl(attention_fwd_kernel<8, 4>, dim3(grid), dim3(th), smem, st, (const bf16*)qkv, (bf16*)out, L, C, hpc, sl2);
+  else if (qpt == 4) launch_pdl(attention_fwd_kernel<4, 4>, dim3(grid), dim3(th), smem, st, (const bf16*)qkv, (bf16*)out, L, C, hpc, sl2);
+  else launch_pdl(attention_fwd_kernel<1, 1>, dim3(grid), dim3(th), smem, st, (const bf16*)qkv, (bf16*)out, L, C, hpc, sl2);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
