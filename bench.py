@@ -451,9 +451,9 @@ def train_section(a, dev, world, rank, C, S, B, method, base, steps, warmup, lab
 
 
 def micro_kernels(dev, peaks):
-    """the HBM-bound kernels of the path that the instrumented training step does not isolate, each timed alone with
-    CUDA events at the configs[3] shape (inputs > L2, L2 flushed between launches), achieved GB/s from ALGORITHMIC bytes
-     against the measured HBM copy peak"""
+    """the HBM-bound kernels of the path that the instrumented training step does not isolate, each timed alone at the
+    configs[3] shape as CUDA-graph replays with CUDA events (L2 flushed before every launch, flush time subtracted),
+    achieved GB/s from ALGORITHMIC bytes against the measured HBM copy peak"""
     import scheduler as sched_mod
     from mdm_b200 import denoiser_ops as ops
     from mdm_b200._lib import check, lib, ptr, stream_ptr
@@ -462,16 +462,27 @@ def micro_kernels(dev, peaks):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def timeit(fn, iters=8):
+        """device time of fn() alone: [flush L2, fn] x iters replayed as ONE CUDA graph minus the same graph without fn
+        (eager timing of 20-100 us kernels measures the Python launch path, not the kernels)"""
         for _ in range(2):
             fn()
-        tot = 0.0
-        for _ in range(iters):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        times = []
+        for with_fn in (True, False):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(iters):
+                    flush.zero_()
+                    if with_fn:
+                        fn()
+            g.replay()
             torch.cuda.synchronize()
-            tot += e0.elapsed_time(e1)
-        return tot / iters
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / iters)
+            del g
+        return max(times[0] - times[1], 1e-4)
 
     def entry(nbytes, ms, what):
         gbs = nbytes / (ms * 1e-3) / 1e9
@@ -495,6 +506,11 @@ def micro_kernels(dev, peaks):
     out["K1_degrade_composite"] = entry(B * (C * hw * 4 * 2 + hw * 4 + hw),
                                         timeit(lambda: Sc._composite(x0, mb, 1, a.mean_option, a.mean_area, want_mask=True, want_degrade_mask=False)),
                                         f"{B}x{C}x{S}x{S} fp32: read x0 + byte mask, write x_t + 1-channel fp32 mask")
+    os.environ["MDM_DEGRADE_FUSED"] = "1"           # the opt-in single-pass cluster form of the same kernel
+    out["K1_single_pass_cluster_variant"] = entry(B * (C * hw * 4 * 2 + hw * 4 + hw),
+                                                  timeit(lambda: Sc._composite(x0, mb, 1, a.mean_option, a.mean_area, want_mask=True, want_degrade_mask=False)),
+                                                  "same shape; one 6-CTA cluster per sample, sample in registers (not the default: slower)")
+    os.environ["MDM_DEGRADE_FUSED"] = "0"
     t_mask = timeit(lambda: Sc.make_mask_bytes(n, x0.device))
     out["mask_generate_threshold"] = {"ms": round(t_mask, 4), "words_per_ns": round(B * hw / (t_mask * 1e6), 2),
                                       "shape": f"{B}x1x{S}x{S} threshold mask from the mt19937 stream (0 algorithmic HBM bytes in, {B * hw} B out)"}
@@ -507,6 +523,9 @@ def micro_kernels(dev, peaks):
                                      ptr(shift), C * hw, hw, 1, ptr(x_next), ptr(x_in_next), None, ptr(ws), B, C, hw, stream_ptr(dev)))
     out["K5_sampler_step"] = entry(B * C * hw * 4 * 5 + 2 * B * hw, timeit(k5),
                                    f"{B}x{C}x{S}x{S} fp32: 5 image passes + two byte masks (SURVEY 8d)")
+    os.environ["MDM_DEGRADE_FUSED"] = "1"
+    out["K5_single_pass_cluster_variant"] = entry(B * C * hw * 4 * 5 + 2 * B * hw, timeit(k5), "same shape; opt-in cluster form (slower)")
+    os.environ["MDM_DEGRADE_FUSED"] = "0"
     Sc.release_rng_to_torch()
     del x0, net, x_t, shift, x_next, x_in_next
     # K4 attention core at the configs[3] (64 tokens) and configs[4] (256 tokens) shapes: read qkv, write out (bf16)

@@ -393,7 +393,8 @@ __global__ void __launch_bounds__(DG_THREADS) add_shift_kernel(const float* __re
 // publishes them in its shared memory, and after one cluster barrier every CTA gathers the C x parts partials through
 // distributed shared memory in a fixed order (same fill value everywhere, deterministic), then composites from
 // registers.  Every tensor crosses HBM exactly once.  Samples that do not fit a cluster of <= 8 CTAs (3x256x256) keep
-// the two-pass kernels.  MDM_DEGRADE_FUSED=0 switches back.
+// the two-pass kernels.  MEASURED SLOWER than the two-pass kernels (see fused_parts below): kept as an opt-in
+// (MDM_DEGRADE_FUSED=1) with its parity test, not the default.
 // =================================================================================================================
 constexpr int K1_VPT = 12, K5_VPT = 8, FUSED_MAX_CLUSTER = 8, FUSED_MAXC = 4;
 
@@ -614,7 +615,12 @@ static inline void launch_fused_cluster(void (*kernel)(KArgs...), int grid, int 
 }
 // parts per channel plane for the fused form, 0 when the sample does not fit a cluster (or the fused form is disabled)
 static int fused_parts(int channels, int hw, int vpt) {
-  static const int enabled = [] { const char* v = getenv("MDM_DEGRADE_FUSED"); return v ? atoi(v) : 1; }();
+  // measured on B200 at 256x3x128x128 (bench.py micro entries, L2 flushed): K1 99 us fused vs 38 us two-pass, K5 205 us vs
+  // 113 us -- a sample held in the registers of a 6-CTA cluster leaves ONE 256-thread CTA per SM whose load, barrier and
+  // store phases do not overlap (10 waves x ~5 us), while the two-pass kernels keep thousands of independent loads in
+  // flight and re-read part of the image from L2.  Opt-in (MDM_DEGRADE_FUSED=1, read per call: the tests switch it).
+  const char* env = getenv("MDM_DEGRADE_FUSED");
+  const int enabled = env ? atoi(env) : 0;
   if (!enabled || (hw & 3) != 0 || channels > FUSED_MAXC) return 0;
   const int cap = DG_THREADS * 4 * vpt;
   const int parts = (hw + cap - 1) / cap;

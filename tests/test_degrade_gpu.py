@@ -208,3 +208,38 @@ def test_uint8_batches_through_run_batch():
         loss = tr._run_batch(0, (x.cuda(),), 0, 1, 0, None, None)[0]
         res.append((loss, net.conv.weight.grad.clone()))
     assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
+
+
+def test_single_pass_cluster_kernels_equal_two_pass(monkeypatch):
+    """MDM_DEGRADE_FUSED=1: K1 and K5 as one cluster kernel per sample (sample in registers, partial sums through DSMEM).
+    Same masks, same composite given the fill; the fill itself may differ by the summation order (<= 2e-6).  Measured
+    slower than the two-pass default on B200, kept opt-in."""
+    import sampler
+    from tests.golden.make_golden import ToyModel, mk_args
+    outs = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("MDM_DEGRADE_FUSED", fused)
+        res = []
+        for C, S, opt, area in ((3, 64, "degraded_area", "image-wise"), (3, 128, "non_degraded_area", "channel-wise"),
+                                (1, 32, "degraded_area", "image-wise"), (3, 16, 0, "image-wise")):
+            a = mk_args(data_size=S, in_channel=C, out_channel=C, ddpm_num_steps=50, select_degrade_pixel="indexing",
+                        ddpm_schedule="log", mean_option=opt, mean_area=area, sample_num=3,
+                        shift_type="1-d_constant", sample_latent_shape="uniform")
+            Sch = scheduler.Scheduler(a)
+            Tp = Sch.update_ddpm_num_steps(50)
+            g = torch.Generator().manual_seed(3)
+            x0 = (torch.rand(3, C, S, S, generator=g) * 2 - 1).cuda()
+            ts = torch.tensor([2, Tp // 2, Tp], device="cuda")
+            torch.manual_seed(5)
+            Sch.adopt_torch_rng("cuda")
+            d = Sch.degrade_training(Sch.get_black_area_num_pixels_time(ts), x0, opt, area)
+            Sch.release_rng_to_torch()
+            torch.manual_seed(6)
+            s0, _ = sampler.Sampler(None, a, Sch, None).sample(ToyModel(Tp, "cuda"), Sch.get_timesteps_epoch(0, 1)[-6:])
+            res.append((d[0].clone(), d[1].clone(), d[2].clone(), d[3].clone(), s0.clone()))
+        outs[fused] = res
+    for two, one in zip(outs["0"], outs["1"]):
+        assert torch.equal(two[1], one[1])                                      # masks
+        for k in (0, 2, 3):
+            torch.testing.assert_close(one[k], two[k], atol=2e-6, rtol=0)       # composite, degrade mask, fill
+        torch.testing.assert_close(one[4], two[4], atol=2e-5, rtol=0)           # six restoration steps
