@@ -206,8 +206,17 @@ typedef struct mdm_conv_args {
                          * x: [N][H][W][cin] low-resolution input, y: the FULL [N][2H][2W][cout] output (this call writes
                          * one parity class), w: [cout][4][cin] from mdm_up2x_weights for that parity; H, W multiples of 16. */
   int up_a, up_b;
+  const float* gn_coef; /* fprop only (inference): GroupNorm + SiLU of the INPUT folded into the operand path.  x is then the
+                         * RAW activation and coef[n][cin][2] = (scale, shift) per sample and channel (mdm_gn_coef_q): the
+                         * kernel computes silu(x * scale + shift) while it fills its halo tiles, zero outside the map
+                         * -- the normalised activation is never written.  3x3, stride 1, H and W multiples of 16. */
 } mdm_conv_args;
 
+/* (scale, shift) table of a GroupNorm site from the quad sums its producers' epilogues accumulated (mdm_conv_args.qsum):
+ * coef[n][c] = (gamma_c rstd, beta_c - mean gamma_c rstd); optional stats[n][G][2] = (mean, rstd).  Feeds
+ * mdm_conv_args.gn_coef. */
+int mdm_gn_coef_q(const float* qa, int qa_quads, const float* qb, const float* gamma, const float* beta, float* coef,
+                  float* stats, int N, int HW, int C, int G, float eps, void* stream);
 /* parity weights of the fused upsample convolution: w32 fp32 [cout][9][cin] (packed layout) -> out bf16
  * [4 = 2 a + b][cout][4 = 2 u + v][cin], W_ab[u][v] = sum of the 3x3 taps that land on low-resolution offset
  * (a - 1 + u, b - 1 + v): rows {0} | {1, 2} for a = 0, {0, 1} | {2} for a = 1, columns alike. */

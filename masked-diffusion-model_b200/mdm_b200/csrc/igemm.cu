@@ -44,6 +44,7 @@
 
 namespace mdm {
 
+typedef __nv_bfloat16 bf16_t;
 constexpr int TILE_M = 128, TILE_N = 128, TILE_K = 64;
 constexpr int A_BYTES = TILE_M * TILE_K * 2;   // 16 KB: one [128 pixel x 64 channel] operand tile
 constexpr int B_BYTES = TILE_N * TILE_K * 2;   // 16 KB
@@ -236,6 +237,12 @@ struct IgemmArgs {
   // squares) of every 4-channel quad of sample n (fp32 atomics; the consumer combines cpg/4 quads per group).
   // Needs H*W % 128 == 0: the 128 rows of a tile belong to one sample.
   float* qsum;
+  // kNorm instantiations (inference): the A operand is the RAW activation a_raw[N][H][W][a_ld]; the halo is filled by four
+  // transform warps that apply GroupNorm + SiLU on the way, y = silu(x * coef[n][c][0] + coef[n][c][1]) (zero outside the map)
+  const void* a_raw;
+  long long a_ld;
+  int a_c;
+  const float* gn_coef;
   // dynamic work distribution (kDyn instantiations): sched[0] = items handed out beyond the first one of every CTA,
   // sched[1] = CTAs that have finished; the last CTA zeroes both for the next launch that gets this pair
   int* sched;
@@ -436,7 +443,12 @@ struct WorkSub<true> {
 // kStats: the store epilogue also accumulates GroupNorm quad sums of the output (IgemmArgs::qsum); a template
 // parameter so that the plain instantiations carry none of that code (measured: +4 % on the level-0 convolutions when
 // it was a run-time branch -- the store epilogue of a 256 x 128 item is as long as its main loop).
-template <int kMode, bool kHalo, int kMT, bool kStats = false, bool kDyn = false>
+// kNorm (halo kernel, inference): GroupNorm + SiLU of the INPUT folded into the operand path.  Warps 7-10 do not serve the
+// epilogue (four epilogue warps remain) but fill the halo slots themselves: 16-byte loads of the raw activation,
+// normalise + SiLU in registers, swizzled 16-byte stores into the slot (the layout TMA would have produced), proxy fence,
+// one arrival on the slot's full barrier.  The normalised activation never exists in HBM: the stand-alone apply pass
+// (read x, write a) and the conv's read of a collapse into one read of x.
+template <int kMode, bool kHalo, int kMT, bool kStats = false, bool kDyn = false, bool kNorm = false>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
              const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
@@ -489,13 +501,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], blockDim.x == IGEMM_THREADS ? 8 : 4);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[s], (!kNorm && blockDim.x == IGEMM_THREADS) ? 8 : 4);   // one arrival per epilogue warp
       mbar_init(&c_full_bar[s], 1);
     }
     if (kDyn) {
       for (int s = 0; s < WQ_SLOTS; ++s) {
         mbar_init(&wq_full[s], 1);
-        mbar_init(&wq_empty[s], 2 + (blockDim.x == IGEMM_THREADS ? 8 : 4));   // B producer, MMA issuer, one per epilogue warp
+        // B producer, MMA issuer, one per epilogue warp (kNorm: four epilogue + four transform warps)
+        mbar_init(&wq_empty[s], 2 + ((kNorm || blockDim.x == IGEMM_THREADS) ? 8 : 4));
       }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -537,9 +550,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           if (kHalo) {
             if (it.halo_it()) {
               if (it.tap == 0) {   // one halo per channel chunk
-                mbar_wait(&a_empty[sa], pa ^ 1);
-                mbar_expect_tx(&a_full[sa], kHaloBytes);
-                tma_load_4d(&mapA0, a_ring + sa * kHaloSlot, &a_full[sa], it.kc * TILE_K, w0 - 1, h0 - 1, n0);
+                if (!kNorm) {      // (kNorm: the transform warps fill this slot; this warp only keeps its slot counter in step)
+                  mbar_wait(&a_empty[sa], pa ^ 1);
+                  mbar_expect_tx(&a_full[sa], kHaloBytes);
+                  tma_load_4d(&mapA0, a_ring + sa * kHaloSlot, &a_full[sa], it.kc * TILE_K, w0 - 1, h0 - 1, n0);
+                }
                 if (++sa == kASlots) { sa = 0; pa ^= 1; }
               }
             } else {               // fused 1x1 shortcut segment: a plain patch in a halo slot
@@ -737,6 +752,89 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       umma_commit(&tmem_full_bar[acc]);
     }
    }
+  } else if (kNorm && warp >= 7) {
+    // ============================== transform producers (kNorm): GroupNorm + SiLU on the way into the halo ==========
+    if (kMode == 0 && kHalo && kMT == 2) {
+      const int tt = (int)threadIdx.x - 224;          // 0 .. 127
+      const int c8 = tt & 7;                          // this thread's 8-channel group inside a 64-channel chunk
+      const bf16_t* xin = reinterpret_cast<const bf16_t*>(args.a_raw);
+      int sa = 0, wn_unused;
+      uint32_t pa = 0;
+      WorkSub<kDyn> feed(args, w_first, w_step, wq_full, wq_empty, wq, true);
+      for (int w = feed.next(wn_unused); w >= 0; w = feed.next(wn_unused)) {
+        const Work k = decode_work(args, w);
+        int w0, h0, n0;
+        tile_origin(args, kHalo, k.m_tile * kMT, w0, h0, n0);
+        IterWalker<kHalo> it;
+        it.init(args, k.it0);
+        for (int i = 0; i < k.nit; ++i) {
+          if (it.halo_it()) {
+            if (it.tap == 0) {
+              float sc[8], sh[8];
+              {
+                const float4* cf = reinterpret_cast<const float4*>(args.gn_coef + ((long long)n0 * args.a_c + it.kc * TILE_K + c8 * 8) * 2);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 t = __ldg(cf + j);
+                  sc[2 * j] = t.x; sh[2 * j] = t.y; sc[2 * j + 1] = t.z; sh[2 * j + 1] = t.w;
+                }
+              }
+              mbar_wait(&a_empty[sa], pa ^ 1);        // the MMAs that read this slot have retired
+              uint8_t* slot = a_ring + sa * kHaloSlot;
+              constexpr int kRows = kHaloW * HALO2_H;   // 324 halo pixels, 8 sixteen-byte pieces each
+              constexpr int kBatch = 7;
+              for (int b0 = 0; b0 < kRows * 8; b0 += 128 * kBatch) {
+                uint4 v[kBatch];
+                bool in[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                  const int idx = b0 + u * 128 + tt;
+                  const int row = idx >> 3;
+                  const int hy = row / kHaloW, hx = row - hy * kHaloW;
+                  const int gy = h0 - 1 + hy, gx = w0 - 1 + hx;
+                  in[u] = idx < kRows * 8 && gy >= 0 && gy < args.H && gx >= 0 && gx < args.W;
+                  v[u] = make_uint4(0u, 0u, 0u, 0u);
+                  if (in[u]) v[u] = __ldg(reinterpret_cast<const uint4*>(xin + (((long long)n0 * args.H + gy) * args.W + gx) * args.a_ld + it.kc * TILE_K + c8 * 8));
+                }
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                  const int idx = b0 + u * 128 + tt;
+                  if (idx < kRows * 8) {
+                    const int row = idx >> 3;
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);          // zero padding stays zero (the reference pads the NORMALISED map)
+                    if (in[u]) {
+                      const uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                      uint32_t ov[4];
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        float z0 = fmaf(__uint_as_float(wv[e] << 16), sc[2 * e], sh[2 * e]);
+                        float z1 = fmaf(__uint_as_float(wv[e] & 0xffff0000u), sc[2 * e + 1], sh[2 * e + 1]);
+                        float t0, t1;
+                        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * z0));
+                        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * z1));
+                        z0 *= fmaf(0.5f, t0, 0.5f);                  // silu(z) = z * sigmoid(z), sigmoid = 0.5 tanh(z / 2) + 0.5
+                        z1 *= fmaf(0.5f, t1, 0.5f);
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(z0, z1);
+                        ov[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                      }
+                      o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                    }
+                    *reinterpret_cast<uint4*>(slot + row * 128 + (((uint32_t)c8 ^ (uint32_t)(row & 7)) << 4)) = o;
+                  }
+                }
+              }
+              fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
+              asm volatile("bar.sync 2, 128;" ::: "memory");
+              if (tt == 0) mbar_arrive(&a_full[sa]);
+              if (++sa == kASlots) { sa = 0; pa ^= 1; }
+            }
+          } else {
+            if (++sa == kASlots) { sa = 0; pa ^= 1; }   // a shortcut-segment patch (loaded by warp 0) takes a slot too
+          }
+          it.next(args);
+        }
+      }
+    }
   } else if ((warp >= 2 && warp <= 5) || warp >= 7) {
     // ============================== epilogue ==================================================
     // FOUR or EIGHT warps (block size 224 / 352, chosen per launch).  With eight, two warps share a TMEM lane quarter
@@ -744,7 +842,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     // group 1 (warps 7-10) chunks 2-3 -- the store epilogue of a 256 x 128 item is as long as its main loop with four
     // warps, which shows once a CTA runs >= 5 items (+10..19 % on those layers); short grids keep four (cheaper launch).
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const bool wide = blockDim.x == IGEMM_THREADS;
+    const bool wide = !kNorm && blockDim.x == IGEMM_THREADS;
     const int grp = warp >= 7 ? 1 : 0;
     const int cc0 = wide ? grp * 2 : 0, cc1 = wide ? cc0 + 2 : TILE_N / 32;   // this warp's chunks
     const int epi_threads = wide ? 256 : 128;
@@ -1146,6 +1244,10 @@ static int ensure_smem_attr() {
     MDM_CUDA((set_smem_attr<0, true, 2, true>()));
     MDM_CUDA((set_smem_attr<0, false, 2, true>()));
     MDM_CUDA((set_smem_attr<0, false, 1, true>()));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 2, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 2, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 2, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
+    MDM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true, 2, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM));
     done = true;
   }
   return MDM_OK;
@@ -1247,6 +1349,14 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
     if (cudaGetDevice(&dev) == cudaSuccess && dev == g_sched_dev) a.sched = sched_pair_for(stream);
   }
   const bool dyn = a.sched != nullptr;
+  if (a.gn_coef) {   // GroupNorm + SiLU folded into the operand path: four epilogue + four transform warps
+    if (a.qsum && dyn) launch_pdl(igemm_kernel<0, true, 2, true, true, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+    else if (a.qsum) launch_pdl(igemm_kernel<0, true, 2, true, false, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+    else if (dyn) launch_pdl(igemm_kernel<0, true, 2, false, true, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+    else launch_pdl(igemm_kernel<0, true, 2, false, false, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+    MDM_LAUNCH_CHECK();
+    return MDM_OK;
+  }
   if (a.mode == 1) launch_variant<1, false, 2, false>(dyn, grid, IGEMM_BLOCK, st, mA0, mB0, mA1, mB1, mC, mD, a);
   else if (a.qsum && a.halo) launch_variant<0, true, 2, true>(dyn, grid, IGEMM_BLOCK, st, mA0, mB0, mA1, mB1, mC, mD, a);
   else if (a.qsum && a.mt == 2) launch_variant<0, false, 2, true>(dyn, grid, IGEMM_BLOCK, st, mA0, mB0, mA1, mB1, mC, mD, a);
@@ -1270,7 +1380,7 @@ static int halo_ok(const mdm_conv_args* c, const void* out, int n_total, int k_c
   (void)k_chunks;
   const int enabled = env_flag("MDM_IGEMM_HALO", 2);                   // read per call: the tests switch modes
   const int force = env_flag("MDM_IGEMM_HALO_FORCE", 0);               // tests: every eligible layer, however small
-  if (c->up2x) return 2;                                               // (checked by the caller: H, W multiples of 16)
+  if (c->up2x || c->gn_coef) return 2;                                 // (checked by the caller: H, W multiples of 16)
   if (!enabled || c->ksize != 3 || c->stride != 1 || out == nullptr || c->y_f32 != nullptr) return 0;
   if (enabled == 1) return (c->H % PATCH_H == 0 && c->W % PATCH_W == 0) ? 1 : 0;
   if (c->H % 16 == 0 && c->W % 16 == 0) {
@@ -1449,6 +1559,14 @@ int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
   a.N_total = c->cout;
   a.bias = c->bias; a.bias2 = c->bias2; a.rowvec = c->rowvec; a.ld_rowvec = c->ld_rowvec; a.rows_per_vec = c->H * c->W;
   a.out_f32 = c->y_f32;
+  if (c->gn_coef) {
+    MDM_CHECK_ARG(c->ksize == 3 && c->stride == 1 && c->y && !c->y_f32 && !c->up2x && c->H % 16 == 0 && c->W % 16 == 0,
+                  "conv_fprop(gn_coef): 3x3 stride-1 layer with a bf16 output on a map that is a multiple of 16 x 16");
+    a.gn_coef = c->gn_coef;
+    a.a_raw = c->x;
+    a.a_ld = c->ld_x;
+    a.a_c = c->cin;
+  }
   if (c->qsum) {
     MDM_CHECK_ARG(c->y != nullptr && ((long long)c->H * c->W) % 128 == 0,
                   "conv_fprop: fused GroupNorm statistics need a bf16 output and H*W %% 128 == 0 (got %d x %d)", c->H, c->W);

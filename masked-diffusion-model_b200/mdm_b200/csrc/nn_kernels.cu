@@ -246,6 +246,44 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
   for (; it < w.count; ++it, p += step, o += ostep) body(ldg16(p), o);
 }
 
+// (scale, shift) per sample and channel from the quad sums of the producers' epilogues: what the convolution's
+// transform warps apply on the way into its halo tiles (igemm.cu: kNorm).  grid = N, C threads-strided.
+__global__ void __launch_bounds__(256) gn_coef_q_kernel(const float* __restrict__ qa, int qa_quads, const float* __restrict__ qb,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float* __restrict__ coef, float* __restrict__ stats, int HW, int C, int G, float eps) {
+  MDM_PDL_ENTER();
+  __shared__ float mr[GN_MAX_GROUPS * 2];
+  const int n = blockIdx.x, cpg = C / G;
+  if ((int)threadIdx.x < G) {
+    double s = 0.0, ss = 0.0;
+    const int qpg = cpg >> 2, qb_quads = (C >> 2) - qa_quads;
+    for (int k = 0; k < qpg; ++k) {
+      const int quad = threadIdx.x * qpg + k;
+      const float* w = quad < qa_quads ? qa + ((long long)n * qa_quads + quad) * 2 : qb + ((long long)n * qb_quads + (quad - qa_quads)) * 2;
+      s += w[0];
+      ss += w[1];
+    }
+    const double cnt = (double)HW * cpg;
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    mr[threadIdx.x * 2] = (float)mean;
+    mr[threadIdx.x * 2 + 1] = rstd;
+    if (stats) {
+      stats[((long long)n * G + threadIdx.x) * 2] = (float)mean;
+      stats[((long long)n * G + threadIdx.x) * 2 + 1] = rstd;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = mr[(c / cpg) * 2], rstd = mr[(c / cpg) * 2 + 1];
+    const float ga = gamma[c], be = beta[c];
+    coef[((long long)n * C + c) * 2] = rstd * ga;
+    coef[((long long)n * C + c) * 2 + 1] = be - mean * rstd * ga;
+  }
+}
+
 // d(silu(z))/dz with one exp and one fast division
 __device__ __forceinline__ float dsilu_fast(float z) {
   const float s = sigmoid_fast(z);
@@ -1772,6 +1810,16 @@ int mdm_gn_silu_fwd_q(const void* x, long long ld_x, void* y, long long ld_y, co
   dim3 grid(nc, N);
   launch_pdl(gn_apply_kernel<4>, dim3(grid), dim3(GN_THREADS), 0, as_stream(stream), (const bf16*)x, ld_x, (bf16*)y, ld_y, gamma, beta,
              (const float*)nullptr, stats, eps, silu, g, qa, qa_quads, qb);
+  MDM_LAUNCH_CHECK();
+  return MDM_OK;
+}
+
+int mdm_gn_coef_q(const float* qa, int qa_quads, const float* qb, const float* gamma, const float* beta, float* coef,
+                  float* stats, int N, int HW, int C, int G, float eps, void* stream) {
+  MDM_CHECK_ARG(qa && gamma && beta && coef && N > 0 && G > 0 && G <= GN_MAX_GROUPS && C % G == 0 && (C / G) % 4 == 0,
+                "gn_coef_q: bad arguments (C=%d G=%d)", C, G);
+  MDM_CHECK_ARG(qa_quads > 0 && qa_quads <= C / 4 && (qa_quads == C / 4 || qb != nullptr), "gn_coef_q: bad quad split %d of %d", qa_quads, C / 4);
+  launch_pdl(gn_coef_q_kernel, dim3(N), dim3(256), 0, as_stream(stream), qa, qa_quads, qb, gamma, beta, coef, stats, HW, C, G, eps);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }

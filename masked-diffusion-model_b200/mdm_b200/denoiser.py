@@ -1027,19 +1027,40 @@ class _Plan:
                                   B, HW, r.cout, G, eps, True)
             else:
                 ops.gn_silu_fwd(H1(), A2(), m.w32(f"{p}.norm2.weight"), m.w32(f"{p}.norm2.bias"), st2, ws2(), B, HW, r.cout, G, eps, True)
-        fw = [
-            norm1,
-            lambda: ops.conv_fprop(A1(), m.w16(f"{p}.conv1.weight"), H1(), B, H, H, 3, 1, bias=m.w32(f"{p}.conv1.bias"), rowvec=tp,
-                                   ld_rowvec=ld_tp, qsum=qt(q_h1)),
-            norm2,
-        ]
-        if r.shortcut:
-            fw.append(lambda: ops.conv_fprop(A2(), m.w16(f"{p}.conv2.weight"), out.val, B, H, H, 3, 1, bias=m.w32(f"{p}.conv2.bias"),
-                                             bias2=m.w32(f"{p}.conv_shortcut.bias"), x2=x.val, w2=m.w16(f"{p}.conv_shortcut.weight"),
-                                             qsum=qt(q_out)))
+        # inference, big maps: GroupNorm + SiLU folded into the consumer convolution's operand path (igemm.cu: kNorm).  The
+        # statistics come from the producers' epilogues (q sums); a small kernel turns them into a per-sample (scale, shift)
+        # table and the convolution normalises the raw activation while it fills its halo tiles -- the normalised tensors
+        # a1 / a2 are never written or read (2 x 2 B per element per site).  MDM_GN_FOLD=0 off, 2 = also on small grids.
+        fold_mode = int(os.environ.get("MDM_GN_FOLD", "1"))
+        items = B * (H // 16) * (H // 16) * ((r.cout + 127) // 128) if H % 16 == 0 else 0
+        fold_ok = (not ng) and win is None and fold_mode > 0 and H % 16 == 0 and (items >= 96 or fold_mode >= 2)
+        fold1 = fold_ok and q_in is not None and r.cin % 64 == 0
+        fold2 = fold_ok and q_h1 is not None
+        coef1 = self.new((B, r.cin, 2), torch.float32) if fold1 else None
+        coef2 = self.new((B, r.cout, 2), torch.float32) if fold2 else None
+        fw = []
+        if fold1:
+            fw.append(lambda: ops.gn_coef_q(q_in[0].t, qt(q_in[1]), m.w32(f"{p}.norm1.weight"), m.w32(f"{p}.norm1.bias"), coef1,
+                                            B, HW, r.cin, G, eps, stats=st1))
+            fw.append(lambda: ops.conv_fprop(x.val, m.w16(f"{p}.conv1.weight"), H1(), B, H, H, 3, 1, bias=m.w32(f"{p}.conv1.bias"),
+                                             rowvec=tp, ld_rowvec=ld_tp, qsum=qt(q_h1), gn_coef=coef1))
         else:
-            fw.append(lambda: ops.conv_fprop(A2(), m.w16(f"{p}.conv2.weight"), out.val, B, H, H, 3, 1, bias=m.w32(f"{p}.conv2.bias"),
-                                             resid=x.val, qsum=qt(q_out)))
+            fw.append(norm1)
+            fw.append(lambda: ops.conv_fprop(A1(), m.w16(f"{p}.conv1.weight"), H1(), B, H, H, 3, 1, bias=m.w32(f"{p}.conv1.bias"),
+                                             rowvec=tp, ld_rowvec=ld_tp, qsum=qt(q_h1)))
+        if fold2:
+            fw.append(lambda: ops.gn_coef_q(q_h1.t, None, m.w32(f"{p}.norm2.weight"), m.w32(f"{p}.norm2.bias"), coef2,
+                                            B, HW, r.cout, G, eps, stats=st2))
+        else:
+            fw.append(norm2)
+        a2_in = (lambda: H1()) if fold2 else A2
+        if r.shortcut:
+            fw.append(lambda: ops.conv_fprop(a2_in(), m.w16(f"{p}.conv2.weight"), out.val, B, H, H, 3, 1, bias=m.w32(f"{p}.conv2.bias"),
+                                             bias2=m.w32(f"{p}.conv_shortcut.bias"), x2=x.val, w2=m.w16(f"{p}.conv_shortcut.weight"),
+                                             qsum=qt(q_out), gn_coef=coef2))
+        else:
+            fw.append(lambda: ops.conv_fprop(a2_in(), m.w16(f"{p}.conv2.weight"), out.val, B, H, H, 3, 1, bias=m.w32(f"{p}.conv2.bias"),
+                                             resid=x.val, qsum=qt(q_out), gn_coef=coef2))
         bw = []
         if ng:
             rd_a2 = self.scratch("d_a2" + sfx, (B, H, H, r.cout))

@@ -29,6 +29,7 @@ class ConvArgs(Structure):
         ("splitk_ws", c_void_p), ("splitk_ws_floats", c_longlong),
         ("qsum", c_void_p),
         ("up2x", c_int), ("up_a", c_int), ("up_b", c_int),
+        ("gn_coef", c_void_p),
     ]
 
 
@@ -40,6 +41,7 @@ _lib.register({
     "mdm_conv_dgrad": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_conv_wgrad": (c_int, [POINTER(ConvArgs), _P]),
     "mdm_up2x_weights": (c_int, [_P, _P, c_int, c_int, _P]),
+    "mdm_gn_coef_q": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
     "mdm_reserve_sms": (c_int, [c_int]),
     "mdm_set_sched_workspace": (c_int, [_P, c_int]),
     "mdm_gn_ws_floats": (_I64, [c_int, c_int, c_int, c_int]),
@@ -110,7 +112,7 @@ def pix_ld(t: torch.Tensor) -> int:
 
 
 def conv_fprop(x, w, y, N, H, W, ksize=3, stride=1, bias=None, rowvec=None, resid=None, accumulate=False,
-               y_f32=None, x2=None, w2=None, bias2=None, cout=None, ld_rowvec=None, qsum=None):
+               y_f32=None, x2=None, w2=None, bias2=None, cout=None, ld_rowvec=None, qsum=None, gn_coef=None):
     """y[N,H,W,cout] = conv(x, w) (+bias +rowvec[n] +resid) ; x: [N,H*s,W*s,cin] view, w packed
     bf16 [cout, k*k, cin]; optional fused 1x1 shortcut (x2, w2)."""
     a = ConvArgs()
@@ -132,8 +134,16 @@ def conv_fprop(x, w, y, N, H, W, ksize=3, stride=1, bias=None, rowvec=None, resi
     if x2 is not None:
         a.x2, a.ld_x2, a.cin2, a.w2 = _dp(x2), pix_ld(x2), x2.shape[-1], _dp(w2)
     a.qsum = _dp(qsum)          # fused GroupNorm statistics of the output: qsum[N, cout/4, 2] += quad (sum, sumsq)
+    a.gn_coef = _dp(gn_coef)    # x is the RAW activation: GroupNorm + SiLU applied while the halo tiles are filled (inference)
     _splitk(a, x.device)
     check(lib().mdm_conv_fprop(ctypes.byref(a), stream_ptr(x.device)))
+
+
+def gn_coef_q(qa, qb, gamma, beta, coef, N, HW, C, G, eps, stats=None):
+    """coef[N, C, 2] = (scale, shift) of a GroupNorm site from its producers' quad sums (qa [N, Ca/4, 2], qb for the second
+    half of a concatenation or None)"""
+    check(lib().mdm_gn_coef_q(ptr(qa), qa.shape[1], ptr(qb), ptr(gamma), ptr(beta), ptr(coef), ptr(stats), N, HW, C, G, eps,
+                              stream_ptr(coef.device)))
 
 
 def up2x_weights(w32, out_bf16, cout, cin):

@@ -268,3 +268,36 @@ def test_fused_upsample_conv(N, H, cin):
     want = torch.stack([yq.sum(dim=(2, 3)), (yq * yq).sum(dim=(2, 3))], dim=-1)
     # the statistics are taken from the fp32 accumulators before the bf16 rounding of y
     assert (q - want).abs().max().item() <= 2e-2 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("N,H,cin,cout,shortcut,stats", [(2, 32, 128, 128, False, True), (3, 16, 256, 128, True, False),
+                                                         (1, 64, 128, 128, False, False), (2, 32, 384, 256, True, True)])
+def test_fprop_with_folded_groupnorm(N, H, cin, cout, shortcut, stats, monkeypatch):
+    """inference: GroupNorm + SiLU of the input applied inside the convolution (transform warps fill the halo tiles with
+    silu(x * scale + shift), zero outside the map) == the stand-alone apply pass followed by the convolution"""
+    from mdm_b200 import denoiser_ops as ops
+    for dyn in ("1", "2"):
+        monkeypatch.setenv("MDM_IGEMM_DYNAMIC", dyn)
+        g = torch.Generator(device="cuda").manual_seed(11)
+        x = torch.randn(N, cin, H, H, device="cuda", generator=g)
+        w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (9 * cin) ** 0.5
+        b = torch.randn(cout, device="cuda", generator=g)
+        coef = torch.stack([1.0 + 0.5 * torch.randn(N, cin, device="cuda", generator=g), 0.5 * torch.randn(N, cin, device="cuda", generator=g)], dim=-1).contiguous()
+        xb, wb = nhwc(x), ops.pack_conv_weight(w).to(torch.bfloat16)
+        xs = torch.randn(N, 192, H, H, device="cuda", generator=g)
+        ws_ = torch.randn(cout, 192, 1, 1, device="cuda", generator=g) / 192 ** 0.5
+        res = torch.randn(N, cout, H, H, device="cuda", generator=g)
+        y = torch.empty(N, H, H, cout, device="cuda", dtype=torch.bfloat16)
+        q = torch.zeros(N, cout // 4, 2, device="cuda") if stats else None
+        kw = dict(x2=nhwc(xs), w2=ops.pack_conv_weight(ws_).to(torch.bfloat16)) if shortcut else dict(resid=nhwc(res))
+        ops.conv_fprop(xb, wb, y, N, H, H, 3, 1, bias=b, qsum=q, gn_coef=coef, **kw)
+        a = nchw(xb) * coef[..., 0][:, :, None, None] + coef[..., 1][:, :, None, None]
+        a = torch.nn.functional.silu(a).to(torch.bfloat16).float()          # the kernel rounds the normalised value to bf16
+        ref = F.conv2d(a, ops.unpack_conv_weight(wb.float(), 3), b, padding=1)
+        ref = ref + (F.conv2d(nchw(nhwc(xs)), ops.unpack_conv_weight(ops.pack_conv_weight(ws_).to(torch.bfloat16).float(), 1)) if shortcut else nchw(nhwc(res)))
+        err = (nchw(y) - ref).abs().max().item()
+        assert err <= 1.2e-2 * ref.abs().max().item(), (dyn, err)
+        if stats:
+            yq = ref.view(N, cout // 4, 4, -1)
+            want = torch.stack([yq.sum(dim=(2, 3)), (yq * yq).sum(dim=(2, 3))], dim=-1)
+            assert (q - want).abs().max().item() <= 2e-2 * want.abs().max().item()

@@ -178,6 +178,31 @@ def test_segmented_backward_equals_whole_backward():
     assert (mine.flat_grad - whole).abs().max().item() <= tol
 
 
+def test_groupnorm_folded_into_convolutions_matches_unfolded(monkeypatch):
+    """inference on big maps: GroupNorm + SiLU folded into the consumer convolutions' operand path (MDM_GN_FOLD) gives the
+    output of the plan that runs the stand-alone apply passes, and stays within the fp32-oracle tolerance.  The
+    two-pass GroupNorm family (hence the producers' quad sums) is forced at 32 x 32 through MDM_GN_CLUSTER=0."""
+    monkeypatch.setenv("MDM_GN_CLUSTER", "0")
+    ref, mine = build_pair(3, 32)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.rand(4, 3, 32, 32, device="cuda", generator=g) * 2 - 1
+    t = torch.tensor([1.0, 250.0, 999.0, 37.0], device="cuda")
+    outs = {}
+    for flag in ("2", "0"):
+        monkeypatch.setenv("MDM_GN_FOLD", flag)
+        mine._plans.clear()
+        with torch.no_grad():
+            mine.eval()
+            outs[flag] = mine(x, t).sample.clone()
+    with torch.no_grad():
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        want = ref(x, t).sample
+    print(f"folded vs unfolded rel L2 = {rel_l2(outs['2'], outs['0']):.3e}; folded vs fp32 oracle = {rel_l2(outs['2'], want):.3e}")
+    assert rel_l2(outs["2"], outs["0"]) <= 1e-2
+    assert rel_l2(outs["2"], want) <= 2e-2
+
+
 def test_inference_graph_replay_matches_eager(monkeypatch):
     """eval-mode forwards replay one CUDA graph after two warm-up calls: same outputs as the eager program, for changing
     inputs, timesteps and weights (the graph reads the static input buffers and the bf16 weight mirror)"""
