@@ -20,6 +20,7 @@ LIB = os.path.join(HERE, "libmdm_sm100.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+FLAGS += [f"-D{d}" for d in os.environ.get("MDM_NVCC_DEFINES", "").split() if d]   # e.g. MDM_IGEMM_DEBUG_WAIT (debug builds only)
 
 
 def _sources():

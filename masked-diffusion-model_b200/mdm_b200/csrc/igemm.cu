@@ -63,6 +63,7 @@ constexpr int MAX_A_SLOTS = 4, MAX_B_SLOTS = 6;
 constexpr int EPI_BYTES = 32768;               // one staging tile: 128 x 128 bf16, or 2 boxes of 128 x 32 fp32
 constexpr int IGEMM_THREADS = 352;             // warps 0: TMA A, 1: MMA, 2-5 (+ 7-10): epilogue, 6: TMA B
 constexpr int IGEMM_THREADS_NARROW = 224;      // launch without warps 7-10: four epilogue warps (short grids)
+constexpr int IGEMM_THREADS_NORM = 480;        // kNorm: + warps 11-14, the transform producers of the A operand
 constexpr int RING_BYTES = 2 * HALO_BYTES + 5 * B_BYTES;    // halo: 2 A + 5 B slots (256-row: 2 x 41 KB + 4 B); plain: 4 A + 4 B slots (128 KB)
 static_assert(2 * HALO2_SLOT + 4 * B_BYTES <= RING_BYTES, "256-row halo ring must fit");
 constexpr int SMEM_EPI_OFF = RING_BYTES;
@@ -105,6 +106,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // bounded wait: a pipeline bug traps (launch fails) instead of hanging the GPU
+#ifdef MDM_IGEMM_DEBUG_WAIT
+__device__ int g_wait_abort;
+__shared__ volatile int g_dbg[8];
+#define DBG(i, v) g_dbg[i] = (v)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*(volatile int*)&g_wait_abort) return;
+    if (clock64() - t0 > 400000000LL) {
+      printf("WAIT TIMEOUT block %d thread %d bar 0x%x parity %u | w0 use %d mma use %d tr use %d stage %d item %d\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity, g_dbg[0], g_dbg[1], g_dbg[2], g_dbg[3], g_dbg[4]);
+      atomicExch(&g_wait_abort, 1);
+      return;
+    }
+  }
+}
+#else
+#define DBG(i, v)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
@@ -112,6 +132,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
+#endif
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -443,13 +464,13 @@ struct WorkSub<true> {
 // kStats: the store epilogue also accumulates GroupNorm quad sums of the output (IgemmArgs::qsum); a template
 // parameter so that the plain instantiations carry none of that code (measured: +4 % on the level-0 convolutions when
 // it was a run-time branch -- the store epilogue of a 256 x 128 item is as long as its main loop).
-// kNorm (halo kernel, inference): GroupNorm + SiLU of the INPUT folded into the operand path.  Warps 7-10 do not serve the
-// epilogue (four epilogue warps remain) but fill the halo slots themselves: 16-byte loads of the raw activation,
+// kNorm (halo kernel, inference): GroupNorm + SiLU of the INPUT folded into the operand path.  Four extra warps (11-14,
+// 480 threads per CTA) fill the halo slots themselves: 16-byte loads of the raw activation (prefetched one chunk ahead),
 // normalise + SiLU in registers, swizzled 16-byte stores into the slot (the layout TMA would have produced), proxy fence,
 // one arrival on the slot's full barrier.  The normalised activation never exists in HBM: the stand-alone apply pass
 // (read x, write a) and the conv's read of a collapse into one read of x.
 template <int kMode, bool kHalo, int kMT, bool kStats = false, bool kDyn = false, bool kNorm = false>
-__global__ void __launch_bounds__(IGEMM_THREADS, 1)
+__global__ void __launch_bounds__(kNorm ? IGEMM_THREADS_NORM : IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
              const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
              const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapD,
@@ -501,14 +522,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], (!kNorm && blockDim.x == IGEMM_THREADS) ? 8 : 4);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[s], blockDim.x >= IGEMM_THREADS ? 8 : 4);   // one arrival per epilogue warp
       mbar_init(&c_full_bar[s], 1);
     }
     if (kDyn) {
       for (int s = 0; s < WQ_SLOTS; ++s) {
         mbar_init(&wq_full[s], 1);
-        // B producer, MMA issuer, one per epilogue warp (kNorm: four epilogue + four transform warps)
-        mbar_init(&wq_empty[s], 2 + ((kNorm || blockDim.x == IGEMM_THREADS) ? 8 : 4));
+        // B producer, MMA issuer, one per epilogue warp (kNorm: + four transform warps)
+        mbar_init(&wq_empty[s], 2 + (blockDim.x >= IGEMM_THREADS ? 8 : 4) + (kNorm ? 4 : 0));
       }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -530,6 +551,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int w_first = blockIdx.x, w_step = gridDim.x;
+#ifdef MDM_IGEMM_DEBUG_WAIT
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("BARS a_full 0x%x a_empty 0x%x b_full 0x%x b_empty 0x%x tmem_full 0x%x tmem_empty 0x%x wq_full 0x%x wq_empty 0x%x c_full 0x%x\n",
+           smem_u32(a_full), smem_u32(a_empty), smem_u32(b_full), smem_u32(b_empty), smem_u32(tmem_full_bar), smem_u32(tmem_empty_bar),
+           smem_u32(wq_full), smem_u32(wq_empty), smem_u32(c_full_bar));
+#endif
   pdl_wait();   // barrier init, TMEM allocation and descriptor prefetch above overlapped the previous kernel's tail
 
   if (warp == 0) {
@@ -548,13 +575,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         it.init(args, k.it0);
         for (int i = 0; i < k.nit; ++i) {
           if (kHalo) {
-            if (it.halo_it()) {
+            if (kNorm) {
+              // the transform warps own the whole A ring (halo chunks AND the shortcut patches): a role that only watched
+              // a slot it does not fill could fall two phases behind, which a parity wait cannot tell from zero
+            } else if (it.halo_it()) {
               if (it.tap == 0) {   // one halo per channel chunk
-                if (!kNorm) {      // (kNorm: the transform warps fill this slot; this warp only keeps its slot counter in step)
-                  mbar_wait(&a_empty[sa], pa ^ 1);
-                  mbar_expect_tx(&a_full[sa], kHaloBytes);
-                  tma_load_4d(&mapA0, a_ring + sa * kHaloSlot, &a_full[sa], it.kc * TILE_K, w0 - 1, h0 - 1, n0);
-                }
+                mbar_wait(&a_empty[sa], pa ^ 1);
+                mbar_expect_tx(&a_full[sa], kHaloBytes);
+                tma_load_4d(&mapA0, a_ring + sa * kHaloSlot, &a_full[sa], it.kc * TILE_K, w0 - 1, h0 - 1, n0);
                 if (++sa == kASlots) { sa = 0; pa ^= 1; }
               }
             } else {               // fused 1x1 shortcut segment: a plain patch in a halo slot
@@ -752,97 +780,141 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       umma_commit(&tmem_full_bar[acc]);
     }
    }
-  } else if (kNorm && warp >= 7) {
+  } else if (kNorm && warp >= 11) {
     // ============================== transform producers (kNorm): GroupNorm + SiLU on the way into the halo ==========
+    // 128 threads; thread t owns the 8-channel group t % 8 of every halo pixel t / 8 + 16 j.  The 21 sixteen-byte loads
+    // of the NEXT halo chunk (next channel chunk, or chunk 0 of the next work item) are issued before this role waits
+    // for its slot, so the memory latency hides behind the MMAs of the chunk in flight.
     if (kMode == 0 && kHalo && kMT == 2) {
-      const int tt = (int)threadIdx.x - 224;          // 0 .. 127
-      const int c8 = tt & 7;                          // this thread's 8-channel group inside a 64-channel chunk
+      const int tt = (int)threadIdx.x - IGEMM_THREADS;   // 0 .. 127
+      const int c8 = tt & 7;
       const bf16_t* xin = reinterpret_cast<const bf16_t*>(args.a_raw);
-      int sa = 0, wn_unused;
-      uint32_t pa = 0;
-      WorkSub<kDyn> feed(args, w_first, w_step, wq_full, wq_empty, wq, true);
-      for (int w = feed.next(wn_unused); w >= 0; w = feed.next(wn_unused)) {
-        const Work k = decode_work(args, w);
+      constexpr int kRows = kHaloW * HALO2_H;            // 324 halo pixels, 8 sixteen-byte pieces each
+      constexpr int kPieces = (kRows * 8 + 127) / 128;   // 21 per thread
+      const int KC = args.seg_kc[0];
+      const int n_sc = args.nseg > 1 ? args.seg_taps[1] * args.seg_kc[1] : 0;   // shortcut-segment slot uses per item (filled by warp 0)
+      uint4 v[kPieces];
+      uint32_t inmask = 0;
+      const int pitch_px = args.a_ld;                    // elements between horizontally adjacent pixels
+      const int pitch_row = args.W * args.a_ld;          // ... vertically adjacent pixels (fits 32 bits: one image row)
+      auto issue = [&](int item, int kc) {
+        const Work k = decode_work(args, item);
         int w0, h0, n0;
         tile_origin(args, kHalo, k.m_tile * kMT, w0, h0, n0);
-        IterWalker<kHalo> it;
-        it.init(args, k.it0);
-        for (int i = 0; i < k.nit; ++i) {
-          if (it.halo_it()) {
-            if (it.tap == 0) {
-              float sc[8], sh[8];
-              {
-                const float4* cf = reinterpret_cast<const float4*>(args.gn_coef + ((long long)n0 * args.a_c + it.kc * TILE_K + c8 * 8) * 2);
+        // element (h0 - 1, w0 - 1) of the halo box: may lie outside the map, only in-bounds pixels are dereferenced
+        const bf16_t* base = xin + (((long long)n0 * args.H + (h0 - 1)) * args.W + (w0 - 1)) * (long long)args.a_ld + kc * TILE_K + c8 * 8;
+        inmask = 0;
+        const int gy0 = h0 - 1, gx0 = w0 - 1;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float4 t = __ldg(cf + j);
-                  sc[2 * j] = t.x; sh[2 * j] = t.y; sc[2 * j + 1] = t.z; sh[2 * j + 1] = t.w;
-                }
-              }
-              mbar_wait(&a_empty[sa], pa ^ 1);        // the MMAs that read this slot have retired
-              uint8_t* slot = a_ring + sa * kHaloSlot;
-              constexpr int kRows = kHaloW * HALO2_H;   // 324 halo pixels, 8 sixteen-byte pieces each
-              constexpr int kBatch = 7;
-              for (int b0 = 0; b0 < kRows * 8; b0 += 128 * kBatch) {
-                uint4 v[kBatch];
-                bool in[kBatch];
-#pragma unroll
-                for (int u = 0; u < kBatch; ++u) {
-                  const int idx = b0 + u * 128 + tt;
-                  const int row = idx >> 3;
-                  const int hy = row / kHaloW, hx = row - hy * kHaloW;
-                  const int gy = h0 - 1 + hy, gx = w0 - 1 + hx;
-                  in[u] = idx < kRows * 8 && gy >= 0 && gy < args.H && gx >= 0 && gx < args.W;
-                  v[u] = make_uint4(0u, 0u, 0u, 0u);
-                  if (in[u]) v[u] = __ldg(reinterpret_cast<const uint4*>(xin + (((long long)n0 * args.H + gy) * args.W + gx) * args.a_ld + it.kc * TILE_K + c8 * 8));
-                }
-#pragma unroll
-                for (int u = 0; u < kBatch; ++u) {
-                  const int idx = b0 + u * 128 + tt;
-                  if (idx < kRows * 8) {
-                    const int row = idx >> 3;
-                    uint4 o = make_uint4(0u, 0u, 0u, 0u);          // zero padding stays zero (the reference pads the NORMALISED map)
-                    if (in[u]) {
-                      const uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-                      uint32_t ov[4];
-#pragma unroll
-                      for (int e = 0; e < 4; ++e) {
-                        float z0 = fmaf(__uint_as_float(wv[e] << 16), sc[2 * e], sh[2 * e]);
-                        float z1 = fmaf(__uint_as_float(wv[e] & 0xffff0000u), sc[2 * e + 1], sh[2 * e + 1]);
-                        float t0, t1;
-                        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * z0));
-                        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * z1));
-                        z0 *= fmaf(0.5f, t0, 0.5f);                  // silu(z) = z * sigmoid(z), sigmoid = 0.5 tanh(z / 2) + 0.5
-                        z1 *= fmaf(0.5f, t1, 0.5f);
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(z0, z1);
-                        ov[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                      }
-                      o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-                    }
-                    *reinterpret_cast<uint4*>(slot + row * 128 + (((uint32_t)c8 ^ (uint32_t)(row & 7)) << 4)) = o;
-                  }
-                }
-              }
-              fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
-              asm volatile("bar.sync 2, 128;" ::: "memory");
-              if (tt == 0) mbar_arrive(&a_full[sa]);
-              if (++sa == kASlots) { sa = 0; pa ^= 1; }
-            }
-          } else {
-            if (++sa == kASlots) { sa = 0; pa ^= 1; }   // a shortcut-segment patch (loaded by warp 0) takes a slot too
+        for (int u = 0; u < kPieces; ++u) {
+          const int row = u * 16 + (tt >> 3);            // halo pixel of piece u, 18 per halo row
+          const int hy = (row * 3641) >> 16;             // row / 18 for row < 340
+          const int hx = row - hy * kHaloW;
+          const bool in = (u * 128 + tt < kRows * 8) && (unsigned)(gy0 + hy) < (unsigned)args.H && (unsigned)(gx0 + hx) < (unsigned)args.W;
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (in) {
+            v[u] = __ldg(reinterpret_cast<const uint4*>(base + (hy * pitch_row + hx * pitch_px)));
+            inmask |= 1u << u;
           }
-          it.next(args);
         }
+        return n0;
+      };
+      int sa = 0, wn = -1;
+      uint32_t pa = 0;
+      WorkSub<kDyn> feed(args, w_first, w_step, wq_full, wq_empty, wq, true);
+      int w = feed.next(wn);
+      int n0 = 0;
+      int dbg_use = 0;
+      (void)dbg_use;
+      if (w >= 0) n0 = issue(w, 0);
+      while (w >= 0) {
+        DBG(4, w);
+        for (int kc = 0; kc < KC; ++kc) {
+          DBG(2, dbg_use++); DBG(3, 1);
+          float sc[8], sh[8];
+          {
+            const float4* cf = reinterpret_cast<const float4*>(args.gn_coef + ((long long)n0 * args.a_c + kc * TILE_K + c8 * 8) * 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 t = __ldg(cf + j);           // halved: silu(z) = (z/2) * (1 + tanh(z/2))
+              sc[2 * j] = 0.5f * t.x; sh[2 * j] = 0.5f * t.y; sc[2 * j + 1] = 0.5f * t.z; sh[2 * j + 1] = 0.5f * t.w;
+            }
+          }
+          mbar_wait(&a_empty[sa], pa ^ 1);          // the MMAs that read this slot have retired
+          DBG(3, 2);
+          uint8_t* slot = a_ring + sa * kHaloSlot;
+#pragma unroll
+          for (int u = 0; u < kPieces; ++u) {
+            const int idx = u * 128 + tt;
+            if (idx < kRows * 8) {
+              const int row = idx >> 3;
+              uint4 o = make_uint4(0u, 0u, 0u, 0u);            // zero padding stays zero (the reference pads the NORMALISED map)
+              if ((inmask >> u) & 1u) {
+                const uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                uint32_t ov[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float z0 = fmaf(__uint_as_float(wv[e] << 16), sc[2 * e], sh[2 * e]);          // z / 2
+                  float z1 = fmaf(__uint_as_float(wv[e] & 0xffff0000u), sc[2 * e + 1], sh[2 * e + 1]);
+                  float t0, t1;
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(z0));
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(z1));
+                  z0 = fmaf(z0, t0, z0);                         // silu(z) = z sigmoid(z) = (z/2) (1 + tanh(z/2))
+                  z1 = fmaf(z1, t1, z1);
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(z0, z1);
+                  ov[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+              }
+              *reinterpret_cast<uint4*>(slot + row * 128 + (((uint32_t)c8 ^ (uint32_t)(row & 7)) << 4)) = o;
+            }
+          }
+          fence_proxy_async();                      // generic-proxy stores -> visible to the tensor core (async proxy)
+          DBG(3, 3);
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (tt == 0) mbar_arrive(&a_full[sa]);
+          if (++sa == kASlots) { sa = 0; pa ^= 1; }
+          // next chunk's loads fly while the MMAs of this one run
+          DBG(3, 6);
+          if (kc + 1 < KC) issue(w, kc + 1);
+          else if (wn >= 0) n0 = issue(wn, 0);
+        }
+        if (n_sc > 0) {                              // fused 1x1 shortcut segment: plain patches in the same ring, by TMA
+          const Work k = decode_work(args, w);
+          int w0, h0, m0, w1, h1, m1;
+          tile_origin(args, kHalo, k.m_tile * kMT, w0, h0, m0);
+          tile_origin(args, kHalo, k.m_tile * kMT + 1, w1, h1, m1);
+          for (int i = 0; i < n_sc; ++i) {
+            DBG(2, dbg_use++); DBG(3, 4);
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            asm volatile("bar.sync 2, 128;" ::: "memory");   // every thread has seen this phase before the slot can move on
+            if (tt == 0) {
+              const int kc = i % args.seg_kc[1];
+              mbar_expect_tx(&a_full[sa], k.nh * A_BYTES);
+              if (k.nh == kMT) {
+                tma_load_4d(&mapA1, a_ring + sa * kHaloSlot, &a_full[sa], kc * TILE_K, w0, h0, m0);
+                tma_load_4d(&mapA1, a_ring + sa * kHaloSlot + A_BYTES, &a_full[sa], kc * TILE_K, w1, h1, m1);
+              } else {
+                tma_load_4d(&mapA1, a_ring + sa * kHaloSlot, &a_full[sa], kc * TILE_K, k.half0 ? w1 : w0, k.half0 ? h1 : h0,
+                            k.half0 ? m1 : m0);
+              }
+            }
+            if (++sa == kASlots) { sa = 0; pa ^= 1; }
+          }
+        }
+        DBG(3, 5);
+        w = feed.next(wn);
       }
+      DBG(3, 7);
     }
-  } else if ((warp >= 2 && warp <= 5) || warp >= 7) {
+  } else if ((warp >= 2 && warp <= 5) || (warp >= 7 && warp <= 10)) {
     // ============================== epilogue ==================================================
     // FOUR or EIGHT warps (block size 224 / 352, chosen per launch).  With eight, two warps share a TMEM lane quarter
     // (a warp may only touch lanes 32 * (warp % 4) ..): group 0 (warps 2-5) takes the 32-column chunks 0-1 of a tile,
     // group 1 (warps 7-10) chunks 2-3 -- the store epilogue of a 256 x 128 item is as long as its main loop with four
     // warps, which shows once a CTA runs >= 5 items (+10..19 % on those layers); short grids keep four (cheaper launch).
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const bool wide = !kNorm && blockDim.x == IGEMM_THREADS;
+    const bool wide = blockDim.x >= IGEMM_THREADS;
     const int grp = warp >= 7 ? 1 : 0;
     const int cc0 = wide ? grp * 2 : 0, cc1 = wide ? cc0 + 2 : TILE_N / 32;   // this warp's chunks
     const int epi_threads = wide ? 256 : 128;
@@ -1349,11 +1421,11 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
     if (cudaGetDevice(&dev) == cudaSuccess && dev == g_sched_dev) a.sched = sched_pair_for(stream);
   }
   const bool dyn = a.sched != nullptr;
-  if (a.gn_coef) {   // GroupNorm + SiLU folded into the operand path: four epilogue + four transform warps
-    if (a.qsum && dyn) launch_pdl(igemm_kernel<0, true, 2, true, true, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-    else if (a.qsum) launch_pdl(igemm_kernel<0, true, 2, true, false, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-    else if (dyn) launch_pdl(igemm_kernel<0, true, 2, false, true, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
-    else launch_pdl(igemm_kernel<0, true, 2, false, false, true>, dim3(grid), dim3(IGEMM_THREADS), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+  if (a.gn_coef) {   // GroupNorm + SiLU folded into the operand path: eight epilogue + four transform warps (480 threads)
+    if (a.qsum && dyn) launch_pdl(igemm_kernel<0, true, 2, true, true, true>, dim3(grid), dim3(IGEMM_THREADS_NORM), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+    else if (a.qsum) launch_pdl(igemm_kernel<0, true, 2, true, false, true>, dim3(grid), dim3(IGEMM_THREADS_NORM), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+    else if (dyn) launch_pdl(igemm_kernel<0, true, 2, false, true, true>, dim3(grid), dim3(IGEMM_THREADS_NORM), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
+    else launch_pdl(igemm_kernel<0, true, 2, false, false, true>, dim3(grid), dim3(IGEMM_THREADS_NORM), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
     MDM_LAUNCH_CHECK();
     return MDM_OK;
   }
