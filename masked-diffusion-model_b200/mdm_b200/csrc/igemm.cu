@@ -782,7 +782,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
    }
   } else if (kNorm && warp >= 11) {
     // ============================== transform producers (kNorm): GroupNorm + SiLU on the way into the halo ==========
-    // 128 threads; thread t owns the 8-channel group t % 8 of every halo pixel t / 8 + 16 j.  The 21 sixteen-byte loads
+    // 128 threads; thread t owns the 8-channel group t % 8 of 21 halo pixels (column t / 8 of every halo row, plus a share
+    // of the two right-hand columns).  The 21 sixteen-byte loads
     // of the NEXT halo chunk (next channel chunk, or chunk 0 of the next work item) are issued before this role waits
     // for its slot, so the memory latency hides behind the MMAs of the chunk in flight.
     if (kMode == 0 && kHalo && kMT == 2) {
@@ -805,16 +806,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         const bf16_t* base = xin + (((long long)n0 * args.H + (h0 - 1)) * args.W + (w0 - 1)) * (long long)args.a_ld + kc * TILE_K + c8 * 8;
         inmask = 0;
         const int gy0 = h0 - 1, gx0 = w0 - 1;
+        // pieces 0..17: halo pixel (u, tt / 8) -- columns 0..15 of halo row u; pieces 18..20: the two right-hand columns
+        // (36 pixels x 8 channel groups over the first 288 slots of 3 x 128).  Affine addresses, one bounds test per piece.
+        const bool col_ok = (unsigned)(gx0 + (tt >> 3)) < (unsigned)args.W;
+        const bf16_t* p = base + (tt >> 3) * pitch_px;
 #pragma unroll
-        for (int u = 0; u < kPieces; ++u) {
-          const int row = u * 16 + (tt >> 3);            // halo pixel of piece u, 18 per halo row
-          const int hy = (row * 3641) >> 16;             // row / 18 for row < 340
-          const int hx = row - hy * kHaloW;
-          const bool in = (u * 128 + tt < kRows * 8) && (unsigned)(gy0 + hy) < (unsigned)args.H && (unsigned)(gx0 + hx) < (unsigned)args.W;
+        for (int u = 0; u < 18; ++u) {
           v[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (in) {
-            v[u] = __ldg(reinterpret_cast<const uint4*>(base + (hy * pitch_row + hx * pitch_px)));
+          if (col_ok && (unsigned)(gy0 + u) < (unsigned)args.H) {
+            v[u] = __ldg(reinterpret_cast<const uint4*>(p + u * pitch_row));
             inmask |= 1u << u;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kPieces - 18; ++j) {
+          const int pix = (tt >> 3) + 16 * j;              // 0..47, 36 used
+          const int hy = pix >> 1, hx = 16 + (pix & 1);
+          v[18 + j] = make_uint4(0u, 0u, 0u, 0u);
+          if (pix < 36 && (unsigned)(gy0 + hy) < (unsigned)args.H && (unsigned)(gx0 + hx) < (unsigned)args.W) {
+            v[18 + j] = __ldg(reinterpret_cast<const uint4*>(base + hy * pitch_row + hx * pitch_px));
+            inmask |= 1u << (18 + j);
           }
         }
         return n0;
@@ -845,9 +856,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           uint8_t* slot = a_ring + sa * kHaloSlot;
 #pragma unroll
           for (int u = 0; u < kPieces; ++u) {
-            const int idx = u * 128 + tt;
-            if (idx < kRows * 8) {
-              const int row = idx >> 3;
+            const int pix = (tt >> 3) + 16 * (u - 18);       // pieces 18..20 (see issue())
+            const int row = u < 18 ? u * kHaloW + (tt >> 3) : (pix >> 1) * kHaloW + 16 + (pix & 1);
+            if (u < 18 || pix < 36) {
               uint4 o = make_uint4(0u, 0u, 0u, 0u);            // zero padding stays zero (the reference pads the NORMALISED map)
               if ((inmask >> u) & 1u) {
                 const uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
