@@ -63,7 +63,9 @@ constexpr int MAX_A_SLOTS = 4, MAX_B_SLOTS = 6;
 constexpr int EPI_BYTES = 32768;               // one staging tile: 128 x 128 bf16, or 2 boxes of 128 x 32 fp32
 constexpr int IGEMM_THREADS = 352;             // warps 0: TMA A, 1: MMA, 2-5 (+ 7-10): epilogue, 6: TMA B
 constexpr int IGEMM_THREADS_NARROW = 224;      // launch without warps 7-10: four epilogue warps (short grids)
-constexpr int IGEMM_THREADS_NORM = 480;        // kNorm: + warps 11-14, the transform producers of the A operand
+constexpr int NORM_WARPS = 8;                  // kNorm: transform-producer warps of the A operand (warps 11 ..)
+constexpr int NORM_THREADS = NORM_WARPS * 32;
+constexpr int IGEMM_THREADS_NORM = IGEMM_THREADS + NORM_THREADS;
 constexpr int RING_BYTES = 2 * HALO_BYTES + 5 * B_BYTES;    // halo: 2 A + 5 B slots (256-row: 2 x 41 KB + 4 B); plain: 4 A + 4 B slots (128 KB)
 static_assert(2 * HALO2_SLOT + 4 * B_BYTES <= RING_BYTES, "256-row halo ring must fit");
 constexpr int SMEM_EPI_OFF = RING_BYTES;
@@ -464,11 +466,14 @@ struct WorkSub<true> {
 // kStats: the store epilogue also accumulates GroupNorm quad sums of the output (IgemmArgs::qsum); a template
 // parameter so that the plain instantiations carry none of that code (measured: +4 % on the level-0 convolutions when
 // it was a run-time branch -- the store epilogue of a 256 x 128 item is as long as its main loop).
-// kNorm (halo kernel, inference): GroupNorm + SiLU of the INPUT folded into the operand path.  Four extra warps (11-14,
-// 480 threads per CTA) fill the halo slots themselves: 16-byte loads of the raw activation (prefetched one chunk ahead),
+// kNorm (halo kernel, inference): GroupNorm + SiLU of the INPUT folded into the operand path.  Eight extra warps (11-18,
+// 608 threads per CTA) fill the halo slots themselves: 16-byte loads of the raw activation (prefetched one chunk ahead),
 // normalise + SiLU in registers, swizzled 16-byte stores into the slot (the layout TMA would have produced), proxy fence,
 // one arrival on the slot's full barrier.  The normalised activation never exists in HBM: the stand-alone apply pass
-// (read x, write a) and the conv's read of a collapse into one read of x.
+// (read x, write a) and the conv's read of a collapse into one read of x.  Measured (256 x 128 x 128, 128 -> 128): the
+// folded convolution costs 1.10 x the plain one (+0.10 ms; the apply pass it replaces is 0.33 ms).  The remaining cost
+// is SRAM bandwidth: the MMAs of this kernel already read shared memory at its limit, and the register path moves every
+// halo byte through the LSU twice (a variant that only signals the barriers runs 6 % FASTER than the plain kernel).
 template <int kMode, bool kHalo, int kMT, bool kStats = false, bool kDyn = false, bool kNorm = false>
 __global__ void __launch_bounds__(kNorm ? IGEMM_THREADS_NORM : IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
@@ -529,7 +534,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       for (int s = 0; s < WQ_SLOTS; ++s) {
         mbar_init(&wq_full[s], 1);
         // B producer, MMA issuer, one per epilogue warp (kNorm: + four transform warps)
-        mbar_init(&wq_empty[s], 2 + (blockDim.x >= IGEMM_THREADS ? 8 : 4) + (kNorm ? 4 : 0));
+        mbar_init(&wq_empty[s], 2 + (blockDim.x >= IGEMM_THREADS ? 8 : 4) + (kNorm ? NORM_WARPS : 0));
       }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -564,6 +569,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     // ============================== TMA producer: A operand ==================================
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
+    uint32_t ka[2] = {0u, 0u};   // kNorm: waits done on a_empty[s] (this thread fills only the shortcut patches)
     WorkPub<kDyn> feed(args, w_first, w_step, wq_full, wq_empty, wq);
     for (int w = feed.next(); w >= 0; w = feed.next()) {
       const Work k = decode_work(args, w);
@@ -576,8 +582,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         for (int i = 0; i < k.nit; ++i) {
           if (kHalo) {
             if (kNorm) {
-              // the transform warps own the whole A ring (halo chunks AND the shortcut patches): a role that only watched
-              // a slot it does not fill could fall two phases behind, which a parity wait cannot tell from zero
+              // the transform warps fill the halo chunks, this thread the shortcut patches.  Each filler has its OWN
+              // "slot free" barrier per slot (a_empty[s] here, a_empty[2 + s] for the transform warps; the MMA issuer
+              // commits to the one whose owner fills the slot next): a role that merely watched a barrier it does not
+              // fill could fall two phases behind, which a parity wait cannot tell from zero
+              if (it.halo_it()) {
+                if (it.tap == 0) sa ^= 1;
+              } else {
+                mbar_wait(&a_empty[sa], ka[sa] & 1);
+                ++ka[sa];
+                mbar_expect_tx(&a_full[sa], k.nh * A_BYTES);
+                if (k.nh == kMT) {
+                  tma_load_4d(&mapA1, a_ring + sa * kHaloSlot, &a_full[sa], it.kc * TILE_K, w0, h0, n0);
+                  if (kMT == 2) tma_load_4d(&mapA1, a_ring + sa * kHaloSlot + A_BYTES, &a_full[sa], it.kc * TILE_K, w1, h1, n1);
+                } else {
+                  tma_load_4d(&mapA1, a_ring + sa * kHaloSlot, &a_full[sa], it.kc * TILE_K, k.half0 ? w1 : w0, k.half0 ? h1 : h0,
+                              k.half0 ? n1 : n0);
+                }
+                sa ^= 1;
+              }
             } else if (it.halo_it()) {
               if (it.tap == 0) {   // one halo per channel chunk
                 mbar_wait(&a_empty[sa], pa ^ 1);
@@ -721,6 +744,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       const uint32_t half_shift = (kMode == 0 && kHalo) ? (uint32_t)k.half0 : 0u;   // tail item: which half of the patch
       uint32_t lo_a = 0;
       int sa_cur = 0, tap = 0;
+      int upos = 0, upos_cur = 0;   // kNorm: A-ring uses of this item so far
+      const int n_uses = kHalo ? args.seg_kc[0] + (args.nseg > 1 ? args.seg_taps[1] * args.seg_kc[1] : 0) : 0;
       // wgrad work items (ci tile 0, first tap) also accumulate the bias gradient: A = dY tile, B = ones, N = 16
       const bool bias_item = kMode == 1 && args.dbias != nullptr && k.y0 == 0;
       const uint32_t idesc16 = (idesc & ~(0x3Fu << 17)) | ((16u >> 3) << 17);
@@ -731,6 +756,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         const bool halo_it = kHalo && i < n_halo;
         if (kHalo && (!halo_it || tap == 0)) {      // this iteration starts on a fresh A-ring slot
           sa_cur = sa;
+          upos_cur = upos++;
           mbar_wait(&a_full[sa], pa);
           lo_a = lo_halo0 + sa * (kHaloSlot >> 4);
           if (++sa == kASlots) { sa = 0; pa ^= 1; }
@@ -773,7 +799,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         }
         umma_commit(&b_empty[sb_cur]);
         if (kHalo) {
-          if (!halo_it || tap == args.seg_taps[0] - 1) umma_commit(&a_empty[sa_cur]);
+          if (!halo_it || tap == args.seg_taps[0] - 1) {
+            if (kNorm) {   // free the slot towards whoever fills it next (two uses on): a halo chunk -> the transform warps
+              const bool next_halo = upos_cur + 2 < args.seg_kc[0] || upos_cur + 2 >= n_uses;
+              umma_commit(&a_empty[(next_halo ? 2 : 0) + sa_cur]);
+            } else {
+              umma_commit(&a_empty[sa_cur]);
+            }
+          }
           if (halo_it && ++tap == args.seg_taps[0]) tap = 0;
         }
       }
@@ -782,137 +815,138 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
    }
   } else if (kNorm && warp >= 11) {
     // ============================== transform producers (kNorm): GroupNorm + SiLU on the way into the halo ==========
-    // 128 threads; thread t owns the 8-channel group t % 8 of 21 halo pixels (column t / 8 of every halo row, plus a share
-    // of the two right-hand columns).  The 21 sixteen-byte loads
+    // 256 threads; thread t owns the 8-channel group t % 8 of 11 halo pixels (column (t / 8) % 16 of every second halo row,
+    // plus a share of the two right-hand columns).  The sixteen-byte loads
     // of the NEXT halo chunk (next channel chunk, or chunk 0 of the next work item) are issued before this role waits
     // for its slot, so the memory latency hides behind the MMAs of the chunk in flight.
     if (kMode == 0 && kHalo && kMT == 2) {
-      const int tt = (int)threadIdx.x - IGEMM_THREADS;   // 0 .. 127
+      const int tt = (int)threadIdx.x - IGEMM_THREADS;   // 0 .. NORM_THREADS - 1
       const int c8 = tt & 7;
+      const int r0 = tt >> 3;                            // 0 .. 31
+      const int col = r0 & 15, rpar = r0 >> 4;           // pieces 0..8: halo pixel (2 u + rpar, col)
       const bf16_t* xin = reinterpret_cast<const bf16_t*>(args.a_raw);
-      constexpr int kRows = kHaloW * HALO2_H;            // 324 halo pixels, 8 sixteen-byte pieces each
-      constexpr int kPieces = (kRows * 8 + 127) / 128;   // 21 per thread
+      constexpr int kRowPieces = HALO2_H / 2;            // 9
+      constexpr int kPieces = kRowPieces + 2;            // + the two right-hand columns: 36 pixels over 32 + 4 threads
+      static_assert(MAX_A_SLOTS >= 4 && NORM_THREADS == 256 && HALO2_W == 18 && HALO2_H == 18, "piece mapping of the transform warps");
       const int KC = args.seg_kc[0];
-      const int n_sc = args.nseg > 1 ? args.seg_taps[1] * args.seg_kc[1] : 0;   // shortcut-segment slot uses per item (filled by warp 0)
+      const int n_sc = args.nseg > 1 ? args.seg_taps[1] * args.seg_kc[1] : 0;   // shortcut-segment slot uses per item
       uint4 v[kPieces];
       uint32_t inmask = 0;
       const int pitch_px = args.a_ld;                    // elements between horizontally adjacent pixels
       const int pitch_row = args.W * args.a_ld;          // ... vertically adjacent pixels (fits 32 bits: one image row)
-      auto issue = [&](int item, int kc) {
+      // halo pixel of piece u (row, column) -- compile-time u
+      auto piece_px = [&](int u, int& hy, int& hx) -> bool {
+        if (u < kRowPieces) { hy = 2 * u + rpar; hx = col; return true; }
+        const int pix = r0 + 32 * (u - kRowPieces);      // 0 .. 63, 36 used
+        hy = pix >> 1; hx = 16 + (pix & 1);
+        return pix < 36;
+      };
+      // per-thread constants of the whole kernel: element offset of every piece from the halo origin, and its byte
+      // offset inside a slot (128 B per halo pixel, 16-byte groups XOR-swizzled by pixel & 7 -- what TMA SWIZZLE_128B writes)
+      int rel[kPieces];
+      uint32_t sts[kPieces];
+#pragma unroll
+      for (int u = 0; u < kPieces; ++u) {
+        int hy, hx;
+        piece_px(u, hy, hx);
+        rel[u] = hy * pitch_row + hx * pitch_px + c8 * 8;
+        const int row = hy * kHaloW + hx;
+        sts[u] = (uint32_t)(row * 128) + (((uint32_t)c8 ^ (uint32_t)(row & 7)) << 4);
+      }
+      // per item: halo origin (element pointer, may lie outside the map: only in-bounds pieces are dereferenced), the
+      // in-bounds mask of this thread's pieces, the sample index (coefficients)
+      const bf16_t* nbase = xin;
+      uint32_t nmask = 0;
+      int n_next = 0;
+      auto locate = [&](int item) {
         const Work k = decode_work(args, item);
         int w0, h0, n0;
         tile_origin(args, kHalo, k.m_tile * kMT, w0, h0, n0);
-        // element (h0 - 1, w0 - 1) of the halo box: may lie outside the map, only in-bounds pixels are dereferenced
-        const bf16_t* base = xin + (((long long)n0 * args.H + (h0 - 1)) * args.W + (w0 - 1)) * (long long)args.a_ld + kc * TILE_K + c8 * 8;
-        inmask = 0;
-        const int gy0 = h0 - 1, gx0 = w0 - 1;
-        // pieces 0..17: halo pixel (u, tt / 8) -- columns 0..15 of halo row u; pieces 18..20: the two right-hand columns
-        // (36 pixels x 8 channel groups over the first 288 slots of 3 x 128).  Affine addresses, one bounds test per piece.
-        const bool col_ok = (unsigned)(gx0 + (tt >> 3)) < (unsigned)args.W;
-        const bf16_t* p = base + (tt >> 3) * pitch_px;
+        nbase = xin + (((long long)n0 * args.H + (h0 - 1)) * args.W + (w0 - 1)) * (long long)args.a_ld;
+        nmask = 0;
 #pragma unroll
-        for (int u = 0; u < 18; ++u) {
-          v[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (col_ok && (unsigned)(gy0 + u) < (unsigned)args.H) {
-            v[u] = __ldg(reinterpret_cast<const uint4*>(p + u * pitch_row));
-            inmask |= 1u << u;
-          }
+        for (int u = 0; u < kPieces; ++u) {
+          int hy, hx;
+          const bool used = piece_px(u, hy, hx);
+          if (used && (unsigned)(h0 - 1 + hy) < (unsigned)args.H && (unsigned)(w0 - 1 + hx) < (unsigned)args.W) nmask |= 1u << u;
         }
+        n_next = n0;
+      };
+      auto issue = [&](const bf16_t* base, uint32_t mask, int kc) {
+        const bf16_t* b = base + kc * TILE_K;
 #pragma unroll
-        for (int j = 0; j < kPieces - 18; ++j) {
-          const int pix = (tt >> 3) + 16 * j;              // 0..47, 36 used
-          const int hy = pix >> 1, hx = 16 + (pix & 1);
-          v[18 + j] = make_uint4(0u, 0u, 0u, 0u);
-          if (pix < 36 && (unsigned)(gy0 + hy) < (unsigned)args.H && (unsigned)(gx0 + hx) < (unsigned)args.W) {
-            v[18 + j] = __ldg(reinterpret_cast<const uint4*>(base + hy * pitch_row + hx * pitch_px));
-            inmask |= 1u << (18 + j);
+        for (int u = 0; u < kPieces; ++u)
+          if ((mask >> u) & 1u) {
+            // streamed once: no L1 allocation (L1 shares its SRAM bandwidth with the operand reads of the MMAs)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(b + rel[u]));
           }
-        }
-        return n0;
       };
       int sa = 0, wn = -1;
-      uint32_t pa = 0;
+      uint32_t kh[2] = {0u, 0u};                   // waits done on this role's "slot free" barrier a_empty[2 + s]
       WorkSub<kDyn> feed(args, w_first, w_step, wq_full, wq_empty, wq, true);
       int w = feed.next(wn);
       int n0 = 0;
+      const bf16_t* base = xin;
       int dbg_use = 0;
       (void)dbg_use;
-      if (w >= 0) n0 = issue(w, 0);
+      if (w >= 0) { locate(w); base = nbase; inmask = nmask; n0 = n_next; issue(base, inmask, 0); }
       while (w >= 0) {
         DBG(4, w);
+        if (wn >= 0) locate(wn);                     // the item after this one (its first chunk is prefetched below)
         for (int kc = 0; kc < KC; ++kc) {
           DBG(2, dbg_use++); DBG(3, 1);
-          float sc[8], sh[8];
+          // halved coefficients as f32x2 pairs: silu(z) = (z/2) (1 + tanh(z/2))
+          unsigned long long sc2[4], sh2[4];
           {
             const float4* cf = reinterpret_cast<const float4*>(args.gn_coef + ((long long)n0 * args.a_c + kc * TILE_K + c8 * 8) * 2);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 t = __ldg(cf + j);           // halved: silu(z) = (z/2) * (1 + tanh(z/2))
-              sc[2 * j] = 0.5f * t.x; sh[2 * j] = 0.5f * t.y; sc[2 * j + 1] = 0.5f * t.z; sh[2 * j + 1] = 0.5f * t.w;
+              const float4 t = __ldg(cf + j);           // {scale, shift} of channels 2j, 2j + 1
+              asm("mov.b64 %0, {%1, %2};" : "=l"(sc2[j]) : "f"(0.5f * t.x), "f"(0.5f * t.z));
+              asm("mov.b64 %0, {%1, %2};" : "=l"(sh2[j]) : "f"(0.5f * t.y), "f"(0.5f * t.w));
             }
           }
-          mbar_wait(&a_empty[sa], pa ^ 1);          // the MMAs that read this slot have retired
+          mbar_wait(&a_empty[2 + sa], (kh[sa] & 1u) ^ 1u);   // the MMAs that read this slot have retired
+          ++kh[sa];
           DBG(3, 2);
           uint8_t* slot = a_ring + sa * kHaloSlot;
 #pragma unroll
           for (int u = 0; u < kPieces; ++u) {
-            const int pix = (tt >> 3) + 16 * (u - 18);       // pieces 18..20 (see issue())
-            const int row = u < 18 ? u * kHaloW + (tt >> 3) : (pix >> 1) * kHaloW + 16 + (pix & 1);
-            if (u < 18 || pix < 36) {
-              uint4 o = make_uint4(0u, 0u, 0u, 0u);            // zero padding stays zero (the reference pads the NORMALISED map)
-              if ((inmask >> u) & 1u) {
-                const uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-                uint32_t ov[4];
+            int hy, hx;
+            if (piece_px(u, hy, hx)) {
+              const uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+              uint32_t ov[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float z0 = fmaf(__uint_as_float(wv[e] << 16), sc[2 * e], sh[2 * e]);          // z / 2
-                  float z1 = fmaf(__uint_as_float(wv[e] & 0xffff0000u), sc[2 * e + 1], sh[2 * e + 1]);
-                  float t0, t1;
-                  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(z0));
-                  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(z1));
-                  z0 = fmaf(z0, t0, z0);                         // silu(z) = z sigmoid(z) = (z/2) (1 + tanh(z/2))
-                  z1 = fmaf(z1, t1, z1);
-                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(z0, z1);
-                  ov[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                }
-                o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+              for (int e = 0; e < 4; ++e) {
+                unsigned long long x2, z2, r2;
+                float z0, z1, t0, t1;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "r"(wv[e] << 16), "r"(wv[e] & 0xffff0000u));
+                asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(z2) : "l"(x2), "l"(sc2[e]), "l"(sh2[e]));      // z / 2
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(z0), "=f"(z1) : "l"(z2));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(z0));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(z1));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "f"(t0), "f"(t1));
+                asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(r2) : "l"(z2), "l"(x2));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(z0), "=f"(z1) : "l"(r2));
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(z0, z1);
+                ov[e] = *reinterpret_cast<const uint32_t*>(&h2);
               }
-              *reinterpret_cast<uint4*>(slot + row * 128 + (((uint32_t)c8 ^ (uint32_t)(row & 7)) << 4)) = o;
+              const bool in = (inmask >> u) & 1u;              // zero padding stays zero (the reference pads the NORMALISED map)
+              *reinterpret_cast<uint4*>(slot + sts[u]) = make_uint4(in ? ov[0] : 0u, in ? ov[1] : 0u, in ? ov[2] : 0u, in ? ov[3] : 0u);
             }
           }
           fence_proxy_async();                      // generic-proxy stores -> visible to the tensor core (async proxy)
           DBG(3, 3);
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          asm volatile("bar.sync 2, %0;" ::"n"(NORM_THREADS) : "memory");
           if (tt == 0) mbar_arrive(&a_full[sa]);
-          if (++sa == kASlots) { sa = 0; pa ^= 1; }
+          sa ^= 1;
           // next chunk's loads fly while the MMAs of this one run
           DBG(3, 6);
-          if (kc + 1 < KC) issue(w, kc + 1);
-          else if (wn >= 0) n0 = issue(wn, 0);
+          if (kc + 1 < KC) issue(base, inmask, kc + 1);
+          else if (wn >= 0) { base = nbase; inmask = nmask; n0 = n_next; issue(base, inmask, 0); }
         }
-        if (n_sc > 0) {                              // fused 1x1 shortcut segment: plain patches in the same ring, by TMA
-          const Work k = decode_work(args, w);
-          int w0, h0, m0, w1, h1, m1;
-          tile_origin(args, kHalo, k.m_tile * kMT, w0, h0, m0);
-          tile_origin(args, kHalo, k.m_tile * kMT + 1, w1, h1, m1);
-          for (int i = 0; i < n_sc; ++i) {
-            DBG(2, dbg_use++); DBG(3, 4);
-            mbar_wait(&a_empty[sa], pa ^ 1);
-            asm volatile("bar.sync 2, 128;" ::: "memory");   // every thread has seen this phase before the slot can move on
-            if (tt == 0) {
-              const int kc = i % args.seg_kc[1];
-              mbar_expect_tx(&a_full[sa], k.nh * A_BYTES);
-              if (k.nh == kMT) {
-                tma_load_4d(&mapA1, a_ring + sa * kHaloSlot, &a_full[sa], kc * TILE_K, w0, h0, m0);
-                tma_load_4d(&mapA1, a_ring + sa * kHaloSlot + A_BYTES, &a_full[sa], kc * TILE_K, w1, h1, m1);
-              } else {
-                tma_load_4d(&mapA1, a_ring + sa * kHaloSlot, &a_full[sa], kc * TILE_K, k.half0 ? w1 : w0, k.half0 ? h1 : h0,
-                            k.half0 ? m1 : m0);
-              }
-            }
-            if (++sa == kASlots) { sa = 0; pa ^= 1; }
-          }
-        }
+        sa ^= n_sc & 1;                              // the shortcut patches (warp 0 loads them) take the next n_sc slots
         DBG(3, 5);
         w = feed.next(wn);
       }
@@ -1432,7 +1466,7 @@ static int launch_igemm(const CUtensorMap& mA0, const CUtensorMap& mB0, const CU
     if (cudaGetDevice(&dev) == cudaSuccess && dev == g_sched_dev) a.sched = sched_pair_for(stream);
   }
   const bool dyn = a.sched != nullptr;
-  if (a.gn_coef) {   // GroupNorm + SiLU folded into the operand path: eight epilogue + four transform warps (480 threads)
+  if (a.gn_coef) {   // GroupNorm + SiLU folded into the operand path: eight epilogue + eight transform warps (608 threads)
     if (a.qsum && dyn) launch_pdl(igemm_kernel<0, true, 2, true, true, true>, dim3(grid), dim3(IGEMM_THREADS_NORM), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
     else if (a.qsum) launch_pdl(igemm_kernel<0, true, 2, true, false, true>, dim3(grid), dim3(IGEMM_THREADS_NORM), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
     else if (dyn) launch_pdl(igemm_kernel<0, true, 2, false, true, true>, dim3(grid), dim3(IGEMM_THREADS_NORM), IGEMM_SMEM, st, mA0, mB0, mA1, mB1, mC, mD, a);
@@ -1643,8 +1677,10 @@ int mdm_conv_fprop(const mdm_conv_args* c, void* stream) {
   a.bias = c->bias; a.bias2 = c->bias2; a.rowvec = c->rowvec; a.ld_rowvec = c->ld_rowvec; a.rows_per_vec = c->H * c->W;
   a.out_f32 = c->y_f32;
   if (c->gn_coef) {
-    MDM_CHECK_ARG(c->ksize == 3 && c->stride == 1 && c->y && !c->y_f32 && !c->up2x && c->H % 16 == 0 && c->W % 16 == 0,
-                  "conv_fprop(gn_coef): 3x3 stride-1 layer with a bf16 output on a map that is a multiple of 16 x 16");
+    MDM_CHECK_ARG(c->ksize == 3 && c->stride == 1 && c->y && !c->y_f32 && !c->up2x && c->H % 16 == 0 && c->W % 16 == 0 &&
+                      c->cin % 64 == 0 && c->cin >= 128,
+                  "conv_fprop(gn_coef): 3x3 stride-1 layer with a bf16 output on a map that is a multiple of 16 x 16, cin a "
+                  "multiple of 64 and >= 128");
     a.gn_coef = c->gn_coef;
     a.a_raw = c->x;
     a.a_ld = c->ld_x;

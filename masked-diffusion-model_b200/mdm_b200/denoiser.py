@@ -1034,8 +1034,8 @@ class _Plan:
         fold_mode = int(os.environ.get("MDM_GN_FOLD", "1"))
         items = B * (H // 16) * (H // 16) * ((r.cout + 127) // 128) if H % 16 == 0 else 0
         fold_ok = (not ng) and win is None and fold_mode > 0 and H % 16 == 0 and (items >= 96 or fold_mode >= 2)
-        fold1 = fold_ok and q_in is not None and r.cin % 64 == 0
-        fold2 = fold_ok and q_h1 is not None
+        fold1 = fold_ok and q_in is not None and r.cin % 64 == 0 and r.cin >= 128
+        fold2 = fold_ok and q_h1 is not None and r.cout % 64 == 0 and r.cout >= 128
         coef1 = self.new((B, r.cin, 2), torch.float32) if fold1 else None
         coef2 = self.new((B, r.cout, 2), torch.float32) if fold2 else None
         fw = []

@@ -271,7 +271,11 @@ def test_fused_upsample_conv(N, H, cin):
 
 
 @pytest.mark.parametrize("N,H,cin,cout,shortcut,stats", [(2, 32, 128, 128, False, True), (3, 16, 256, 128, True, False),
-                                                         (1, 64, 128, 128, False, False), (2, 32, 384, 256, True, True)])
+                                                         (1, 64, 128, 128, False, False), (2, 32, 384, 256, True, True),
+                                                         # several work items per CTA (the operand ring wraps across items,
+                                                         # odd and even slot uses per item, two cout tiles, tail items)
+                                                         (20, 64, 256, 128, True, True), (40, 32, 128, 256, True, False),
+                                                         (160, 16, 256, 128, False, True)])
 def test_fprop_with_folded_groupnorm(N, H, cin, cout, shortcut, stats, monkeypatch):
     """inference: GroupNorm + SiLU of the input applied inside the convolution (transform warps fill the halo tiles with
     silu(x * scale + shift), zero outside the map) == the stand-alone apply pass followed by the convolution"""
