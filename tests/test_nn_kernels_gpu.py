@@ -22,7 +22,10 @@ def _nhwc_view(N, H, W, C, c_total=None, c_off=0, seed=0, scale=1.0):
     (4, 32, 128, None, 0, True), (3, 16, 256, 384, 128, True), (2, 8, 384, None, 0, True), (5, 4, 512, 1024, 512, False),
     (2, 2, 768, None, 0, True), (7, 1, 1024, None, 0, True), (2, 64, 128, 256, 0, True),
     # cluster-per-sample single-pass kernels: 16-CTA clusters (fwd 384 ch: ragged 5-pixel rows; bwd 256 ch)
-    (2, 32, 384, None, 0, True), (3, 32, 256, 512, 256, True), (150, 16, 128, None, 0, True)])
+    (2, 32, 384, None, 0, True), (3, 32, 256, 512, 256, True), (150, 16, 128, None, 0, True),
+    # training-batch small maps: a sample is split into channel slabs of whole groups (grid N x slabs), cpg 4 / 8 / 12 / 24
+    (128, 16, 128, None, 0, True), (128, 8, 256, 512, 256, True), (96, 8, 384, None, 0, True), (128, 4, 768, None, 0, False),
+    (128, 2, 512, 1024, 0, True)])
 def test_groupnorm_silu_fwd_bwd(N, H, C, c_total, c_off, silu, cluster_bwd, monkeypatch):
     from mdm_b200 import denoiser_ops as ops
     monkeypatch.setenv("MDM_GN_CLUSTER_BWD", cluster_bwd)
