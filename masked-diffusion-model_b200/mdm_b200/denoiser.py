@@ -925,7 +925,14 @@ class _Plan:
         store epilogues accumulate the statistics instead and the activation is read once"""
         if not self.fused_stats or HW % 128 != 0 or (C // G) % 4 != 0:
             return False
-        return ops.gn_fwd_kind(self.B, HW, C, G) == 2
+        kind = ops.gn_fwd_kind(self.B, HW, C, G)
+        if kind == 2:
+            return True
+        # inference: a medium map (one-pass cluster kernel) whose consumer convolution can fold the normalisation into its
+        # operand path (_emit_resnet) takes its statistics from the producers as well -- the GroupNorm pass disappears
+        H = math.isqrt(HW)
+        return (not self.need_grad and int(os.environ.get("MDM_GN_FOLD", "1")) > 0 and kind == 1 and H * H == HW and H % 16 == 0
+                and C % 64 == 0 and C >= 128)
 
     def _want_q(self, x):
         """mark the producers of x (both halves of a concatenation) to emit quad sums; False if one of them cannot"""
