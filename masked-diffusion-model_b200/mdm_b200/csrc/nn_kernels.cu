@@ -1555,68 +1555,125 @@ __global__ void __launch_bounds__(256, 2) attention_fwd_kernel(const bf16* __res
   }
 }
 
-__global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
-                                     int L, int C, float scale) {
+// Backward of the attention core, no atomics.  One CTA = HPC adjacent heads of one sample, one thread per (token, head).
+// q, k, v, dO of the CTA's heads live in shared memory as fp32 [token][head][8] (a warp reads 32-byte rows, the threads
+// of a warp that share a head read the same address).  Phase A (thread = query row): one pass for the softmax statistics
+// and the output row (D_i = dO_i . O_i), one pass for dq_i = sum_j ds_ij k_j with ds_ij = p_ij (dO_i . v_j - D_i) scale.
+// Phase B (thread = key row): dk_j = sum_i ds_ij q_i and dv_j = sum_i p_ij dO_i from the staged (m_i, 1 / l_i, D_i).
+// 72 FMAs + 3 exp2 per (query, key, head); round 1's kernel did 16 shared-memory float atomics (CAS loops) per pair.
+__global__ void __launch_bounds__(1024) attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                              bf16* __restrict__ dqkv, int L, int C, int HPC, float scale) {
   MDM_PDL_ENTER();
-  extern __shared__ float att_sm[];  // K, V, dK, dV : 4 * L * 8
+  extern __shared__ float att_sm[];  // K, V, Q, dO: T x 8 each; statistics: T x 4
+  const int T = L * HPC;
   float* Ks = att_sm;
-  float* Vs = Ks + L * ATT_D;
-  float* dKs = Vs + L * ATT_D;
-  float* dVs = dKs + L * ATT_D;
-  const int head = blockIdx.x, n = blockIdx.y;
-  const bf16* base = qkv + (long long)n * L * 3 * C + head * ATT_D;
-  for (int i = threadIdx.x; i < L * ATT_D; i += blockDim.x) {
-    const int j = i / ATT_D, d = i % ATT_D;
-    Ks[i] = __bfloat162float(base[(long long)j * 3 * C + C + d]);
-    Vs[i] = __bfloat162float(base[(long long)j * 3 * C + 2 * C + d]);
-    dKs[i] = 0.f;
-    dVs[i] = 0.f;
+  float* Vs = Ks + (size_t)T * ATT_D;
+  float* Qs = Vs + (size_t)T * ATT_D;
+  float* Gs = Qs + (size_t)T * ATT_D;
+  float4* St = reinterpret_cast<float4*>(Gs + (size_t)T * ATT_D);
+  const int t = threadIdx.x;
+  if (t >= T) return;                  // (no barrier below is reached by a partial CTA: blockDim.x == T)
+  const int h = t % HPC, i = t / HPC;
+  const int n = blockIdx.y;
+  const long long col = (long long)(blockIdx.x * HPC + h) * ATT_D;
+  const bf16* row = qkv + ((long long)n * L + i) * 3 * C + col;
+  float q[ATT_D], g[ATT_D];
+  {
+    float k[ATT_D], v[ATT_D];
+    unpack8(ldg16(row), q);
+    unpack8(ldg16(row + C), k);
+    unpack8(ldg16(row + 2 * C), v);
+    unpack8(ldg16(dout + ((long long)n * L + i) * C + col), g);
+    float4* d;
+    d = reinterpret_cast<float4*>(Ks + (size_t)t * ATT_D); d[0] = make_float4(k[0], k[1], k[2], k[3]); d[1] = make_float4(k[4], k[5], k[6], k[7]);
+    d = reinterpret_cast<float4*>(Vs + (size_t)t * ATT_D); d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
+    d = reinterpret_cast<float4*>(Qs + (size_t)t * ATT_D); d[0] = make_float4(q[0], q[1], q[2], q[3]); d[1] = make_float4(q[4], q[5], q[6], q[7]);
+    d = reinterpret_cast<float4*>(Gs + (size_t)t * ATT_D); d[0] = make_float4(g[0], g[1], g[2], g[3]); d[1] = make_float4(g[4], g[5], g[6], g[7]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < L; i += blockDim.x) {
-    float q[ATT_D], dO[ATT_D], dq[ATT_D];
-    for (int d = 0; d < ATT_D; ++d) {
-      q[d] = __bfloat162float(base[(long long)i * 3 * C + d]);
-      dO[d] = __bfloat162float(dout[((long long)n * L + i) * C + head * ATT_D + d]);
-      dq[d] = 0.f;
-    }
-    float m = -INFINITY, l = 0.f;
+  const float sl2 = scale * 1.4426950408889634f;   // scores in the exp2 domain
+  auto dot8 = [](const float (&a)[ATT_D], const float4& x, const float4& y) {
+    float r = a[0] * x.x;
+    r = fmaf(a[1], x.y, r); r = fmaf(a[2], x.z, r); r = fmaf(a[3], x.w, r);
+    r = fmaf(a[4], y.x, r); r = fmaf(a[5], y.y, r); r = fmaf(a[6], y.z, r); r = fmaf(a[7], y.w, r);
+    return r;
+  };
+  auto axpy8 = [](float (&acc)[ATT_D], float w, const float4& x, const float4& y) {
+    acc[0] = fmaf(w, x.x, acc[0]); acc[1] = fmaf(w, x.y, acc[1]); acc[2] = fmaf(w, x.z, acc[2]); acc[3] = fmaf(w, x.w, acc[3]);
+    acc[4] = fmaf(w, y.x, acc[4]); acc[5] = fmaf(w, y.y, acc[5]); acc[6] = fmaf(w, y.z, acc[6]); acc[7] = fmaf(w, y.w, acc[7]);
+  };
+  const float4* K4 = reinterpret_cast<const float4*>(Ks) + 2 * h;   // row j of this head: K4[2 j HPC], K4[2 j HPC + 1]
+  const float4* V4 = reinterpret_cast<const float4*>(Vs) + 2 * h;
+  const float4* Q4 = reinterpret_cast<const float4*>(Qs) + 2 * h;
+  const float4* G4 = reinterpret_cast<const float4*>(Gs) + 2 * h;
+  const int rs = 2 * HPC;              // float4 stride between tokens
+  // ---- phase A1: softmax statistics and D_i
+  float qs[ATT_D];
+#pragma unroll
+  for (int d = 0; d < ATT_D; ++d) qs[d] = q[d] * sl2;
+  float m = -INFINITY, l = 0.f, D;
+  {
+    float o[ATT_D];
+#pragma unroll
+    for (int d = 0; d < ATT_D; ++d) o[d] = 0.f;
+#pragma unroll 4
     for (int j = 0; j < L; ++j) {
-      float s = 0.f;
-      for (int d = 0; d < ATT_D; ++d) s += q[d] * Ks[j * ATT_D + d];
-      s *= scale;
-      const float mn = fmaxf(m, s);
-      l = l * __expf(m - mn) + __expf(s - mn);
-      m = mn;
-    }
-    const float inv = 1.0f / l;
-    float Di = 0.f;  // sum_j P_ij * (dO_i . v_j)
-    for (int j = 0; j < L; ++j) {
-      float s = 0.f, dp = 0.f;
-      for (int d = 0; d < ATT_D; ++d) { s += q[d] * Ks[j * ATT_D + d]; dp += dO[d] * Vs[j * ATT_D + d]; }
-      Di += __expf(s * scale - m) * inv * dp;
-    }
-    for (int jj = 0; jj < L; ++jj) {
-      const int j = (jj + i) % L;  // stagger to spread the shared-memory atomics
-      float s = 0.f, dp = 0.f;
-      for (int d = 0; d < ATT_D; ++d) { s += q[d] * Ks[j * ATT_D + d]; dp += dO[d] * Vs[j * ATT_D + d]; }
-      const float p = __expf(s * scale - m) * inv;
-      const float ds = p * (dp - Di) * scale;
-      for (int d = 0; d < ATT_D; ++d) {
-        dq[d] += ds * Ks[j * ATT_D + d];
-        atomicAdd(&dKs[j * ATT_D + d], ds * q[d]);
-        atomicAdd(&dVs[j * ATT_D + d], p * dO[d]);
+      const float sc = dot8(qs, K4[j * rs], K4[j * rs + 1]);
+      if (sc > m) {                    // rare after the first keys
+        const float corr = exp2f(m - sc);
+        l *= corr;
+#pragma unroll
+        for (int d = 0; d < ATT_D; ++d) o[d] *= corr;
+        m = sc;
       }
+      const float pj = exp2f(sc - m);
+      l += pj;
+      axpy8(o, pj, V4[j * rs], V4[j * rs + 1]);
     }
-    bf16* o = dqkv + ((long long)n * L + i) * 3 * C + head * ATT_D;
-    for (int d = 0; d < ATT_D; ++d) o[d] = __float2bfloat16(dq[d]);
+    float dd = 0.f;
+#pragma unroll
+    for (int d = 0; d < ATT_D; ++d) dd = fmaf(g[d], o[d], dd);
+    D = dd / l;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < L * ATT_D; i += blockDim.x) {
-    const int j = i / ATT_D, d = i % ATT_D;
-    bf16* o = dqkv + ((long long)n * L + j) * 3 * C + head * ATT_D;
-    o[C + d] = __float2bfloat16(dKs[i]);
-    o[2 * C + d] = __float2bfloat16(dVs[i]);
+  const float inv = 1.0f / l;
+  St[t] = make_float4(m, inv, D, 0.f);
+  // ---- phase A2: dq
+  {
+    float dq[ATT_D];
+#pragma unroll
+    for (int d = 0; d < ATT_D; ++d) dq[d] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < L; ++j) {
+      const float4 ka = K4[j * rs], kb = K4[j * rs + 1];
+      const float pj = exp2f(dot8(qs, ka, kb) - m) * inv;
+      const float dp = dot8(g, V4[j * rs], V4[j * rs + 1]);
+      axpy8(dq, pj * (dp - D) * scale, ka, kb);
+    }
+    *reinterpret_cast<uint4*>(dqkv + ((long long)n * L + i) * 3 * C + col) = pack8(dq);
+  }
+  __syncthreads();                     // every row's statistics are staged
+  // ---- phase B: this thread's token as a KEY row
+  {
+    float k[ATT_D], v[ATT_D], dk[ATT_D], dv[ATT_D];
+    {
+      const float4 ka = K4[i * rs], kb = K4[i * rs + 1], va = V4[i * rs], vb = V4[i * rs + 1];
+      k[0] = ka.x * sl2; k[1] = ka.y * sl2; k[2] = ka.z * sl2; k[3] = ka.w * sl2; k[4] = kb.x * sl2; k[5] = kb.y * sl2; k[6] = kb.z * sl2; k[7] = kb.w * sl2;
+      v[0] = va.x; v[1] = va.y; v[2] = va.z; v[3] = va.w; v[4] = vb.x; v[5] = vb.y; v[6] = vb.z; v[7] = vb.w;
+    }
+#pragma unroll
+    for (int d = 0; d < ATT_D; ++d) dk[d] = dv[d] = 0.f;
+#pragma unroll 4
+    for (int ii = 0; ii < L; ++ii) {
+      const float4 qa = Q4[ii * rs], qb = Q4[ii * rs + 1], ga = G4[ii * rs], gb = G4[ii * rs + 1];
+      const float4 st = St[ii * HPC + h];
+      const float pj = exp2f(dot8(k, qa, qb) - st.x) * st.y;
+      const float dp = dot8(v, ga, gb);
+      axpy8(dk, pj * (dp - st.z) * scale, qa, qb);
+      axpy8(dv, pj, ga, gb);
+    }
+    bf16* o = dqkv + ((long long)n * L + i) * 3 * C + col;
+    *reinterpret_cast<uint4*>(o + C) = pack8(dk);
+    *reinterpret_cast<uint4*>(o + 2 * C) = pack8(dv);
   }
 }
 
@@ -2032,15 +2089,25 @@ int mdm_attention_fwd(const void* qkv, void* out, int N, int L, int C, void* str
 
 int mdm_attention_bwd(const void* qkv, const void* dout, void* dqkv, int N, int L, int C, void* stream) {
   MDM_CHECK_ARG(qkv && dout && dqkv && C % ATT_D == 0 && L >= 1 && L <= 1024, "attention_bwd: bad arguments");
-  const int th = L < 32 ? 32 : (L > 256 ? 256 : ((L + 31) / 32) * 32);
-  const size_t smem = (size_t)4 * L * ATT_D * sizeof(float);
+  MDM_CHECK_ARG(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)dout % 16 == 0) && ((uintptr_t)dqkv % 16 == 0), "attention_bwd: pointers must be 16-byte aligned");
+  const int heads = C / ATT_D;
+  // heads per CTA: one thread per (token, head), at most 1024; few heads per CTA on long sequences (the rows of a warp
+  // that share a head share their shared-memory reads), many on short ones (enough threads per CTA)
+  int hpc = 1024 / L;
+  const int want = L >= 32 ? 8 : 64;
+  if (hpc > want) hpc = want;
+  if (hpc > heads) hpc = heads;
+  if (hpc < 1) hpc = 1;
+  while (heads % hpc != 0) --hpc;
+  const int th = L * hpc;
+  const size_t smem = (size_t)th * (4 * ATT_D + 4) * sizeof(float);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     MDM_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  dim3 grid(C / ATT_D, N);
-  launch_pdl(attention_bwd_kernel, dim3(grid), dim3(th), smem, as_stream(stream), (const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, L, C, 1.0f / sqrtf((float)ATT_D));
+  dim3 grid(heads / hpc, N);
+  launch_pdl(attention_bwd_kernel, dim3(grid), dim3(th), smem, as_stream(stream), (const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, L, C, hpc, 1.0f / sqrtf((float)ATT_D));
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }

@@ -11,9 +11,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=128); ap.add_argument("--size", type=int, default=32)
 ap.add_argument("--channels", type=int, default=3); ap.add_argument("--method", default="base")
 ap.add_argument("--out", default="gpurun_out/ops_profile.json")
+ap.add_argument("--base", type=int, default=128, help="block_out_channels base (256 = BASELINE configs[4])")
 pa = ap.parse_args()
 a = argparse.Namespace(batch=pa.batch, size=pa.size, channels=pa.channels, method=pa.method, no_graph=True)
-tr, model, acc = bench.build_trainer(a, bench.workload_args(a))
+tr, model, acc = bench.build_trainer(a, bench.workload_args(a), base=pa.base)
 model.wgrad_side_stream = False      # serialise the weight-gradient GEMMs with the main chain: one kernel at a time under every event pair
 dev = torch.device("cuda", 0)
 x = (torch.rand(pa.batch, pa.channels, pa.size, pa.size) * 2 - 1).to(dev)

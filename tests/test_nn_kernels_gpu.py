@@ -112,7 +112,8 @@ def test_upsample_and_adjoint():
     assert torch.allclose(dx.float(), want_dx, atol=3e-2, rtol=1e-2)
 
 
-@pytest.mark.parametrize("N,L,C", [(4, 4, 512), (2, 16, 512), (3, 64, 512), (2, 256, 512), (2, 1, 512)])
+@pytest.mark.parametrize("N,L,C", [(4, 4, 512), (2, 16, 512), (3, 64, 512), (2, 256, 512), (2, 1, 512),
+                                   (8, 256, 1024), (2, 1024, 64), (128, 4, 512), (3, 64, 24)])
 def test_attention_core(N, L, C):
     from mdm_b200 import denoiser_ops as ops
     g = torch.Generator(device="cuda").manual_seed(11)
