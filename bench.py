@@ -536,7 +536,13 @@ def micro_kernels(dev, peaks):
         e = entry(Bt * L * Ca * 2 * 4, ms, f"{Bt} x {L} tokens x {Ca} channels ({Ca // 8} heads of 8), bf16: read q,k,v, write out")
         e["tflops"] = round(4.0 * Bt * L * L * Ca / (ms * 1e-3) / 1e12, 2)
         out[f"K4_attention_fwd_{tag}"] = e
-        del qkv, att
+        # backward of the core: read q,k,v + dO, write dq,dk,dv; 72 FMAs per (query, key, head) = 18 B L^2 C flops
+        dqkv = torch.empty_like(qkv)
+        ms = timeit(lambda: ops.attention_bwd(qkv, att, dqkv, Bt, L, Ca))
+        e = entry(Bt * L * Ca * 2 * 7, ms, f"{Bt} x {L} tokens x {Ca} channels, bf16: read q,k,v,dO, write dq,dk,dv")
+        e["tflops"] = round(18.0 * Bt * L * L * Ca / (ms * 1e-3) / 1e12, 2)
+        out[f"K4_attention_bwd_{tag}"] = e
+        del qkv, att, dqkv
     # first / last convolution (3 image channels) at the configs[3] shape
     img = torch.rand(B, C, S, S, device=dev)
     g_in = torch.zeros(B, S, S, 64, device=dev, dtype=torch.bfloat16)
