@@ -209,7 +209,8 @@ typedef struct mdm_conv_args {
   const float* gn_coef; /* fprop only (inference): GroupNorm + SiLU of the INPUT folded into the operand path.  x is then the
                          * RAW activation and coef[n][cin][2] = (scale, shift) per sample and channel (mdm_gn_coef_q): the
                          * kernel computes silu(x * scale + shift) while it fills its halo tiles, zero outside the map
-                         * -- the normalised activation is never written.  3x3, stride 1, H and W multiples of 16. */
+                         * -- the normalised activation is never written.  3x3, stride 1, H and W multiples of 16, cin a multiple of
+                         * 64 and >= 128.  Reference site: models/unet/unet6.py:358-360 (norm -> act -> conv). */
 } mdm_conv_args;
 
 /* (scale, shift) table of a GroupNorm site from the quad sums its producers' epilogues accumulated (mdm_conv_args.qsum):
