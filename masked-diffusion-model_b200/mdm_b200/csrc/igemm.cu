@@ -107,10 +107,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: a pipeline bug traps (launch fails) instead of hanging the GPU
+// bounded wait: a pipeline bug traps (launch fails) instead of hanging the GPU.
+// Debug build (MDM_NVCC_DEFINES=MDM_IGEMM_DEBUG_WAIT python mdm_b200/build.py): the first wait that times out prints
+// which barrier (shared-memory address, see the BARS line) and parity it was waiting for and where the transform warps
+// of its CTA stood, then every other wait in the grid gives up, so the kernel ends and the printf buffer is flushed --
+// how the two-phase aliasing of the operand ring was found.
 #ifdef MDM_IGEMM_DEBUG_WAIT
 __device__ int g_wait_abort;
-__shared__ volatile int g_dbg[8];
+__shared__ volatile int g_dbg[4];      // transform warps: {ring use, stage, work item}
 #define DBG(i, v) g_dbg[i] = (v)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -118,8 +122,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (*(volatile int*)&g_wait_abort) return;
     if (clock64() - t0 > 400000000LL) {
-      printf("WAIT TIMEOUT block %d thread %d bar 0x%x parity %u | w0 use %d mma use %d tr use %d stage %d item %d\n", blockIdx.x, threadIdx.x,
-             smem_u32(bar), parity, g_dbg[0], g_dbg[1], g_dbg[2], g_dbg[3], g_dbg[4]);
+      printf("WAIT TIMEOUT block %d thread %d bar 0x%x parity %u | transform: use %d stage %d item %d\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity, g_dbg[0], g_dbg[1], g_dbg[2]);
       atomicExch(&g_wait_abort, 1);
       return;
     }
@@ -892,10 +896,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       (void)dbg_use;
       if (w >= 0) { locate(w); base = nbase; inmask = nmask; n0 = n_next; issue(base, inmask, 0); }
       while (w >= 0) {
-        DBG(4, w);
+        DBG(2, w);
         if (wn >= 0) locate(wn);                     // the item after this one (its first chunk is prefetched below)
         for (int kc = 0; kc < KC; ++kc) {
-          DBG(2, dbg_use++); DBG(3, 1);
+          DBG(0, dbg_use++); DBG(1, 1);
           // halved coefficients as f32x2 pairs: silu(z) = (z/2) (1 + tanh(z/2))
           unsigned long long sc2[4], sh2[4];
           {
@@ -909,7 +913,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           }
           mbar_wait(&a_empty[2 + sa], (kh[sa] & 1u) ^ 1u);   // the MMAs that read this slot have retired
           ++kh[sa];
-          DBG(3, 2);
+          DBG(1, 2);
           uint8_t* slot = a_ring + sa * kHaloSlot;
 #pragma unroll
           for (int u = 0; u < kPieces; ++u) {
@@ -937,20 +941,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             }
           }
           fence_proxy_async();                      // generic-proxy stores -> visible to the tensor core (async proxy)
-          DBG(3, 3);
+          DBG(1, 3);
           asm volatile("bar.sync 2, %0;" ::"n"(NORM_THREADS) : "memory");
           if (tt == 0) mbar_arrive(&a_full[sa]);
           sa ^= 1;
           // next chunk's loads fly while the MMAs of this one run
-          DBG(3, 6);
+          DBG(1, 4);
           if (kc + 1 < KC) issue(base, inmask, kc + 1);
           else if (wn >= 0) { base = nbase; inmask = nmask; n0 = n_next; issue(base, inmask, 0); }
         }
         sa ^= n_sc & 1;                              // the shortcut patches (warp 0 loads them) take the next n_sc slots
-        DBG(3, 5);
+        DBG(1, 5);
         w = feed.next(wn);
       }
-      DBG(3, 7);
+      DBG(1, 6);
     }
   } else if ((warp >= 2 && warp <= 5) || (warp >= 7 && warp <= 10)) {
     // ============================== epilogue ==================================================
