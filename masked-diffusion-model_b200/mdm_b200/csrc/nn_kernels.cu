@@ -1555,48 +1555,54 @@ __global__ void __launch_bounds__(256, 2) attention_fwd_kernel(const bf16* __res
   }
 }
 
-// Backward of the attention core, no atomics.  One CTA = HPC adjacent heads of one sample, one thread per (token, head).
-// q, k, v, dO of the CTA's heads live in shared memory as fp32 [token][head][8] (a warp reads 32-byte rows, the threads
-// of a warp that share a head read the same address).  Phase A (thread = query row): one pass for the softmax statistics
-// and the output row (D_i = dO_i . O_i), one pass for dq_i = sum_j ds_ij k_j with ds_ij = p_ij (dO_i . v_j - D_i) scale.
-// Phase B (thread = key row): dk_j = sum_i ds_ij q_i and dv_j = sum_i p_ij dO_i from the staged (m_i, 1 / l_i, D_i).
-// 72 FMAs + 3 exp2 per (query, key, head); round 1's kernel did 16 shared-memory float atomics (CAS loops) per pair.
-__global__ void __launch_bounds__(1024) attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
-                                                              bf16* __restrict__ dqkv, int L, int C, int HPC, float scale) {
+// Backward of the attention core, no atomics.  One CTA = HPC adjacent heads of one sample; q, k, v, dO of the CTA's heads
+// live in shared memory as fp32 [token][head][8] (a warp reads 32-byte rows, the threads of a warp that share a head
+// read the same address).  A thread owns QPT (token, head) rows -- tokens i, i + L / QPT, ... -- so every staged row it
+// reads feeds QPT rows of arithmetic (the first version, one row per thread, waited on shared memory: ncu short-scoreboard
+// stall 14.9 per issue).  Phase A (rows as QUERIES): one pass for the softmax statistics and the output row
+// (D_i = dO_i . O_i), one pass for dq_i = sum_j ds_ij k_j with ds_ij = p_ij (dO_i . v_j - D_i) scale.  Phase B (rows as
+// KEYS): dk_j = sum_i ds_ij q_i and dv_j = sum_i p_ij dO_i from the staged (m_i, 1 / l_i, D_i).  72 FMAs + 3 exp2 per
+// (query, key, head); round 1's kernel did 16 shared-memory float atomics (CAS loops) per pair.
+template <int QPT>
+__global__ void __launch_bounds__(1024 / QPT) attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                                    bf16* __restrict__ dqkv, int L, int C, int HPC, float scale) {
   MDM_PDL_ENTER();
   extern __shared__ float att_sm[];  // K, V, Q, dO: T x 8 each; statistics: T x 4
-  const int T = L * HPC;
+  const int T = L * HPC;             // rows of this CTA; blockDim.x == T / QPT
   float* Ks = att_sm;
   float* Vs = Ks + (size_t)T * ATT_D;
   float* Qs = Vs + (size_t)T * ATT_D;
   float* Gs = Qs + (size_t)T * ATT_D;
   float4* St = reinterpret_cast<float4*>(Gs + (size_t)T * ATT_D);
   const int t = threadIdx.x;
-  if (t >= T) return;                  // (no barrier below is reached by a partial CTA: blockDim.x == T)
-  const int h = t % HPC, i = t / HPC;
+  const int h = t % HPC, i0 = t / HPC, istep = L / QPT;   // this thread's tokens: i0 + a * istep
   const int n = blockIdx.y;
   const long long col = (long long)(blockIdx.x * HPC + h) * ATT_D;
-  const bf16* row = qkv + ((long long)n * L + i) * 3 * C + col;
-  float q[ATT_D], g[ATT_D];
-  {
+  float q[QPT][ATT_D], g[QPT][ATT_D];
+#pragma unroll
+  for (int a = 0; a < QPT; ++a) {
+    const int i = i0 + a * istep;
+    const int r = i * HPC + h;
+    const bf16* row = qkv + ((long long)n * L + i) * 3 * C + col;
     float k[ATT_D], v[ATT_D];
-    unpack8(ldg16(row), q);
+    unpack8(ldg16(row), q[a]);
     unpack8(ldg16(row + C), k);
     unpack8(ldg16(row + 2 * C), v);
-    unpack8(ldg16(dout + ((long long)n * L + i) * C + col), g);
+    unpack8(ldg16(dout + ((long long)n * L + i) * C + col), g[a]);
     float4* d;
-    d = reinterpret_cast<float4*>(Ks + (size_t)t * ATT_D); d[0] = make_float4(k[0], k[1], k[2], k[3]); d[1] = make_float4(k[4], k[5], k[6], k[7]);
-    d = reinterpret_cast<float4*>(Vs + (size_t)t * ATT_D); d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
-    d = reinterpret_cast<float4*>(Qs + (size_t)t * ATT_D); d[0] = make_float4(q[0], q[1], q[2], q[3]); d[1] = make_float4(q[4], q[5], q[6], q[7]);
-    d = reinterpret_cast<float4*>(Gs + (size_t)t * ATT_D); d[0] = make_float4(g[0], g[1], g[2], g[3]); d[1] = make_float4(g[4], g[5], g[6], g[7]);
+    d = reinterpret_cast<float4*>(Ks + (size_t)r * ATT_D); d[0] = make_float4(k[0], k[1], k[2], k[3]); d[1] = make_float4(k[4], k[5], k[6], k[7]);
+    d = reinterpret_cast<float4*>(Vs + (size_t)r * ATT_D); d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
+    d = reinterpret_cast<float4*>(Qs + (size_t)r * ATT_D); d[0] = make_float4(q[a][0], q[a][1], q[a][2], q[a][3]); d[1] = make_float4(q[a][4], q[a][5], q[a][6], q[a][7]);
+    d = reinterpret_cast<float4*>(Gs + (size_t)r * ATT_D); d[0] = make_float4(g[a][0], g[a][1], g[a][2], g[a][3]); d[1] = make_float4(g[a][4], g[a][5], g[a][6], g[a][7]);
   }
   __syncthreads();
   const float sl2 = scale * 1.4426950408889634f;   // scores in the exp2 domain
-  auto dot8 = [](const float (&a)[ATT_D], const float4& x, const float4& y) {
-    float r = a[0] * x.x;
-    r = fmaf(a[1], x.y, r); r = fmaf(a[2], x.z, r); r = fmaf(a[3], x.w, r);
-    r = fmaf(a[4], y.x, r); r = fmaf(a[5], y.y, r); r = fmaf(a[6], y.z, r); r = fmaf(a[7], y.w, r);
-    return r;
+  auto dot8 = [](const float (&a)[ATT_D], const float4& x, const float4& y) {   // two chains of four
+    float r0 = a[0] * x.x, r1 = a[4] * y.x;
+    r0 = fmaf(a[1], x.y, r0); r1 = fmaf(a[5], y.y, r1);
+    r0 = fmaf(a[2], x.z, r0); r1 = fmaf(a[6], y.z, r1);
+    r0 = fmaf(a[3], x.w, r0); r1 = fmaf(a[7], y.w, r1);
+    return r0 + r1;
   };
   auto axpy8 = [](float (&acc)[ATT_D], float w, const float4& x, const float4& y) {
     acc[0] = fmaf(w, x.x, acc[0]); acc[1] = fmaf(w, x.y, acc[1]); acc[2] = fmaf(w, x.z, acc[2]); acc[3] = fmaf(w, x.w, acc[3]);
@@ -1608,72 +1614,102 @@ __global__ void __launch_bounds__(1024) attention_bwd_kernel(const bf16* __restr
   const float4* G4 = reinterpret_cast<const float4*>(Gs) + 2 * h;
   const int rs = 2 * HPC;              // float4 stride between tokens
   // ---- phase A1: softmax statistics and D_i
-  float qs[ATT_D];
+  float m[QPT], inv[QPT], D[QPT];
 #pragma unroll
-  for (int d = 0; d < ATT_D; ++d) qs[d] = q[d] * sl2;
-  float m = -INFINITY, l = 0.f, D;
-  {
-    float o[ATT_D];
+  for (int a = 0; a < QPT; ++a) {
+    m[a] = -INFINITY;
 #pragma unroll
-    for (int d = 0; d < ATT_D; ++d) o[d] = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < L; ++j) {
-      const float sc = dot8(qs, K4[j * rs], K4[j * rs + 1]);
-      if (sc > m) {                    // rare after the first keys
-        const float corr = exp2f(m - sc);
-        l *= corr;
-#pragma unroll
-        for (int d = 0; d < ATT_D; ++d) o[d] *= corr;
-        m = sc;
-      }
-      const float pj = exp2f(sc - m);
-      l += pj;
-      axpy8(o, pj, V4[j * rs], V4[j * rs + 1]);
-    }
-    float dd = 0.f;
-#pragma unroll
-    for (int d = 0; d < ATT_D; ++d) dd = fmaf(g[d], o[d], dd);
-    D = dd / l;
+    for (int d = 0; d < ATT_D; ++d) q[a][d] *= sl2;
   }
-  const float inv = 1.0f / l;
-  St[t] = make_float4(m, inv, D, 0.f);
+  {
+    float l[QPT], o[QPT][ATT_D];
+#pragma unroll
+    for (int a = 0; a < QPT; ++a) {
+      l[a] = 0.f;
+#pragma unroll
+      for (int d = 0; d < ATT_D; ++d) o[a][d] = 0.f;
+    }
+#pragma unroll 2
+    for (int j = 0; j < L; ++j) {
+      const float4 ka = K4[j * rs], kb = K4[j * rs + 1], va = V4[j * rs], vb = V4[j * rs + 1];
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) {
+        const float sc = dot8(q[a], ka, kb);
+        if (sc > m[a]) {               // rare after the first keys
+          const float corr = exp2f(m[a] - sc);
+          l[a] *= corr;
+#pragma unroll
+          for (int d = 0; d < ATT_D; ++d) o[a][d] *= corr;
+          m[a] = sc;
+        }
+        const float pj = exp2f(sc - m[a]);
+        l[a] += pj;
+        axpy8(o[a], pj, va, vb);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < QPT; ++a) {
+      float dd = 0.f;
+#pragma unroll
+      for (int d = 0; d < ATT_D; ++d) dd = fmaf(g[a][d], o[a][d], dd);
+      inv[a] = 1.0f / l[a];
+      D[a] = dd * inv[a];
+      St[(i0 + a * istep) * HPC + h] = make_float4(m[a], inv[a], D[a], 0.f);
+    }
+  }
   // ---- phase A2: dq
   {
-    float dq[ATT_D];
+    float dq[QPT][ATT_D];
 #pragma unroll
-    for (int d = 0; d < ATT_D; ++d) dq[d] = 0.f;
-#pragma unroll 4
+    for (int a = 0; a < QPT; ++a)
+#pragma unroll
+      for (int d = 0; d < ATT_D; ++d) dq[a][d] = 0.f;
+#pragma unroll 2
     for (int j = 0; j < L; ++j) {
-      const float4 ka = K4[j * rs], kb = K4[j * rs + 1];
-      const float pj = exp2f(dot8(qs, ka, kb) - m) * inv;
-      const float dp = dot8(g, V4[j * rs], V4[j * rs + 1]);
-      axpy8(dq, pj * (dp - D) * scale, ka, kb);
+      const float4 ka = K4[j * rs], kb = K4[j * rs + 1], va = V4[j * rs], vb = V4[j * rs + 1];
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) {
+        const float pj = exp2f(dot8(q[a], ka, kb) - m[a]) * inv[a];
+        const float dp = dot8(g[a], va, vb);
+        axpy8(dq[a], pj * (dp - D[a]) * scale, ka, kb);
+      }
     }
-    *reinterpret_cast<uint4*>(dqkv + ((long long)n * L + i) * 3 * C + col) = pack8(dq);
+#pragma unroll
+    for (int a = 0; a < QPT; ++a)
+      *reinterpret_cast<uint4*>(dqkv + ((long long)n * L + i0 + a * istep) * 3 * C + col) = pack8(dq[a]);
   }
   __syncthreads();                     // every row's statistics are staged
-  // ---- phase B: this thread's token as a KEY row
+  // ---- phase B: this thread's tokens as KEY rows (q / g registers are reused for k * sl2 / v)
   {
-    float k[ATT_D], v[ATT_D], dk[ATT_D], dv[ATT_D];
-    {
-      const float4 ka = K4[i * rs], kb = K4[i * rs + 1], va = V4[i * rs], vb = V4[i * rs + 1];
-      k[0] = ka.x * sl2; k[1] = ka.y * sl2; k[2] = ka.z * sl2; k[3] = ka.w * sl2; k[4] = kb.x * sl2; k[5] = kb.y * sl2; k[6] = kb.z * sl2; k[7] = kb.w * sl2;
-      v[0] = va.x; v[1] = va.y; v[2] = va.z; v[3] = va.w; v[4] = vb.x; v[5] = vb.y; v[6] = vb.z; v[7] = vb.w;
-    }
+    float dk[QPT][ATT_D], dv[QPT][ATT_D];
 #pragma unroll
-    for (int d = 0; d < ATT_D; ++d) dk[d] = dv[d] = 0.f;
-#pragma unroll 4
+    for (int a = 0; a < QPT; ++a) {
+      const int i = i0 + a * istep;
+      const float4 ka = K4[i * rs], kb = K4[i * rs + 1], va = V4[i * rs], vb = V4[i * rs + 1];
+      q[a][0] = ka.x * sl2; q[a][1] = ka.y * sl2; q[a][2] = ka.z * sl2; q[a][3] = ka.w * sl2;
+      q[a][4] = kb.x * sl2; q[a][5] = kb.y * sl2; q[a][6] = kb.z * sl2; q[a][7] = kb.w * sl2;
+      g[a][0] = va.x; g[a][1] = va.y; g[a][2] = va.z; g[a][3] = va.w; g[a][4] = vb.x; g[a][5] = vb.y; g[a][6] = vb.z; g[a][7] = vb.w;
+#pragma unroll
+      for (int d = 0; d < ATT_D; ++d) dk[a][d] = dv[a][d] = 0.f;
+    }
+#pragma unroll 2
     for (int ii = 0; ii < L; ++ii) {
       const float4 qa = Q4[ii * rs], qb = Q4[ii * rs + 1], ga = G4[ii * rs], gb = G4[ii * rs + 1];
       const float4 st = St[ii * HPC + h];
-      const float pj = exp2f(dot8(k, qa, qb) - st.x) * st.y;
-      const float dp = dot8(v, ga, gb);
-      axpy8(dk, pj * (dp - st.z) * scale, qa, qb);
-      axpy8(dv, pj, ga, gb);
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) {
+        const float pj = exp2f(dot8(q[a], qa, qb) - st.x) * st.y;
+        const float dp = dot8(g[a], ga, gb);
+        axpy8(dk[a], pj * (dp - st.z) * scale, qa, qb);
+        axpy8(dv[a], pj, ga, gb);
+      }
     }
-    bf16* o = dqkv + ((long long)n * L + i) * 3 * C + col;
-    *reinterpret_cast<uint4*>(o + C) = pack8(dk);
-    *reinterpret_cast<uint4*>(o + 2 * C) = pack8(dv);
+#pragma unroll
+    for (int a = 0; a < QPT; ++a) {
+      bf16* o = dqkv + ((long long)n * L + i0 + a * istep) * 3 * C + col;
+      *reinterpret_cast<uint4*>(o + C) = pack8(dk[a]);
+      *reinterpret_cast<uint4*>(o + 2 * C) = pack8(dv[a]);
+    }
   }
 }
 
@@ -2099,15 +2135,19 @@ int mdm_attention_bwd(const void* qkv, const void* dout, void* dqkv, int N, int 
   if (hpc > heads) hpc = heads;
   if (hpc < 1) hpc = 1;
   while (heads % hpc != 0) --hpc;
-  const int th = L * hpc;
-  const size_t smem = (size_t)th * (4 * ATT_D + 4) * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    MDM_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  const int rows = L * hpc;
+  const int qpt = (L % 2 == 0 && rows >= 128) ? 2 : 1;    // rows per thread
+  const size_t smem = (size_t)rows * (4 * ATT_D + 4) * sizeof(float);
+  static size_t smem_set[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > smem_set[qpt - 1]) {
+    if (qpt == 2) MDM_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else MDM_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[qpt - 1] = smem;
   }
   dim3 grid(heads / hpc, N);
-  launch_pdl(attention_bwd_kernel, dim3(grid), dim3(th), smem, as_stream(stream), (const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, L, C, hpc, 1.0f / sqrtf((float)ATT_D));
+  const float sc = 1.0f / sqrtf((float)ATT_D);
+  if (qpt == 2) launch_pdl(attention_bwd_kernel<2>, dim3(grid), dim3(rows / 2), smem, as_stream(stream), (const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, L, C, hpc, sc);
+  else launch_pdl(attention_bwd_kernel<1>, dim3(grid), dim3(rows), smem, as_stream(stream), (const bf16*)qkv, (const bf16*)dout, (bf16*)dqkv, L, C, hpc, sc);
   MDM_LAUNCH_CHECK();
   return MDM_OK;
 }
