@@ -931,8 +931,12 @@ class _Plan:
         # inference: a medium map (one-pass cluster kernel) whose consumer convolution can fold the normalisation into its
         # operand path (_emit_resnet) takes its statistics from the producers as well -- the GroupNorm pass disappears
         H = math.isqrt(HW)
-        return (not self.need_grad and int(os.environ.get("MDM_GN_FOLD", "1")) > 0 and kind == 1 and H * H == HW and H % 16 == 0
-                and C % 64 == 0 and C >= 128)
+        if (not self.need_grad and int(os.environ.get("MDM_GN_FOLD", "1")) > 0 and kind == 1 and H * H == HW and H % 16 == 0
+                and C % 64 == 0 and C >= 128):
+            return True
+        # training, medium maps: statistics from the producers' epilogues + the apply pass instead of the one-pass cluster
+        # kernel (MDM_GN_FUSED_STATS_MEDIUM=0 restores it): c2 7.95 -> 7.83 ms, c3 10.43 -> 10.23 ms per step
+        return kind == 1 and int(os.environ.get("MDM_GN_FUSED_STATS_MEDIUM", "1")) > 0
 
     def _want_q(self, x):
         """mark the producers of x (both halves of a concatenation) to emit quad sums; False if one of them cannot"""
