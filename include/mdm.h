@@ -77,11 +77,15 @@ int mdm_rng_seed_host(uint32_t* state_host /*[625]*/, uint32_t seed);
  *     draw of at least MDM_RNG_PAR_MIN_WORDS words is split over ceil(n / (blocks_per_cta * 624)) CTAs and every `rng`
  *     buffer passed to the draw functions must be MDM_RNG_PAR_WORDS uint32 long: words 640 .. 1264 stage the advanced
  *     state (all CTAs read the old state; one tiny follow-up kernel commits the new one).  NULL / 0 disables.
+ *   mdm_rng_set_par_stride: pieces of stride * blocks_per_cta blocks per CTA (every stride-th polynomial of the table);
+ *     returns the previous value.  Every CTA pays the same jump, so a draw that runs next to other kernels (the masks
+ *     of sampler.py:183-199 under the denoiser) costs less SM time with fewer, longer pieces; 1 = shortest draw alone.
  *   mdm_rng_advance_host: host utility, the state after n more draws (same polynomial arithmetic; CPU tests). */
 #define MDM_RNG_PAR_WORDS 1280
 #define MDM_RNG_PAR_MIN_WORDS 262144
 int mdm_rng_jump_table_host(uint32_t* polys_host, int n_polys, int blocks_per_cta);
 int mdm_rng_enable_parallel(const uint32_t* polys_dev, int n_polys, int blocks_per_cta);
+int mdm_rng_set_par_stride(int stride);
 int mdm_rng_advance_host(const uint32_t* state_in_host /*[625]*/, int64_t n, uint32_t* state_out_host /*[625]*/);
 
 /* n raw 32-bit outputs (untransformed) */

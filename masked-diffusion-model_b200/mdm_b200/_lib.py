@@ -29,6 +29,7 @@ _SIGS = {
     "mdm_rng_seed_host": (c_int, [_P, c_uint32]),
     "mdm_rng_jump_table_host": (c_int, [_P, c_int, c_int]),
     "mdm_rng_enable_parallel": (c_int, [_P, c_int, c_int]),
+    "mdm_rng_set_par_stride": (c_int, [c_int]),
     "mdm_rng_advance_host": (c_int, [_P, c_int64, _P]),
     "mdm_rng_raw": (c_int, [_P, _P, c_int64, _P]),
     "mdm_rng_skip": (c_int, [_P, c_int64, _P]),

@@ -65,7 +65,7 @@ constexpr size_t MT_SMEM_PAR = (MT_SEQ_BLOCKS * MT_N + MT_N + MT_JUMP_GROUPS * M
 // c = 0: window 0 straight from the state).
 template <class Emit>
 __global__ void __launch_bounds__(MT_THREADS, 1)
-mt_stream_kernel(uint32_t* rng, const uint32_t* __restrict__ polys, int blocks_per_cta, int64_t n, Emit emit) {
+mt_stream_kernel(uint32_t* rng, const uint32_t* __restrict__ polys, int blocks_per_cta, int poly_stride, int64_t n, Emit emit) {
   MDM_PDL_ENTER();
   extern __shared__ __align__(16) uint32_t mt_sm[];
   uint32_t* seq = mt_sm;                           // [33][624] during the jump; windows 0 / 1 afterwards
@@ -84,7 +84,9 @@ mt_stream_kernel(uint32_t* rng, const uint32_t* __restrict__ polys, int blocks_p
   if (c > 0) {
     uint32_t* poly = mt_sm + MT_SEQ_BLOCKS * MT_N;
     uint32_t* part = poly + MT_N;
-    const uint32_t* g = polys + (size_t)(c - 1) * MT_N;
+    // the table holds x^{(j B - 1) 624} mod phi for j = 1 ..; a CTA that owns poly_stride * B blocks uses every
+    // poly_stride-th entry (blocks_per_cta is then poly_stride * B)
+    const uint32_t* g = polys + ((size_t)c * poly_stride - 1) * MT_N;
     if (k < MT_N) poly[k] = g[k];
     for (int t = 1; t < MT_SEQ_BLOCKS; ++t) {
       if (k < MT_N) seq[t * MT_N + k] = mt_next_word(seq + (t - 1) * MT_N, k);
@@ -198,7 +200,7 @@ struct EmitThreshold {
 
 // parallel generation: table lent by the caller (mdm_rng_enable_parallel)
 static const uint32_t* g_polys = nullptr;
-static int g_npolys = 0, g_blocks_per_cta = 0, g_polys_dev = -1;
+static int g_npolys = 0, g_blocks_per_cta = 0, g_polys_dev = -1, g_par_stride = 1;
 
 template <class Emit>
 struct EmitShifted {   // a later launch of a draw that exceeds the table: indices continue where the previous one stopped
@@ -216,7 +218,7 @@ static int launch_stream(uint32_t* rng, int64_t n, Emit e, void* stream) {
   const bool par = g_polys != nullptr && n >= MDM_RNG_PAR_MIN_WORDS && cudaGetDevice(&dev) == cudaSuccess && dev == g_polys_dev;
   if (!par) {
     launch_pdl(mt_stream_kernel<Emit>, dim3(1), dim3(MT_THREADS), MT_SMEM_SERIAL, as_stream(stream), rng,
-               (const uint32_t*)nullptr, 1 << 24, n, e);
+               (const uint32_t*)nullptr, 1 << 24, 1, n, e);
     MDM_LAUNCH_CHECK();
     return MDM_OK;
   }
@@ -226,16 +228,25 @@ static int launch_stream(uint32_t* rng, int64_t n, Emit e, void* stream) {
     MDM_CUDA(cudaFuncSetAttribute(mt_stream_kernel<EmitShifted<Emit>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM_PAR));
     attr_set = true;
   }
-  const int64_t W = (int64_t)g_blocks_per_cta * MT_N;
-  const int64_t per_launch = W * (g_npolys + 1);       // CTA 0 needs no polynomial
+  // CTAs of a launch: every CTA pays the same jump (~0.3 ms of one SM) whatever it then generates, so a draw that
+  // runs NEXT TO other kernels (the sampler's masks under the denoiser) is cheaper in SM time with fewer, longer pieces.
+  // mdm_rng_set_par_stride(s) / MDM_RNG_PAR_STRIDE = s: pieces of s x blocks_per_cta blocks (default 1: shortest wall
+  // time of the draw alone; the sampler's loop asks for 8: 34.77 -> 34.38 ms per c4 denoising step).
+  const char* sv = getenv("MDM_RNG_PAR_STRIDE");
+  int stride = sv ? atoi(sv) : g_par_stride;
+  if (stride < 1) stride = 1;
+  if (stride > g_npolys) stride = g_npolys;
+  const int bpc = g_blocks_per_cta * stride;
+  const int64_t W = (int64_t)bpc * MT_N;
+  const int64_t per_launch = W * (g_npolys / stride + 1);       // CTA 0 needs no polynomial
   for (int64_t done = 0; done < n; done += per_launch) {
     const int64_t m = n - done < per_launch ? n - done : per_launch;
     const int ctas = (int)((m + W - 1) / W);
     if (done == 0)
-      launch_pdl(mt_stream_kernel<Emit>, dim3(ctas), dim3(MT_THREADS), MT_SMEM_PAR, as_stream(stream), rng, g_polys, g_blocks_per_cta, m, e);
+      launch_pdl(mt_stream_kernel<Emit>, dim3(ctas), dim3(MT_THREADS), MT_SMEM_PAR, as_stream(stream), rng, g_polys, bpc, stride, m, e);
     else
       launch_pdl(mt_stream_kernel<EmitShifted<Emit>>, dim3(ctas), dim3(MT_THREADS), MT_SMEM_PAR, as_stream(stream), rng, g_polys,
-                 g_blocks_per_cta, m, EmitShifted<Emit>{e, done});
+                 bpc, stride, m, EmitShifted<Emit>{e, done});
     MDM_LAUNCH_CHECK();
     if (ctas > 1) {
       launch_pdl(mt_commit_kernel, dim3(1), dim3(MT_THREADS), 0, as_stream(stream), rng);
@@ -320,6 +331,12 @@ int mdm_rng_seed_host(uint32_t* s, uint32_t seed) {
   for (int j = 1; j < MT_N; ++j) s[j] = 1812433253u * (s[j - 1] ^ (s[j - 1] >> 30)) + (uint32_t)j;
   s[MT_N] = MT_N;
   return MDM_OK;
+}
+
+int mdm_rng_set_par_stride(int stride) {
+  const int old = g_par_stride;
+  g_par_stride = stride < 1 ? 1 : stride;
+  return old;
 }
 
 int mdm_rng_enable_parallel(const uint32_t* polys_dev, int n_polys, int blocks_per_cta) {

@@ -174,6 +174,9 @@ class Sampler:
         from mdm_b200 import denoiser_ops as _dops
         static_lists = os.environ.get("MDM_IGEMM_DYNAMIC", "1") == "0"
         reserved_before = _dops.reserve_sms(int(os.environ.get("MDM_SAMPLER_RESERVE_SMS", "1" if static_lists else "0")))
+        # the loop's mask / noise draws run UNDER the denoiser: fewer, longer pieces per draw (every CTA of a parallel
+        # draw pays the same jump) -- 34.77 -> 34.38 ms per step at 256x3x128x128
+        stride_before = lib().mdm_rng_set_par_stride(int(os.environ.get("MDM_SAMPLER_RNG_STRIDE", "8")))
         try:
             with torch.no_grad():
                 for i in range(T - 1, -1, -1):
@@ -230,6 +233,7 @@ class Sampler:
                     shift_e, sb, sc, sp = shift_ne, nb, nc, np_
         finally:
             _dops.reserve_sms(reserved_before)
+            lib().mdm_rng_set_par_stride(stride_before)
         S.release_rng_to_torch()
         visual = [h.cpu() for h in hist] if history else [None] * len(HISTORY_NAMES)
         return sample_0, visual
