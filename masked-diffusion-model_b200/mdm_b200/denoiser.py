@@ -935,8 +935,10 @@ class _Plan:
                 and C % 64 == 0 and C >= 128):
             return True
         # training, medium maps: statistics from the producers' epilogues + the apply pass instead of the one-pass cluster
-        # kernel (MDM_GN_FUSED_STATS_MEDIUM=0 restores it): c2 7.95 -> 7.83 ms, c3 10.43 -> 10.23 ms per step
-        return kind == 1 and int(os.environ.get("MDM_GN_FUSED_STATS_MEDIUM", "1")) > 0
+        # kernel.  Opt-in (MDM_GN_FUSED_STATS_MEDIUM=1): on one GPU c2 7.95 -> 7.83 ms, c3 10.43 -> 10.23 ms per step, but the
+        # one 8-GPU run taken with it was SLOWER (8.86 vs 8.43 ms per step) and the round's GPU budget ended before that
+        # could be repeated -- the default stays the configuration whose scaling was measured twice.
+        return kind == 1 and int(os.environ.get("MDM_GN_FUSED_STATS_MEDIUM", "0")) > 0
 
     def _want_q(self, x):
         """mark the producers of x (both halves of a concatenation) to emit quad sums; False if one of them cannot"""
